@@ -1,0 +1,106 @@
+"""ctypes binding of ``libll_b200.so`` (the C ABI declared in ``include/ll_api.h``).
+
+There is NO fallback: if the library is missing, or the device is not a B200-class
+(sm_100) GPU, every op raises.  PyTorch is only used for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import build as _build
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_voidp = ctypes.c_void_p
+
+LL_OK, LL_EINVAL, LL_EARCH, LL_ECUDA = 0, -1, -2, -3
+
+
+class LLError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libll_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ll_view3(ctypes.Structure):
+    _fields_ = [("ptr", c_voidp), ("sb", c_i64), ("sy", c_i64), ("sx", c_i64)]
+
+
+class ll_lift_job(ctypes.Structure):
+    _fields_ = [("src", ll_view3), ("din", ll_view3), ("dout", ll_view3),
+                ("nb", ctypes.c_int32), ("ny", ctypes.c_int32), ("nx", ctypes.c_int32)]
+
+
+# name -> (restype, argtypes); mirrors include/ll_api.h declaration by declaration
+_P = c_voidp  # device pointers are passed as integers (tensor.data_ptr())
+SIGNATURES = {
+    "ll_last_error": (ctypes.c_char_p, []),
+    "ll_version": (c_int, []),
+    "ll_check_device": (c_int, []),
+    "ll_sm_count": (c_int, []),
+    "ll_pack_lift_step": (c_int, [_P] * 10 + [_P]),
+    "ll_lift_step": (c_int, [ctypes.POINTER(ll_lift_job), c_int, _P, c_float, c_float, c_int, _P]),
+    "ll_lift_level_scratch_floats": (ctypes.c_size_t, [c_int, c_int, c_int]),
+    "ll_lift_level_fwd": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, _P, c_int, c_int, c_int,
+                                  ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, _P]),
+    "ll_lift_level_inv": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, _P, c_int, c_int, c_int,
+                                  ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, _P]),
+    "ll_dwt97_fwd_level": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, _P]),
+    "ll_dwt97_inv_level": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, _P]),
+    "ll_pack_ae1": (c_int, [_P] * 8 + [c_int, c_int, _P, _P]),
+    "ll_ae1_apply": (c_int, [_P, _P, _P, _P, c_int, c_int, c_i64, _P]),
+}
+
+_lib = None
+_device_ok = {}
+
+
+def load(build_if_missing=True):
+    """Load (building first if stale and nvcc is present) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_missing:
+        try:
+            path = _build.build()
+        except Exception as e:  # no nvcc on this box: use the shipped .so if there is one
+            if not os.path.isfile(path):
+                raise RuntimeError(f"libll_b200.so is missing and could not be built: {e}") from e
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} is missing: run `python -m "
+                           f"{__package__}.build` (there is no CPU / PyTorch fallback)")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != LL_OK:
+        raise LLError(rc, load().ll_last_error().decode(errors="replace"))
+
+
+def require_device(t):
+    """The tensor must live on a CUDA device this library can run on."""
+    if not t.is_cuda:
+        raise RuntimeError("ll_b200 ops need CUDA tensors: there is no CPU fallback")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _device_ok:
+        with torch.cuda.device(idx):
+            check(load().ll_check_device())
+        _device_ok[idx] = True
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return t.data_ptr() if t is not None else None

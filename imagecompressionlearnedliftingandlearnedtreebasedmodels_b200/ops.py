@@ -1,0 +1,187 @@
+"""Tensor-level wrappers over the C ABI (``include/ll_api.h``).
+
+Each function checks devices/dtypes, allocates outputs/scratch with torch, and
+enqueues the CUDA work on torch's current stream.  Nothing here computes on the
+host and nothing falls back to PyTorch arithmetic.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import c_voidp, check, ptr, require_device, stream_ptr
+
+LIFT_BLOB_FLOATS = 13656
+AE1_BLOB_FLOATS = 2212
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------- learned lifting
+def pack_lift_step(pre_w, conv):
+    """``pre_w``: convBlock[k].weight (1,1,3,1); ``conv``: dict conv1..conv4 -> (weight, bias).
+    Returns the device blob of one lifting step (ll_pack_lift_step)."""
+    require_device(pre_w)
+    lib = _lib.load()
+    args = [_f32c(pre_w.detach(), "pre_w")]
+    for k in ("conv1", "conv2", "conv3", "conv4"):
+        w, b = conv[k]
+        args += [_f32c(w.detach(), k + ".weight"), _f32c(b.detach(), k + ".bias")]
+    exp = [(3,), (16 * 25,), (16,), (16 * 16 * 25,), (16,), (16 * 16 * 25,), (16,), (16 * 25,), (1,)]
+    for a, e in zip(args, exp):
+        if a.numel() != e[0]:
+            raise ValueError(f"pack_lift_step: parameter with {a.numel()} elements, expected {e[0]} "
+                             "(the CUDA path is built for clrch=1, filtersize=5, depth_scale=2)")
+    blob = torch.empty(LIFT_BLOB_FLOATS, dtype=torch.float32, device=pre_w.device)
+    with torch.cuda.device(pre_w.device):
+        check(lib.ll_pack_lift_step(*[ptr(a) for a in args], ptr(blob), stream_ptr()))
+    return blob
+
+
+def _blob_array(blobs):
+    if len(blobs) != 4:
+        raise ValueError("need the 4 packed lifting steps")
+    return (c_voidp * 4)(*[ptr(b) for b in blobs])
+
+
+def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, ll_out=None, yh_out=None):
+    """x (B,1,h,w) -> (LL (B,1,h/2,w/2), Yh (B,3,h/2,w/2) = [LH,HL,HH])."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, C, h, w = x.shape
+    if C != 1:
+        raise ValueError("learned lifting runs on single-channel planes (clrch == 1)")
+    if h % 2 or w % 2:
+        raise ValueError(f"lift_level_fwd: h, w must be even, got {h}x{w}")
+    lib = _lib.load()
+    ll = ll_out if ll_out is not None else torch.empty(B, 1, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    yh = yh_out if yh_out is not None else torch.empty(B, 3, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    n = lib.ll_lift_level_scratch_floats(B, h, w)
+    scratch = torch.empty(max(n, 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.ll_lift_level_fwd(ptr(x), x.stride(0), ptr(ll), ll.stride(0), ptr(yh), yh.stride(0), ptr(scratch),
+                                    B, h, w, _blob_array(blobs), float(res_weight), int(bool(linear)), int(scale),
+                                    ptr(nh), ptr(nl), stream_ptr()))
+    return ll, yh
+
+
+def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None):
+    """(LL (B,1,h2,w2), Yh (B,3,h2,w2)) -> x (B,1,2*h2,2*w2)."""
+    require_device(ll)
+    ll = _f32c(ll, "ll")
+    yh = _f32c(yh, "yh")
+    B, C, h2, w2 = ll.shape
+    if C != 1 or tuple(yh.shape) != (B, 3, h2, w2):
+        raise ValueError(f"lift_level_inv: shapes {tuple(ll.shape)} / {tuple(yh.shape)}")
+    h, w = 2 * h2, 2 * w2
+    lib = _lib.load()
+    x = torch.empty(B, 1, h, w, dtype=torch.float32, device=ll.device)
+    n = lib.ll_lift_level_scratch_floats(B, h, w)
+    scratch = torch.empty(max(n, 1), dtype=torch.float32, device=ll.device)
+    with torch.cuda.device(ll.device):
+        check(lib.ll_lift_level_inv(ptr(ll), ll.stride(0), ptr(yh), yh.stride(0), ptr(x), x.stride(0), ptr(scratch),
+                                    B, h, w, _blob_array(blobs), float(res_weight), int(bool(linear)), int(scale),
+                                    ptr(nh), ptr(nl), stream_ptr()))
+    return x
+
+
+# ----------------------------------------------------------------------------- CDF 9/7
+def dwt97_forward(x, J):
+    """DWTForward(J, 'periodization', 'bior4.4'): x (B,C,H,W) -> (Yl (B,C,h,w), [Yh_j (B,C,3,h_j,w_j)])."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, C, H, W = x.shape
+    if H % (1 << J) or W % (1 << J):
+        raise ValueError(f"dwt97_forward: H, W must be divisible by 2^{J}, got {H}x{W}")
+    lib = _lib.load()
+    N = B * C
+    cur = x
+    yh = []
+    with torch.cuda.device(x.device):
+        for _ in range(J):
+            h, w = cur.shape[-2], cur.shape[-1]
+            ll = torch.empty(B, C, h // 2, w // 2, dtype=torch.float32, device=x.device)
+            y = torch.empty(B, C, 3, h // 2, w // 2, dtype=torch.float32, device=x.device)
+            check(lib.ll_dwt97_fwd_level(ptr(cur), h * w, ptr(ll), (h // 2) * (w // 2), ptr(y), 3 * (h // 2) * (w // 2),
+                                         N, h, w, stream_ptr()))
+            yh.append(y)
+            cur = ll
+    return cur, yh
+
+
+def dwt97_inverse(yl, yh):
+    """DWTInverse('periodization', 'bior4.4')((Yl, Yh))."""
+    require_device(yl)
+    lib = _lib.load()
+    cur = _f32c(yl, "yl")
+    B, C = cur.shape[0], cur.shape[1]
+    N = B * C
+    with torch.cuda.device(cur.device):
+        for y in yh[::-1]:
+            y = _f32c(y, "yh")
+            h2, w2 = y.shape[-2], y.shape[-1]
+            if tuple(cur.shape[-2:]) != (h2, w2) or y.shape[2] != 3:
+                raise ValueError(f"dwt97_inverse: shape mismatch {tuple(cur.shape)} vs {tuple(y.shape)}")
+            x = torch.empty(B, C, 2 * h2, 2 * w2, dtype=torch.float32, device=cur.device)
+            check(lib.ll_dwt97_inv_level(ptr(cur), h2 * w2, ptr(y), 3 * h2 * w2, ptr(x), 4 * h2 * w2, N, 2 * h2, 2 * w2,
+                                         stream_ptr()))
+            cur = x
+    return cur
+
+
+# ----------------------------------------------------------------------------- pointwise auto-encoder
+def pack_ae1(layers, C, transposed):
+    """``layers``: 4 (weight, bias) pairs of ae_down (Conv2d) or ae_up (ConvTranspose2d)."""
+    dev = layers[0][0].device
+    require_device(layers[0][0])
+    lib = _lib.load()
+    args = []
+    for w, b in layers:
+        args += [_f32c(w.detach(), "w"), _f32c(b.detach(), "b")]
+    exp = [32 * C, 32 * C, 1024 * C, 32 * C, 1024 * C, 32 * C, 32 * C, C]
+    for a, e in zip(args, exp):
+        if a.numel() != e:
+            raise ValueError(f"pack_ae1: parameter with {a.numel()} elements, expected {e}")
+    blob = torch.empty(C * AE1_BLOB_FLOATS, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.ll_pack_ae1(*[ptr(a) for a in args], C, int(bool(transposed)), ptr(blob), stream_ptr()))
+    return blob
+
+
+def ae1_apply(x, blob, want_round=False):
+    """Pointwise 1->32->32->32->1 tanh MLP per channel of x (B,C,H,W); optionally also round(y)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, C = x.shape[0], x.shape[1]
+    n = x[0, 0].numel() if B * C else 0
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    q = torch.empty_like(x) if want_round else None
+    with torch.cuda.device(x.device):
+        check(lib.ll_ae1_apply(ptr(x), ptr(y), ptr(q), ptr(blob), B, C, n, stream_ptr()))
+    return (y, q) if want_round else y
+
+
+def lift_step(jobs, blob, sign, res_weight=0.1, linear=False):
+    """One fused lifting step on up to two (src, din, dout) triples of equally shaped
+    3-D strided views (B, ny, nx); the 3-tap pre-filter runs along dim 1.  dout may alias din."""
+    lib = _lib.load()
+    if not 1 <= len(jobs) <= 2:
+        raise ValueError("lift_step takes 1 or 2 jobs")
+    arr = (_lib.ll_lift_job * len(jobs))()
+    dev = jobs[0][0].device
+    for a, (src, din, dout) in zip(arr, jobs):
+        for t in (src, din, dout):
+            require_device(t)
+            if t.dtype != torch.float32 or t.dim() != 3 or t.shape != src.shape:
+                raise ValueError("lift_step: views must be float32, 3-D and equally shaped")
+        for f, t in (("src", src), ("din", din), ("dout", dout)):
+            v = getattr(a, f)
+            v.ptr, v.sb, v.sy, v.sx = t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
+        a.nb, a.ny, a.nx = src.shape
+    with torch.cuda.device(dev):
+        check(lib.ll_lift_step(arr, len(jobs), ptr(blob), float(sign), float(res_weight), int(bool(linear)), stream_ptr()))

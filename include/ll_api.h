@@ -1,0 +1,128 @@
+/*
+ * ll_api.h -- C ABI of the B200-native learned-lifting / tree-entropy hot path.
+ *
+ * Plain `extern "C"` entry points, plain pointers and sizes, no torch / C++ types.
+ * The reference (uberkk/ImageCompressionLearnedLiftingandLearnedTreeBasedModels) is
+ * pure Python/PyTorch and has no FFI layer of its own; each entry point below cites
+ * the reference function (file:line under /root/reference) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 unless stated; the caller (PyTorch)
+ *    owns all buffers, outputs and scratch included;
+ *  - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *    void*); no hidden synchronisation, re-entrant for distinct streams;
+ *  - return value: LL_OK or a negative code; ll_last_error() gives a message for
+ *    the calling thread;
+ *  - strides are in ELEMENTS.
+ */
+#ifndef LL_API_H
+#define LL_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LL_OK 0
+#define LL_EINVAL (-1) /* bad shape / alignment / argument           */
+#define LL_EARCH (-2)  /* current device is not sm_100 (B200)        */
+#define LL_ECUDA (-3)  /* CUDA launch/runtime failure, see last error */
+
+typedef void* ll_stream_t; /* cudaStream_t */
+
+const char* ll_last_error(void);
+int ll_version(void);
+/* 0 if the current CUDA device can run this library (compute capability 10.x). */
+int ll_check_device(void);
+int ll_sm_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* Learned lifting (K2)                                                       */
+/* ------------------------------------------------------------------------- */
+
+/* A (batch, y, x) strided view of fp32 data. */
+typedef struct ll_view3 {
+  float* ptr;
+  int64_t sb, sy, sx;
+} ll_view3;
+
+/* One lifting-step job: dout = din + sign * (skip + res_weight * CNN(skip)),
+ * skip = 3-tap pre-filter of `src` along y.  All three views are (nb, ny, nx). */
+typedef struct ll_lift_job {
+  ll_view3 src, din, dout;
+  int32_t nb, ny, nx;
+} ll_lift_job;
+
+#define LL_LIFT_BLOB_FLOATS 13656
+
+/* Packs one lifting step's parameters into the kernel's blob layout (device to
+ * device, on `stream`).  pre_w: (3,) taps of convBlock[k] (lifting_dwt_nets.py:784-827);
+ * w1..b4: P_block_v2 conv1..conv4 weight/bias in torch layout
+ * (graphs/layers/P_block_v2.py:16-36).  blob: LL_LIFT_BLOB_FLOATS floats. */
+int ll_pack_lift_step(const float* pre_w, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* w3, const float* b3, const float* w4, const float* b4, float* blob,
+                      ll_stream_t stream);
+
+/* One lifting step over up to 2 independent jobs in a single launch.  Replaces one
+ * "skip = convBlock[k](src); dst = dst +- (skip + P|U[j](skip) * w)" group of
+ * lifting_forward_row_2_stage_lifting (graphs/layers/wavelet_forward_v2.py:58-74) /
+ * lifting_inverse_row_2_stage_lifting (graphs/layers/wavelet_inverse_v2.py:76-90),
+ * including P_block_v2.forward (graphs/layers/P_block_v2.py:40-55).
+ * sign = +1 forward, -1 inverse, 0 = write the raw CNN output (stand-alone P_block_v2.forward,
+ * pass pre-filter taps (0,1,0)); linear != 0 drops both tanh (linearity_flag == 0). */
+int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float res_weight,
+                 int linear, ll_stream_t stream);
+
+/* One full 2-D lifting level, forward: x (B,h,w) -> ll (B,h/2,w/2), yh (B,3,h/2,w/2)
+ * ordered LH,HL,HH.  Replaces wavelet_forward_v2.one_level_lifting
+ * (graphs/layers/wavelet_forward_v2.py:26-54).  blobs[4]: packed steps 1..4.
+ * scratch: ll_lift_level_scratch_floats(B,h,w) floats.  x_sb/ll_sb/yh_sb: batch
+ * strides (elements) so that outputs can be slices of larger tensors; rows are dense.
+ * scale: 0, or 1 with nh/nl device scalars (wavelet_forward_v2.py:76-80). */
+size_t ll_lift_level_scratch_floats(int B, int h, int w);
+int ll_lift_level_fwd(const float* x, int64_t x_sb, float* ll, int64_t ll_sb, float* yh, int64_t yh_sb,
+                      float* scratch, int B, int h, int w, const float* const* blobs, float res_weight,
+                      int linear, int scale, const float* nh, const float* nl, ll_stream_t stream);
+/* Inverse level: (ll, yh) -> x.  Replaces wavelet_inverse_v2.one_level_lifting +
+ * reconstruct_fun (graphs/layers/wavelet_inverse_v2.py:20-56, 68-92). */
+int ll_lift_level_inv(const float* ll, int64_t ll_sb, const float* yh, int64_t yh_sb, float* x, int64_t x_sb,
+                      float* scratch, int B, int h, int w, const float* const* blobs, float res_weight,
+                      int linear, int scale, const float* nh, const float* nl, ll_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* CDF 9/7 fixed-filter DWT (K1)                                              */
+/* ------------------------------------------------------------------------- */
+
+/* One level of pytorch_wavelets.DWTForward(mode='periodization', wave='bior4.4')
+ * as used by DWTPytorchWaveletsLayer.encode (graphs/layers/lifting_dwt_nets.py:228-231,250):
+ * x (N,h,w) planes -> ll (N,h/2,w/2), yh (N,3,h/2,w/2) ordered LH,HL,HH.
+ * N = B*C planes; *_sn are plane strides in elements, rows dense. */
+int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* ll, int64_t ll_sn, float* yh, int64_t yh_sn,
+                       int N, int h, int w, ll_stream_t stream);
+/* One level of DWTInverse (lifting_dwt_nets.py:231,274): (ll, yh) -> x (N,h,w), h,w = output size. */
+int ll_dwt97_inv_level(const float* ll, int64_t ll_sn, const float* yh, int64_t yh_sn, float* x, int64_t x_sn,
+                       int N, int h, int w, ll_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Pointwise subband auto-encoder (v1) fused with the quantiser               */
+/* ------------------------------------------------------------------------- */
+
+#define LL_AE1_BLOB_FLOATS 2212 /* per channel: w0[32] b0[32] W1[32x32] b1[32] W2[32x32] b2[32] w3[32] b3[1] pad[3] */
+
+/* SubbandAutoEncoder.encode / .decode (graphs/layers/lifting_dwt_nets.py:99-125):
+ * per channel c of x (B,C,n): 1 -> 32 tanh -> 32 tanh -> 32 tanh -> 1.
+ * blob: C * LL_AE1_BLOB_FLOATS packed by ll_pack_ae1.  If q != NULL also writes
+ * q = rint(y) (torch.round, half to even) -- the quantised symbols. */
+int ll_pack_ae1(const float* w0, const float* b0, const float* w1, const float* b1, const float* w2,
+                const float* b2, const float* w3, const float* b3, int C, int transposed, float* blob,
+                ll_stream_t stream);
+int ll_ae1_apply(const float* x, float* y, float* q, const float* blob, int B, int C, int64_t n,
+                 ll_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LL_API_H */
