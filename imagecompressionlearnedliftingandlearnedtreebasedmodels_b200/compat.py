@@ -154,3 +154,151 @@ class DWTInverse(nn.Module):
     def forward(self, coeffs):
         yl, yh = coeffs
         return ops.dwt97_inverse(yl, yh)
+
+
+# --------------------------------------------------------------------------- entropy models
+
+
+def draw_noise(like):
+    """The reference's noise draw: ``torch.empty_like(x).uniform_(-0.5, 0.5)`` (compressai
+    EntropyModel.quantize), one draw per call, in call order."""
+    return torch.empty_like(like).uniform_(-0.5, 0.5)
+
+
+class EntropyModel(nn.Module):
+    """compressai 1.2.1 ``EntropyModel`` surface used by the reference: ``quantize`` and the
+    (empty) CDF buffers that appear in checkpoints."""
+
+    def __init__(self, likelihood_bound=1e-9, entropy_coder=None, entropy_coder_precision=16):
+        super().__init__()
+        self.entropy_coder_precision = int(entropy_coder_precision)
+        self.use_likelihood_bound = likelihood_bound > 0
+        if self.use_likelihood_bound:
+            self.likelihood_lower_bound = LowerBound(likelihood_bound)
+        self.register_buffer("_offset", torch.IntTensor())
+        self.register_buffer("_quantized_cdf", torch.IntTensor())
+        self.register_buffer("_cdf_length", torch.IntTensor())
+
+    def quantize(self, inputs, mode, means=None):
+        if mode not in ("noise", "dequantize", "symbols"):
+            raise ValueError(f'Invalid quantization mode: "{mode}"')
+        if mode == "noise":
+            return ops.quantize(inputs, draw_noise(inputs))
+        if means is not None:
+            q = ops.quantize(inputs - means)
+            return q + means if mode == "dequantize" else q.int()
+        q = ops.quantize(inputs)
+        return q if mode == "dequantize" else q.int()
+
+
+class GaussianConditional(EntropyModel):
+    """compressai 1.2.1 ``GaussianConditional(scale_table=None, scale_bound=0.11)``; ``forward``
+    returns (outputs, likelihood) like the original, ``bits`` is the fused fast path."""
+
+    def __init__(self, scale_table, *args, scale_bound=0.11, tail_mass=1e-9, **kwargs):
+        super().__init__(*args, **kwargs)
+        if scale_table is not None:
+            raise NotImplementedError("scale tables are only used by the serial coder (out of scope)")
+        if abs(float(scale_bound) - 0.11) > 1e-12:
+            raise NotImplementedError("the CUDA rate kernel is built for scale_bound = 0.11 (the reference's value)")
+        self.tail_mass = float(tail_mass)
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self.register_buffer("scale_table", torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
+
+    def bits(self, inputs, ms, training=None, want_y=False, acc=None):
+        """-log2 likelihood with sigma/mu interleaved on the channels of ``ms`` (B,2C,H,W)."""
+        if training is None:
+            training = self.training
+        noise = draw_noise(inputs) if training else None
+        return ops.gauss_rate(inputs, ms, noise, want_y, acc)
+
+    def forward(self, inputs, scales, means=None, training=None):
+        if means is None:
+            means = torch.zeros_like(inputs)
+        ms = torch.stack((scales, means), dim=2).flatten(1, 2)   # channel 2c = sigma, 2c+1 = mu
+        bits, y = self.bits(inputs, ms, training, want_y=True)
+        return y, torch.exp2(-bits)
+
+
+class EntropyBottleneck(EntropyModel):
+    """compressai 1.2.1 ``EntropyBottleneck`` (filters (3,3,3,3), init_scale 10)."""
+
+    def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3), **kwargs):
+        super().__init__(*args, **kwargs)
+        self.channels = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        if self.filters != (3, 3, 3, 3):
+            raise NotImplementedError("the CUDA kernel is built for filters (3,3,3,3) (the reference's default)")
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        filters = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        channels = self.channels
+        for i in range(len(self.filters) + 1):
+            init = np.log(np.expm1(1 / scale / filters[i + 1]))
+            matrix = torch.Tensor(channels, filters[i + 1], filters[i])
+            matrix.data.fill_(init)
+            self.register_parameter(f"_matrix{i:d}", nn.Parameter(matrix))
+            bias = torch.Tensor(channels, filters[i + 1], 1)
+            nn.init.uniform_(bias, -0.5, 0.5)
+            self.register_parameter(f"_bias{i:d}", nn.Parameter(bias))
+            if i < len(self.filters):
+                factor = torch.Tensor(channels, filters[i + 1], 1)
+                nn.init.zeros_(factor)
+                self.register_parameter(f"_factor{i:d}", nn.Parameter(factor))
+        self.quantiles = nn.Parameter(torch.Tensor(channels, 1, 3))
+        init = torch.Tensor([-self.init_scale, 0, self.init_scale])
+        self.quantiles.data = init.repeat(self.quantiles.size(0), 1, 1)
+        target = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-target, 0, target]))
+        from .graphs.layers._packing import PackCache
+        self._cache = PackCache()
+
+    def _param_list(self):
+        ps = []
+        for i in range(5):
+            ps.append(getattr(self, f"_matrix{i:d}"))
+            ps.append(getattr(self, f"_bias{i:d}"))
+            if i < 4:
+                ps.append(getattr(self, f"_factor{i:d}"))
+        ps.append(self.quantiles)
+        return ps
+
+    def _blob(self):
+        ps = self._param_list()
+        return self._cache.get(ps, lambda: ops.pack_eb(ps, self.channels))
+
+    def _get_medians(self):
+        return self.quantiles[:, :, 1:2].detach()
+
+    def _logits_cumulative(self, inputs, stop_gradient):
+        logits = inputs
+        for i in range(len(self.filters) + 1):
+            matrix = getattr(self, f"_matrix{i:d}")
+            bias = getattr(self, f"_bias{i:d}")
+            if stop_gradient:
+                matrix, bias = matrix.detach(), bias.detach()
+            logits = torch.matmul(F.softplus(matrix), logits) + bias
+            if i < len(self.filters):
+                factor = getattr(self, f"_factor{i:d}")
+                if stop_gradient:
+                    factor = factor.detach()
+                logits = logits + torch.tanh(factor) * torch.tanh(logits)
+        return logits
+
+    def loss(self):
+        """Auxiliary quantile loss (tiny, host-side bookkeeping: plain torch ops)."""
+        logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
+        return torch.abs(logits - self.target).sum()
+
+    def rate(self, x, training=None, acc=None):
+        """(y, bits) through the fused CUDA kernel."""
+        if training is None:
+            training = self.training
+        noise = draw_noise(x) if training else None
+        return ops.eb_rate(x, self._blob(), noise, acc)
+
+    def forward(self, x, training=None):
+        y, bits = self.rate(x, training)
+        return y, torch.exp2(-bits)

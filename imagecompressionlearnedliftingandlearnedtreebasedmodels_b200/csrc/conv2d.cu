@@ -1,0 +1,177 @@
+// conv2d.cu -- fp32 SIMT direct convolution for the small context CNNs of the entropy models.
+//
+// Covers every conv of the tree-based entropy layers that is not a dense contraction large
+// enough for the tensor cores: MaskedConv2d chains (csc_xe / csc_list, LiftingBasedDWT_net.py:
+// 298-317), the masked 5x5 csc (:274-277), plc's first 3->243 conv on the nearest-2x-upsampled
+// parent (:271,355), the grouped 1x1 cgp MLP (:280-290), onlyEZWT's 1x1 head (:792-794) and the
+// ZTBlock CNNs (:618-680).  Cross-correlation, zero padding K/2, stride 1, optional LeakyReLU(0.01)
+// on the output, optional nearest-2x upsampling of the input fused into the load (replaces
+// repeat_interleave(2,2).repeat_interleave(2,3), :348,367), and an output-channel remap so that
+// torch.cat((plc0,csc0,plc1,csc1,plc2,csc2)) (:357-359) is a write pattern, not a copy.
+//
+// Tiling: CTA = 8x32 output pixels x 32 output channels, thread = 4 pixels x 8 channels on
+// packed FFMA2 (channel pairs), input channels staged 8 at a time through shared memory.
+#include "ll_common.cuh"
+
+namespace ll {
+
+constexpr int CV_THREADS = 256;
+constexpr int CV_TH = 8, CV_TW = 32;  // output tile
+constexpr int CV_CO = 32;             // output channels per CTA
+constexpr int CV_CI = 8;              // input channels per stage
+
+struct ConvParams {
+  const float* x;
+  const float* w;
+  const float* b;
+  float* y;
+  int B, Cin, H, W, Cout, groups;
+  int upsample2, lrelu;
+  long long x_sb, y_sb;       // batch strides (elements)
+  int co_group, co_stride, co_off;  // output channel remap: (co / co_group) * co_stride + co_off + co % co_group
+  int tiles_x, tiles_y, co_tiles_per_group;
+};
+
+template <int K>
+__global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int PAD = K / 2;
+  constexpr int IH = CV_TH + K - 1, IW = CV_TW + K - 1;
+  constexpr int IWP = IW + 1;  // pitch
+  constexpr int KK = K * K;
+  __shared__ __align__(16) float s_in[CV_CI * IH * IWP];
+  __shared__ __align__(16) float s_w[CV_CI * KK * CV_CO];
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int tx0 = (tile % p.tiles_x) * CV_TW, ty0 = (tile / p.tiles_x) * CV_TH;
+  const int g = blockIdx.y / p.co_tiles_per_group;
+  const int cin_g = p.Cin / p.groups, cout_g = p.Cout / p.groups;
+  const int co0 = (blockIdx.y % p.co_tiles_per_group) * CV_CO;  // within the group
+  const int b = blockIdx.z;
+
+  // thread -> (pixel group, channel group)
+  const int cg = tid >> 6;         // 0..3: 8 output channels each
+  const int pg = tid & 63;         // 0..63
+  const int py = pg >> 3, px = (pg & 7) * 4;
+
+  float2 acc[4][4];
+#pragma unroll
+  for (int c2 = 0; c2 < 4; ++c2) {
+    const int co = co0 + cg * 8 + 2 * c2;
+    const float b0 = (p.b && co < cout_g) ? p.b[g * cout_g + co] : 0.f;
+    const float b1 = (p.b && co + 1 < cout_g) ? p.b[g * cout_g + co + 1] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][c2] = make_float2(b0, b1);
+  }
+
+  const int Hs = p.upsample2 ? p.H / 2 : p.H, Ws = p.upsample2 ? p.W / 2 : p.W;
+  const float* xb = p.x + (long long)b * p.x_sb + (long long)g * cin_g * Hs * Ws;
+
+  for (int ci0 = 0; ci0 < cin_g; ci0 += CV_CI) {
+    __syncthreads();
+    // stage input tile (zero outside the image / beyond the channel count)
+    for (int e = tid; e < CV_CI * IH * IW; e += CV_THREADS) {
+      const int ci = e / (IH * IW), r = (e / IW) % IH, c = e % IW;
+      const int gy = ty0 + r - PAD, gx = tx0 + c - PAD;
+      float v = 0.f;
+      if (ci0 + ci < cin_g && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+        const int sy = p.upsample2 ? (gy >> 1) : gy, sx = p.upsample2 ? (gx >> 1) : gx;
+        v = xb[((long long)(ci0 + ci) * Hs + sy) * Ws + sx];
+      }
+      s_in[(ci * IH + r) * IWP + c] = v;
+    }
+    // stage weights [ci][tap][co]
+    for (int e = tid; e < CV_CI * KK * CV_CO; e += CV_THREADS) {
+      const int co = e % CV_CO, tap = (e / CV_CO) % KK, ci = e / (CV_CO * KK);
+      float v = 0.f;
+      if (co0 + co < cout_g && ci0 + ci < cin_g)
+        v = p.w[((long long)(g * cout_g + co0 + co) * cin_g + (ci0 + ci)) * KK + tap];
+      s_w[e] = v;
+    }
+    __syncthreads();
+    const int nci = min(CV_CI, cin_g - ci0);
+    for (int ci = 0; ci < nci; ++ci) {
+#pragma unroll
+      for (int dy = 0; dy < K; ++dy) {
+        const float* arow = &s_in[(ci * IH + py + dy) * IWP + px];
+        float a[4 + K - 1];
+#pragma unroll
+        for (int k = 0; k < 4 + K - 1; ++k) a[k] = arow[k];
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const float* wp = &s_w[(ci * KK + dy * K + dx) * CV_CO + cg * 8];
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 av = make_float2(a[i + dx], a[i + dx]);
+            acc[i][0] = __ffma2_rn(av, make_float2(w0.x, w0.y), acc[i][0]);
+            acc[i][1] = __ffma2_rn(av, make_float2(w0.z, w0.w), acc[i][1]);
+            acc[i][2] = __ffma2_rn(av, make_float2(w1.x, w1.y), acc[i][2]);
+            acc[i][3] = __ffma2_rn(av, make_float2(w1.z, w1.w), acc[i][3]);
+          }
+        }
+      }
+    }
+  }
+
+  const int oy = ty0 + py, ox = tx0 + px;
+  if (oy >= p.H) return;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int co = co0 + cg * 8 + c;
+    if (co >= cout_g) break;
+    const int cog = g * cout_g + co;
+    const int cm = (cog / p.co_group) * p.co_stride + p.co_off + (cog % p.co_group);
+    float* yo = p.y + (long long)b * p.y_sb + ((long long)cm * p.H + oy) * p.W + ox;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (ox + i < p.W) {
+        float v = (c & 1) ? acc[i][c >> 1].y : acc[i][c >> 1].x;
+        if (p.lrelu) v = v > 0.f ? v : v * 0.01f;
+        yo[i] = v;
+      }
+    }
+  }
+}
+
+}  // namespace ll
+
+using namespace ll;
+
+extern "C" {
+
+int ll_conv2d(const float* x, int64_t x_sb, const float* w, const float* b, float* y, int64_t y_sb, int B, int Cin,
+              int H, int W, int Cout, int K, int groups, int upsample2, int lrelu, int co_group, int co_stride,
+              int co_off, ll_stream_t stream) {
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H < 0 || W < 0 || groups <= 0) return fail(LL_EINVAL, "ll_conv2d: bad extents");
+  if (Cin % groups || Cout % groups) return fail(LL_EINVAL, "ll_conv2d: channels not divisible by groups");
+  if (K != 1 && K != 3 && K != 5) return fail(LL_EINVAL, "ll_conv2d: kernel size %d not supported (1, 3, 5)", K);
+  if (upsample2 && ((H & 1) || (W & 1))) return fail(LL_EINVAL, "ll_conv2d: upsample2 needs even output size");
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!x || !w || !y) return fail(LL_EINVAL, "ll_conv2d: null pointer");
+  if (co_group <= 0) {
+    co_group = Cout;
+    co_stride = 0;
+    co_off = 0;
+  }
+  ConvParams p = {};
+  p.x = x; p.w = w; p.b = b; p.y = y;
+  p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.groups = groups;
+  p.upsample2 = upsample2; p.lrelu = lrelu;
+  p.x_sb = x_sb; p.y_sb = y_sb;
+  p.co_group = co_group; p.co_stride = co_stride; p.co_off = co_off;
+  p.tiles_x = (W + CV_TW - 1) / CV_TW;
+  p.tiles_y = (H + CV_TH - 1) / CV_TH;
+  p.co_tiles_per_group = (Cout / groups + CV_CO - 1) / CV_CO;
+  if (B > 65535 || p.co_tiles_per_group * groups > 65535) return fail(LL_EINVAL, "ll_conv2d: grid too large");
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y), (unsigned)(p.co_tiles_per_group * groups), (unsigned)B);
+  cudaStream_t st = as_stream(stream);
+  if (K == 1) conv2d_kernel<1><<<grid, CV_THREADS, 0, st>>>(p);
+  else if (K == 3) conv2d_kernel<3><<<grid, CV_THREADS, 0, st>>>(p);
+  else conv2d_kernel<5><<<grid, CV_THREADS, 0, st>>>(p);
+  LL_LAUNCH_OK("conv2d_kernel");
+  return LL_OK;
+}
+
+}  // extern "C"

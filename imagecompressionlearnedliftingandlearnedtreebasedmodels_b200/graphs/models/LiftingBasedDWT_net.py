@@ -1,0 +1,414 @@
+"""Codec model and the tree-based subband entropy layers (reference:
+graphs/models/LiftingBasedDWT_net.py).
+
+``LiftingBasedDWTNetWrapper`` (:35-99), ``LiftingBasedDWTNet`` (:100-180),
+``DWTFactorizedEntropyLayer`` (:182-231), ``DWTConditioned2EntropyLayerZTsepSubbands``
+(:233-372), ``DWTConditioned2EntropyLayerZTBlock`` (:558-757), ``onlyEZWT`` (:759-840): same
+constructors, sub-module names and registration order (checkpoints load with strict=True,
+seeded construction reproduces the reference's initial weights); ``forward`` bodies run on the
+sm_100a kernels.  The serial per-coefficient coder (``test`` / ``compress_ar`` /
+``decompress_ar``, :374-556) is out of scope.
+"""
+import math
+
+import torch
+from torch import nn
+
+from ... import ops
+from ...compat import EntropyBottleneck, GaussianConditional
+from ..layers.lifting_dwt_nets import DWTPytorchWaveletsLayer, LiftingBasedNeuralWaveletv4
+from ..layers.masked_conv2d import MaskedConv2d
+
+SCALES_MIN = 0.11
+SCALES_MAX = 256
+SCALES_LEVELS = 64
+# images per launch group inside the context models: bounds the 243/486-channel intermediates
+# (level 0 of a 512x768 plane needs ~0.6 GB per image in fp32)
+CTX_BATCH_CHUNK = 8
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+def _conv(seq_item, x, lrelu=False, **kw):
+    """nn.Conv2d / MaskedConv2d through the direct-conv kernel."""
+    if isinstance(seq_item, MaskedConv2d):
+        return seq_item(x, lrelu=lrelu, **kw)
+    return ops.conv2d(x, seq_item.weight, seq_item.bias, groups=seq_item.groups, lrelu=lrelu, **kw)
+
+
+def _chain(seq, x):
+    """Conv / LeakyReLU alternation of an nn.Sequential with the activation fused into the conv."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        act = i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU)
+        x = _conv(m, x, lrelu=act)
+        i += 2 if act else 1
+    return x
+
+
+class LiftingBasedDWTNetWrapper(nn.Module):
+    """Per-colour-plane dispatch (:35-99): ``clrch == 1`` builds three independent nets."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.clrch = config.clrch
+        if self.clrch == 3:
+            self.model = LiftingBasedDWTNet(config)
+        elif self.clrch == 1:
+            self.model0 = LiftingBasedDWTNet(config)
+            self.model1 = LiftingBasedDWTNet(config)
+            self.model2 = LiftingBasedDWTNet(config)
+
+    def planes(self):
+        return [self.model] if self.clrch == 3 else [self.model0, self.model1, self.model2]
+
+    def set_bit_accumulator(self, acc):
+        """Route sum(self-information) of every subband into ``acc`` (float64[1] on the device)."""
+        for m in self.planes():
+            m.entropymodel.bit_acc = acc
+
+    def forward(self, x):
+        if self.clrch == 3:
+            return self.model.forward(x)
+        outs = [m(x[:, c:c + 1, :, :]) for c, m in enumerate(self.planes())]
+        xhat = torch.cat([o[0] for o in outs], dim=1)
+        si_xe = torch.cat([o[1] for o in outs], dim=1)
+        si_xo = []
+        for o in outs:
+            si_xo.extend(o[2])
+        return xhat, si_xe, si_xo
+
+    def display(self, x):
+        pass
+
+    def aux_loss(self):
+        return sum(m.aux_loss() for m in self.planes())
+
+    def compress(self, x):
+        raise NotImplementedError("compress(): the serial per-coefficient rANS coder (LiftingBasedDWT_net.py:374-556) "
+                                  "is outside the data-parallel hot path this package implements")
+
+
+class LiftingBasedDWTNet(nn.Module):
+    """Transform + entropy model of one plane (:100-180)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.clrch = config.clrch
+        if config.netType == "CDF97":
+            self.autoencoder = DWTPytorchWaveletsLayer(config)
+        elif config.netType == "LiftingBasedNeuralWaveletv4":
+            self.autoencoder = LiftingBasedNeuralWaveletv4(config)
+        else:
+            raise ValueError(f"netType {config.netType!r} is outside the lifting hot path "
+                             "(supported: 'CDF97', 'LiftingBasedNeuralWaveletv4')")
+        self.entropy_layer = config.entropy_layer
+        if self.entropy_layer == "factorized":
+            self.entropymodel = DWTFactorizedEntropyLayer(config)
+        elif self.entropy_layer == "onlyEZWT":
+            self.entropymodel = onlyEZWT(config)
+        elif self.entropy_layer == "conditioned2ZTsepSubbands":
+            self.entropymodel = DWTConditioned2EntropyLayerZTsepSubbands(config)
+        elif self.entropy_layer == "DWTConditioned2EntropyLayerZTBlock":
+            self.entropymodel = DWTConditioned2EntropyLayerZTBlock(config)
+
+    def compress(self, x):
+        raise NotImplementedError("compress(): serial coder out of scope (see module docstring)")
+
+    def forward(self, x):
+        """x (B,C,H,W) -> (xhat, si_xe, si_xo_list) (:154-170)."""
+        if self.entropy_layer not in ("factorized", "conditioned2ZTsepSubbands",
+                                      "DWTConditioned2EntropyLayerZTBlock", "onlyEZWT"):
+            raise ValueError
+        out_xe, out_xo_list = self.autoencoder.encode(x)
+        si_xe, si_xo_list, xe_qnt, xo_list_qnt = self.entropymodel(out_xe, out_xo_list)
+        xhat = self.autoencoder.decode(xe_qnt, xo_list_qnt)
+        return xhat, si_xe, si_xo_list
+
+    def display(self, x):
+        pass
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+
+def _sos_ses(config):
+    se, so = 1 * config.clrch, 3 * config.clrch
+    ses, sos = [], []
+    for _ in range(config.dwtlevels):
+        sos.append(so)
+        ses.append(se)
+        so = se * 3
+        se = se * 1
+    return ses, sos
+
+
+class DWTFactorizedEntropyLayer(nn.Module):
+    """Fully factorized model (:182-231)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.num_lifting_layers = config.dwtlevels
+        assert self.num_lifting_layers > 0
+        self.clrch = config.clrch
+        self.se, self.so = 1, 3
+        se, so = self.se * self.clrch, self.so * self.clrch
+        self.ent_out_xo_list = nn.ModuleList()
+        self.scl_out_xo_list = nn.ParameterList()
+        self.scb_out_xo_list = nn.ParameterList()
+        for i in range(0, self.num_lifting_layers, 1):
+            self.ent_out_xo_list.append(EntropyBottleneck(channels=so))
+            self.scl_out_xo_list.append(nn.Parameter(nn.init.constant_(torch.empty(1, so, 1, 1), i + 1.0)))
+            self.scb_out_xo_list.append(nn.Parameter(nn.init.constant_(torch.empty(1, so, 1, 1), 1.0)))
+            so = se * self.so
+            se = se * self.se
+        self.ent_out_xe = EntropyBottleneck(channels=se / self.se)
+        self.scl_out_xe = nn.Parameter(nn.init.constant_(torch.empty(1, int(se / self.se), 1, 1), 5.0))
+        self.scb_out_xe = nn.Parameter(nn.init.constant_(torch.empty(1, int(se / self.se), 1, 1), 1.0 / 5.0))
+        self.bit_acc = None
+
+    def forward(self, out_xe, out_xo_list):
+        qs, sis = [], []
+        for i in range(self.num_lifting_layers):
+            q, bits = self.ent_out_xo_list[i].rate(out_xo_list[i], self.training, self.bit_acc)
+            sis.append(bits)
+            qs.append(q)
+        xe_q, si_xe = self.ent_out_xe.rate(out_xe, self.training, self.bit_acc)
+        return si_xe, sis, xe_q, qs
+
+
+class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
+    """Causal spatial context + parent-subband (zero-tree) context (:233-372)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.num_lifting_layers = config.dwtlevels
+        self.scale_table = get_scale_table()
+        self.config = config
+        assert self.num_lifting_layers > 0
+        self.clrch = config.clrch
+        self.se, self.so = 1, 3
+        self.ses, self.sos = _sos_ses(config)
+        self.plc_list = nn.ModuleList()
+        self.csc_list = nn.ModuleList()
+        self.cgp_out_xo_list = nn.ModuleList()
+        self.ent_out_xo_list = nn.ModuleList()
+        self.scl_out_xo_list = nn.ParameterList()
+        self.scb_out_xo_list = nn.ParameterList()
+        for i in range(0, self.num_lifting_layers - 1, 1):
+            inn_ch1 = self.sos[i + 1]
+            out_ch1 = inn_ch1 * 81
+            self.plc_list.append(nn.Sequential(nn.Conv2d(inn_ch1, out_ch1, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(),
+                                               nn.Conv2d(out_ch1, out_ch1, kernel_size=3, stride=1, padding=1)))
+            inn_ch2 = self.sos[i]
+            out_ch2 = inn_ch2 * 81
+            self.csc_list.append(MaskedConv2d(mask_type='A', in_channels=inn_ch2, out_channels=out_ch2, kernel_size=5,
+                                              stride=1, padding=2, groups=inn_ch2))
+            inn_ch = out_ch1 + out_ch2
+            out_ch = self.sos[i] * 2
+            self.cgp_out_xo_list.append(nn.Sequential(
+                nn.Conv2d(inn_ch, inn_ch, kernel_size=1, stride=1, padding=0, groups=inn_ch1), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(inn_ch, inn_ch // 3, kernel_size=1, stride=1, padding=0, groups=inn_ch1), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(inn_ch // 3, inn_ch // 9, kernel_size=1, stride=1, padding=0, groups=inn_ch1), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(inn_ch // 9, out_ch, kernel_size=1, stride=1, padding=0, groups=inn_ch1)))
+            self.ent_out_xo_list.append(GaussianConditional(scale_table=None, scale_bound=0.11))
+        i = self.num_lifting_layers - 1
+        self.csc_list.append(self._causal_chain(self.sos[i]))
+        self.ent_out_xo_list.append(GaussianConditional(scale_table=None, scale_bound=0.11))
+        self.csc_xe = self._causal_chain(self.ses[i])
+        self.ent_out_xe = GaussianConditional(scale_table=None, scale_bound=0.11)
+        self.bit_acc = None
+
+    @staticmethod
+    def _causal_chain(inn):
+        o = inn * 81
+        mk = lambda t, ci, co: MaskedConv2d(mask_type=t, in_channels=ci, out_channels=co, kernel_size=3, stride=1,
+                                            padding=1, groups=inn)
+        return nn.Sequential(mk('A', inn, o), nn.LeakyReLU(inplace=True), mk('B', o, o), nn.LeakyReLU(inplace=True),
+                             mk('B', o, o // 3), nn.LeakyReLU(inplace=True), mk('B', o // 3, o // 9),
+                             nn.LeakyReLU(inplace=True), mk('B', o // 9, inn * 2))
+
+    def _level(self, i, x, q, con):
+        """sigma/mu maps (B,6,h,w) of conditioned level i from the quantised child ``q`` and the
+        half-resolution quantised parent ``con`` (:352-362)."""
+        B, C, h, w = x.shape
+        ms = torch.empty(B, 2 * C, h, w, dtype=torch.float32, device=x.device)
+        plc, cgp, csc = self.plc_list[i], self.cgp_out_xo_list[i], self.csc_list[i]
+        nper = plc[0].out_channels // C        # 81
+        for b0 in range(0, B, CTX_BATCH_CHUNK):
+            b1 = min(B, b0 + CTX_BATCH_CHUNK)
+            cat = torch.empty(b1 - b0, 2 * nper * C, h, w, dtype=torch.float32, device=x.device)
+            # (plc0, csc0, plc1, csc1, plc2, csc2) channel order of :357-359 as write patterns
+            csc(q[b0:b1], out=cat, co_group=nper, co_stride=2 * nper, co_off=nper)
+            t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
+            ops.conv2d(t, plc[2].weight, plc[2].bias, out=cat, co_group=nper, co_stride=2 * nper, co_off=0)
+            del t
+            ms[b0:b1] = _chain(cgp, cat)
+            del cat
+        return ms
+
+    def forward(self, out_xe, out_xo_list):
+        L = self.num_lifting_layers
+        mode = "noise" if self.training else "dequantize"
+        acc = self.bit_acc
+        xe_q = self.ent_out_xe.quantize(out_xe, mode)
+        si_xe = self.ent_out_xe.bits(out_xe, _chain(self.csc_xe, xe_q), self.training, acc=acc)
+        qs, sis = [], []
+        i = L - 1
+        q = self.ent_out_xo_list[i].quantize(out_xo_list[i], mode)
+        sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], _chain(self.csc_list[i], q), self.training, acc=acc))
+        qs.append(q)
+        con = q
+        for i in range(L - 2, -1, -1):
+            q = self.ent_out_xo_list[i].quantize(out_xo_list[i], mode)
+            ms = self._level(i, out_xo_list[i], q, con)
+            sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], ms, self.training, acc=acc))
+            qs.append(q)
+            con = q
+        qs.reverse()
+        sis.reverse()
+        return si_xe, sis, xe_q, qs
+
+    def test(self, out_xe, out_xo_list):
+        raise NotImplementedError("serial coder (test/compress_ar/decompress_ar) is out of scope")
+
+
+class DWTConditioned2EntropyLayerZTBlock(nn.Module):
+    """Parent + 2x2 polyphase block conditioning, phases ee -> eo -> oe -> oo (:558-757)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.num_lifting_layers = config.dwtlevels
+        self.dwtLevels = config.dwtlevels
+        assert self.num_lifting_layers > 0
+        self.clrch = config.clrch
+        self.multiplier = 8
+        self.se = 1
+        self.so = 3
+        self.ses, self.sos = _sos_ses(config)
+        names = [f"dep_{k}_list_{s}" for s in ("mu", "sigma") for k in (1, 2, 3, 4)]
+        for n in names:
+            setattr(self, n, nn.ModuleList())
+        self.cgp_out_xo_list = nn.ModuleList()
+        self.ent_out_xo_list = nn.ModuleList()
+        self.scl_out_xo_list = nn.ParameterList()
+        self.scb_out_xo_list = nn.ParameterList()
+        hid = 32
+
+        def net(cin):
+            return nn.Sequential(
+                nn.Conv2d(cin, hid, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(hid, hid, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(hid, hid, kernel_size=1, stride=1, padding=0), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(hid, hid, kernel_size=1, stride=1, padding=0), nn.LeakyReLU(inplace=True),
+                nn.Conv2d(hid, 1, kernel_size=1, stride=1, padding=0))
+
+        for i in range(0, self.num_lifting_layers - 1, 1):
+            for j in range(3):
+                self.ent_out_xo_list.append(GaussianConditional(scale_table=None, scale_bound=0.11))
+                self.scl_out_xo_list.append(nn.Parameter(nn.init.constant_(torch.empty(1, self.sos[i], 1, 1), i * 1.0 + 1.0)))
+                self.scb_out_xo_list.append(nn.Parameter(nn.init.constant_(torch.empty(1, self.sos[i], 1, 1), 1.0)))
+                # construction order of the reference: mu nets 1..4, then sigma nets 1..4
+                for s in ("mu", "sigma"):
+                    for k in (1, 2, 3, 4):
+                        getattr(self, f"dep_{k}_list_{s}").append(net(k))
+        self.ent_out_xo_list.append(GaussianConditional(scale_table=None, scale_bound=0.11))
+        self.gaussian_conditional = GaussianConditional(None)
+        self.ent_out_xe = EntropyBottleneck(channels=1)
+        self.ent_out_xo = EntropyBottleneck(channels=3)
+        self.bit_acc = None
+
+    def forward(self, out_xe, out_xo_list):
+        L = self.dwtLevels
+        acc = self.bit_acc
+        mode = "noise" if self.training else "dequantize"
+        xe_q, si_xe = self.ent_out_xe.rate(out_xe, self.training, acc)
+        qs, sis = [], []
+        q, si = self.ent_out_xo.rate(out_xo_list[L - 1], self.training, acc)
+        qs.append(q)
+        sis.append(si)
+        con = q
+        for i in range(0, L - 1):
+            lvl = L - i - 2
+            si_j, q_j = [], []
+            for j in range(3):
+                gc = self.ent_out_xo_list[(L - i - 1) * 3 - j - 1]
+                xin = out_xo_list[lvl][:, j:j + 1].contiguous()
+                B, _, H, W = xin.shape
+                ms = torch.empty(B, 2, H, W, dtype=torch.float32, device=xin.device)   # ch0 sigma, ch1 mu
+                qq = gc.quantize(xin, mode)
+                ee, eo, oe = qq[:, :, 0::2, 0::2], qq[:, :, 0::2, 1::2], qq[:, :, 1::2, 0::2]
+                d1 = con[:, j:j + 1]
+                n = j + i * 3
+                deps = [d1, torch.cat((d1, ee), 1), torch.cat((d1, ee, eo), 1), torch.cat((d1, ee, eo, oe), 1)]
+                slots = [(0, 0), (0, 1), (1, 0), (1, 1)]
+                for k, (dep, (ry, rx)) in enumerate(zip(deps, slots), start=1):
+                    ms[:, 1:2, ry::2, rx::2] = _chain(getattr(self, f"dep_{k}_list_mu")[n], dep)
+                    ms[:, 0:1, ry::2, rx::2] = _chain(getattr(self, f"dep_{k}_list_sigma")[n], dep)
+                si_j.append(gc.bits(xin, ms, self.training, acc=acc))
+                q_j.append(qq)
+            sis.append(torch.cat(si_j, dim=1))
+            con = torch.cat(q_j, dim=1)
+            qs.append(con)
+        qs.reverse()
+        sis.reverse()
+        return si_xe, sis, xe_q, qs
+
+
+class onlyEZWT(nn.Module):
+    """Coarsest level + LL factorized, finer levels conditioned on the parent subband (:759-840)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.num_lifting_layers = config.dwtlevels
+        self.scale_table = get_scale_table()
+        self.config = config
+        assert self.num_lifting_layers > 0
+        self.clrch = config.clrch
+        self.se, self.so = 1, 3
+        self.ses, self.sos = _sos_ses(config)
+        self.plc_list = nn.ModuleList()
+        self.ent_out_xo_list = nn.ModuleList()
+        for i in range(0, self.num_lifting_layers - 1, 1):
+            inn_ch1 = self.sos[i + 1]
+            out_ch1 = inn_ch1 * 81
+            self.plc_list.append(nn.Sequential(
+                nn.Conv2d(inn_ch1, out_ch1, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(),
+                nn.Conv2d(out_ch1, out_ch1, kernel_size=3, stride=1, padding=1), nn.LeakyReLU(),
+                nn.Conv2d(out_ch1, 6, kernel_size=1, stride=1, padding=0)))
+            self.ent_out_xo_list.append(GaussianConditional(scale_table=None, scale_bound=0.11))
+        self.ent_out_xe = EntropyBottleneck(channels=1)
+        self.ent_out_xo = EntropyBottleneck(channels=3)
+        self.bit_acc = None
+
+    def forward(self, out_xe, out_xo_list):
+        L = self.num_lifting_layers
+        acc = self.bit_acc
+        xe_q, si_xe = self.ent_out_xe.rate(out_xe, self.training, acc)
+        qs, sis = [], []
+        q, si = self.ent_out_xo.rate(out_xo_list[L - 1], self.training, acc)
+        qs.append(q)
+        sis.append(si)
+        con = q
+        for i in range(L - 2, -1, -1):
+            plc = self.plc_list[i]
+            x = out_xo_list[i]
+            B = x.shape[0]
+            ms = torch.empty(B, 6, x.shape[2], x.shape[3], dtype=torch.float32, device=x.device)
+            for b0 in range(0, B, CTX_BATCH_CHUNK):
+                b1 = min(B, b0 + CTX_BATCH_CHUNK)
+                t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
+                t = ops.conv2d(t, plc[2].weight, plc[2].bias, lrelu=True)
+                ops.conv2d(t, plc[4].weight, plc[4].bias, out=ms[b0:b1])
+                del t
+            bits, q = self.ent_out_xo_list[i].bits(x, ms, self.training, want_y=True, acc=acc)
+            sis.append(bits)
+            qs.append(q)
+            con = q
+        qs.reverse()
+        sis.reverse()
+        return si_xe, sis, xe_q, qs

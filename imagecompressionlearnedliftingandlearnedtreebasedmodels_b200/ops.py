@@ -185,3 +185,96 @@ def lift_step(jobs, blob, sign, res_weight=0.1, linear=False):
         a.nb, a.ny, a.nx = src.shape
     with torch.cuda.device(dev):
         check(lib.ll_lift_step(arr, len(jobs), ptr(blob), float(sign), float(res_weight), int(bool(linear)), stream_ptr()))
+
+
+# ----------------------------------------------------------------------------- entropy-model kernels
+EB_BLOB_FLOATS = 64
+
+
+def conv2d(x, weight, bias=None, groups=1, lrelu=False, upsample2=False, out=None, co_group=0, co_stride=0, co_off=0):
+    """fp32 direct conv, stride 1, zero padding K//2 (ll_conv2d).  ``x`` (B,Cin,H,W) or the
+    half-resolution parent when ``upsample2``; ``out`` may be a larger tensor written through the
+    channel remap ``(co // co_group) * co_stride + co_off + co % co_group``."""
+    require_device(x)
+    x = _f32c(x, "x")
+    w = _f32c(weight.detach(), "weight")
+    b = _f32c(bias.detach(), "bias") if bias is not None else None
+    B, Cin, Hs, Ws = x.shape
+    H, W = (2 * Hs, 2 * Ws) if upsample2 else (Hs, Ws)
+    Cout, cin_g, K, K2 = w.shape
+    if K != K2 or cin_g * groups != Cin:
+        raise ValueError(f"conv2d: weight {tuple(w.shape)} does not fit input {tuple(x.shape)} with groups={groups}")
+    if out is None:
+        out = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x.device)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape[2:]) != (H, W) or out.shape[0] != B:
+        raise ValueError("conv2d: bad out tensor")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        check(lib.ll_conv2d(ptr(x), x.stride(0) if B > 1 else Cin * Hs * Ws, ptr(w), ptr(b), ptr(out),
+                            out.stride(0) if B > 1 else out[0].numel(), B, Cin, H, W, Cout, K, groups,
+                            int(bool(upsample2)), int(bool(lrelu)), co_group, co_stride, co_off, stream_ptr()))
+    return out
+
+
+def quantize(x, noise=None):
+    """round-half-even(x), or x + noise in training (ll_quantize)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    if noise is not None:
+        noise = _f32c(noise, "noise")
+    q = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_quantize(ptr(x), ptr(noise), ptr(q), x.numel(), stream_ptr()))
+    return q
+
+
+def new_bit_accumulator(device):
+    return torch.zeros(1, dtype=torch.float64, device=device)
+
+
+def gauss_rate(x, ms, noise=None, want_y=False, acc=None):
+    """bits = -log2 GaussianConditional likelihood.  x (B,C,H,W); ms (B,2C,H,W) with sigma on even
+    and mu on odd channels.  Returns bits (and y if ``want_y``); ``acc`` (float64[1]) += sum(bits)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    ms = _f32c(ms, "ms")
+    B, C, H, W = x.shape
+    if tuple(ms.shape) != (B, 2 * C, H, W):
+        raise ValueError(f"gauss_rate: ms {tuple(ms.shape)} vs x {tuple(x.shape)}")
+    if noise is not None:
+        noise = _f32c(noise, "noise")
+    bits = torch.empty_like(x)
+    y = torch.empty_like(x) if want_y else None
+    hw = H * W
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_gauss_rate(ptr(x), C * hw, ptr(ms), 2 * C * hw, ptr(noise), ptr(bits), C * hw, ptr(y),
+                                        B, C, hw, ptr(acc), stream_ptr()))
+    return (bits, y) if want_y else bits
+
+
+def pack_eb(params, C):
+    """params: the 15 EntropyBottleneck tensors in registration order (see ll_pack_eb)."""
+    dev = params[0].device
+    require_device(params[0])
+    ps = [_f32c(p.detach(), "eb param") for p in params]
+    if len(ps) != 15:
+        raise ValueError("pack_eb: need 15 parameter tensors (filters (3,3,3,3))")
+    blob = torch.empty(C * EB_BLOB_FLOATS, dtype=torch.float32, device=dev)
+    arr = (c_voidp * 15)(*[ptr(p) for p in ps])
+    with torch.cuda.device(dev):
+        check(_lib.load().ll_pack_eb(arr, C, ptr(blob), stream_ptr()))
+    return blob
+
+
+def eb_rate(x, blob, noise=None, acc=None):
+    """EntropyBottleneck forward: returns (y, bits) for x (B,C,H,W)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    if noise is not None:
+        noise = _f32c(noise, "noise")
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    bits = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_eb_rate(ptr(x), ptr(noise), ptr(blob), ptr(y), ptr(bits), B, C, H * W, ptr(acc), stream_ptr()))
+    return y, bits

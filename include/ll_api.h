@@ -122,6 +122,47 @@ int ll_pack_ae1(const float* w0, const float* b0, const float* w1, const float* 
 int ll_ae1_apply(const float* x, float* y, float* q, const float* blob, int B, int C, int64_t n,
                  ll_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* Context CNNs and rate kernels of the tree-based entropy models             */
+/* ------------------------------------------------------------------------- */
+
+/* fp32 direct convolution (cross-correlation, stride 1, zero padding K/2, K in {1,3,5}):
+ * y[b, map(co)] = act(bias[co] + sum w[co, ci, u, v] * x[b, ci, ...]).  x (B,Cin,H,W) -- or
+ * (B,Cin,H/2,W/2) when upsample2 != 0 (nearest 2x upsampling fused into the load; replaces
+ * repeat_interleave(2,2).repeat_interleave(2,3), LiftingBasedDWT_net.py:348,367); w in torch
+ * layout (Cout, Cin/groups, K, K) with any MaskedConv2d mask (graphs/layers/masked_conv2d.py:
+ * 5-21) already multiplied in; lrelu != 0 applies LeakyReLU(0.01).  Output channel remap:
+ * map(co) = (co / co_group) * co_stride + co_off + co % co_group (co_group <= 0: identity), which
+ * turns torch.cat((plc0,csc0,plc1,csc1,plc2,csc2)) (:357-359) into a write pattern.
+ * Replaces nn.Conv2d / MaskedConv2d forward of csc_xe, csc_list, plc_list, cgp_out_xo_list
+ * (:269-318), onlyEZWT.plc_list (:789-794) and the ZTBlock dep_* CNNs (:618-680). */
+int ll_conv2d(const float* x, int64_t x_sb, const float* w, const float* b, float* y, int64_t y_sb, int B, int Cin,
+              int H, int W, int Cout, int K, int groups, int upsample2, int lrelu, int co_group, int co_stride,
+              int co_off, ll_stream_t stream);
+
+/* EntropyModel.quantize (compressai 1.2.1; call sites :330,341,352,719): q = round-half-even(x)
+ * when noise == NULL ("dequantize"), else q = x + noise ("noise"; the caller draws U(-1/2,1/2)). */
+int ll_quantize(const float* x, const float* noise, float* q, int64_t n, ll_stream_t stream);
+
+/* GaussianConditional.forward(x, sigma, means=mu) followed by -log2 (:334-335,345-346,364-365,
+ * 752-754,832-833).  x (B,C,hw) with batch stride x_sb; ms (B,2C,hw): channel 2c = sigma, 2c+1 = mu
+ * (the reference's [:,0::2] / [:,1::2] split); noise NULL (eval: y = round(x-mu)+mu) or (B,C,hw)
+ * dense (training: y = x + noise).  bits (B,C,hw) with batch stride bits_sb; y optional dense
+ * output of the (de)quantised tensor; sum_out optional double accumulator += sum(bits)
+ * (TrainRDLoss.forward3's reductions, graphs/losses/rate_dist.py:35-42). */
+int ll_gauss_rate(const float* x, int64_t x_sb, const float* ms, int64_t ms_sb, const float* noise, float* bits,
+                  int64_t bits_sb, float* y, int B, int C, int64_t hw, double* sum_out, ll_stream_t stream);
+
+#define LL_EB_BLOB_FLOATS 64
+/* EntropyBottleneck (compressai 1.2.1, filters (3,3,3,3)); params = 15 device pointers in
+ * registration order: _matrix0,_bias0,_factor0, ..., _matrix3,_bias3,_factor3, _matrix4,_bias4,
+ * quantiles.  blob: C * LL_EB_BLOB_FLOATS (softplus / tanh of the shape parameters precomputed). */
+int ll_pack_eb(const float* const* params, int C, float* blob, ll_stream_t stream);
+/* EntropyBottleneck.forward + -log2 (:204-210,689-690,800-801) on dense (B,C,hw):
+ * y = round(x - median_c) + median_c (noise NULL) or x + noise; bits = -log2 max(p, 1e-9). */
+int ll_eb_rate(const float* x, const float* noise, const float* blob, float* y, float* bits, int B, int C, int64_t hw,
+               double* sum_out, ll_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
