@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native learned-lifting hot path.
+
+Workload (BASELINE.json configs[1]): learned lifting DWT (predict/update CNNs), 4 levels,
+forward + inverse, batch 16 of 512x768 synthetic images, three colour planes (three
+independent networks, clrch=1), fp32.  Metric: megapixels/s (image pixels B*H*W per step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+* own arm: one process per GPU (torchrun for N>1), weak scaling -- every rank transforms its
+  own batch, no data-path collective; barrier + device-event timing, max over ranks.
+* ``--impl reference``: the reference's CPU path for the same workload = the oracle port
+  (oracle/, torch-on-CPU restatement checked bit-for-bit against the unmodified reference in
+  the dev container; the reference itself cannot travel to the GPU box), all host threads,
+  each step a bounded sample (one image) of the workload.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, H, W, LEVELS = 16, 512, 768, 4
+ALG_BYTES_PER_PLANE_PX = 2 * 8.0 * sum(4.0 ** -l for l in range(LEVELS))   # fwd + inv, SURVEY.md 8(d): 21.25
+ALG_FLOP_PER_PLANE_PX = 2 * 144532.0                                        # fwd + inv learned lifting, SURVEY.md 8(d)
+WORKLOAD = "learned lifting DWT 4-level forward+inverse, batch 16 of 512x768, 3 colour planes (configs[1])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # under load = the upper half of the samples (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_models(dev):
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers.lifting_dwt_nets import \
+        LiftingBasedNeuralWaveletv4
+    from oracle import model as om
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder", dwtlevels=LEVELS)
+    torch.manual_seed(1337)
+    nets = [LiftingBasedNeuralWaveletv4(cfg) for _ in range(3)]   # random-init weights of the architecture
+    return [n.to(dev).eval() for n in nets], cfg
+
+
+def synthetic_input(seed):
+    from oracle import model as om
+    g = torch.Generator().manual_seed(seed)
+    return om.preprocess(torch.rand(B, 3, H, W, generator=g))
+
+
+def run_own(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this package has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import _lib, ops
+    _lib.load()
+    nets, cfg = build_models(dev)
+    x_host = synthetic_input(1337 + rank).pin_memory()
+    out_host = torch.empty_like(x_host).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step_resident():
+        outs = []
+        for c, net in enumerate(nets):
+            yl, yh = net.transform(x_dev[:, c:c + 1])
+            outs.append(net.inverse_transform(yl, yh))
+        return outs
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        for c, net in enumerate(nets):
+            yl, yh = net.transform(xd[:, c:c + 1])
+            rec = net.inverse_transform(yl, yh)
+            out_host[:, c:c + 1].copy_(rec, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = ops.launch_count()
+            ev0.record()
+            for _ in range(steps):
+                fn()
+            ev1.record()
+            timed.launches = ops.launch_count() - n0
+            barrier()
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    launches = timed.launches
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup))
+    with torch.no_grad():
+        rec = torch.cat(step_resident(), dim=1)
+    pr_err = float((rec - x_dev).abs().max().item())
+
+    mp_step = B * H * W / 1e6
+    ms_step = ms_total / args.steps
+    value = world * mp_step / (ms_step * 1e-3)
+    e2e_value = world * mp_step / (ms_e2e / args.steps * 1e-3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    plane_px = 3 * B * H * W
+    alg_bytes = ALG_BYTES_PER_PLANE_PX * plane_px
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    flops = ALG_FLOP_PER_PLANE_PX * plane_px
+    fp32_peak = ops.fma_peak_tflops()
+    line = {
+        "metric": "megapixels/sec encode+decode (learned lifting DWT forward+inverse)", "value": value, "unit": "MP/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "levels": LEVELS,
+                   "weights": "random init (seed 1337), block_property=same, SubbandAutoEncoder not in the timed path",
+                   "l2": "inputs+outputs+scratch per step (3 planes x 3 x 25 MB, read and rewritten 12x per level) exceed the 126 MB L2",
+                   "parallelism": f"image-parallel x{world}, no collective"},
+        "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                "api": "LiftingBasedNeuralWaveletv4.transform / .inverse_transform on pinned host tensors"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                     "kernel": "ll::lift_step_kernel",
+                     "note": "K2 is FP32-FMA-bound by design (13.6 kFLOP per algorithmic byte); see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32_fma", "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": fp32_peak,
+                          "unit": "TFLOP/s", "frac": flops / (ms_step * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                          "peak_kind": "measured in this run: FFMA2 register-only loop, all SMs",
+                          "flops": "useful conv MACs x2 (SURVEY.md 8d), halo recompute not counted"},
+        "check": {"perfect_reconstruction_max_abs_err": pr_err},
+    }
+    line["dwt97"] = dwt97_probe(dev, pk)
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def dwt97_probe(dev, pk):
+    """HBM-bound fixed-filter kernels (K1) on the same image shape: 4-level CDF 9/7 forward and
+    inverse on 16x3 planes of 512x768; algorithmic 10.625 B per plane pixel per direction."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    x = torch.rand(B, 3, H, W, device=dev) - 0.5
+    yl, yh = ops.dwt97_forward(x, LEVELS)
+    res = {}
+    for name, fn in (("fwd", lambda: ops.dwt97_forward(x, LEVELS)), ("inv", lambda: ops.dwt97_inverse(yl, yh))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        ev0.record()
+        for _ in range(n):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / n
+        gbs = 8.0 * sum(4.0 ** -l for l in range(LEVELS)) * 3 * B * H * W / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
+    res["note"] = "150 MB in+out per level-0 launch (> L2 126 MB); back-to-back launches, CUDA events"
+    return res
+
+
+def cpu_port_step(x_img, sds, cfg):
+    """One image (3 planes) through the oracle port: 4-level forward + inverse."""
+    from oracle import lifting as olift
+    with torch.no_grad():
+        for c in range(3):
+            yl, yh = olift.transform_forward(x_img[:, c:c + 1], sds[c], "m.autoencoder.", cfg)
+            olift.transform_inverse(yl, yh, sds[c], "m.autoencoder.", cfg)
+
+
+def cpu_models():
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers.lifting_dwt_nets import \
+        LiftingBasedNeuralWaveletv4
+    from oracle import model as om
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder", dwtlevels=LEVELS)
+    torch.manual_seed(1337)
+    sds = []
+    for _ in range(3):
+        n = LiftingBasedNeuralWaveletv4(cfg)
+        sds.append({"m.autoencoder." + k: v.detach() for k, v in n.state_dict().items()})
+    return sds, cfg
+
+
+def cpu_baseline(budget_s=12.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sds, cfg = cpu_models()
+    x = synthetic_input(1337)[0:1]
+    cpu_port_step(x, sds, cfg)     # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        cpu_port_step(x, sds, cfg)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 8:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": (H * W / 1e6) / dt, "unit": "MP/s", "cores": cores, "kind": "port",
+            "sample": f"{n} x one 512x768 image (3 planes, 4-level forward+inverse) of the batch-16 workload, "
+                      f"torch {torch.__version__} CPU, {cores} threads; oracle port == unmodified reference bit-for-bit in the dev container"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sds, cfg = cpu_models()
+    x = synthetic_input(1337)[0:1]
+    for _ in range(args.warmup):
+        cpu_port_step(x, sds, cfg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(x, sds, cfg)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = (H * W / 1e6) / dt
+    line = {
+        "impl": "reference", "metric": "megapixels/sec encode+decode (learned lifting DWT forward+inverse)", "value": v,
+        "unit": "MP/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "levels": LEVELS,
+                   "step": "bounded sample: one 512x768 image (3 planes) per step"},
+        "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": "one 512x768 image (3 planes, 4-level forward+inverse) per step; oracle port of the "
+                                   "reference's torch-CPU path (the Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

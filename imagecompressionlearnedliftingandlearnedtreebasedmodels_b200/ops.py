@@ -11,6 +11,18 @@ import torch
 from . import _lib
 from ._lib import c_voidp, check, ptr, require_device, stream_ptr
 
+_LAUNCHES = 0   # CUDA kernels of this library enqueued so far (bench.py's gpu_launches)
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def _count(n):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
 LIFT_BLOB_FLOATS = 13656
 AE1_BLOB_FLOATS = 2212
 
@@ -39,6 +51,7 @@ def pack_lift_step(pre_w, conv):
     blob = torch.empty(LIFT_BLOB_FLOATS, dtype=torch.float32, device=pre_w.device)
     with torch.cuda.device(pre_w.device):
         check(lib.ll_pack_lift_step(*[ptr(a) for a in args], ptr(blob), stream_ptr()))
+    _count(1)
     return blob
 
 
@@ -66,6 +79,7 @@ def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=
         check(lib.ll_lift_level_fwd(ptr(x), x.stride(0), ptr(ll), ll.stride(0), ptr(yh), yh.stride(0), ptr(scratch),
                                     B, h, w, _blob_array(blobs), float(res_weight), int(bool(linear)), int(scale),
                                     ptr(nh), ptr(nl), stream_ptr()))
+    _count(8 + (6 if scale else 0))
     return ll, yh
 
 
@@ -86,6 +100,7 @@ def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None
         check(lib.ll_lift_level_inv(ptr(ll), ll.stride(0), ptr(yh), yh.stride(0), ptr(x), x.stride(0), ptr(scratch),
                                     B, h, w, _blob_array(blobs), float(res_weight), int(bool(linear)), int(scale),
                                     ptr(nh), ptr(nl), stream_ptr()))
+    _count(8 + (6 if scale else 0))
     return x
 
 
@@ -108,6 +123,7 @@ def dwt97_forward(x, J):
             y = torch.empty(B, C, 3, h // 2, w // 2, dtype=torch.float32, device=x.device)
             check(lib.ll_dwt97_fwd_level(ptr(cur), h * w, ptr(ll), (h // 2) * (w // 2), ptr(y), 3 * (h // 2) * (w // 2),
                                          N, h, w, stream_ptr()))
+            _count(1)
             yh.append(y)
             cur = ll
     return cur, yh
@@ -129,6 +145,7 @@ def dwt97_inverse(yl, yh):
             x = torch.empty(B, C, 2 * h2, 2 * w2, dtype=torch.float32, device=cur.device)
             check(lib.ll_dwt97_inv_level(ptr(cur), h2 * w2, ptr(y), 3 * h2 * w2, ptr(x), 4 * h2 * w2, N, 2 * h2, 2 * w2,
                                          stream_ptr()))
+            _count(1)
             cur = x
     return cur
 
@@ -149,6 +166,7 @@ def pack_ae1(layers, C, transposed):
     blob = torch.empty(C * AE1_BLOB_FLOATS, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.ll_pack_ae1(*[ptr(a) for a in args], C, int(bool(transposed)), ptr(blob), stream_ptr()))
+    _count(1)
     return blob
 
 
@@ -163,6 +181,7 @@ def ae1_apply(x, blob, want_round=False):
     q = torch.empty_like(x) if want_round else None
     with torch.cuda.device(x.device):
         check(lib.ll_ae1_apply(ptr(x), ptr(y), ptr(q), ptr(blob), B, C, n, stream_ptr()))
+    _count(1)
     return (y, q) if want_round else y
 
 
@@ -185,6 +204,7 @@ def lift_step(jobs, blob, sign, res_weight=0.1, linear=False):
         a.nb, a.ny, a.nx = src.shape
     with torch.cuda.device(dev):
         check(lib.ll_lift_step(arr, len(jobs), ptr(blob), float(sign), float(res_weight), int(bool(linear)), stream_ptr()))
+    _count(1)
 
 
 # ----------------------------------------------------------------------------- entropy-model kernels
@@ -213,6 +233,7 @@ def conv2d(x, weight, bias=None, groups=1, lrelu=False, upsample2=False, out=Non
         check(lib.ll_conv2d(ptr(x), x.stride(0) if B > 1 else Cin * Hs * Ws, ptr(w), ptr(b), ptr(out),
                             out.stride(0) if B > 1 else out[0].numel(), B, Cin, H, W, Cout, K, groups,
                             int(bool(upsample2)), int(bool(lrelu)), co_group, co_stride, co_off, stream_ptr()))
+    _count(1)
     return out
 
 
@@ -225,6 +246,7 @@ def quantize(x, noise=None):
     q = torch.empty_like(x)
     with torch.cuda.device(x.device):
         check(_lib.load().ll_quantize(ptr(x), ptr(noise), ptr(q), x.numel(), stream_ptr()))
+    _count(1)
     return q
 
 
@@ -249,6 +271,7 @@ def gauss_rate(x, ms, noise=None, want_y=False, acc=None):
     with torch.cuda.device(x.device):
         check(_lib.load().ll_gauss_rate(ptr(x), C * hw, ptr(ms), 2 * C * hw, ptr(noise), ptr(bits), C * hw, ptr(y),
                                         B, C, hw, ptr(acc), stream_ptr()))
+    _count(1)
     return (bits, y) if want_y else bits
 
 
@@ -263,6 +286,7 @@ def pack_eb(params, C):
     arr = (c_voidp * 15)(*[ptr(p) for p in ps])
     with torch.cuda.device(dev):
         check(_lib.load().ll_pack_eb(arr, C, ptr(blob), stream_ptr()))
+    _count(1)
     return blob
 
 
@@ -277,4 +301,25 @@ def eb_rate(x, blob, noise=None, acc=None):
     bits = torch.empty_like(x)
     with torch.cuda.device(x.device):
         check(_lib.load().ll_eb_rate(ptr(x), ptr(noise), ptr(blob), ptr(y), ptr(bits), B, C, H * W, ptr(acc), stream_ptr()))
+    _count(1)
     return y, bits
+
+
+# ----------------------------------------------------------------------------- measurement helper
+def fma_peak_tflops(device=None, iters=4096):
+    """Measured FP32 FMA-pipe peak (TFLOP/s) of the current device: register-only FFMA2 loop."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    lib = _lib.load()
+    out = torch.zeros(4, dtype=torch.float32, device=device)
+    blocks = lib.ll_sm_count() * 8
+    best = 0.0
+    with torch.cuda.device(device):
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.ll_fma_peak_probe(ptr(out), blocks, iters, stream_ptr()))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = max(best, blocks * 256.0 * iters * 256.0 / (ms * 1e-3) / 1e12)
+    return best

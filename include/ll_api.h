@@ -163,6 +163,10 @@ int ll_pack_eb(const float* const* params, int C, float* blob, ll_stream_t strea
 int ll_eb_rate(const float* x, const float* noise, const float* blob, float* y, float* bits, int B, int C, int64_t hw,
                double* sum_out, ll_stream_t stream);
 
+/* Measurement helper (no reference counterpart): register-only FFMA2 loop used by bench.py to
+ * measure the device's FP32 FMA-pipe peak.  FLOPs = blocks * 256 * iters * 256. */
+int ll_fma_peak_probe(float* out, int blocks, int iters, ll_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,23 +45,25 @@ def rel_err(a, b):
 
 def flip_audit(q_gpu, q_ref, pre_ref, eps=1e-4):
     """Symbol parity.  Quantised tensors are integers (``round(x)``) or mean-shifted integers
-    (``round(x - mu) + mu`` for EntropyBottleneck / onlyEZWT outputs).  A sample *matches* when
-    it agrees to fp32 noise; a mismatch is a one-step flip and is only tolerated where the
-    oracle's pre-quantiser value sits within ``eps`` of a rounding boundary -- checked exactly
-    for plain rounding (``frac(x) = 0.5``), and for mean-shifted rounding by the flip being
-    exactly one quantisation step.  Returns (n_mismatch, n_unexplained)."""
-    diff = (q_gpu - q_ref).abs()
-    mism = diff > 1e-5 * (1 + q_ref.abs())
+    (``round(x - mu) + mu`` for EntropyBottleneck / onlyEZWT outputs, where mu itself is a
+    context-CNN output carrying fp32 noise).  The difference is split into an integer number of
+    quantisation steps k and a remainder: a sample *matches* when k == 0 and the remainder is
+    within 1e-4 relative (exactly 0 for plain rounding); a mismatch must be a single step
+    (|k| == 1) and, for plain rounding, the oracle's pre-quantiser value must sit within ``eps``
+    of the rounding boundary (frac = 0.5).  Returns (n_mismatch, n_unexplained)."""
+    d = q_gpu - q_ref
+    k = torch.round(d)
+    integer_q = bool((q_ref == torch.round(q_ref)).all())
+    rem_tol = 0.0 if integer_q else 1e-4
+    rem_ok = (d - k).abs() <= rem_tol * (1 + q_ref.abs())
+    mism = (k != 0) | ~rem_ok
     n = int(mism.sum())
     if n == 0:
         return 0, 0
-    one_step = (diff[mism] - 1).abs() < 1e-3
-    integer_q = bool((q_ref == torch.round(q_ref)).all())
+    ok = (k[mism].abs() == 1) & rem_ok[mism]
     if integer_q:
         frac = (pre_ref[mism] - torch.floor(pre_ref[mism]) - 0.5).abs()
-        ok = one_step & (frac <= eps)
-    else:
-        ok = one_step
+        ok = ok & (frac <= eps)
     return n, int((~ok).sum())
 
 
