@@ -109,12 +109,18 @@ int ll_emul_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll
   p.tiles_x = (w / 2 + DW_TX - 1) / DW_TX;
   p.tiles_y = (h / 2 + DW_TY - 1) / DW_TY;
   p.x = x; p.x_sn = x_sn; p.llo = llp; p.ll_sn = ll_sn; p.yho = yh; p.yh_sn = yh_sn;
-  std::vector<float> smv(DWF_SM_TOTAL + 4);
+  std::vector<float> smv((DWF_SM_TOTAL > DFF_SM_TOTAL ? DWF_SM_TOTAL : DFF_SM_TOTAL) + 4);
   float* sm = (float*)(((uintptr_t)smv.data() + 15) & ~(uintptr_t)15);
   const long long tiles = (long long)N * p.tiles_x * p.tiles_y;
   for (long long b = 0; b < tiles; ++b) {
     for (int i = 0; i < DWF_SM_TOTAL; ++i) sm[i] = __builtin_nanf("");
     const DwtTile t = dwt_tile(p, b);
+    if (dwt_fast_ok(p)) {
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_load(p, t, sm, tid);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_rows(sm, tid);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_cols(p, t, sm, tid);
+      continue;
+    }
     for (int tid = 0; tid < DW_THREADS; ++tid) dwtf_load(p, t, sm, tid);
     for (int tid = 0; tid < DW_THREADS; ++tid) dwtf_rows(sm, tid);
     for (int tid = 0; tid < DW_THREADS; ++tid) dwtf_cols(p, t, sm, tid);
@@ -129,12 +135,18 @@ int ll_emul_dwt97_inv_level(const float* llp, int64_t ll_sn, const float* yh, in
   p.tiles_x = (w / 2 + DW_TX - 1) / DW_TX;
   p.tiles_y = (h / 2 + DW_TY - 1) / DW_TY;
   p.xo = x; p.x_sn = x_sn; p.ll = llp; p.ll_sn = ll_sn; p.yh = yh; p.yh_sn = yh_sn;
-  std::vector<float> smv(DWI_SM_TOTAL + 4);
+  std::vector<float> smv((DWI_SM_TOTAL > DIF_SM_TOTAL ? DWI_SM_TOTAL : DIF_SM_TOTAL) + 4);
   float* sm = (float*)(((uintptr_t)smv.data() + 15) & ~(uintptr_t)15);
   const long long tiles = (long long)N * p.tiles_x * p.tiles_y;
   for (long long b = 0; b < tiles; ++b) {
     for (int i = 0; i < DWI_SM_TOTAL; ++i) sm[i] = __builtin_nanf("");
     const DwtTile t = dwt_tile(p, b);
+    if (dwt_fast_ok(p)) {
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_load(p, t, sm, tid);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_cols(sm, tid);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_rows(p, t, sm, tid);
+      continue;
+    }
     for (int tid = 0; tid < DW_THREADS; ++tid) dwti_load(p, t, sm, tid);
     for (int tid = 0; tid < DW_THREADS; ++tid) dwti_cols(p, t, sm, tid);
     for (int tid = 0; tid < DW_THREADS; ++tid) dwti_rows(p, t, sm, tid);

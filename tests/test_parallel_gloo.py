@@ -1,0 +1,58 @@
+"""N>1 host logic on the CPU: world_size-2 gloo run of the sharding helpers bench.py and the
+multi-GPU encode path use (no data-path collective exists on this path)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = parallel.shard_indices(7, rank, world)
+        slowest = parallel.max_over_ranks(10.0 + rank)
+        total_bits, total_px = parallel.sum_over_ranks([100.0 * (rank + 1), float(len(mine))])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            out.put((gathered, slowest, total_bits, total_px))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_sharding_and_reductions():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    gathered, slowest, bits, px = q.get()
+    assert sorted(gathered[0] + gathered[1]) == list(range(7))      # a partition: every unit exactly once
+    assert not set(gathered[0]) & set(gathered[1])
+    assert slowest == 11.0 and bits == 300.0 and px == 7.0
+
+
+def test_tiles_config5():
+    boxes = parallel.tiles_of(2048, 2048, 8)
+    assert len(boxes) == 8
+    cover = torch.zeros(2048, 2048, dtype=torch.int32)
+    for y0, y1, x0, x1 in boxes:
+        assert (y1 - y0) % 32 == 0 and (x1 - x0) % 32 == 0           # 5 lifting levels divide evenly
+        cover[y0:y1, x0:x1] += 1
+    assert int(cover.min()) == 1 and int(cover.max()) == 1
