@@ -50,6 +50,9 @@ SIGNATURES = {
                                   ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, _P]),
     "ll_dwt97_fwd_level": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, _P]),
     "ll_dwt97_inv_level": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, _P]),
+    "ll_dwt97_scratch_floats": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
+    "ll_dwt97_fwd": (c_int, [_P, _P, ctypes.POINTER(c_voidp), _P, c_int, c_int, c_int, c_int, _P]),
+    "ll_dwt97_inv": (c_int, [_P, ctypes.POINTER(c_voidp), _P, _P, c_int, c_int, c_int, c_int, _P]),
     "ll_pack_ae1": (c_int, [_P] * 8 + [c_int, c_int, _P, _P]),
     "ll_ae1_apply": (c_int, [_P, _P, _P, _P, c_int, c_int, c_i64, _P]),
     "ll_conv2d": (c_int, [_P, c_i64, _P, _P, _P, c_i64] + [c_int] * 12 + [_P]),

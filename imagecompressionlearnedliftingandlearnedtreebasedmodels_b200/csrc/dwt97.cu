@@ -26,26 +26,85 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_inv_kernel(const __grid_cons
   dwti_rows(p, t, sm, tid);
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS), used to prefetch the next tile while the
+// current one is being filtered: without it every CTA of a wave loads, filters and stores in
+// lock-step and DRAM idles during the compute phases (ncu: long-scoreboard stall 4.0 per issue).
+struct CopyAsync16 {
+  __device__ __forceinline__ void operator()(float* dst, const float* src) const {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  }
+};
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Persistent, double-buffered: smem = in[2] | lo | hi.  The phase functions address the input
+// tile at sm + DFF_SM_IN and lo/hi at fixed offsets, so buffer b is presented by shifting the
+// base pointer: lo/hi live at the same absolute place for both (layout below).
+constexpr int DFF_IN_FLOATS = DWF_R * DFF_PI;
+constexpr int DFF_PIPE_TOTAL = 2 * DFF_IN_FLOATS + 2 * DWF_R * DFF_PM;
+
 __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
+  // layout: [in0][in1][lo][hi]
   const int tid = threadIdx.x;
-  const DwtTile t = dwt_tile(p, blockIdx.x);
-  dwtff_load(p, t, sm, tid);
-  __syncthreads();
-  dwtff_rows(sm, tid);
-  __syncthreads();
-  dwtff_cols(p, t, sm, tid);
+  const long long ntiles = (long long)p.N * p.tiles_x * p.tiles_y;
+  long long t = blockIdx.x;
+  if (t >= ntiles) return;
+  float* in0 = sm;
+  float* in1 = sm + DFF_IN_FLOATS;
+  float* mid = sm + 2 * DFF_IN_FLOATS - DFF_SM_LO;  // so that mid + DFF_SM_LO / DFF_SM_HI land after both inputs
+  dwtff_load(p, dwt_tile(p, t), in0, tid, CopyAsync16());
+  cp_commit();
+  for (int it = 0;; ++it) {
+    float* cur = (it & 1) ? in1 : in0;
+    float* nxt = (it & 1) ? in0 : in1;
+    const long long tn = t + gridDim.x;
+    if (tn < ntiles) dwtff_load(p, dwt_tile(p, tn), nxt, tid, CopyAsync16());
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    dwtff_rows(cur, mid, tid);
+    __syncthreads();
+    dwtff_cols(p, dwt_tile(p, t), mid, tid);
+    __syncthreads();
+    if (tn >= ntiles) break;
+    t = tn;
+  }
 }
+
+constexpr int DIF_SB_FLOATS = 4 * DWI_R * DIF_P;
+constexpr int DIF_PIPE_TOTAL = 2 * DIF_SB_FLOATS + 2 * 2 * DW_TY * DIF_P;
 
 __global__ void __launch_bounds__(DW_THREADS) dwt97_inv_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
-  const DwtTile t = dwt_tile(p, blockIdx.x);
-  dwtif_load(p, t, sm, tid);
-  __syncthreads();
-  dwtif_cols(sm, tid);
-  __syncthreads();
-  dwtif_rows(p, t, sm, tid);
+  const long long ntiles = (long long)p.N * p.tiles_x * p.tiles_y;
+  long long t = blockIdx.x;
+  if (t >= ntiles) return;
+  float* sb0 = sm;
+  float* sb1 = sm + DIF_SB_FLOATS;
+  float* mid = sm + 2 * DIF_SB_FLOATS - DIF_SM_LO;
+  dwtif_load(p, dwt_tile(p, t), sb0, tid, CopyAsync16());
+  cp_commit();
+  for (int it = 0;; ++it) {
+    float* cur = (it & 1) ? sb1 : sb0;
+    float* nxt = (it & 1) ? sb0 : sb1;
+    const long long tn = t + gridDim.x;
+    if (tn < ntiles) dwtif_load(p, dwt_tile(p, tn), nxt, tid, CopyAsync16());
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    dwtif_cols(cur, mid, tid);
+    __syncthreads();
+    dwtif_rows(p, dwt_tile(p, t), mid, tid);
+    __syncthreads();
+    if (tn >= ntiles) break;
+    t = tn;
+  }
 }
 
 static int fill(DwtParams& p, int N, int h, int w, const char* who) {
@@ -80,7 +139,7 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
   p.yho = yh;
   p.yh_sn = yh_sn;
   constexpr size_t smem = DWF_SM_TOTAL * sizeof(float);
-  constexpr size_t smem_fast = DFF_SM_TOTAL * sizeof(float);
+  constexpr size_t smem_fast = DFF_PIPE_TOTAL * sizeof(float);
   static thread_local bool attr[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
@@ -89,7 +148,8 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
     LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
     attr[dev] = true;
   }
-  if (dwt_fast_ok(p)) dwt97_fwd_fast_kernel<<<(unsigned)tiles, DW_THREADS, smem_fast, as_stream(stream)>>>(p);
+  const long long pgrid = (long long)sm_count_cached() * 3;   // 3 resident CTAs per SM (70 KB each)
+  if (dwt_fast_ok(p)) dwt97_fwd_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream)>>>(p);
   else dwt97_fwd_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_fwd_kernel");
   return LL_OK;
@@ -111,11 +171,69 @@ int ll_dwt97_inv_level(const float* llp, int64_t ll_sn, const float* yh, int64_t
   p.yh = yh;
   p.yh_sn = yh_sn;
   constexpr size_t smem = DWI_SM_TOTAL * sizeof(float);
-  constexpr size_t smem_fast = DIF_SM_TOTAL * sizeof(float);
-  static_assert(smem <= 48 * 1024 && smem_fast <= 48 * 1024, "inverse kernels fit the default shared-memory limit");
-  if (dwt_fast_ok(p)) dwt97_inv_fast_kernel<<<(unsigned)tiles, DW_THREADS, smem_fast, as_stream(stream)>>>(p);
+  constexpr size_t smem_fast = DIF_PIPE_TOTAL * sizeof(float);
+  static_assert(smem <= 48 * 1024, "generic inverse kernel fits the default shared-memory limit");
+  static thread_local bool attr[64] = {false};
+  int dev = 0;
+  LL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr[dev]) {
+    LL_CUDA_OK(cudaFuncSetAttribute(dwt97_inv_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+    attr[dev] = true;
+  }
+  const long long pgrid = (long long)sm_count_cached() * 3;
+  if (dwt_fast_ok(p)) dwt97_inv_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream)>>>(p);
   else dwt97_inv_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_inv_kernel");
+  return LL_OK;
+}
+
+
+size_t ll_dwt97_scratch_floats(int N, int h, int w, int J) {
+  // intermediate LL planes of levels 0..J-2 (forward) / reconstructed LL planes of levels J-1..1 (inverse)
+  size_t n = 0;
+  for (int j = 1; j < J; ++j) n += (size_t)N * (h >> j) * (w >> j);
+  return n;
+}
+
+int ll_dwt97_fwd(const float* x, float* yl, float* const* yh, float* scratch, int N, int h, int w, int J,
+                 ll_stream_t stream) {
+  if (J < 1 || J > 16) return fail(LL_EINVAL, "ll_dwt97_fwd: J out of range");
+  if ((h % (1 << J)) || (w % (1 << J))) return fail(LL_EINVAL, "ll_dwt97_fwd: h, w must be divisible by 2^J (got %d x %d, J=%d)", h, w, J);
+  if ((long long)N * h * w == 0) return LL_OK;
+  if (!x || !yl || !yh || (J > 1 && !scratch)) return fail(LL_EINVAL, "ll_dwt97_fwd: null pointer");
+  const float* cur = x;
+  float* sc = scratch;
+  for (int j = 0; j < J; ++j) {
+    const int hh = h >> j, ww = w >> j;
+    const long long sub = (long long)(hh / 2) * (ww / 2);
+    float* out_ll = (j == J - 1) ? yl : sc;
+    if (!yh[j]) return fail(LL_EINVAL, "ll_dwt97_fwd: null yh[%d]", j);
+    int rc = ll_dwt97_fwd_level(cur, (long long)hh * ww, out_ll, sub, yh[j], 3 * sub, N, hh, ww, stream);
+    if (rc) return rc;
+    cur = out_ll;
+    if (j < J - 1) sc += (size_t)N * sub;
+  }
+  return LL_OK;
+}
+
+int ll_dwt97_inv(const float* yl, const float* const* yh, float* x, float* scratch, int N, int h, int w, int J,
+                 ll_stream_t stream) {
+  if (J < 1 || J > 16) return fail(LL_EINVAL, "ll_dwt97_inv: J out of range");
+  if ((h % (1 << J)) || (w % (1 << J))) return fail(LL_EINVAL, "ll_dwt97_inv: h, w must be divisible by 2^J (got %d x %d, J=%d)", h, w, J);
+  if ((long long)N * h * w == 0) return LL_OK;
+  if (!x || !yl || !yh || (J > 1 && !scratch)) return fail(LL_EINVAL, "ll_dwt97_inv: null pointer");
+  const float* cur = yl;
+  float* sc = scratch;
+  for (int j = J - 1; j >= 0; --j) {
+    const int hh = h >> j, ww = w >> j;   // output size of this level
+    const long long sub = (long long)(hh / 2) * (ww / 2);
+    float* out = (j == 0) ? x : sc;
+    if (!yh[j]) return fail(LL_EINVAL, "ll_dwt97_inv: null yh[%d]", j);
+    int rc = ll_dwt97_inv_level(cur, sub, yh[j], 3 * sub, out, (long long)hh * ww, N, hh, ww, stream);
+    if (rc) return rc;
+    cur = out;
+    if (j > 0) sc += (size_t)N * hh * ww;
+  }
   return LL_OK;
 }
 

@@ -263,26 +263,44 @@ constexpr int DFF_SM_LO = DFF_SM_IN + DWF_R * DFF_PI;
 constexpr int DFF_SM_HI = DFF_SM_LO + DWF_R * DFF_PM;
 constexpr int DFF_SM_TOTAL = DFF_SM_HI + DWF_R * DFF_PM;
 
-LL_HD void dwtff_load(const DwtParams& p, const DwtTile& t, float* sm, int tid) {
+// fast wrap for indices that are at most a few extents out of range
+LL_HD int wrapf(int a, int n) {
+  if (a < 0) a += n;
+  if (a >= n) {
+    a -= n;
+    if (a >= n) a %= n;
+  }
+  return a < 0 ? wrapi(a, n) : a;
+}
+
+struct CopySync16 {  // host emulation / generic: plain 16-byte copy
+  LL_HD void operator()(float* dst, const float* src) const {
+    *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+  }
+};
+
+template <class CP>
+LL_HD void dwtff_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, CP cp) {
   const float* base = p.x + (long long)t.n * p.x_sn;
   constexpr int C4 = DWF_C / 4;
   for (int e = tid; e < DWF_R * C4; e += DW_THREADS) {
     const int rr = e / C4, c4 = e % C4;
-    const int gr = wrapi(2 * t.y0 - 4 + rr, p.h);
-    const int gc = wrapi(2 * t.x0 - 4 + 4 * c4, p.w);
-    const float4 v = *reinterpret_cast<const float4*>(base + (long long)gr * p.w + gc);
-    *reinterpret_cast<float4*>(&sm[DFF_SM_IN + rr * DFF_PI + 4 * c4]) = v;
+    const int gr = wrapf(2 * t.y0 - 4 + rr, p.h);
+    const int gc = wrapf(2 * t.x0 - 4 + 4 * c4, p.w);
+    cp(&sm[DFF_SM_IN + rr * DFF_PI + 4 * c4], base + (long long)gr * p.w + gc);
   }
 }
 
-LL_HD void dwtff_rows(float* sm, int tid) {
+// ``in`` / ``mid`` are view bases: the input tile is at in + DFF_SM_IN, lo/hi at mid + DFF_SM_LO/HI
+// (same base in the single-buffer layout, different bases in the double-buffered kernel).
+LL_HD void dwtff_rows(const float* in, float* mid, int tid) {
   // item = (row pair, 16 groups of 4 outputs); a warp covers 2 rows x 16 groups
   const int warp = tid >> 5, lane = tid & 31;
   const int g = (lane & 3) | ((lane >> 3) << 2);
   const int r = (lane >> 2) & 1;
   for (int rp = warp; rp < DWF_R / 2; rp += DW_THREADS / 32) {
     const int rr = 2 * rp + r;
-    const float* q = &sm[DFF_SM_IN + rr * DFF_PI + 8 * g];
+    const float* q = &in[DFF_SM_IN + rr * DFF_PI + 8 * g];
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
@@ -302,8 +320,8 @@ LL_HD void dwtff_rows(float* sm, int tid) {
 #pragma unroll
       for (int k = 2; k <= 7; ++k) hi[i] = fmaf(LL_DEC_HI(k), v[2 * i + 9 - k], hi[i]);
     }
-    *reinterpret_cast<float4*>(&sm[DFF_SM_LO + rr * DFF_PM + 4 * g]) = float4{lo[0], lo[1], lo[2], lo[3]};
-    *reinterpret_cast<float4*>(&sm[DFF_SM_HI + rr * DFF_PM + 4 * g]) = float4{hi[0], hi[1], hi[2], hi[3]};
+    *reinterpret_cast<float4*>(&mid[DFF_SM_LO + rr * DFF_PM + 4 * g]) = float4{lo[0], lo[1], lo[2], lo[3]};
+    *reinterpret_cast<float4*>(&mid[DFF_SM_HI + rr * DFF_PM + 4 * g]) = float4{hi[0], hi[1], hi[2], hi[3]};
   }
 }
 
@@ -352,34 +370,35 @@ constexpr int DIF_SM_LO = DIF_SM_SB + 4 * DWI_R * DIF_P;   // [2 TY][DIF_P]
 constexpr int DIF_SM_HI = DIF_SM_LO + 2 * DW_TY * DIF_P;
 constexpr int DIF_SM_TOTAL = DIF_SM_HI + 2 * DW_TY * DIF_P;
 
-LL_HD void dwtif_load(const DwtParams& p, const DwtTile& t, float* sm, int tid) {
+template <class CP>
+LL_HD void dwtif_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, CP cp) {
   const int h2 = p.h / 2, w2 = p.w / 2;
   const long long sub = (long long)h2 * w2;
   constexpr int C4 = DIF_P / 4;   // 18
   for (int e = tid; e < 4 * DWI_R * C4; e += DW_THREADS) {
     const int s = e / (DWI_R * C4);
     const int i = (e / C4) % DWI_R, c4 = e % C4;
-    const int gy = wrapi(t.y0 - 2 + i, h2), gx = wrapi(t.x0 - 4 + 4 * c4, w2);
+    const int gy = wrapf(t.y0 - 2 + i, h2), gx = wrapf(t.x0 - 4 + 4 * c4, w2);
     const long long o = (long long)gy * w2 + gx;
     const float* src = (s == 0) ? p.ll + (long long)t.n * p.ll_sn + o
                                 : p.yh + (long long)t.n * p.yh_sn + (s == 1 ? 0 : s == 2 ? sub : 2 * sub) + o;
-    *reinterpret_cast<float4*>(&sm[DIF_SM_SB + (s * DWI_R + i) * DIF_P + 4 * c4]) = *reinterpret_cast<const float4*>(src);
+    cp(&sm[DIF_SM_SB + (s * DWI_R + i) * DIF_P + 4 * c4], src);
   }
 }
 
-LL_HD void dwtif_cols(float* sm, int tid) {
+LL_HD void dwtif_cols(const float* sb, float* mid, int tid) {
   // item = (lo|hi, group of 4 j's, column): 2 x 4 x 72 = 576
   for (int e = tid; e < 2 * (DW_TY / 4) * DIF_P; e += DW_THREADS) {
     const int c = e % DIF_P, jg = (e / DIF_P) % (DW_TY / 4), which = e / (DIF_P * (DW_TY / 4));
-    const float* lo = &sm[DIF_SM_SB + ((which ? 2 : 0) * DWI_R + 4 * jg) * DIF_P + c];
-    const float* hi = &sm[DIF_SM_SB + ((which ? 3 : 1) * DWI_R + 4 * jg) * DIF_P + c];
+    const float* lo = &sb[DIF_SM_SB + ((which ? 2 : 0) * DWI_R + 4 * jg) * DIF_P + c];
+    const float* hi = &sb[DIF_SM_SB + ((which ? 3 : 1) * DWI_R + 4 * jg) * DIF_P + c];
     float l[8], h[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       l[i] = lo[i * DIF_P];
       h[i] = hi[i * DIF_P];
     }
-    float* o = &sm[(which ? DIF_SM_HI : DIF_SM_LO) + (8 * jg) * DIF_P + c];
+    float* o = &mid[(which ? DIF_SM_HI : DIF_SM_LO) + (8 * jg) * DIF_P + c];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float el = 0.f, eh = 0.f, ol = 0.f, oh = 0.f;

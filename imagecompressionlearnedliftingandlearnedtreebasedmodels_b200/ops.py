@@ -110,44 +110,40 @@ def dwt97_forward(x, J):
     require_device(x)
     x = _f32c(x, "x")
     B, C, H, W = x.shape
-    if H % (1 << J) or W % (1 << J):
+    if J < 1 or H % (1 << J) or W % (1 << J):
         raise ValueError(f"dwt97_forward: H, W must be divisible by 2^{J}, got {H}x{W}")
     lib = _lib.load()
     N = B * C
-    cur = x
-    yh = []
+    yh = [torch.empty(B, C, 3, H >> (j + 1), W >> (j + 1), dtype=torch.float32, device=x.device) for j in range(J)]
+    yl = torch.empty(B, C, H >> J, W >> J, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(max(lib.ll_dwt97_scratch_floats(N, H, W, J), 1), dtype=torch.float32, device=x.device)
+    arr = (c_voidp * J)(*[ptr(t) for t in yh])
     with torch.cuda.device(x.device):
-        for _ in range(J):
-            h, w = cur.shape[-2], cur.shape[-1]
-            ll = torch.empty(B, C, h // 2, w // 2, dtype=torch.float32, device=x.device)
-            y = torch.empty(B, C, 3, h // 2, w // 2, dtype=torch.float32, device=x.device)
-            check(lib.ll_dwt97_fwd_level(ptr(cur), h * w, ptr(ll), (h // 2) * (w // 2), ptr(y), 3 * (h // 2) * (w // 2),
-                                         N, h, w, stream_ptr()))
-            _count(1)
-            yh.append(y)
-            cur = ll
-    return cur, yh
+        check(lib.ll_dwt97_fwd(ptr(x), ptr(yl), arr, ptr(scratch), N, H, W, J, stream_ptr()))
+    _count(J)
+    return yl, yh
 
 
 def dwt97_inverse(yl, yh):
     """DWTInverse('periodization', 'bior4.4')((Yl, Yh))."""
     require_device(yl)
     lib = _lib.load()
-    cur = _f32c(yl, "yl")
-    B, C = cur.shape[0], cur.shape[1]
+    yl = _f32c(yl, "yl")
+    yh = [_f32c(y, "yh") for y in yh]
+    J = len(yh)
+    B, C, h, w = yl.shape
+    H, W = h << J, w << J
+    for j, y in enumerate(yh):
+        if tuple(y.shape) != (B, C, 3, H >> (j + 1), W >> (j + 1)):
+            raise ValueError(f"dwt97_inverse: yh[{j}] has shape {tuple(y.shape)}, expected {(B, C, 3, H >> (j + 1), W >> (j + 1))}")
     N = B * C
-    with torch.cuda.device(cur.device):
-        for y in yh[::-1]:
-            y = _f32c(y, "yh")
-            h2, w2 = y.shape[-2], y.shape[-1]
-            if tuple(cur.shape[-2:]) != (h2, w2) or y.shape[2] != 3:
-                raise ValueError(f"dwt97_inverse: shape mismatch {tuple(cur.shape)} vs {tuple(y.shape)}")
-            x = torch.empty(B, C, 2 * h2, 2 * w2, dtype=torch.float32, device=cur.device)
-            check(lib.ll_dwt97_inv_level(ptr(cur), h2 * w2, ptr(y), 3 * h2 * w2, ptr(x), 4 * h2 * w2, N, 2 * h2, 2 * w2,
-                                         stream_ptr()))
-            _count(1)
-            cur = x
-    return cur
+    x = torch.empty(B, C, H, W, dtype=torch.float32, device=yl.device)
+    scratch = torch.empty(max(lib.ll_dwt97_scratch_floats(N, H, W, J), 1), dtype=torch.float32, device=yl.device)
+    arr = (c_voidp * J)(*[ptr(t) for t in yh])
+    with torch.cuda.device(yl.device):
+        check(lib.ll_dwt97_inv(ptr(yl), arr, ptr(x), ptr(scratch), N, H, W, J, stream_ptr()))
+    _count(J)
+    return x
 
 
 # ----------------------------------------------------------------------------- pointwise auto-encoder

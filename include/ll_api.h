@@ -106,6 +106,15 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* ll, int64_t ll_sn, f
 int ll_dwt97_inv_level(const float* ll, int64_t ll_sn, const float* yh, int64_t yh_sn, float* x, int64_t x_sn,
                        int N, int h, int w, ll_stream_t stream);
 
+/* All J levels in one call (DWTForward(J,...)(x) / DWTInverse(...)((Yl, Yh)), lifting_dwt_nets.py:250,274):
+ * x (N,h,w) dense planes; yl (N,h>>J,w>>J); yh[j] (N,3,h>>(j+1),w>>(j+1)), finest first;
+ * scratch: ll_dwt97_scratch_floats(N,h,w,J) floats for the intermediate LL planes. */
+size_t ll_dwt97_scratch_floats(int N, int h, int w, int J);
+int ll_dwt97_fwd(const float* x, float* yl, float* const* yh, float* scratch, int N, int h, int w, int J,
+                 ll_stream_t stream);
+int ll_dwt97_inv(const float* yl, const float* const* yh, float* x, float* scratch, int N, int h, int w, int J,
+                 ll_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Pointwise subband auto-encoder (v1) fused with the quantiser               */
 /* ------------------------------------------------------------------------- */

@@ -116,8 +116,8 @@ int ll_emul_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll
     for (int i = 0; i < DWF_SM_TOTAL; ++i) sm[i] = __builtin_nanf("");
     const DwtTile t = dwt_tile(p, b);
     if (dwt_fast_ok(p)) {
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_load(p, t, sm, tid);
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_rows(sm, tid);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_load(p, t, sm, tid, CopySync16());
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_rows(sm, sm, tid);
       for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_cols(p, t, sm, tid);
       continue;
     }
@@ -142,8 +142,8 @@ int ll_emul_dwt97_inv_level(const float* llp, int64_t ll_sn, const float* yh, in
     for (int i = 0; i < DWI_SM_TOTAL; ++i) sm[i] = __builtin_nanf("");
     const DwtTile t = dwt_tile(p, b);
     if (dwt_fast_ok(p)) {
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_load(p, t, sm, tid);
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_cols(sm, tid);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_load(p, t, sm, tid, CopySync16());
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_cols(sm, sm, tid);
       for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_rows(p, t, sm, tid);
       continue;
     }
