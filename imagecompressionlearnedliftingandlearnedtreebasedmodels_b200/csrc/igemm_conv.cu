@@ -1,0 +1,506 @@
+// igemm_conv.cu -- tcgen05 / TMEM implicit-GEMM convolution for the dense context CNNs (K3).
+//
+// Replaces the 243->243 3x3 conv of plc_list[i] (graphs/models/LiftingBasedDWT_net.py:271-272,355;
+// onlyEZWT :789-794) and the dense grouped 1x1 layers of the cgp MLP (:280-290): the only convs of
+// the tree-based entropy models whose channel counts make them dense contractions (62 % of the
+// entropy-model FLOPs sit in plc alone).  These nets only produce (sigma, mu)
+// of the rate model -- they move bpp (tolerance 0.1 %), never a quantised symbol -- so the
+// operands are BF16 with FP32 accumulation in tensor memory.
+//
+//   GEMM view   D[m, n] = sum_{tap, ci} A_tap[m, ci] * W[tap][n][ci]
+//               m = pixel of a 8x16 tile (M = 128), n = output channel (N = Npad <= 256),
+//               k = (tap, ci): 9 (or 1) taps x Kpad input channels, 64 channels (128 B) per k-block.
+//   A operand   activations, NHWC bf16 (B, H, W, Kpad): one TMA box {64 ch, 16 x, 8 y, 1 b} per
+//               (tap, k-block) at (x0 + dx, y0 + dy); out-of-image coordinates are zero-filled by
+//               TMA = the conv's zero padding.  Lands as 128 rows x 128 B, SWIZZLE_128B, K-major.
+//   B operand   weights packed [tap][Npad][Kpad] bf16 (ll_pack_igemm_weight): TMA box {64, Npad, 1}.
+//   pipeline    warp 0 = TMA producer, warp 1 = MMA issuer (one thread, tcgen05.mma
+//               cta_group::1 kind::f16, M128 x Npad x K16), warps 2-5 = epilogue
+//               (tcgen05.ld 32x32b -> bias, LeakyReLU -> global).  4 smem stages (full/empty
+//               mbarriers), 2 accumulator stages of 256 TMEM columns (tmem_full/tmem_empty), so the
+//               epilogue of tile t overlaps the MMAs of tile t+1.  Persistent: grid = #SMs, static
+//               round-robin over (b, tile_y, tile_x); neighbouring CTAs work on neighbouring tiles
+//               at the same time so halos and weight tiles are L2 hits.
+//   outputs     fp32 NCHW through the channel remap of ll_conv2d (torch.cat as a write pattern)
+//               and/or bf16 NHWC at a channel offset (feeds the next igemm layer).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "ll_common.cuh"
+
+namespace ll {
+
+constexpr int IG_TW = 16, IG_TH = 8;
+constexpr int IG_BM = IG_TW * IG_TH;   // 128
+constexpr int IG_BK = 64;              // bf16 per k-block (one 128-byte swizzle row)
+constexpr int IG_STAGES = 4;
+constexpr int IG_MAXN = 256;
+constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;     // 16 KB
+constexpr int IG_B_BYTES = IG_MAXN * IG_BK * 2;   // 32 KB
+constexpr int IG_STAGE_BYTES = IG_A_BYTES + IG_B_BYTES;
+constexpr int IG_THREADS = 192;
+constexpr int IG_TMEM_COLS = 512;
+constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXN * 4;
+
+struct IgemmParams {
+  const float* bias;
+  float* out_f32;          // NCHW fp32 (may be null)
+  long long out_sb;        // batch stride (elements)
+  int co_group, co_stride, co_off;
+  __nv_bfloat16* out_bf16; // NHWC bf16 (may be null)
+  int out_cstride, out_coff;
+  int B, H, W, Cout, Npad, kblocks, taps, lrelu;
+  int tiles_x, tiles_y;
+  long long ntiles;
+};
+
+// ---------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; BF16 inputs, FP32 accumulation.
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address   [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version 1 (sm_100) [46,48)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B [61,64)
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(IG_THREADS, 1)
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms are 1024-byte aligned
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bars = base + IG_STAGES * IG_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (IG_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * IG_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * IG_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + IG_STAGES * IG_STAGE_BYTES + 8 * (2 * IG_STAGES + 4));
+  float* s_bias = reinterpret_cast<float*>(gen + IG_STAGES * IG_STAGE_BYTES + 1024);
+  int* s_cmap = reinterpret_cast<int*>(s_bias + IG_MAXN);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < IG_MAXN; i += IG_THREADS) {
+    s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    s_cmap[i] = (i / p.co_group) * p.co_stride + p.co_off + (i % p.co_group);
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < IG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(IG_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int iters = p.taps * p.kblocks;
+  const uint32_t stage_tx = IG_A_BYTES + (uint32_t)p.Npad * IG_BK * 2;
+  const long long per_img = (long long)p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const int b = (int)(t / per_img);
+        const int r = (int)(t % per_img);
+        const int y0 = (r / p.tiles_x) * IG_TH, x0 = (r % p.tiles_x) * IG_TW;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), stage_tx);
+            const uint32_t sa = base + stage * IG_STAGE_BYTES;
+            tma_load_4d(sa, &tmA, full_bar(stage), kb * IG_BK, x0 + dx, y0 + dy, b);
+            tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), kb * IG_BK, 0, tap);
+            if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = Npad, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(IG_BM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * IG_MAXN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * IG_STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + IG_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < IG_BK / 16; ++k)   // 32 bytes (16 bf16) per MMA along K: +2 in 16-byte units
+            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          tc_commit(empty_bar(stage));           // smem stage reusable once these MMAs have read it
+          if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));               // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int ty = row / IG_TW, tx = row % IG_TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int nchunks = p.Npad / 32 + ((p.Npad % 32) ? 1 : 0);
+    for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+      const int b = (int)(t / per_img);
+      const int r = (int)(t % per_img);
+      const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
+      const bool valid = y < p.H && x < p.W;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * IG_MAXN;
+      float* of = p.out_f32 ? p.out_f32 + (long long)b * p.out_sb + (long long)y * p.W + x : nullptr;
+      __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff : nullptr;
+      const long long plane = (long long)p.H * p.W;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        tc_ld32(taddr + c * 32, v);
+        tc_wait_ld();
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+            f[j] = (p.lrelu && a < 0.f) ? a * 0.01f : a;
+          }
+          if (of) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < p.Cout) of[(long long)s_cmap[c * 32 + j] * plane] = f[j];
+          }
+          if (ob) {
+            if (c * 32 + 32 <= p.Cout && ((p.out_coff + c * 32) % 8 == 0) && (p.out_cstride % 8 == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(ob + c * 32 + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < p.Cout) ob[c * 32 + j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(IG_TMEM_COLS) : "memory");
+  }
+}
+
+// plc head: conv3x3 (Cin<=4 -> Cout) on the (optionally nearest-2x-upsampled) parent, + bias,
+// LeakyReLU, written as NHWC bf16 with channels [Cout, Cpad) zeroed.  One thread = one pixel x 8 channels.
+constexpr int HD_THREADS = 256;
+__global__ void __launch_bounds__(HD_THREADS)
+ctx_head_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W, int Cout, int Cpad, int upsample2,
+                     int lrelu) {
+  extern __shared__ float s_w[];   // [Cpad][Cin*9] + bias[Cpad]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < Cpad * K; i += HD_THREADS) s_w[i] = (i / K) < Cout ? w[i] : 0.f;
+  float* s_b = s_w + Cpad * K;
+  for (int i = threadIdx.x; i < Cpad; i += HD_THREADS) s_b[i] = (bias && i < Cout) ? bias[i] : 0.f;
+  __syncthreads();
+  const int groups = Cpad / 8;
+  const int Hs = upsample2 ? H / 2 : H, Ws = upsample2 ? W / 2 : W;
+  const long long total = (long long)B * H * W * groups;
+  for (long long e = (long long)blockIdx.x * HD_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * HD_THREADS) {
+    const int g = (int)(e % groups);
+    const long long px = e / groups;
+    const int xx = (int)(px % W), yy = (int)((px / W) % H), b = (int)(px / ((long long)W * H));
+    float in[36];
+    for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const int sy = upsample2 ? gy >> 1 : gy, sx = upsample2 ? gx >> 1 : gx;
+          v = x[(((long long)b * Cin + ci) * Hs + sy) * Ws + sx];
+        }
+        in[ci * 9 + t] = v;
+      }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float* wr = s_w + (g * 8 + c) * K;
+      float a = s_b[g * 8 + c];
+      for (int k = 0; k < K; ++k) a = fmaf(in[k], wr[k], a);
+      o[c] = (lrelu && a < 0.f) ? a * 0.01f : a;
+    }
+    uint4 pk;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(out + px * Cpad + g * 8) = pk;
+  }
+}
+
+// (Co, Ci, R, S) fp32 -> [R*S][Npad][Kpad] bf16, zero padded.
+__global__ void pack_igemm_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Co, int Ci,
+                                         int taps, int Npad, int Kpad) {
+  const long long total = (long long)taps * Npad * Kpad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(e % Kpad), co = (int)((e / Kpad) % Npad), tap = (int)(e / ((long long)Kpad * Npad));
+    float v = 0.f;
+    if (co < Co && ci < Ci) v = w[((long long)co * Ci + ci) * taps + tap];
+    wp[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// fp32 NCHW channel slice -> bf16 NHWC channel slice (used to drop csc's output into the cgp input layout)
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, long long x_sb, __nv_bfloat16* __restrict__ out,
+                                         int B, int C, int H, int W, int out_cstride, int out_coff) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)B * hw * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const long long px = e / C;
+    const int b = (int)(px / hw);
+    const long long s = px % hw;
+    out[px * out_cstride + out_coff + c] = __float2bfloat16_rn(x[(long long)b * x_sb + (long long)c * hw + s]);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+}  // namespace ll
+
+using namespace ll;
+
+extern "C" {
+
+int ll_ctx_head_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
+                     int Cpad, int upsample2, int lrelu, ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || Cin < 1 || Cin > 4 || Cout < 1 || Cpad < Cout || Cpad % 8)
+    return fail(LL_EINVAL, "ll_ctx_head_nhwc: bad extents (Cin in 1..4, Cpad multiple of 8 and >= Cout)");
+  if (upsample2 && ((H & 1) || (W & 1))) return fail(LL_EINVAL, "ll_ctx_head_nhwc: upsample2 needs even output size");
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!x || !w || !out) return fail(LL_EINVAL, "ll_ctx_head_nhwc: null pointer");
+  const size_t smem = (size_t)(Cpad * Cin * 9 + Cpad) * sizeof(float);
+  if (smem > 48 * 1024) LL_CUDA_OK(cudaFuncSetAttribute(ctx_head_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long total = (long long)B * H * W * (Cpad / 8);
+  long long blocks = (total + HD_THREADS - 1) / HD_THREADS;
+  const long long cap = (long long)sm_count_cached() * 8;
+  if (blocks > cap) blocks = cap;
+  ctx_head_nhwc_kernel<<<(unsigned)blocks, HD_THREADS, smem, as_stream(stream)>>>(
+      x, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, Cin, H, W, Cout, Cpad, upsample2, lrelu);
+  LL_LAUNCH_OK("ctx_head_nhwc_kernel");
+  return LL_OK;
+}
+
+int ll_pack_igemm_weight(const float* w, void* wp, int Co, int Ci, int taps, int Npad, int Kpad, ll_stream_t stream) {
+  if (Co < 1 || Ci < 1 || (taps != 1 && taps != 9) || Npad < Co || Kpad < Ci || Npad % 16 || Npad > IG_MAXN || Kpad % IG_BK)
+    return fail(LL_EINVAL, "ll_pack_igemm_weight: bad extents (taps 1|9, Npad %%16 <= 256, Kpad %%64)");
+  if (!w || !wp) return fail(LL_EINVAL, "ll_pack_igemm_weight: null pointer");
+  const long long total = (long long)taps * Npad * Kpad;
+  pack_igemm_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(wp), Co, Ci, taps, Npad, Kpad);
+  LL_LAUNCH_OK("pack_igemm_weight_kernel");
+  return LL_OK;
+}
+
+int ll_nchw_to_nhwc_bf16(const float* x, int64_t x_sb, void* out, int B, int C, int H, int W, int out_cstride, int out_coff,
+                         ll_stream_t stream) {
+  if (B < 0 || C < 1 || H < 0 || W < 0 || out_cstride < C + out_coff || out_coff < 0)
+    return fail(LL_EINVAL, "ll_nchw_to_nhwc_bf16: bad extents");
+  const long long total = (long long)B * H * W * C;
+  if (total == 0) return LL_OK;
+  if (!x || !out) return fail(LL_EINVAL, "ll_nchw_to_nhwc_bf16: null pointer");
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count_cached() * 16;
+  if (blocks > cap) blocks = cap;
+  nchw_to_nhwc_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_sb, reinterpret_cast<__nv_bfloat16*>(out), B, C,
+                                                                          H, W, out_cstride, out_coff);
+  LL_LAUNCH_OK("nchw_to_nhwc_bf16_kernel");
+  return LL_OK;
+}
+
+int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Kpad, int Npad, int Cout,
+                  int taps, int lrelu, float* out_f32, int64_t out_sb, int co_group, int co_stride, int co_off,
+                  void* out_bf16, int out_cstride, int out_coff, ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || Kpad < IG_BK || Kpad % IG_BK || Npad < 16 || Npad % 16 || Npad > IG_MAXN || Cout < 1 ||
+      Cout > Npad || (taps != 1 && taps != 9))
+    return fail(LL_EINVAL, "ll_igemm_conv: bad extents (Kpad %%64, Npad %%16 in 16..256, Cout <= Npad, taps 1|9)");
+  if (B > 65535 * 4 || H > (1 << 20) || W > (1 << 20)) return fail(LL_EINVAL, "ll_igemm_conv: extents too large");
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!x_nhwc || !wp || (!out_f32 && !out_bf16)) return fail(LL_EINVAL, "ll_igemm_conv: null pointer");
+  if (((uintptr_t)x_nhwc & 15) || ((uintptr_t)wp & 15)) return fail(LL_EINVAL, "ll_igemm_conv: operands must be 16-byte aligned");
+  if (out_bf16 && (out_cstride < out_coff + Cout || out_coff < 0)) return fail(LL_EINVAL, "ll_igemm_conv: bad NHWC output slice");
+  if (co_group <= 0) { co_group = Npad; co_stride = 0; co_off = 0; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LL_ECUDA, "ll_igemm_conv: cuTensorMapEncodeTiled not available from the driver");
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Kpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Kpad * 2, (cuuint64_t)W * Kpad * 2, (cuuint64_t)H * W * Kpad * 2};
+    cuuint32_t box[4] = {IG_BK, IG_TW, IG_TH, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_nhwc), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Kpad, (cuuint64_t)Npad, (cuuint64_t)taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Npad * Kpad * 2};
+    cuuint32_t box[3] = {IG_BK, (cuuint32_t)Npad, 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wp), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  IgemmParams p = {};
+  p.bias = bias;
+  p.out_f32 = out_f32; p.out_sb = out_sb;
+  p.co_group = co_group; p.co_stride = co_stride; p.co_off = co_off;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.out_cstride = out_cstride; p.out_coff = out_coff;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Npad = Npad; p.kblocks = Kpad / IG_BK; p.taps = taps; p.lrelu = lrelu;
+  p.tiles_x = (W + IG_TW - 1) / IG_TW;
+  p.tiles_y = (H + IG_TH - 1) / IG_TH;
+  p.ntiles = (long long)B * p.tiles_x * p.tiles_y;
+  static thread_local bool attr[64] = {false};
+  int dev = 0;
+  LL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr[dev]) {
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_BYTES));
+    attr[dev] = true;
+  }
+  const long long sms = sm_count_cached();
+  const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
+  igemm_conv_kernel<<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
+  LL_LAUNCH_OK("igemm_conv_kernel");
+  return LL_OK;
+}
+
+}  // extern "C"

@@ -233,6 +233,96 @@ def conv2d(x, weight, bias=None, groups=1, lrelu=False, upsample2=False, out=Non
     return out
 
 
+# ----------------------------------------------------------------------------- tcgen05 context CNNs
+IG_BK = 64      # input channels per k-block (one 128-byte swizzle row of bf16)
+
+
+def _pad_to(n, m):
+    return (n + m - 1) // m * m
+
+
+def ctx_head_nhwc(x, weight, bias, upsample2=False, lrelu=True, cpad=None):
+    """3x3 conv (Cin <= 4) + bias + LeakyReLU on the (optionally nearest-2x-upsampled) parent,
+    written channels-last in bf16: returns (B,H,W,Cpad) bf16 with channels >= Cout zeroed."""
+    require_device(x)
+    x = _f32c(x, "x")
+    w = _f32c(weight.detach(), "weight")
+    b = _f32c(bias.detach(), "bias") if bias is not None else None
+    B, Cin, Hs, Ws = x.shape
+    H, W = (2 * Hs, 2 * Ws) if upsample2 else (Hs, Ws)
+    Cout = w.shape[0]
+    if tuple(w.shape[1:]) != (Cin, 3, 3):
+        raise ValueError(f"ctx_head_nhwc: weight {tuple(w.shape)} does not fit input {tuple(x.shape)}")
+    cpad = cpad or _pad_to(Cout, IG_BK)
+    out = torch.empty(B, H, W, cpad, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_ctx_head_nhwc(ptr(x), ptr(w), ptr(b), ptr(out), B, Cin, H, W, Cout, cpad,
+                                           int(bool(upsample2)), int(bool(lrelu)), stream_ptr()))
+    _count(1)
+    return out
+
+
+def pack_igemm_weight(weight, npad=None, kpad=None):
+    """(Co,Ci,R,S) fp32 -> bf16 [R*S][Npad][Kpad] device blob for ``igemm_conv``."""
+    require_device(weight)
+    w = _f32c(weight.detach(), "weight")
+    Co, Ci, R, S = w.shape
+    taps = R * S
+    npad = npad or _pad_to(Co, 16)
+    kpad = kpad or _pad_to(Ci, IG_BK)
+    wp = torch.empty(taps, npad, kpad, dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        check(_lib.load().ll_pack_igemm_weight(ptr(w), ptr(wp), Co, Ci, taps, npad, kpad, stream_ptr()))
+    _count(1)
+    return wp
+
+
+def nchw_to_nhwc_bf16(x, out, coff):
+    """fp32 (B,C,H,W) -> channels [coff, coff+C) of the bf16 NHWC tensor ``out`` (B,H,W,Ctot)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, C, H, W = x.shape
+    if out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape[:3]) != (B, H, W):
+        raise ValueError("nchw_to_nhwc_bf16: bad out tensor")
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_nchw_to_nhwc_bf16(ptr(x), x.stride(0) if B > 1 else C * H * W, ptr(out), B, C, H, W,
+                                               out.shape[3], coff, stream_ptr()))
+    _count(1)
+    return out
+
+
+def igemm_conv(x_nhwc, wp, bias, cout, lrelu=False, out=None, co_group=0, co_stride=0, co_off=0,
+               out_nhwc=None, nhwc_coff=0):
+    """tcgen05 implicit-GEMM conv (3x3 when wp has 9 taps, 1x1 when 1) of a bf16 NHWC tensor
+    (B,H,W,Kpad).  ``out``: fp32 NCHW tensor written through the channel remap of ``conv2d``;
+    ``out_nhwc``: bf16 NHWC tensor written at channel offset ``nhwc_coff``.  At least one."""
+    require_device(x_nhwc)
+    if x_nhwc.dtype != torch.bfloat16 or not x_nhwc.is_contiguous() or x_nhwc.dim() != 4:
+        raise TypeError("igemm_conv: x must be a contiguous bf16 (B,H,W,K) tensor")
+    if wp.dtype != torch.bfloat16 or not wp.is_contiguous() or wp.dim() != 3:
+        raise TypeError("igemm_conv: wp must come from pack_igemm_weight")
+    B, H, W, kpad = x_nhwc.shape
+    taps, npad, kp = wp.shape
+    if kp != kpad:
+        raise ValueError(f"igemm_conv: packed weight has Kpad={kp}, input has {kpad} channels")
+    b = _f32c(bias.detach(), "bias") if bias is not None else None
+    if out is None and out_nhwc is None:
+        out = torch.empty(B, cout, H, W, dtype=torch.float32, device=x_nhwc.device)
+    if out is not None and (out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape[2:]) != (H, W)
+                            or out.shape[0] != B):
+        raise ValueError("igemm_conv: bad out tensor")
+    if out_nhwc is not None and (out_nhwc.dtype != torch.bfloat16 or not out_nhwc.is_contiguous()
+                                 or tuple(out_nhwc.shape[:3]) != (B, H, W)):
+        raise ValueError("igemm_conv: bad out_nhwc tensor")
+    with torch.cuda.device(x_nhwc.device):
+        check(_lib.load().ll_igemm_conv(
+            ptr(x_nhwc), ptr(wp), ptr(b), B, H, W, kpad, npad, cout, taps, int(bool(lrelu)),
+            ptr(out), (out.stride(0) if B > 1 else out[0].numel()) if out is not None else 0, co_group, co_stride, co_off,
+            ptr(out_nhwc), out_nhwc.shape[3] if out_nhwc is not None else 0, nhwc_coff, stream_ptr()))
+    _count(1)
+    return out if out is not None else out_nhwc
+
+
 def quantize(x, noise=None):
     """round-half-even(x), or x + noise in training (ll_quantize)."""
     require_device(x)

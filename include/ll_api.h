@@ -149,6 +149,38 @@ int ll_conv2d(const float* x, int64_t x_sb, const float* w, const float* b, floa
               int H, int W, int Cout, int K, int groups, int upsample2, int lrelu, int co_group, int co_stride,
               int co_off, ll_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* Dense context CNNs on the tcgen05 tensor cores (K3)                        */
+/* ------------------------------------------------------------------------- */
+
+/* First conv of plc_list[i] (Conv2d(3, 243, 3, padding=1) + LeakyReLU on the nearest-2x-upsampled
+ * quantised parent, LiftingBasedDWT_net.py:271,348,355; onlyEZWT :789-790): x fp32 (B,Cin,H,W) --
+ * or (B,Cin,H/2,W/2) when upsample2 != 0 -- w (Cout,Cin,3,3), fp32 FMA, result rounded to BF16 and
+ * written channels-last: out bf16 (B,H,W,Cpad), channels [Cout,Cpad) = 0.  Cin <= 4, Cpad % 8 == 0. */
+int ll_ctx_head_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,
+                     int Cout, int Cpad, int upsample2, int lrelu, ll_stream_t stream);
+
+/* Weight packing for ll_igemm_conv: torch layout (Co,Ci,R,S) fp32 (taps = R*S in {1,9}) ->
+ * bf16 [taps][Npad][Kpad], zero padded; Npad % 16 == 0 (<= 256), Kpad % 64 == 0. */
+int ll_pack_igemm_weight(const float* w, void* wp, int Co, int Ci, int taps, int Npad, int Kpad, ll_stream_t stream);
+
+/* fp32 NCHW (B,C,H,W; batch stride x_sb) -> channels [out_coff, out_coff+C) of a bf16 NHWC tensor
+ * with out_cstride channels per pixel (drops csc_list[i]'s output into the cgp input layout). */
+int ll_nchw_to_nhwc_bf16(const float* x, int64_t x_sb, void* out, int B, int C, int H, int W, int out_cstride,
+                         int out_coff, ll_stream_t stream);
+
+/* Implicit-GEMM convolution on tcgen05 / TMEM (BF16 operands, FP32 accumulation), stride 1,
+ * zero padding: taps == 9 -> 3x3 (the 243->243 conv of plc_list[i][2], :272,355; onlyEZWT :791),
+ * taps == 1 -> 1x1 (dense per-group layers of cgp_out_xo_list, :280-290).
+ * x_nhwc bf16 (B,H,W,Kpad); wp from ll_pack_igemm_weight; bias fp32[Cout] or NULL; lrelu != 0
+ * applies LeakyReLU(0.01).  Outputs (either or both):
+ *   out_f32  fp32 NCHW with batch stride out_sb and the ll_conv2d channel remap
+ *            (co / co_group) * co_stride + co_off + co % co_group (co_group <= 0: identity);
+ *   out_bf16 bf16 NHWC with out_cstride channels per pixel, written at [out_coff, out_coff+Cout). */
+int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Kpad, int Npad,
+                  int Cout, int taps, int lrelu, float* out_f32, int64_t out_sb, int co_group, int co_stride,
+                  int co_off, void* out_bf16, int out_cstride, int out_coff, ll_stream_t stream);
+
 /* EntropyModel.quantize (compressai 1.2.1; call sites :330,341,352,719): q = round-half-even(x)
  * when noise == NULL ("dequantize"), else q = x + noise ("noise"; the caller draws U(-1/2,1/2)). */
 int ll_quantize(const float* x, const float* noise, float* q, int64_t n, ll_stream_t stream);
