@@ -56,10 +56,12 @@ SIGNATURES = {
     "ll_pack_ae1": (c_int, [_P] * 8 + [c_int, c_int, _P, _P]),
     "ll_ae1_apply": (c_int, [_P, _P, _P, _P, c_int, c_int, c_i64, _P]),
     "ll_conv2d": (c_int, [_P, c_i64, _P, _P, _P, c_i64] + [c_int] * 12 + [_P]),
-    "ll_ctx_head_nhwc": (c_int, [_P, _P, _P, _P] + [c_int] * 8 + [_P]),
+    "ll_ctx_conv_nhwc": (c_int, [_P, _P, _P, _P] + [c_int] * 15 + [_P]),
+    "ll_cgp_tail_rate": (c_int, [_P, c_i64, _P, _P, _P, _P, _P, c_i64, _P, _P, c_i64, _P, _P, c_int, c_int, c_int, c_int, c_i64, _P, _P]),
     "ll_pack_igemm_weight": (c_int, [_P, _P] + [c_int] * 5 + [_P]),
     "ll_nchw_to_nhwc_bf16": (c_int, [_P, c_i64, _P] + [c_int] * 6 + [_P]),
-    "ll_igemm_conv": (c_int, [_P, _P, _P] + [c_int] * 8 + [_P, c_i64, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    "ll_igemm_conv": (c_int, [_P, _P, _P] + [c_int] * 9 + [ctypes.POINTER(c_int), c_int, _P, c_i64, c_int, c_int, c_int, _P,
+                              c_int, c_int, c_int, _P]),
     "ll_quantize": (c_int, [_P, _P, _P, c_i64, _P]),
     "ll_gauss_rate": (c_int, [_P, c_i64, _P, c_i64, _P, _P, c_i64, _P, c_int, c_int, c_i64, _P, _P]),
     "ll_pack_eb": (c_int, [ctypes.POINTER(c_voidp), c_int, _P, _P]),

@@ -41,7 +41,9 @@ constexpr int IG_B_BYTES = IG_MAXN * IG_BK * 2;   // 32 KB
 constexpr int IG_STAGE_BYTES = IG_A_BYTES + IG_B_BYTES;
 constexpr int IG_THREADS = 192;
 constexpr int IG_TMEM_COLS = 512;
-constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXN * 4;
+constexpr int IG_MAXG = 3;       // channel groups per launch (the cgp MLP has groups = 3)
+constexpr int IG_MAXSLOTS = 12;  // k-blocks per (group, tap)
+constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXG * IG_MAXN * 4;
 
 struct IgemmParams {
   const float* bias;
@@ -52,7 +54,9 @@ struct IgemmParams {
   int out_cstride, out_coff;
   int B, H, W, Cout, Npad, kblocks, taps, lrelu;
   int tiles_x, tiles_y;
-  long long ntiles;
+  long long ntiles;                       // tiles x groups
+  int groups, out_gstride;                // NHWC channel stride between groups
+  int a_koff[IG_MAXG][IG_MAXSLOTS];       // input-channel coordinate of each k-block, per group
 };
 
 // ---------------------------------------------------------------------------------------- PTX
@@ -152,13 +156,14 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * IG_STAGES + 2 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + IG_STAGES * IG_STAGE_BYTES + 8 * (2 * IG_STAGES + 4));
   float* s_bias = reinterpret_cast<float*>(gen + IG_STAGES * IG_STAGE_BYTES + 1024);
-  int* s_cmap = reinterpret_cast<int*>(s_bias + IG_MAXN);
+  int* s_cmap = reinterpret_cast<int*>(s_bias + IG_MAXG * IG_MAXN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < IG_MAXN; i += IG_THREADS) {
-    s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
-    s_cmap[i] = (i / p.co_group) * p.co_stride + p.co_off + (i % p.co_group);
+  for (int i = threadIdx.x; i < p.groups * IG_MAXN; i += IG_THREADS) {
+    const int g = i / IG_MAXN, c = i % IG_MAXN, co = g * p.Cout + c;   // channel index across groups
+    s_bias[i] = (p.bias && c < p.Cout) ? p.bias[co] : 0.f;
+    s_cmap[i] = (co / p.co_group) * p.co_stride + p.co_off + (co % p.co_group);
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -185,14 +190,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int iters = p.taps * p.kblocks;
   const uint32_t stage_tx = IG_A_BYTES + (uint32_t)p.Npad * IG_BK * 2;
   const long long per_img = (long long)p.tiles_x * p.tiles_y;
+  const int G = p.groups;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const int b = (int)(t / per_img);
-        const int r = (int)(t % per_img);
+        const int g = (int)(t % G);
+        const long long tt = t / G;
+        const int b = (int)(tt / per_img);
+        const int r = (int)(tt % per_img);
         const int y0 = (r / p.tiles_x) * IG_TH, x0 = (r % p.tiles_x) * IG_TW;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
@@ -200,8 +208,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), stage_tx);
             const uint32_t sa = base + stage * IG_STAGE_BYTES;
-            tma_load_4d(sa, &tmA, full_bar(stage), kb * IG_BK, x0 + dx, y0 + dy, b);
-            tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), kb * IG_BK, 0, tap);
+            tma_load_4d(sa, &tmA, full_bar(stage), p.a_koff[g][kb], x0 + dx, y0 + dy, b);
+            tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), kb * IG_BK, 0, g * p.taps + tap);
             if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -242,15 +250,19 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     const int nchunks = p.Npad / 32 + ((p.Npad % 32) ? 1 : 0);
     for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      const int b = (int)(t / per_img);
-      const int r = (int)(t % per_img);
+      const int g = (int)(t % G);
+      const long long tt = t / G;
+      const int b = (int)(tt / per_img);
+      const int r = (int)(tt % per_img);
       const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
+      const float* gb = s_bias + g * IG_MAXN;
+      const int* gm = s_cmap + g * IG_MAXN;
       const bool valid = y < p.H && x < p.W;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * IG_MAXN;
       float* of = p.out_f32 ? p.out_f32 + (long long)b * p.out_sb + (long long)y * p.W + x : nullptr;
-      __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff : nullptr;
+      __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff + g * p.out_gstride : nullptr;
       const long long plane = (long long)p.H * p.W;
       for (int c = 0; c < nchunks; ++c) {
         uint32_t v[32];
@@ -260,16 +272,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+            float a = __uint_as_float(v[j]) + gb[c * 32 + j];
             f[j] = (p.lrelu && a < 0.f) ? a * 0.01f : a;
           }
           if (of) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < p.Cout) of[(long long)s_cmap[c * 32 + j] * plane] = f[j];
+              if (c * 32 + j < p.Cout) of[(long long)gm[c * 32 + j] * plane] = f[j];
           }
           if (ob) {
-            if (c * 32 + 32 <= p.Cout && ((p.out_coff + c * 32) % 8 == 0) && (p.out_cstride % 8 == 0)) {
+            // every Npad channel is written (the padded ones are exact zeros: zero weights, zero bias), so a
+            // consumer igemm layer never multiplies uninitialised memory
+            if (c * 32 + 32 <= p.Npad && ((p.out_coff + g * p.out_gstride) % 8 == 0) && (p.out_cstride % 8 == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 pk;
@@ -282,7 +296,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < p.Cout) ob[c * 32 + j] = __float2bfloat16_rn(f[j]);
+                if (c * 32 + j < p.Npad) ob[c * 32 + j] = __float2bfloat16_rn(f[j]);
             }
           }
         }
@@ -302,52 +316,77 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-// plc head: conv3x3 (Cin<=4 -> Cout) on the (optionally nearest-2x-upsampled) parent, + bias,
-// LeakyReLU, written as NHWC bf16 with channels [Cout, Cpad) zeroed.  One thread = one pixel x 8 channels.
+// Small-Cin convs of the context models written channels-last in bf16 for the igemm layers:
+//   plc head  Conv2d(3, 243, 3, padding=1) + LeakyReLU on the nearest-2x-upsampled parent (:271,355)
+//   csc       MaskedConv2d('A', 3, 243, 5, padding=2, groups=3) on the quantised child (:274-277,353);
+//             only the first `live_taps` taps in row-major order are non-zero under the mask (12 of 25).
+// One thread = one pixel x 8 consecutive destination channels (one 16-byte store).  Destination
+// channel d of the covered region maps to conv channel co = (d / co_gstride) * co_group + d % co_gstride
+// (valid when d % co_gstride < co_group and co < Cout); every other destination channel of the
+// region is written as 0, so a consumer igemm layer never reads uninitialised memory.
 constexpr int HD_THREADS = 256;
-__global__ void __launch_bounds__(HD_THREADS)
-ctx_head_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                     __nv_bfloat16* __restrict__ out, int B, int Cin, int H, int W, int Cout, int Cpad, int upsample2,
-                     int lrelu) {
-  extern __shared__ float s_w[];   // [Cpad][Cin*9] + bias[Cpad]
-  const int K = Cin * 9;
-  for (int i = threadIdx.x; i < Cpad * K; i += HD_THREADS) s_w[i] = (i / K) < Cout ? w[i] : 0.f;
-  float* s_b = s_w + Cpad * K;
-  for (int i = threadIdx.x; i < Cpad; i += HD_THREADS) s_b[i] = (bias && i < Cout) ? bias[i] : 0.f;
+constexpr int HD_MAXIN = 32;
+struct SmallConvParams {
+  const float* x; const float* w; const float* bias;
+  __nv_bfloat16* out;
+  int B, Cin, H, W, Cout, groups, K, live_taps, upsample2, lrelu;
+  int out_cstride, out_coff, co_group, co_gstride, region;
+};
+__global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_constant__ SmallConvParams p) {
+  extern __shared__ float s_w[];   // [Cout][cin_g * live_taps] + bias[Cout]
+  const int cin_g = p.Cin / p.groups, cout_g = p.Cout / p.groups;
+  const int KK = p.K * p.K, nin = cin_g * p.live_taps;
+  for (int i = threadIdx.x; i < p.Cout * nin; i += HD_THREADS) {
+    const int co = i / nin, r = i % nin, ci = r / p.live_taps, t = r % p.live_taps;
+    s_w[i] = p.w[((long long)co * cin_g + ci) * KK + t];
+  }
+  float* s_b = s_w + p.Cout * nin;
+  for (int i = threadIdx.x; i < p.Cout; i += HD_THREADS) s_b[i] = p.bias ? p.bias[i] : 0.f;
   __syncthreads();
-  const int groups = Cpad / 8;
-  const int Hs = upsample2 ? H / 2 : H, Ws = upsample2 ? W / 2 : W;
-  const long long total = (long long)B * H * W * groups;
+  const int slots = p.region / 8;
+  const int Hs = p.upsample2 ? p.H / 2 : p.H, Ws = p.upsample2 ? p.W / 2 : p.W;
+  const int pad = p.K / 2;
+  const long long total = (long long)p.B * p.H * p.W * slots;
   for (long long e = (long long)blockIdx.x * HD_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * HD_THREADS) {
-    const int g = (int)(e % groups);
-    const long long px = e / groups;
-    const int xx = (int)(px % W), yy = (int)((px / W) % H), b = (int)(px / ((long long)W * H));
-    float in[36];
-    for (int ci = 0; ci < Cin; ++ci)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int gy = yy + t / 3 - 1, gx = xx + t % 3 - 1;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-          const int sy = upsample2 ? gy >> 1 : gy, sx = upsample2 ? gx >> 1 : gx;
-          v = x[(((long long)b * Cin + ci) * Hs + sy) * Ws + sx];
-        }
-        in[ci * 9 + t] = v;
-      }
+    const int m = (int)(e % slots);
+    const long long px = e / slots;
+    const int d0 = m * 8;
+    const int gd = d0 / p.co_gstride, j0 = d0 % p.co_gstride;
+    const int co0 = gd * p.co_group + j0;
     float o[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float* wr = s_w + (g * 8 + c) * K;
-      float a = s_b[g * 8 + c];
-      for (int k = 0; k < K; ++k) a = fmaf(in[k], wr[k], a);
-      o[c] = (lrelu && a < 0.f) ? a * 0.01f : a;
+    for (int c = 0; c < 8; ++c) o[c] = 0.f;
+    if (j0 < p.co_group && co0 < p.Cout) {
+      const int xx = (int)(px % p.W), yy = (int)((px / p.W) % p.H), b = (int)(px / ((long long)p.W * p.H));
+      const int g = co0 / cout_g;                       // conv group of this slot (host guarantees it is unique)
+      float in[HD_MAXIN];
+      for (int ci = 0; ci < cin_g; ++ci)
+        for (int t = 0; t < p.live_taps; ++t) {
+          const int gy = yy + t / p.K - pad, gx = xx + t % p.K - pad;
+          float v = 0.f;
+          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+            const int sy = p.upsample2 ? gy >> 1 : gy, sx = p.upsample2 ? gx >> 1 : gx;
+            v = p.x[(((long long)b * p.Cin + g * cin_g + ci) * Hs + sy) * Ws + sx];
+          }
+          in[ci * p.live_taps + t] = v;
+        }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int co = co0 + c;
+        if (j0 + c < p.co_group && co < p.Cout) {
+          const float* wr = s_w + co * nin;
+          float a = s_b[co];
+          for (int k = 0; k < nin; ++k) a = fmaf(in[k], wr[k], a);
+          o[c] = (p.lrelu && a < 0.f) ? a * 0.01f : a;
+        }
+      }
     }
     uint4 pk;
     __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
     __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(out + px * Cpad + g * 8) = pk;
+    *reinterpret_cast<uint4*>(p.out + px * p.out_cstride + p.out_coff + d0) = pk;
   }
 }
 
@@ -398,22 +437,35 @@ using namespace ll;
 
 extern "C" {
 
-int ll_ctx_head_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
-                     int Cpad, int upsample2, int lrelu, ll_stream_t stream) {
-  if (B < 0 || H < 0 || W < 0 || Cin < 1 || Cin > 4 || Cout < 1 || Cpad < Cout || Cpad % 8)
-    return fail(LL_EINVAL, "ll_ctx_head_nhwc: bad extents (Cin in 1..4, Cpad multiple of 8 and >= Cout)");
-  if (upsample2 && ((H & 1) || (W & 1))) return fail(LL_EINVAL, "ll_ctx_head_nhwc: upsample2 needs even output size");
+int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
+                     int K, int groups, int live_taps, int upsample2, int lrelu, int out_cstride, int out_coff,
+                     int co_group, int co_gstride, int region, ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || Cin < 1 || Cout < 1 || groups < 1 || Cin % groups || Cout % groups || (K != 1 && K != 3 && K != 5))
+    return fail(LL_EINVAL, "ll_ctx_conv_nhwc: bad extents");
+  if (live_taps < 1 || live_taps > K * K || (Cin / groups) * live_taps > HD_MAXIN)
+    return fail(LL_EINVAL, "ll_ctx_conv_nhwc: (Cin/groups) * live_taps must be in 1..%d", HD_MAXIN);
+  if (co_group <= 0) { co_group = Cout; co_gstride = region > 0 ? region : Cout; }
+  if (region <= 0 || region % 8 || out_coff % 8 || out_cstride % 8 || out_coff < 0 || out_cstride < out_coff + region || co_gstride < co_group)
+    return fail(LL_EINVAL, "ll_ctx_conv_nhwc: region / offsets must be multiples of 8 channels inside the output pixel");
+  if (groups > 1 && (co_group != Cout / groups || co_gstride % 8))
+    return fail(LL_EINVAL, "ll_ctx_conv_nhwc: grouped convs need co_group == Cout/groups and an 8-aligned group stride");
+  if (upsample2 && ((H & 1) || (W & 1))) return fail(LL_EINVAL, "ll_ctx_conv_nhwc: upsample2 needs even output size");
   if ((long long)B * H * W == 0) return LL_OK;
-  if (!x || !w || !out) return fail(LL_EINVAL, "ll_ctx_head_nhwc: null pointer");
-  const size_t smem = (size_t)(Cpad * Cin * 9 + Cpad) * sizeof(float);
-  if (smem > 48 * 1024) LL_CUDA_OK(cudaFuncSetAttribute(ctx_head_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long total = (long long)B * H * W * (Cpad / 8);
+  if (!x || !w || !out) return fail(LL_EINVAL, "ll_ctx_conv_nhwc: null pointer");
+  SmallConvParams p = {};
+  p.x = x; p.w = w; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.groups = groups; p.K = K; p.live_taps = live_taps;
+  p.upsample2 = upsample2; p.lrelu = lrelu;
+  p.out_cstride = out_cstride; p.out_coff = out_coff; p.co_group = co_group; p.co_gstride = co_gstride; p.region = region;
+  const size_t smem = (size_t)(Cout * (Cin / groups) * live_taps + Cout) * sizeof(float);
+  if (smem > 200 * 1024) return fail(LL_EINVAL, "ll_ctx_conv_nhwc: weights do not fit shared memory");
+  if (smem > 48 * 1024) LL_CUDA_OK(cudaFuncSetAttribute(ctx_conv_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long total = (long long)B * H * W * (region / 8);
   long long blocks = (total + HD_THREADS - 1) / HD_THREADS;
   const long long cap = (long long)sm_count_cached() * 8;
   if (blocks > cap) blocks = cap;
-  ctx_head_nhwc_kernel<<<(unsigned)blocks, HD_THREADS, smem, as_stream(stream)>>>(
-      x, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, Cin, H, W, Cout, Cpad, upsample2, lrelu);
-  LL_LAUNCH_OK("ctx_head_nhwc_kernel");
+  ctx_conv_nhwc_kernel<<<(unsigned)blocks, HD_THREADS, smem, as_stream(stream)>>>(p);
+  LL_LAUNCH_OK("ctx_conv_nhwc_kernel");
   return LL_OK;
 }
 
@@ -444,25 +496,32 @@ int ll_nchw_to_nhwc_bf16(const float* x, int64_t x_sb, void* out, int B, int C, 
   return LL_OK;
 }
 
-int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Kpad, int Npad, int Cout,
-                  int taps, int lrelu, float* out_f32, int64_t out_sb, int co_group, int co_stride, int co_off,
-                  void* out_bf16, int out_cstride, int out_coff, ll_stream_t stream) {
+int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Cin_total, int Kpad,
+                  int Npad, int Cout, int taps, int groups, const int* koff, int lrelu, float* out_f32, int64_t out_sb,
+                  int co_group, int co_stride, int co_off, void* out_bf16, int out_cstride, int out_coff, int out_gstride,
+                  ll_stream_t stream) {
   if (B < 0 || H < 0 || W < 0 || Kpad < IG_BK || Kpad % IG_BK || Npad < 16 || Npad % 16 || Npad > IG_MAXN || Cout < 1 ||
       Cout > Npad || (taps != 1 && taps != 9))
     return fail(LL_EINVAL, "ll_igemm_conv: bad extents (Kpad %%64, Npad %%16 in 16..256, Cout <= Npad, taps 1|9)");
+  if (groups < 1 || groups > IG_MAXG || Kpad / IG_BK > IG_MAXSLOTS)
+    return fail(LL_EINVAL, "ll_igemm_conv: groups in 1..%d, at most %d k-blocks per group", IG_MAXG, IG_MAXSLOTS);
+  if (Cin_total < IG_BK || Cin_total % 8) return fail(LL_EINVAL, "ll_igemm_conv: input channel count must be >= 64 and a multiple of 8");
+  if (!koff && (groups != 1 || Cin_total != Kpad)) return fail(LL_EINVAL, "ll_igemm_conv: koff is required when groups > 1 or Cin_total != Kpad");
   if (B > 65535 * 4 || H > (1 << 20) || W > (1 << 20)) return fail(LL_EINVAL, "ll_igemm_conv: extents too large");
   if ((long long)B * H * W == 0) return LL_OK;
   if (!x_nhwc || !wp || (!out_f32 && !out_bf16)) return fail(LL_EINVAL, "ll_igemm_conv: null pointer");
   if (((uintptr_t)x_nhwc & 15) || ((uintptr_t)wp & 15)) return fail(LL_EINVAL, "ll_igemm_conv: operands must be 16-byte aligned");
-  if (out_bf16 && (out_cstride < out_coff + Cout || out_coff < 0)) return fail(LL_EINVAL, "ll_igemm_conv: bad NHWC output slice");
-  if (co_group <= 0) { co_group = Npad; co_stride = 0; co_off = 0; }
+  if (out_bf16 && (out_coff < 0 || out_gstride < 0 || out_cstride < out_coff + (groups - 1) * out_gstride + Npad))
+    return fail(LL_EINVAL, "ll_igemm_conv: bad NHWC output slice (all Npad channels of every group are written)");
+  if (groups > 1 && out_bf16 && out_gstride < Npad) return fail(LL_EINVAL, "ll_igemm_conv: NHWC group stride < Npad");
+  if (co_group <= 0) { co_group = 1 << 30; co_stride = 0; co_off = 0; }
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LL_ECUDA, "ll_igemm_conv: cuTensorMapEncodeTiled not available from the driver");
 
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)Kpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t gstr[3] = {(cuuint64_t)Kpad * 2, (cuuint64_t)W * Kpad * 2, (cuuint64_t)H * W * Kpad * 2};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin_total, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cin_total * 2, (cuuint64_t)W * Cin_total * 2, (cuuint64_t)H * W * Cin_total * 2};
     cuuint32_t box[4] = {IG_BK, IG_TW, IG_TH, 1};
     cuuint32_t est[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_nhwc), gdim, gstr, box, est,
@@ -471,7 +530,7 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
     if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
-    cuuint64_t gdim[3] = {(cuuint64_t)Kpad, (cuuint64_t)Npad, (cuuint64_t)taps};
+    cuuint64_t gdim[3] = {(cuuint64_t)Kpad, (cuuint64_t)Npad, (cuuint64_t)taps * groups};
     cuuint64_t gstr[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Npad * Kpad * 2};
     cuuint32_t box[3] = {IG_BK, (cuuint32_t)Npad, 1};
     cuuint32_t est[3] = {1, 1, 1};
@@ -488,7 +547,15 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
   p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Npad = Npad; p.kblocks = Kpad / IG_BK; p.taps = taps; p.lrelu = lrelu;
   p.tiles_x = (W + IG_TW - 1) / IG_TW;
   p.tiles_y = (H + IG_TH - 1) / IG_TH;
-  p.ntiles = (long long)B * p.tiles_x * p.tiles_y;
+  p.ntiles = (long long)B * p.tiles_x * p.tiles_y * groups;
+  p.groups = groups; p.out_gstride = out_gstride;
+  for (int g = 0; g < groups; ++g)
+    for (int k = 0; k < p.kblocks; ++k) {
+      const int off = koff ? koff[g * p.kblocks + k] : k * IG_BK;
+      if (off < 0 || off + IG_BK > Cin_total || off % 8)
+        return fail(LL_EINVAL, "ll_igemm_conv: k-block offset %d outside the %d input channels or not a multiple of 8", off, Cin_total);
+      p.a_koff[g][k] = off;
+    }
   static thread_local bool attr[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));

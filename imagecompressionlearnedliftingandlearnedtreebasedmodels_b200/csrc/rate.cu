@@ -36,6 +36,19 @@ __global__ void quantize_kernel(const float* __restrict__ x, const float* __rest
     q[i] = noise ? __fadd_rn(x[i], noise[i]) : rintf(x[i]);
 }
 
+// GaussianConditional.forward + -log2 for one coefficient, in the reference's operation order.
+__device__ __forceinline__ float gauss_bits(float xv, float sg, float mu, const float* noise, float& y) {
+  if (noise) y = __fadd_rn(xv, *noise);
+  else y = __fadd_rn(rintf(__fsub_rn(xv, mu)), mu);
+  const float v = fabsf(__fsub_rn(y, mu));
+  const float s = fmaxf(sg, 0.11f);
+  const float kc = -0.70710678118654752440f;  // float(-(2 ** -0.5))
+  const float up = 0.5f * erfcf(kc * __fdiv_rn(0.5f - v, s));
+  const float lo = 0.5f * erfcf(kc * __fdiv_rn(-0.5f - v, s));
+  const float pr = fmaxf(up - lo, 1e-9f);
+  return -log2f(pr);
+}
+
 // x: (B, C, hw) with batch stride x_sb and channel offset folded into the pointer;
 // ms: (B, 2C, hw): channel 2c = sigma, 2c+1 = mu.
 __global__ void __launch_bounds__(RT_THREADS) gauss_rate_kernel(
@@ -53,17 +66,74 @@ __global__ void __launch_bounds__(RT_THREADS) gauss_rate_kernel(
     const float sg = ms[b * ms_sb + (2 * c) * hw + pix];
     const float mu = ms[b * ms_sb + (2 * c + 1) * hw + pix];
     float y;
-    if (noise) y = __fadd_rn(xv, noise[(b * C + c) * hw + pix]);
-    else y = __fadd_rn(rintf(__fsub_rn(xv, mu)), mu);
-    const float v = fabsf(__fsub_rn(y, mu));
-    const float s = fmaxf(sg, 0.11f);
-    const float kc = -0.70710678118654752440f;  // float(-(2 ** -0.5))
-    const float up = 0.5f * erfcf(kc * __fdiv_rn(0.5f - v, s));
-    const float lo = 0.5f * erfcf(kc * __fdiv_rn(-0.5f - v, s));
-    const float pr = fmaxf(up - lo, 1e-9f);
-    const float bt = -log2f(pr);
+    const float bt = gauss_bits(xv, sg, mu, noise ? &noise[(b * C + c) * hw + pix] : nullptr, y);
     bits[b * bits_sb + c * hw + pix] = bt;
     if (yout) yout[(b * C + c) * hw + pix] = y;
+    local += bt;
+  }
+  if (sum_out) {
+    const float t = block_sum(local, red);
+    if (threadIdx.x == 0) atomicAdd(sum_out, (double)t);
+  }
+}
+
+// cgp tail: C2 -> C3 (LeakyReLU) -> (sigma, mu) per group and pixel, then the Gaussian rate.
+// grid.y = group; one thread = one pixel; weights of the group in shared memory (broadcast reads).
+constexpr int TL_MAXC2 = 64, TL_MAXC3 = 32;
+__global__ void __launch_bounds__(RT_THREADS) cgp_tail_rate_kernel(
+    const float* __restrict__ h2, long long h2_sb, const float* __restrict__ w3, const float* __restrict__ b3,
+    const float* __restrict__ w4, const float* __restrict__ b4, const float* __restrict__ x, long long x_sb,
+    const float* __restrict__ noise, float* __restrict__ bits, long long bits_sb, float* __restrict__ yout,
+    float* __restrict__ ms_out, int B, int G, int C2, int C3, long long hw, double* __restrict__ sum_out) {
+  __shared__ __align__(16) float s_w3[TL_MAXC2 * TL_MAXC3];   // transposed [c][k], zero padded to 32 k
+  __shared__ float s_b3[TL_MAXC3], s_w4[2 * TL_MAXC3], s_b4[2];
+  __shared__ float red[RT_THREADS / 32];
+  const int g = blockIdx.y;
+  for (int i = threadIdx.x; i < C2 * TL_MAXC3; i += RT_THREADS) {
+    const int c = i / TL_MAXC3, k = i % TL_MAXC3;
+    s_w3[i] = k < C3 ? w3[((long long)g * C3 + k) * C2 + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < C3; i += RT_THREADS) s_b3[i] = b3[g * C3 + i];
+  for (int i = threadIdx.x; i < 2 * C3; i += RT_THREADS) s_w4[i] = w4[(long long)g * 2 * C3 + i];
+  if (threadIdx.x < 2) s_b4[threadIdx.x] = b4[g * 2 + threadIdx.x];
+  __syncthreads();
+  float local = 0.f;
+  const long long total = (long long)B * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, pix = i % hw;
+    const float* hp = h2 + b * h2_sb + (long long)g * C2 * hw + pix;
+    float h[TL_MAXC3];
+#pragma unroll
+    for (int k = 0; k < TL_MAXC3; ++k) h[k] = k < C3 ? s_b3[k] : 0.f;
+    for (int c = 0; c < C2; ++c) {
+      const float v = hp[(long long)c * hw];
+#pragma unroll
+      for (int k = 0; k < TL_MAXC3; k += 4)
+        if (k < C3) {
+          const float4 w = *reinterpret_cast<const float4*>(&s_w3[c * TL_MAXC3 + k]);
+          h[k] = fmaf(w.x, v, h[k]);
+          h[k + 1] = fmaf(w.y, v, h[k + 1]);
+          h[k + 2] = fmaf(w.z, v, h[k + 2]);
+          h[k + 3] = fmaf(w.w, v, h[k + 3]);
+        }
+    }
+    float sg = s_b4[0], mu = s_b4[1];
+#pragma unroll
+    for (int k = 0; k < TL_MAXC3; ++k)
+      if (k < C3) {
+        const float a = h[k] < 0.f ? h[k] * 0.01f : h[k];
+        sg = fmaf(s_w4[k], a, sg);
+        mu = fmaf(s_w4[C3 + k], a, mu);
+      }
+    const float xv = x[b * x_sb + (long long)g * hw + pix];
+    float y;
+    const float bt = gauss_bits(xv, sg, mu, noise ? &noise[(b * G + g) * hw + pix] : nullptr, y);
+    bits[b * bits_sb + (long long)g * hw + pix] = bt;
+    if (yout) yout[(b * G + g) * hw + pix] = y;
+    if (ms_out) {
+      ms_out[(b * 2 * G + 2 * g) * hw + pix] = sg;
+      ms_out[(b * 2 * G + 2 * g + 1) * hw + pix] = mu;
+    }
     local += bt;
   }
   if (sum_out) {
@@ -199,6 +269,21 @@ int ll_gauss_rate(const float* x, int64_t x_sb, const float* ms, int64_t ms_sb, 
   gauss_rate_kernel<<<grid_for(total), RT_THREADS, 0, as_stream(stream)>>>(x, x_sb, ms, ms_sb, noise, bits, bits_sb, y, C,
                                                                            hw, total, sum_out);
   LL_LAUNCH_OK("gauss_rate_kernel");
+  return LL_OK;
+}
+
+int ll_cgp_tail_rate(const float* h2, int64_t h2_sb, const float* w3, const float* b3, const float* w4, const float* b4,
+                     const float* x, int64_t x_sb, const float* noise, float* bits, int64_t bits_sb, float* y,
+                     float* ms_out, int B, int G, int C2, int C3, int64_t hw, double* sum_out, ll_stream_t stream) {
+  if (B < 0 || G < 1 || G > 65535 || hw < 0 || C2 < 1 || C2 > TL_MAXC2 || C3 < 1 || C3 > TL_MAXC3)
+    return fail(LL_EINVAL, "ll_cgp_tail_rate: bad extents (C2 <= %d, C3 <= %d)", TL_MAXC2, TL_MAXC3);
+  const long long total = (long long)B * hw;
+  if (total == 0) return LL_OK;
+  if (!h2 || !w3 || !b3 || !w4 || !b4 || !x || !bits) return fail(LL_EINVAL, "ll_cgp_tail_rate: null pointer");
+  dim3 grid((unsigned)grid_for(total), (unsigned)G);
+  cgp_tail_rate_kernel<<<grid, RT_THREADS, 0, as_stream(stream)>>>(h2, h2_sb, w3, b3, w4, b4, x, x_sb, noise, bits, bits_sb,
+                                                                   y, ms_out, B, G, C2, C3, hw, sum_out);
+  LL_LAUNCH_OK("cgp_tail_rate_kernel");
   return LL_OK;
 }
 

@@ -15,7 +15,9 @@ import torch
 from torch import nn
 
 from ... import ops
+from ... import compat
 from ...compat import EntropyBottleneck, GaussianConditional
+from ..layers._packing import PackCache
 from ..layers.lifting_dwt_nets import DWTPytorchWaveletsLayer, LiftingBasedNeuralWaveletv4
 from ..layers.masked_conv2d import MaskedConv2d
 
@@ -136,6 +138,14 @@ class LiftingBasedDWTNet(nn.Module):
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
 
 
+def _ctx_precision(config):
+    """New optional config key (default keeps the reference's config files valid): "bf16" | "fp32"."""
+    v = config.get("ctx_precision", "bf16") if hasattr(config, "get") else getattr(config, "ctx_precision", "bf16")
+    if v not in ("bf16", "fp32"):
+        raise ValueError(f"ctx_precision must be 'bf16' or 'fp32', got {v!r}")
+    return v
+
+
 def _sos_ses(config):
     se, so = 1 * config.clrch, 3 * config.clrch
     ses, sos = [], []
@@ -222,6 +232,10 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         self.csc_xe = self._causal_chain(self.ses[i])
         self.ent_out_xe = GaussianConditional(scale_table=None, scale_bound=0.11)
         self.bit_acc = None
+        # "bf16": dense context CNNs (plc conv2, cgp layers 1-2) on the tcgen05 tensor cores;
+        # "fp32": everything on the exact-fp32 SIMT kernels.  Only (sigma, mu) -- i.e. bpp -- differ.
+        self.ctx_precision = _ctx_precision(config)
+        self._tc_cache = [PackCache() for _ in range(self.num_lifting_layers)]
 
     @staticmethod
     def _causal_chain(inn):
@@ -232,9 +246,72 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
                              mk('B', o, o // 3), nn.LeakyReLU(inplace=True), mk('B', o // 3, o // 9),
                              nn.LeakyReLU(inplace=True), mk('B', o // 9, inn * 2))
 
+    # ---- tensor-core path (default): BF16 tcgen05 implicit GEMMs, FP32 accumulation -------------
+    def _tc_pack(self, i):
+        """Packed BF16 weights of level i: plc conv2 (9 taps, 256x256), cgp layer 1 (per group
+        K = [128-channel window of plc | 128-channel csc slot], N = 192) and layer 2 (K = 192, N = 64)."""
+        plc, cgp = self.plc_list[i], self.cgp_out_xo_list[i]
+        srcs = [plc[2].weight, cgp[0].weight, cgp[2].weight]
+
+        def build():
+            C = self.sos[i]
+            nper = plc[0].out_channels // C                      # 81
+            n1, n2 = cgp[0].out_channels // C, cgp[2].out_channels // C   # 162, 54
+            starts = [(nper * g) // 64 * 64 for g in range(C)]
+            if C > 3 or nper > 128 or any(nper * g + nper > starts[g] + 128 for g in range(C)) or \
+                    C * nper > 256 or n1 > 192 or n2 > 64:
+                raise NotImplementedError("tensor-core context path is laid out for clrch=1 (3 subbands x 81 channels)")
+            dev = plc[2].weight.device
+            wp_plc = ops.pack_igemm_weight(plc[2].weight, npad=256, kpad=256)
+            w1 = cgp[0].weight.detach()[:, :, 0, 0]              # (C*n1, 2*nper)
+            w2 = cgp[2].weight.detach()[:, :, 0, 0]              # (C*n2, n1)
+            l1, l2, k1 = [], [], []
+            for g in range(C):
+                wg = torch.zeros(n1, 256, 1, 1, device=dev)
+                off = nper * g - starts[g]
+                wg[:, off:off + nper, 0, 0] = w1[n1 * g:n1 * (g + 1), :nper]
+                wg[:, 128:128 + nper, 0, 0] = w1[n1 * g:n1 * (g + 1), nper:]
+                l1.append(ops.pack_igemm_weight(wg, npad=192, kpad=256))
+                l2.append(ops.pack_igemm_weight(w2[n2 * g:n2 * (g + 1)].reshape(n2, n1, 1, 1).contiguous(), npad=64, kpad=192))
+                k1.append([starts[g], starts[g] + 64, 256 + 128 * g, 256 + 128 * g + 64])
+            k2 = [[192 * g, 192 * g + 64, 192 * g + 128] for g in range(C)]
+            return dict(plc=wp_plc, l1=torch.stack(l1).contiguous(), l2=torch.stack(l2).contiguous(), k1=k1, k2=k2,
+                        nper=nper, n1=n1, n2=n2)
+
+        return self._tc_cache[i].get(srcs, build)
+
+    def _level_bits_tc(self, i, x, q, con, noise, acc):
+        """Self-information (B,3,h,w) of conditioned level i on the tensor cores: head -> plc igemm and
+        csc land in one NHWC bf16 tensor; cgp layers 1-2 are grouped 1x1 igemms; layers 3-4 are fused
+        with the Gaussian rate (:352-365)."""
+        B, C, h, w = x.shape
+        pk = self._tc_pack(i)
+        plc, cgp, csc = self.plc_list[i], self.cgp_out_xo_list[i], self.csc_list[i]
+        csc.apply_mask()
+        bits = torch.empty(B, C, h, w, dtype=torch.float32, device=x.device)
+        for b0 in range(0, B, CTX_BATCH_CHUNK):
+            b1 = min(B, b0 + CTX_BATCH_CHUNK)
+            n = b1 - b0
+            g_in = torch.empty(n, h, w, 256 + 128 * C, dtype=torch.bfloat16, device=x.device)
+            t = ops.ctx_conv_nhwc(con[b0:b1], plc[0].weight, plc[0].bias, upsample2=True, lrelu=True, region=256)
+            ops.igemm_conv(t, pk["plc"], plc[2].bias, plc[2].out_channels, out_nhwc=g_in, nhwc_coff=0)
+            del t
+            ops.ctx_conv_nhwc(q[b0:b1], csc.weight, csc.bias, groups=csc.groups, live_taps=12, out=g_in, coff=256,
+                              co_group=pk["nper"], co_gstride=128, region=128 * C)
+            h1 = torch.empty(n, h, w, 192 * C, dtype=torch.bfloat16, device=x.device)
+            ops.igemm_conv(g_in, pk["l1"], cgp[0].bias, pk["n1"], lrelu=True, out_nhwc=h1, nhwc_gstride=192, koff=pk["k1"])
+            del g_in
+            h2 = ops.igemm_conv(h1, pk["l2"], cgp[2].bias, pk["n2"], lrelu=True, koff=pk["k2"])
+            del h1
+            bits[b0:b1] = ops.cgp_tail_rate(h2, cgp[4].weight, cgp[4].bias, cgp[6].weight, cgp[6].bias, x[b0:b1],
+                                            noise[b0:b1] if noise is not None else None, acc=acc)
+            del h2
+        return bits
+
     def _level(self, i, x, q, con):
         """sigma/mu maps (B,6,h,w) of conditioned level i from the quantised child ``q`` and the
-        half-resolution quantised parent ``con`` (:352-362)."""
+        half-resolution quantised parent ``con`` (:352-362) -- exact-fp32 SIMT path
+        (``ctx_precision = "fp32"``)."""
         B, C, h, w = x.shape
         ms = torch.empty(B, 2 * C, h, w, dtype=torch.float32, device=x.device)
         plc, cgp, csc = self.plc_list[i], self.cgp_out_xo_list[i], self.csc_list[i]
@@ -265,8 +342,12 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         con = q
         for i in range(L - 2, -1, -1):
             q = self.ent_out_xo_list[i].quantize(out_xo_list[i], mode)
-            ms = self._level(i, out_xo_list[i], q, con)
-            sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], ms, self.training, acc=acc))
+            if self.ctx_precision == "bf16":
+                noise = compat.draw_noise(out_xo_list[i]) if self.training else None
+                sis.append(self._level_bits_tc(i, out_xo_list[i].contiguous(), q, con, noise, acc))
+            else:
+                ms = self._level(i, out_xo_list[i], q, con)
+                sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], ms, self.training, acc=acc))
             qs.append(q)
             con = q
         qs.reverse()
@@ -399,6 +480,9 @@ class onlyEZWT(nn.Module):
             x = out_xo_list[i]
             B = x.shape[0]
             ms = torch.empty(B, 6, x.shape[2], x.shape[3], dtype=torch.float32, device=x.device)
+            # exact fp32 on purpose: this layer's mu is part of the *dequantised* output
+            # (round(x - mu) + mu, :832) and so of the reconstruction (1e-4 tolerance); BF16 operands
+            # would move it by ~1e-3.  (cond2ZT returns plain round(x): there mu only feeds the rate.)
             for b0 in range(0, B, CTX_BATCH_CHUNK):
                 b1 = min(B, b0 + CTX_BATCH_CHUNK)
                 t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)

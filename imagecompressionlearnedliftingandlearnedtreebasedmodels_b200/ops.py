@@ -241,23 +241,30 @@ def _pad_to(n, m):
     return (n + m - 1) // m * m
 
 
-def ctx_head_nhwc(x, weight, bias, upsample2=False, lrelu=True, cpad=None):
-    """3x3 conv (Cin <= 4) + bias + LeakyReLU on the (optionally nearest-2x-upsampled) parent,
-    written channels-last in bf16: returns (B,H,W,Cpad) bf16 with channels >= Cout zeroed."""
+def ctx_conv_nhwc(x, weight, bias, groups=1, live_taps=None, upsample2=False, lrelu=False, out=None, coff=0,
+                  co_group=0, co_gstride=0, region=None):
+    """Small-Cin conv (plc head / masked csc) in fp32, written channels-last in bf16 (ll_ctx_conv_nhwc).
+    ``out`` (B,H,W,Ctot) bf16 or None (allocated with ``region`` channels, default Cout padded to 64);
+    the ``region`` channels from ``coff`` are all written (unmapped ones as zeros)."""
     require_device(x)
     x = _f32c(x, "x")
     w = _f32c(weight.detach(), "weight")
     b = _f32c(bias.detach(), "bias") if bias is not None else None
     B, Cin, Hs, Ws = x.shape
     H, W = (2 * Hs, 2 * Ws) if upsample2 else (Hs, Ws)
-    Cout = w.shape[0]
-    if tuple(w.shape[1:]) != (Cin, 3, 3):
-        raise ValueError(f"ctx_head_nhwc: weight {tuple(w.shape)} does not fit input {tuple(x.shape)}")
-    cpad = cpad or _pad_to(Cout, IG_BK)
-    out = torch.empty(B, H, W, cpad, dtype=torch.bfloat16, device=x.device)
+    Cout, cin_g, K, K2 = w.shape
+    if K != K2 or cin_g * groups != Cin:
+        raise ValueError(f"ctx_conv_nhwc: weight {tuple(w.shape)} does not fit input {tuple(x.shape)} with groups={groups}")
+    if region is None:
+        region = _pad_to(Cout, IG_BK) if co_group <= 0 else _pad_to((Cout // co_group) * co_gstride, 8)
+    if out is None:
+        out = torch.empty(B, H, W, coff + region, dtype=torch.bfloat16, device=x.device)
+    elif out.dtype != torch.bfloat16 or not out.is_contiguous() or tuple(out.shape[:3]) != (B, H, W):
+        raise ValueError("ctx_conv_nhwc: bad out tensor")
     with torch.cuda.device(x.device):
-        check(_lib.load().ll_ctx_head_nhwc(ptr(x), ptr(w), ptr(b), ptr(out), B, Cin, H, W, Cout, cpad,
-                                           int(bool(upsample2)), int(bool(lrelu)), stream_ptr()))
+        check(_lib.load().ll_ctx_conv_nhwc(ptr(x), ptr(w), ptr(b), ptr(out), B, Cin, H, W, Cout, K, groups,
+                                           K * K if live_taps is None else live_taps, int(bool(upsample2)),
+                                           int(bool(lrelu)), out.shape[3], coff, co_group, co_gstride, region, stream_ptr()))
     _count(1)
     return out
 
@@ -292,22 +299,35 @@ def nchw_to_nhwc_bf16(x, out, coff):
 
 
 def igemm_conv(x_nhwc, wp, bias, cout, lrelu=False, out=None, co_group=0, co_stride=0, co_off=0,
-               out_nhwc=None, nhwc_coff=0):
-    """tcgen05 implicit-GEMM conv (3x3 when wp has 9 taps, 1x1 when 1) of a bf16 NHWC tensor
-    (B,H,W,Kpad).  ``out``: fp32 NCHW tensor written through the channel remap of ``conv2d``;
-    ``out_nhwc``: bf16 NHWC tensor written at channel offset ``nhwc_coff``.  At least one."""
+               out_nhwc=None, nhwc_coff=0, nhwc_gstride=0, koff=None):
+    """tcgen05 implicit-GEMM conv of a bf16 NHWC tensor (B,H,W,Cin_total).  ``wp``: (taps,Npad,Kpad) from
+    ``pack_igemm_weight`` or a stack (G,taps,Npad,Kpad) for ``G`` channel groups; ``koff`` (G x Kpad/64
+    ints): first input channel of every 64-channel k-block per group.  ``out``: fp32 NCHW
+    (B, >= G*cout mapped channels, H, W) written through the channel remap of ``conv2d``; ``out_nhwc``:
+    bf16 NHWC written at ``nhwc_coff + g*nhwc_gstride`` (all Npad channels per group).  ``cout`` is per group."""
     require_device(x_nhwc)
     if x_nhwc.dtype != torch.bfloat16 or not x_nhwc.is_contiguous() or x_nhwc.dim() != 4:
-        raise TypeError("igemm_conv: x must be a contiguous bf16 (B,H,W,K) tensor")
-    if wp.dtype != torch.bfloat16 or not wp.is_contiguous() or wp.dim() != 3:
+        raise TypeError("igemm_conv: x must be a contiguous bf16 (B,H,W,C) tensor")
+    if wp.dtype != torch.bfloat16 or not wp.is_contiguous() or wp.dim() not in (3, 4):
         raise TypeError("igemm_conv: wp must come from pack_igemm_weight")
-    B, H, W, kpad = x_nhwc.shape
-    taps, npad, kp = wp.shape
-    if kp != kpad:
-        raise ValueError(f"igemm_conv: packed weight has Kpad={kp}, input has {kpad} channels")
+    B, H, W, ctot = x_nhwc.shape
+    G = wp.shape[0] if wp.dim() == 4 else 1
+    taps, npad, kpad = wp.shape[-3:]
+    kb = kpad // IG_BK
+    if koff is None:
+        if G != 1 or kpad != ctot:
+            raise ValueError(f"igemm_conv: koff is needed (groups={G}, Kpad={kpad}, input channels={ctot})")
+        karr = None
+    else:
+        flat = [int(v) for row in koff for v in row] if isinstance(koff[0], (list, tuple)) else [int(v) for v in koff]
+        if len(flat) != G * kb:
+            raise ValueError(f"igemm_conv: koff has {len(flat)} entries, expected {G}x{kb}")
+        karr = (ctypes.c_int * len(flat))(*flat)
     b = _f32c(bias.detach(), "bias") if bias is not None else None
+    if b is not None and b.numel() != G * cout:
+        raise ValueError(f"igemm_conv: bias has {b.numel()} elements, expected {G * cout}")
     if out is None and out_nhwc is None:
-        out = torch.empty(B, cout, H, W, dtype=torch.float32, device=x_nhwc.device)
+        out = torch.empty(B, G * cout, H, W, dtype=torch.float32, device=x_nhwc.device)
     if out is not None and (out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape[2:]) != (H, W)
                             or out.shape[0] != B):
         raise ValueError("igemm_conv: bad out tensor")
@@ -316,11 +336,37 @@ def igemm_conv(x_nhwc, wp, bias, cout, lrelu=False, out=None, co_group=0, co_str
         raise ValueError("igemm_conv: bad out_nhwc tensor")
     with torch.cuda.device(x_nhwc.device):
         check(_lib.load().ll_igemm_conv(
-            ptr(x_nhwc), ptr(wp), ptr(b), B, H, W, kpad, npad, cout, taps, int(bool(lrelu)),
+            ptr(x_nhwc), ptr(wp), ptr(b), B, H, W, ctot, kpad, npad, cout, taps, G, karr, int(bool(lrelu)),
             ptr(out), (out.stride(0) if B > 1 else out[0].numel()) if out is not None else 0, co_group, co_stride, co_off,
-            ptr(out_nhwc), out_nhwc.shape[3] if out_nhwc is not None else 0, nhwc_coff, stream_ptr()))
+            ptr(out_nhwc), out_nhwc.shape[3] if out_nhwc is not None else 0, nhwc_coff, nhwc_gstride, stream_ptr()))
     _count(1)
     return out if out is not None else out_nhwc
+
+
+def cgp_tail_rate(h2, w3, b3, w4, b4, x, noise=None, want_y=False, want_ms=False, acc=None):
+    """Last two grouped 1x1 layers of the cgp MLP + Gaussian rate (ll_cgp_tail_rate).  h2 (B,G*C2,H,W)
+    fp32; w3 (G*C3,C2,1,1); w4 (2G,C3,1,1); x (B,G,H,W).  Returns bits (+ y, + ms (B,2G,H,W))."""
+    require_device(x)
+    x = _f32c(x, "x")
+    h2 = _f32c(h2, "h2")
+    B, G, H, W = x.shape
+    C2, C3 = w3.shape[1], w4.shape[1]
+    if h2.shape[1] != G * C2 or w3.shape[0] != G * C3 or w4.shape[0] != 2 * G or tuple(h2.shape[2:]) != (H, W):
+        raise ValueError("cgp_tail_rate: shape mismatch")
+    if noise is not None:
+        noise = _f32c(noise, "noise")
+    w3c, b3c, w4c, b4c = (_f32c(t.detach(), "w") for t in (w3, b3, w4, b4))
+    bits = torch.empty_like(x)
+    y = torch.empty_like(x) if want_y else None
+    ms = torch.empty(B, 2 * G, H, W, dtype=torch.float32, device=x.device) if want_ms else None
+    hw = H * W
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_cgp_tail_rate(ptr(h2), h2.stride(0) if B > 1 else G * C2 * hw, ptr(w3c), ptr(b3c), ptr(w4c),
+                                           ptr(b4c), ptr(x), G * hw, ptr(noise), ptr(bits), G * hw, ptr(y), ptr(ms),
+                                           B, G, C2, C3, hw, ptr(acc), stream_ptr()))
+    _count(1)
+    res = (bits,) + ((y,) if want_y else ()) + ((ms,) if want_ms else ())
+    return res[0] if len(res) == 1 else res
 
 
 def quantize(x, noise=None):

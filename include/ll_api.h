@@ -153,12 +153,18 @@ int ll_conv2d(const float* x, int64_t x_sb, const float* w, const float* b, floa
 /* Dense context CNNs on the tcgen05 tensor cores (K3)                        */
 /* ------------------------------------------------------------------------- */
 
-/* First conv of plc_list[i] (Conv2d(3, 243, 3, padding=1) + LeakyReLU on the nearest-2x-upsampled
- * quantised parent, LiftingBasedDWT_net.py:271,348,355; onlyEZWT :789-790): x fp32 (B,Cin,H,W) --
- * or (B,Cin,H/2,W/2) when upsample2 != 0 -- w (Cout,Cin,3,3), fp32 FMA, result rounded to BF16 and
- * written channels-last: out bf16 (B,H,W,Cpad), channels [Cout,Cpad) = 0.  Cin <= 4, Cpad % 8 == 0. */
-int ll_ctx_head_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,
-                     int Cout, int Cpad, int upsample2, int lrelu, ll_stream_t stream);
+/* Small-Cin convs of the context models, fp32 FMA, result rounded to BF16 and written channels-last
+ * for the tensor-core layers: the first conv of plc_list[i] (Conv2d(3,243,3,padding=1) + LeakyReLU on
+ * the nearest-2x-upsampled quantised parent, LiftingBasedDWT_net.py:271,348,355; onlyEZWT :789-790)
+ * and csc_list[i] (MaskedConv2d 'A' 5x5, 3->243, groups=3, :274-277,353).  x fp32 (B,Cin,H,W) -- or
+ * (B,Cin,H/2,W/2) when upsample2 != 0; w (Cout,Cin/groups,K,K) with the mask multiplied in; only the
+ * first live_taps taps (row-major) are evaluated (12 for mask 'A' 5x5, K*K for a dense conv).
+ * out bf16 (B,H,W,out_cstride): the `region` channels from out_coff are all written -- destination
+ * channel d holds conv channel (d / co_gstride) * co_group + d % co_gstride when d % co_gstride <
+ * co_group, else 0 (co_group <= 0: identity).  Channel counts/offsets are multiples of 8. */
+int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,
+                     int Cout, int K, int groups, int live_taps, int upsample2, int lrelu, int out_cstride,
+                     int out_coff, int co_group, int co_gstride, int region, ll_stream_t stream);
 
 /* Weight packing for ll_igemm_conv: torch layout (Co,Ci,R,S) fp32 (taps = R*S in {1,9}) ->
  * bf16 [taps][Npad][Kpad], zero padded; Npad % 16 == 0 (<= 256), Kpad % 64 == 0. */
@@ -171,15 +177,29 @@ int ll_nchw_to_nhwc_bf16(const float* x, int64_t x_sb, void* out, int B, int C, 
 
 /* Implicit-GEMM convolution on tcgen05 / TMEM (BF16 operands, FP32 accumulation), stride 1,
  * zero padding: taps == 9 -> 3x3 (the 243->243 conv of plc_list[i][2], :272,355; onlyEZWT :791),
- * taps == 1 -> 1x1 (dense per-group layers of cgp_out_xo_list, :280-290).
- * x_nhwc bf16 (B,H,W,Kpad); wp from ll_pack_igemm_weight; bias fp32[Cout] or NULL; lrelu != 0
- * applies LeakyReLU(0.01).  Outputs (either or both):
- *   out_f32  fp32 NCHW with batch stride out_sb and the ll_conv2d channel remap
+ * taps == 1 -> 1x1 (dense per-group layers of cgp_out_xo_list, :280-290; onlyEZWT's head :792-794).
+ * x_nhwc bf16 (B,H,W,Cin_total).  `groups` independent GEMMs share the launch (<= 3): group g reads
+ * Kpad/64 blocks of 64 input channels starting at channel koff[g*(Kpad/64) + k] (koff == NULL:
+ * groups == 1 and blocks 0,64,...), its weights are wp[g] (bf16 [groups][taps][Npad][Kpad] from
+ * ll_pack_igemm_weight), its bias is bias[g*Cout ...]; lrelu != 0 applies LeakyReLU(0.01).
+ * Outputs (either or both):
+ *   out_f32  fp32 NCHW, batch stride out_sb, channel map(g*Cout + c) with the ll_conv2d remap
  *            (co / co_group) * co_stride + co_off + co % co_group (co_group <= 0: identity);
- *   out_bf16 bf16 NHWC with out_cstride channels per pixel, written at [out_coff, out_coff+Cout). */
-int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Kpad, int Npad,
-                  int Cout, int taps, int lrelu, float* out_f32, int64_t out_sb, int co_group, int co_stride,
-                  int co_off, void* out_bf16, int out_cstride, int out_coff, ll_stream_t stream);
+ *   out_bf16 bf16 NHWC with out_cstride channels per pixel: group g writes ALL Npad channels at
+ *            out_coff + g*out_gstride (channels >= Cout are exact zeros). */
+int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Cin_total, int Kpad,
+                  int Npad, int Cout, int taps, int groups, const int* koff, int lrelu, float* out_f32, int64_t out_sb,
+                  int co_group, int co_stride, int co_off, void* out_bf16, int out_cstride, int out_coff,
+                  int out_gstride, ll_stream_t stream);
+
+/* Tail of the cgp MLP fused with the rate: per group g (= child subband) and pixel,
+ * h = LeakyReLU(W3[g] h2 + b3[g]) (C2 -> C3), (sigma, mu) = W4[g] h + b4[g], then exactly
+ * ll_gauss_rate on x[:, g] (:286-290,361-365).  h2 fp32 (B, G*C2, hw) batch stride h2_sb; w3
+ * (G*C3, C2), w4 (G*2, C3) in torch layout; ms_out optional (B, 2G, hw) dense; other arguments as
+ * ll_gauss_rate.  C2 <= 64, C3 <= 32. */
+int ll_cgp_tail_rate(const float* h2, int64_t h2_sb, const float* w3, const float* b3, const float* w4, const float* b4,
+                     const float* x, int64_t x_sb, const float* noise, float* bits, int64_t bits_sb, float* y,
+                     float* ms_out, int B, int G, int C2, int C3, int64_t hw, double* sum_out, ll_stream_t stream);
 
 /* EntropyModel.quantize (compressai 1.2.1; call sites :330,341,352,719): q = round-half-even(x)
  * when noise == NULL ("dequantize"), else q = x + noise ("noise"; the caller draws U(-1/2,1/2)). */

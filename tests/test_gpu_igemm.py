@@ -72,6 +72,7 @@ def test_igemm_outputs_remap_and_nhwc():
     cat = torch.full((B, 486, H, W), 7.0, device=DEV)
     nh = torch.full((B, H, W, 576), 7.0, dtype=torch.bfloat16, device=DEV)
     ops.igemm_conv(xn, wp, b, Cout, out=cat, co_group=81, co_stride=162, co_off=0, out_nhwc=nh, nhwc_coff=192)
+    npad = wp.shape[1]                                                   # 256: the NHWC path writes every padded channel
     ref = F.conv2d(_bf(x), _bf(w), b, padding=1)
     scale = ref.abs().max().item()
     for k in range(3):
@@ -80,24 +81,91 @@ def test_igemm_outputs_remap_and_nhwc():
         assert (cat[:, 162 * k + 81:162 * k + 162] == 7.0).all()       # csc slots untouched
     got = nh[..., 192:192 + 243].float().permute(0, 3, 1, 2)
     assert (got - ref).abs().max().item() <= 1e-2 * scale               # bf16 output rounding
-    assert (nh[..., :192] == 7.0).all() and (nh[..., 192 + 243:] == 7.0).all()
+    assert (nh[..., :192] == 7.0).all() and (nh[..., 192 + 243:192 + npad] == 0).all() and (nh[..., 192 + npad:] == 7.0).all()
 
 
 @pytest.mark.parametrize("up", [True, False])
-def test_ctx_head_nhwc_matches_torch(up):
+def test_ctx_conv_nhwc_head_matches_torch(up):
     ops = _ops()
     torch.manual_seed(4)
     B, H, W = 2, 12, 20
     con = torch.round(torch.randn(B, 3, H // 2 if up else H, W // 2 if up else W) * 3).to(DEV)
     w = ((torch.rand(243, 3, 3, 3) * 2 - 1) * 0.3).to(DEV)
     b = (torch.rand(243) - 0.5).to(DEV)
-    out = ops.ctx_head_nhwc(con, w, b, upsample2=up, lrelu=True)
+    out = ops.ctx_conv_nhwc(con, w, b, upsample2=up, lrelu=True, region=256)
     assert tuple(out.shape) == (B, H, W, 256) and out.dtype == torch.bfloat16
     src = con.repeat_interleave(2, 2).repeat_interleave(2, 3) if up else con
     ref = F.leaky_relu(F.conv2d(src, w, b, padding=1), 0.01)
     got = out[..., :243].float().permute(0, 3, 1, 2)
     assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     assert (out[..., 243:] == 0).all()
+
+
+def test_ctx_conv_nhwc_masked_grouped_csc():
+    """csc_list[i]: MaskedConv2d('A', 3, 243, 5, padding=2, groups=3) written into 128-channel group slots."""
+    ops = _ops()
+    torch.manual_seed(6)
+    B, H, W = 2, 10, 18
+    q = torch.round(torch.randn(B, 3, H, W) * 4).to(DEV)
+    w = ((torch.rand(243, 1, 5, 5) * 2 - 1) * 0.2)
+    mask = torch.ones(5, 5)
+    mask[2, 2:] = 0
+    mask[3:] = 0
+    w = (w * mask).to(DEV)
+    b = (torch.rand(243) - 0.5).to(DEV)
+    out = torch.full((B, H, W, 256 + 384), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.ctx_conv_nhwc(q, w, b, groups=3, live_taps=12, out=out, coff=256, co_group=81, co_gstride=128, region=384)
+    ref = F.conv2d(q, w, b, padding=2, groups=3)
+    for g in range(3):
+        got = out[..., 256 + 128 * g:256 + 128 * g + 81].float().permute(0, 3, 1, 2)
+        assert (got - ref[:, 81 * g:81 * g + 81]).abs().max().item() <= 1e-2 * ref.abs().max().item()
+        assert (out[..., 256 + 128 * g + 81:256 + 128 * (g + 1)] == 0).all()
+    assert (out[..., :256] == 7.0).all()
+
+
+def test_igemm_grouped_1x1_with_koff():
+    """cgp layer shape: 3 groups, each reading 4 k-blocks at per-group channel offsets of one NHWC tensor."""
+    ops = _ops()
+    torch.manual_seed(8)
+    B, H, W, C = 2, 16, 24, 640
+    x = (torch.rand(B, H, W, C) * 2 - 1).to(torch.bfloat16).to(DEV)
+    koff = [[0, 64, 256, 320], [64, 128, 384, 448], [128, 192, 512, 576]]
+    wg = [((torch.rand(162, 256, 1, 1) * 2 - 1) * 0.1).to(DEV) for _ in range(3)]
+    bias = (torch.rand(3 * 162) - 0.5).to(DEV)
+    wp = torch.stack([ops.pack_igemm_weight(w, npad=192, kpad=256) for w in wg]).contiguous()
+    h1 = torch.full((B, H, W, 576), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.igemm_conv(x, wp, bias, 162, lrelu=True, out_nhwc=h1, nhwc_gstride=192, koff=koff)
+    f32 = ops.igemm_conv(x, wp, bias, 162, lrelu=True, koff=koff)          # fp32 NCHW, channel g*162 + c
+    xf = x.float()
+    for g in range(3):
+        xin = torch.cat([xf[..., o:o + 64] for o in koff[g]], dim=-1)       # (B,H,W,256)
+        ref = F.leaky_relu(xin @ _bf(wg[g][:, :, 0, 0]).t() + bias[162 * g:162 * (g + 1)], 0.01)
+        scale = ref.abs().max().item()
+        assert (f32[:, 162 * g:162 * (g + 1)].permute(0, 2, 3, 1) - ref).abs().max().item() <= 2e-3 * scale
+        assert (h1[..., 192 * g:192 * g + 162].float() - ref).abs().max().item() <= 1e-2 * scale
+        assert (h1[..., 192 * g + 162:192 * (g + 1)] == 0).all()             # padded channels are exact zeros
+
+
+def test_cgp_tail_rate_matches_torch():
+    ops = _ops()
+    from oracle import thirdparty as tp
+    torch.manual_seed(9)
+    B, G, H, W = 2, 3, 12, 20
+    h2 = torch.randn(B, G * 54, H, W)
+    w3, b3 = torch.randn(G * 18, 54, 1, 1) * 0.2, torch.randn(G * 18) * 0.1
+    w4, b4 = torch.randn(G * 2, 18, 1, 1) * 0.3, torch.randn(G * 2) * 0.1
+    b4[0::2] += 3.0
+    x = torch.randn(B, G, H, W) * 5
+    a = F.leaky_relu(F.conv2d(h2, w3, b3, groups=G), 0.01)
+    ms = F.conv2d(a, w4, b4, groups=G)
+    _, lik = tp.gaussian_conditional_forward(x, ms[:, 0::2], ms[:, 1::2], False)
+    ref = -torch.log2(lik)
+    acc = torch.zeros(1, dtype=torch.float64, device=DEV)
+    bits, gms = ops.cgp_tail_rate(h2.to(DEV), w3.to(DEV), b3.to(DEV), w4.to(DEV), b4.to(DEV), x.to(DEV), want_ms=True, acc=acc)
+    assert (gms.cpu() - ms).abs().max().item() <= 1e-4 * ms.abs().max().item()
+    rs = abs(float(bits.double().sum().cpu() - ref.double().sum())) / float(ref.double().sum())
+    assert rs < 1e-3
+    assert abs(float(acc.item()) - float(bits.double().sum().item())) <= 1e-3 * float(acc.item())
 
 
 def test_nchw_to_nhwc_bf16_slice():

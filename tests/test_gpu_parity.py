@@ -24,10 +24,22 @@ def _planes(model):
     return [model.model0, model.model1, model.model2]
 
 
-@pytest.mark.parametrize("name", EVAL_CASES)
-def test_model_forward_matches_reference_golden(name):
+TC_LAYERS = ("conditioned2ZTsepSubbands",)   # entropy layers with a tensor-core (bf16) context path
+PREC_CASES = [(k, "fp32") for k in EVAL_CASES] + \
+             [(k, "bf16") for k in EVAL_CASES if META[k]["config"].get("entropy_layer") in TC_LAYERS]
+
+
+@pytest.mark.parametrize("name,prec", PREC_CASES)
+def test_model_forward_matches_reference_golden(name, prec):
+    """fp32: every context CNN on the exact SIMT kernels (strict per-subband checks).  bf16 (the
+    default): plc / cgp on the tcgen05 tensor cores -- symbols, coefficients and reconstruction are
+    untouched (the context nets only feed the rate), bpp must stay within north_star's 0.1 %; the
+    per-subband totals of these 16x16 .. 8x12 golden subbands get 0.5 % (BF16 operand rounding does
+    not average out over a few hundred coefficients)."""
     m = META[name]
-    model, cfg = product_model(m["config"])
+    model, cfg = product_model(dict(m["config"], ctx_precision=prec))
+    tol_sub = 1e-3 if prec == "fp32" else 5e-3
+    fo = 1e-3 if prec == "fp32" else 1.0
     keyed_state(model)
     model = model.to(DEV).eval()
     g = load_case(name)
@@ -50,7 +62,8 @@ def test_model_forward_matches_reference_golden(name):
     assert rel_err(xhat.cpu(), g["xhat"]) < 1e-4
     assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=1e-3)[2]
     for i, s in enumerate(si_xo):
-        assert bits_check(s.cpu(), g[f"si_xo_{i}"], tol_sum=1e-3)[2], (i, bits_check(s.cpu(), g[f"si_xo_{i}"]))
+        assert bits_check(s.cpu(), g[f"si_xo_{i}"], tol_sum=tol_sub, frac_outliers=fo)[2], \
+            (i, bits_check(s.cpu(), g[f"si_xo_{i}"]))
     B, _, H, W = g["x"].shape
     bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
     bpp = bits / (B * H * W)
@@ -59,12 +72,13 @@ def test_model_forward_matches_reference_golden(name):
     assert abs(float(acc.item()) / 2 / (B * H * W) - m["bpp"]) <= 1e-3 * m["bpp"]
 
 
-def test_training_mode_noise_parity():
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_training_mode_noise_parity(prec):
     """Training mode: noise is drawn in Python in the reference's call order and handed to the
     kernels; with the same noise tensors the rate matches the oracle."""
     name = "cdf97_cond2zt_L2_train"
     m = META[name]
-    model, cfg = product_model(m["config"])
+    model, cfg = product_model(dict(m["config"], ctx_precision=prec))
     sd = keyed_state(model)
     model = model.to(DEV).train()
     g = load_case(name)
@@ -80,8 +94,13 @@ def test_training_mode_noise_parity():
         compat.draw_noise = orig
     assert rel_err(xhat.cpu(), g["xhat"]) < 1e-4
     assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=1e-3)[2]
+    tot, ref = float(si_xe.double().sum()), float(g["si_xe"].double().sum())
     for i, s in enumerate(si_xo):
-        assert bits_check(s.cpu(), g[f"si_xo_{i}"], tol_sum=1e-3)[2]
+        assert bits_check(s.cpu(), g[f"si_xo_{i}"], tol_sum=1e-3 if prec == "fp32" else 5e-3,
+                          frac_outliers=1e-3 if prec == "fp32" else 1.0)[2]
+        tot += float(s.double().sum())
+        ref += float(g[f"si_xo_{i}"].double().sum())
+    assert abs(tot - ref) <= 1e-3 * ref                    # bpp within 0.1 % in either precision
 
 
 def test_lifting_level_golden():
