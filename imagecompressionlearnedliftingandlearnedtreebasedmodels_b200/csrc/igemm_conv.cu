@@ -324,69 +324,117 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // channel d of the covered region maps to conv channel co = (d / co_gstride) * co_group + d % co_gstride
 // (valid when d % co_gstride < co_group and co < Cout); every other destination channel of the
 // region is written as 0, so a consumer igemm layer never reads uninitialised memory.
+// Mapping: one warp = 4 consecutive pixels of a row x 32 slots of 8 destination channels (lane = slot),
+// so every pixel is stored as one contiguous 512-byte run.  Weights live in shared memory k-major
+// ([tap][dest channel], zero where unmapped): two LDS.128 per tap feed 8 channels x 4 pixels of packed
+// FFMA2; the (K-1+4)-wide input window of the 4 pixels is loaded once into registers (warp-uniform
+// addresses for a dense conv).
 constexpr int HD_THREADS = 256;
-constexpr int HD_MAXIN = 32;
+constexpr int HD_PX = 4;
 struct SmallConvParams {
   const float* x; const float* w; const float* bias;
   __nv_bfloat16* out;
-  int B, Cin, H, W, Cout, groups, K, live_taps, upsample2, lrelu;
+  int B, Cin, H, W, Cout, groups, upsample2, lrelu;
   int out_cstride, out_coff, co_group, co_gstride, region;
 };
+
+template <int CIN_G, int K, int LIVE>
 __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_constant__ SmallConvParams p) {
-  extern __shared__ float s_w[];   // [Cout][cin_g * live_taps] + bias[Cout]
-  const int cin_g = p.Cin / p.groups, cout_g = p.Cout / p.groups;
-  const int KK = p.K * p.K, nin = cin_g * p.live_taps;
-  for (int i = threadIdx.x; i < p.Cout * nin; i += HD_THREADS) {
-    const int co = i / nin, r = i % nin, ci = r / p.live_taps, t = r % p.live_taps;
-    s_w[i] = p.w[((long long)co * cin_g + ci) * KK + t];
+  constexpr int NIN = CIN_G * LIVE;
+  constexpr int ROWS = (LIVE + K - 1) / K;           // live kernel rows (3 of 5 under mask 'A')
+  constexpr int WCOLS = HD_PX + K - 1;
+  constexpr int PAD = K / 2;
+  extern __shared__ __align__(16) float s_w[];       // [NIN][region] + bias[region]
+  const int cout_g = p.Cout / p.groups;
+  float* s_b = s_w + NIN * p.region;
+  for (int i = threadIdx.x; i < (NIN + 1) * p.region; i += HD_THREADS) {
+    const int k = i / p.region, d = i % p.region;
+    const int gd = d / p.co_gstride, j = d % p.co_gstride, co = gd * p.co_group + j;
+    float v = 0.f;
+    if (j < p.co_group && co < p.Cout) {
+      if (k < NIN) v = p.w[((long long)co * CIN_G + k / LIVE) * (K * K) + k % LIVE];
+      else v = p.bias ? p.bias[co] : 0.f;
+    }
+    s_w[i] = v;
   }
-  float* s_b = s_w + p.Cout * nin;
-  for (int i = threadIdx.x; i < p.Cout; i += HD_THREADS) s_b[i] = p.bias ? p.bias[i] : 0.f;
   __syncthreads();
-  const int slots = p.region / 8;
+  const int lane = threadIdx.x & 31;
+  const int chunks = (p.region / 8 + 31) / 32;       // 32-slot chunks per pixel
+  const int qx = (p.W + HD_PX - 1) / HD_PX;          // pixel quads per row
   const int Hs = p.upsample2 ? p.H / 2 : p.H, Ws = p.upsample2 ? p.W / 2 : p.W;
-  const int pad = p.K / 2;
-  const long long total = (long long)p.B * p.H * p.W * slots;
-  for (long long e = (long long)blockIdx.x * HD_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * HD_THREADS) {
-    const int m = (int)(e % slots);
-    const long long px = e / slots;
-    const int d0 = m * 8;
-    const int gd = d0 / p.co_gstride, j0 = d0 % p.co_gstride;
-    const int co0 = gd * p.co_group + j0;
-    float o[8];
+  const long long nwork = (long long)p.B * p.H * qx * chunks;
+  const long long wstride = (long long)gridDim.x * (HD_THREADS / 32);
+  for (long long wk = (long long)blockIdx.x * (HD_THREADS / 32) + (threadIdx.x >> 5); wk < nwork; wk += wstride) {
+    const int ch = (int)(wk % chunks);
+    long long r = wk / chunks;
+    const int x0 = (int)(r % qx) * HD_PX;
+    r /= qx;
+    const int yy = (int)(r % p.H), b = (int)(r / p.H);
+    const int slot = ch * 32 + lane;
+    const int d0 = slot * 8;
+    if (d0 >= p.region) continue;
+    const int gd = d0 / p.co_gstride, j0 = d0 % p.co_gstride, co0 = gd * p.co_group + j0;
+    const bool live = j0 < p.co_group && co0 < p.Cout;
+    float2 acc[HD_PX][4];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&s_b[d0]), b1 = *reinterpret_cast<const float4*>(&s_b[d0 + 4]);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) o[c] = 0.f;
-    if (j0 < p.co_group && co0 < p.Cout) {
-      const int xx = (int)(px % p.W), yy = (int)((px / p.W) % p.H), b = (int)(px / ((long long)p.W * p.H));
-      const int g = co0 / cout_g;                       // conv group of this slot (host guarantees it is unique)
-      float in[HD_MAXIN];
-      for (int ci = 0; ci < cin_g; ++ci)
-        for (int t = 0; t < p.live_taps; ++t) {
-          const int gy = yy + t / p.K - pad, gx = xx + t % p.K - pad;
-          float v = 0.f;
-          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-            const int sy = p.upsample2 ? gy >> 1 : gy, sx = p.upsample2 ? gx >> 1 : gx;
-            v = p.x[(((long long)b * p.Cin + g * cin_g + ci) * Hs + sy) * Ws + sx];
+      for (int q = 0; q < HD_PX; ++q) {
+        acc[q][0] = make_float2(b0.x, b0.y); acc[q][1] = make_float2(b0.z, b0.w);
+        acc[q][2] = make_float2(b1.x, b1.y); acc[q][3] = make_float2(b1.z, b1.w);
+      }
+    }
+    if (live) {
+      const int g = co0 / cout_g;                    // conv group of this slot (unique: checked on the host)
+#pragma unroll
+      for (int ci = 0; ci < CIN_G; ++ci) {
+        float win[ROWS][WCOLS];
+        const float* xc = p.x + ((long long)b * p.Cin + g * CIN_G + ci) * Hs * Ws;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) {
+          const int gy = yy + rr - PAD;
+          const bool yok = gy >= 0 && gy < p.H;
+          const int sy = p.upsample2 ? gy >> 1 : gy;
+#pragma unroll
+          for (int cc = 0; cc < WCOLS; ++cc) {
+            const int gx = x0 + cc - PAD;
+            float v = 0.f;
+            if (yok && gx >= 0 && gx < p.W) v = __ldg(xc + (long long)sy * Ws + (p.upsample2 ? gx >> 1 : gx));
+            win[rr][cc] = v;
           }
-          in[ci * p.live_taps + t] = v;
         }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int co = co0 + c;
-        if (j0 + c < p.co_group && co < p.Cout) {
-          const float* wr = s_w + co * nin;
-          float a = s_b[co];
-          for (int k = 0; k < nin; ++k) a = fmaf(in[k], wr[k], a);
-          o[c] = (p.lrelu && a < 0.f) ? a * 0.01f : a;
+        for (int t = 0; t < LIVE; ++t) {
+          const float* wr = s_w + (ci * LIVE + t) * p.region + d0;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+          const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w);
+          const float2 wc = make_float2(w1.x, w1.y), wd = make_float2(w1.z, w1.w);
+#pragma unroll
+          for (int q = 0; q < HD_PX; ++q) {
+            const float v = win[t / K][q + t % K];
+            const float2 vv = make_float2(v, v);
+            acc[q][0] = __ffma2_rn(vv, wa, acc[q][0]);
+            acc[q][1] = __ffma2_rn(vv, wb, acc[q][1]);
+            acc[q][2] = __ffma2_rn(vv, wc, acc[q][2]);
+            acc[q][3] = __ffma2_rn(vv, wd, acc[q][3]);
+          }
         }
       }
     }
-    uint4 pk;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(p.out + px * p.out_cstride + p.out_coff + d0) = pk;
+#pragma unroll
+    for (int q = 0; q < HD_PX; ++q) {
+      if (x0 + q >= p.W) break;
+      uint32_t pk[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float2 a = acc[q][c];
+        if (p.lrelu) { a.x = a.x < 0.f ? a.x * 0.01f : a.x; a.y = a.y < 0.f ? a.y * 0.01f : a.y; }
+        __nv_bfloat162 h = __floats2bfloat162_rn(a.x, a.y);
+        pk[c] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      const long long px = ((long long)b * p.H + yy) * p.W + x0 + q;
+      *reinterpret_cast<uint4*>(p.out + px * p.out_cstride + p.out_coff + d0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
   }
 }
 
@@ -440,10 +488,13 @@ extern "C" {
 int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
                      int K, int groups, int live_taps, int upsample2, int lrelu, int out_cstride, int out_coff,
                      int co_group, int co_gstride, int region, ll_stream_t stream) {
-  if (B < 0 || H < 0 || W < 0 || Cin < 1 || Cout < 1 || groups < 1 || Cin % groups || Cout % groups || (K != 1 && K != 3 && K != 5))
+  if (B < 0 || H < 0 || W < 0 || Cin < 1 || Cout < 1 || groups < 1 || Cin % groups || Cout % groups)
     return fail(LL_EINVAL, "ll_ctx_conv_nhwc: bad extents");
-  if (live_taps < 1 || live_taps > K * K || (Cin / groups) * live_taps > HD_MAXIN)
-    return fail(LL_EINVAL, "ll_ctx_conv_nhwc: (Cin/groups) * live_taps must be in 1..%d", HD_MAXIN);
+  const int cin_g = Cin / groups;
+  const bool head = (cin_g == 3 && K == 3 && live_taps == 9), csc = (cin_g == 1 && K == 5 && live_taps == 12);
+  if (!head && !csc)
+    return fail(LL_EINVAL, "ll_ctx_conv_nhwc: built for (Cin/groups=3, K=3, 9 taps) and (Cin/groups=1, K=5, 12 live taps), got (%d, %d, %d)",
+                cin_g, K, live_taps);
   if (co_group <= 0) { co_group = Cout; co_gstride = region > 0 ? region : Cout; }
   if (region <= 0 || region % 8 || out_coff % 8 || out_cstride % 8 || out_coff < 0 || out_cstride < out_coff + region || co_gstride < co_group)
     return fail(LL_EINVAL, "ll_ctx_conv_nhwc: region / offsets must be multiples of 8 channels inside the output pixel");
@@ -454,17 +505,23 @@ int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* ou
   if (!x || !w || !out) return fail(LL_EINVAL, "ll_ctx_conv_nhwc: null pointer");
   SmallConvParams p = {};
   p.x = x; p.w = w; p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.groups = groups; p.K = K; p.live_taps = live_taps;
+  p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.groups = groups;
   p.upsample2 = upsample2; p.lrelu = lrelu;
   p.out_cstride = out_cstride; p.out_coff = out_coff; p.co_group = co_group; p.co_gstride = co_gstride; p.region = region;
-  const size_t smem = (size_t)(Cout * (Cin / groups) * live_taps + Cout) * sizeof(float);
+  const size_t smem = (size_t)(cin_g * live_taps + 1) * region * sizeof(float);
   if (smem > 200 * 1024) return fail(LL_EINVAL, "ll_ctx_conv_nhwc: weights do not fit shared memory");
-  if (smem > 48 * 1024) LL_CUDA_OK(cudaFuncSetAttribute(ctx_conv_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long total = (long long)B * H * W * (region / 8);
-  long long blocks = (total + HD_THREADS - 1) / HD_THREADS;
-  const long long cap = (long long)sm_count_cached() * 8;
+  const int chunks = (region / 8 + 31) / 32;
+  const long long nwork = (long long)B * H * ((W + HD_PX - 1) / HD_PX) * chunks;
+  long long blocks = (nwork + HD_THREADS / 32 - 1) / (HD_THREADS / 32);
+  const long long cap = (long long)sm_count_cached() * 4;
   if (blocks > cap) blocks = cap;
-  ctx_conv_nhwc_kernel<<<(unsigned)blocks, HD_THREADS, smem, as_stream(stream)>>>(p);
+  if (head) {
+    if (smem > 48 * 1024) LL_CUDA_OK(cudaFuncSetAttribute(ctx_conv_nhwc_kernel<3, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx_conv_nhwc_kernel<3, 3, 9><<<(unsigned)blocks, HD_THREADS, smem, as_stream(stream)>>>(p);
+  } else {
+    if (smem > 48 * 1024) LL_CUDA_OK(cudaFuncSetAttribute(ctx_conv_nhwc_kernel<1, 5, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx_conv_nhwc_kernel<1, 5, 12><<<(unsigned)blocks, HD_THREADS, smem, as_stream(stream)>>>(p);
+  }
   LL_LAUNCH_OK("ctx_conv_nhwc_kernel");
   return LL_OK;
 }
