@@ -221,6 +221,7 @@ def run_own(args):
         "check": {"perfect_reconstruction_max_abs_err": pr_err},
     }
     line["dwt97"] = dwt97_probe(dev, pk)
+    line["context_cnn"] = context_probe(dev, pk)
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
     print(json.dumps(line))
@@ -250,6 +251,54 @@ def dwt97_probe(dev, pk):
         gbs = 8.0 * sum(4.0 ** -l for l in range(LEVELS)) * 3 * B * H * W / (ms * 1e-3) / 1e9
         res[name] = {"ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
     res["note"] = "150 MB in+out per level-0 launch (> L2 126 MB); back-to-back launches, CUDA events"
+    return res
+
+
+def context_probe(dev, pk):
+    """Tensor-core side of the path (K3): the 243->243 3x3 plc conv as a tcgen05 implicit GEMM on
+    8 planes of 256x384 (level-0 subband of a 512x768 image), and the whole conditioned2ZT entropy
+    model (eval forward, bf16 context path) on the subbands of 16 planes of 512x768."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import \
+        DWTConditioned2EntropyLayerZTsepSubbands
+    from oracle import model as om
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / n
+
+    nb, h, w = 8, H // 2, W // 2
+    x = torch.zeros(nb, h, w, 256, dtype=torch.bfloat16, device=dev)
+    x[..., :243] = torch.randn(nb, h, w, 243, device=dev).to(torch.bfloat16)
+    wt = torch.randn(243, 243, 3, 3, device=dev) * 0.02
+    bias = torch.randn(243, device=dev)
+    wp = ops.pack_igemm_weight(wt, npad=256, kpad=256)
+    out = torch.empty(nb, h, w, 256, dtype=torch.bfloat16, device=dev)
+    ms = timed(lambda: ops.igemm_conv(x, wp, bias, 243, out_nhwc=out), 10)
+    useful = 2.0 * nb * h * w * 243 * 243 * 9 / (ms * 1e-3) / 1e12
+    issued = 2.0 * nb * h * w * 256 * 256 * 9 / (ms * 1e-3) / 1e12
+    res = {"plc_igemm": {"ms": ms, "tflops_useful": useful, "tflops_issued": issued, "peak": pk["bf16_tflops"],
+                         "frac_useful": useful / pk["bf16_tflops"], "frac_issued": issued / pk["bf16_tflops"],
+                         "bound": "tensor", "dtype": "bf16 operands, fp32 accumulate (TMEM)",
+                         "shape": "M=8x256x384 px, N=243 (pad 256), K=9x243 (pad 9x256); in+out 806 MB > L2"}}
+    del x, out
+    cfg = om.default_cfg(dwtlevels=LEVELS)
+    torch.manual_seed(1337)
+    em = DWTConditioned2EntropyLayerZTsepSubbands(cfg).to(dev).eval()
+    xe = torch.randn(B, 1, H >> LEVELS, W >> LEVELS, device=dev) * 4
+    xo = [torch.randn(B, 3, H >> (l + 1), W >> (l + 1), device=dev) * 4 for l in range(LEVELS)]
+    with torch.no_grad():
+        ms = timed(lambda: em(xe, xo), 3)
+    res["cond2zt_entropy_model"] = {"ms_per_plane_batch16": ms, "mp_per_s_3_planes": B * H * W / 1e6 / (3 * ms * 1e-3),
+                                    "flops_per_plane_px": 430482, "note": "quantise + context CNNs + Gaussian rate + bit sums"}
     return res
 
 
