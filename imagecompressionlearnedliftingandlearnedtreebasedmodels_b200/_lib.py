@@ -67,6 +67,7 @@ SIGNATURES = {
     "ll_pack_eb": (c_int, [ctypes.POINTER(c_voidp), c_int, _P, _P]),
     "ll_eb_rate": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_i64, _P, _P]),
     "ll_fma_peak_probe": (c_int, [_P, c_int, c_int, _P]),
+    "ll_tc_tf32_probe": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
 }
 
 _lib = None

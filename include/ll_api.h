@@ -224,6 +224,14 @@ int ll_pack_eb(const float* const* params, int C, float* blob, ll_stream_t strea
 int ll_eb_rate(const float* x, const float* noise, const float* blob, float* y, float* bits, int B, int C, int64_t hw,
                double* sum_out, ll_stream_t stream);
 
+/* Unit probe of the tensor-core building block of the learned-lifting kernel (no reference
+ * counterpart): D (128,64) = A (128, 8*kblocks) x B (8*kblocks, 64), fp32 in/out, computed with
+ * tcgen05.mma kind::tf32 (A resident in tensor memory, B in MN-major SWIZZLE_128B shared-memory atoms);
+ * split != 0 uses the 3xTF32 hi/lo split (fp32-level accuracy).  cycles (device, optional) receives
+ * the SM cycles of one chain.  kblocks <= 20. */
+int ll_tc_tf32_probe(const float* A, const float* B, float* D, int kblocks, int split, int reps, long long* cycles,
+                     ll_stream_t stream);
+
 /* Measurement helper (no reference counterpart): register-only FFMA2 loop used by bench.py to
  * measure the device's FP32 FMA-pipe peak.  FLOPs = blocks * 256 * iters * 256. */
 int ll_fma_peak_probe(float* out, int blocks, int iters, ll_stream_t stream);
