@@ -5,6 +5,11 @@
 
 namespace ll {
 
+int launch_lift_step_tc(const LiftParams& p, cudaStream_t stream);                                  // lift_tc.cu
+int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream);         // lift_tc.cu
+static int g_lift_mode = LL_LIFT_TC;
+static int g_lift_dbg = 0;
+
 __global__ void __launch_bounds__(LS_THREADS, 1) lift_step_kernel(const __grid_constant__ LiftParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
@@ -71,6 +76,8 @@ static int launch_lift_step(const ll_lift_job* jobs, int njobs, const float* blo
     p.total_units += p.units[j];
   }
   if (p.total_units == 0) return LL_OK;  // empty input: nothing to do
+  p.dbg = g_lift_dbg;
+  if (g_lift_mode == LL_LIFT_TC) return launch_lift_step_tc(p, stream);
   static thread_local bool attr_set[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
@@ -124,8 +131,18 @@ int ll_pack_lift_step(const float* pre_w, const float* w1, const float* b1, cons
     return fail(LL_EINVAL, "ll_pack_lift_step: null pointer");
   pack_lift_step_kernel<<<(BL_TOTAL + 255) / 256, 256, 0, as_stream(stream)>>>(pre_w, w1, b1, w2, b2, w3, b3, w4, b4, blob);
   LL_LAUNCH_OK("pack_lift_step_kernel");
+  return launch_pack_lift_tc(w2, w3, blob, as_stream(stream));
+}
+
+int ll_lift_set_mode(int mode) {
+  g_lift_dbg = mode >> 8;   // undocumented: timing experiments (results are wrong when non-zero)
+  mode &= 0xff;
+  if (mode != LL_LIFT_FP32 && mode != LL_LIFT_TC) return fail(LL_EINVAL, "ll_lift_set_mode: unknown mode %d", mode);
+  g_lift_mode = mode;
   return LL_OK;
 }
+
+int ll_lift_get_mode(void) { return g_lift_mode; }
 
 int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float res_weight, int linear,
                  ll_stream_t stream) {

@@ -56,8 +56,11 @@ constexpr int BL_W3 = BL_B2 + 16;    // [ci][tap][co]
 constexpr int BL_B3 = BL_W3 + 6400;  // 16
 constexpr int BL_W4 = BL_B3 + 16;    // [ci 16][tap 25]
 constexpr int BL_B4 = BL_W4 + 400;   // 1 (+3 pad)
-constexpr int BL_TOTAL = BL_B4 + 4;
-static_assert(BL_TOTAL == LL_LIFT_BLOB_FLOATS, "blob layout");
+constexpr int BL_TOTAL = BL_B4 + 4;   // end of the part the SIMT kernel stages in shared memory
+// tensor-core weight block (lift_tc.cu): [layer 2][term hi|lo][row dx*16+co (80)][col dy*16+ci (80)]
+constexpr int BL_TC = BL_TOTAL;
+constexpr int BL_ALL = BL_TC + 4 * 80 * 80;
+static_assert(BL_ALL == LL_LIFT_BLOB_FLOATS, "blob layout");
 
 // shared memory layout (floats)
 constexpr int SM_A1 = 0;
@@ -81,6 +84,7 @@ struct LiftParams {
   int nstrips[2], nchunks[2];
   long long units[2];  // nb * nstrips * nchunks per job
   long long total_units;
+  int dbg;             // timing experiments only (lift_tc.cu): bit 0 no MMA, 1 no E-B, 2 no conv1, 3 no conv4, 4 no E-A
 };
 
 struct f2 {

@@ -1,0 +1,495 @@
+// lift_tc.cu -- one learned lifting step with the two 16->16 5x5 layers on the tcgen05 tensor cores.
+//
+//   dout = din + sign * (skip + rw * CNN(skip)),  same function as lift_step_body.cuh (reference:
+//   graphs/layers/wavelet_forward_v2.py:58-74, wavelet_inverse_v2.py:76-90, P_block_v2.py:40-55).
+//
+// 94 % of the step's arithmetic is conv2 / conv3 (16 -> 16 channels, 5x5).  With only 16 output
+// channels a pixel-major implicit GEMM would be N = 16; instead the WEIGHTS are the M operand:
+//     D[(dx, co)][x] = sum_{dy, ci} W[co][ci][dy][dx] * in[ci][y + dy - 2][x]          (M = 80 of 128, N = 64 columns)
+//     out[co][y][x]  = sum_dx D[(dx, co)][x + dx - 2]
+// The vertical taps are whole-row shifts of the B operand (a different shared-memory row address per
+// MMA: the MMA's own implicit im2col); the horizontal taps become 5 partial planes that the epilogue
+// sums with shifted reads.  A (weights, hi and lo halves of both layers: 320 columns) stays resident
+// in tensor memory for the whole persistent CTA; B (activations) lives in shared-memory ring buffers
+// in the MN-major SWIZZLE_128B_BASE32B layout (atom = 4 channels x 32 columns).
+//
+// Precision: the path feeds the quantiser, so plain TF32/BF16 is not acceptable.  Every product is
+// split 3xTF32 -- A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with hi = rna_tf32(v), lo = rna_tf32(v - hi), FP32
+// accumulation in TMEM -- which measures 4e-7 .. 1.4e-6 of the output scale against float64, the same
+// as an FP32 FMA chain (tests/test_gpu_tc_probe.py).  30 MMAs (M128 x N64 x K8) per output row and
+// layer, 32.5 cycles each when issued straight-line by one elected lane.
+//
+// Pipeline: the CTA marches down a strip of 52 output columns one row per step.  Per step t
+//   workers (8 warps):  [E-A] accumulators of the previous step: TMEM -> shared partial planes
+//                       [E-B] conv2 row t-4: sum dx, bias, tanh, hi/lo split -> a2 ring
+//                             conv3 row t-8: sum dx, bias, + o1 -> a3 ring (fp32)
+//                       [S]   skip row t+3; conv1 row t (FP32 SIMT) -> a1 ring (hi/lo) and o1 ring;
+//                             conv4 + output row t-11 (FP32 SIMT)
+//   MMA warp:           after the workers freed the accumulators: conv2 row t-3 and conv3 row t-7
+//                       (60 tcgen05.mma), one tcgen05.commit.
+// One block barrier per step; a row produced in step s is consumed in steps > s, ring depths follow.
+// Every intermediate is forced to 0 outside the plane (each conv zero-pads its own input).
+#include <stdint.h>
+#include <string.h>
+
+#include "lift_step_body.cuh"
+#include "ll_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ll {
+
+constexpr int TC_THREADS = 288;  // 8 worker warps + 1 MMA warp
+constexpr int TC_WO = 52;        // output columns per strip
+constexpr int TC_RA = 6;         // a1 / a2 ring rows
+constexpr int TC_R3 = 6;         // a3 ring rows
+constexpr int TC_RO = 9;         // o1 ring rows
+constexpr int TC_RS = 16;        // skip ring rows
+constexpr int TC_SLOT = 8192;    // bytes per a1/a2 ring row: [term 2][cig 2][na 2][ka 2][4 ch][128 B]
+constexpr int TC_P3 = 60;        // a3 / o1 pitch (floats)
+constexpr int TC_PP = 68;        // partial-plane pitch
+constexpr int TC_PS = 72;        // skip pitch
+// tensor-memory columns
+constexpr int TM_W = 0;          // [layer 2][term 2][dy 5][ci 16]
+constexpr int TM_ACC2 = 320, TM_ACC3 = 384;
+// shared memory (bytes from the 1024-aligned base)
+constexpr int TS_RA1 = 0;
+constexpr int TS_RA2 = TS_RA1 + TC_RA * TC_SLOT;
+constexpr int TS_A3 = TS_RA2 + TC_RA * TC_SLOT;
+constexpr int TS_O1 = TS_A3 + TC_R3 * 16 * TC_P3 * 4;
+constexpr int TS_P2 = TS_O1 + TC_RO * 16 * TC_P3 * 4;
+constexpr int TS_P3 = TS_P2 + 80 * TC_PP * 4;
+constexpr int TS_SK = TS_P3 + 80 * TC_PP * 4;
+constexpr int TS_W = TS_SK + TC_RS * TC_PS * 4;
+// small weights (floats): pre[4] W1[25][16] b1[16] b2[16] b3[16] W4[16][25] b4[4]
+constexpr int SW_PRE = 0, SW_W1 = 4, SW_B1 = 404, SW_B2 = 420, SW_B3 = 436, SW_W4 = 452, SW_B4 = 852, SW_TOTAL = 856;
+constexpr int TS_BAR = TS_W + SW_TOTAL * 4;
+constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;
+static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TS_RA2 % 1024 == 0 && TS_A3 % 16 == 0 && TS_O1 % 16 == 0 && TS_P2 % 16 == 0 && TS_SK % 16 == 0 && TS_W % 16 == 0 && TS_BAR % 8 == 0, "align");
+
+// byte offset of 4 consecutive columns i..i+3 (i % 4 == 0) of channel ci inside a ring row (hi half)
+__device__ __forceinline__ int ring_off(int ci, int i) {
+  const int r = ci & 3;
+  return (ci >> 3) * 2048 + (i >> 5) * 1024 + ((ci >> 2) & 1) * 512 + r * 128 + ((((i & 31) >> 3) ^ r) << 5) + ((i & 7) << 2);
+}
+
+__device__ __forceinline__ void split_store(uint8_t* row, int ci, int i, const float (&v)[4]) {
+  float hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    hi[k] = tf32_rna(v[k]);
+    lo[k] = tf32_rna(v[k] - hi[k]);
+  }
+  uint8_t* q = row + ring_off(ci, i);
+  *reinterpret_cast<float4*>(q) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<float4*>(q + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct TcSeg {
+  int j, b, x0, ya, yb, ny, nx;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __grid_constant__ LiftParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  float* A3 = reinterpret_cast<float*>(gen + TS_A3);
+  float* O1 = reinterpret_cast<float*>(gen + TS_O1);
+  float* P2 = reinterpret_cast<float*>(gen + TS_P2);
+  float* P3 = reinterpret_cast<float*>(gen + TS_P3);
+  float* SK = reinterpret_cast<float*>(gen + TS_SK);
+  float* SW = reinterpret_cast<float*>(gen + TS_W);
+  const uint32_t bar_mma = base + TS_BAR, bar_free = base + TS_BAR + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + TS_BAR + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_free, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < SW_TOTAL; i += TC_THREADS) {
+    float v = 0.f;
+    if (i < 4) v = p.blob[BL_PRE + i];
+    else if (i < SW_B1) v = p.blob[BL_W1 + (i - SW_W1)];
+    else if (i < SW_B2) v = p.blob[BL_B1 + (i - SW_B1)];
+    else if (i < SW_B3) v = p.blob[BL_B2 + (i - SW_B2)];
+    else if (i < SW_W4) v = p.blob[BL_B3 + (i - SW_B3)];
+    else if (i < SW_B4) v = p.blob[BL_W4 + (i - SW_W4)];
+    else if (i == SW_B4) v = p.blob[BL_B4];
+    SW[i] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {   // weights -> tensor memory: row m = dx*16 + co (rows 80..127 zero), 4 regions of 80 columns
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int reg = 0; reg < 4; ++reg) {
+      const float* src = p.blob + BL_TC + ((long long)reg * 80 + tid) * 80;
+      for (int c = 0; c < 80; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tid < 80 ? __float_as_uint(src[c + k]) : 0u;
+        tmem_st8(trow + TM_W + reg * 80 + c, v);
+      }
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // instruction descriptor: D fp32, A/B tf32, A K-major (TMEM), B MN-major, N = 64, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t desc_ra1 = umma_desc_mn_sw128_32b(base + TS_RA1, 1024, 512);
+  const uint64_t desc_ra2 = umma_desc_mn_sw128_32b(base + TS_RA2, 1024, 512);
+
+  const int ncta = gridDim.x;
+  const long long lo_u = p.total_units * (long long)blockIdx.x / ncta;
+  const long long hi_u = p.total_units * (long long)(blockIdx.x + 1) / ncta;
+  uint32_t n = 0;   // global step counter (mbarrier phases)
+
+  for (long long u = lo_u; u < hi_u;) {
+    // ---- segment: a run of consecutive 8-row chunks of one strip -------------------------------
+    TcSeg s;
+    {
+      long long v = u;
+      int j = 0;
+      if (v >= p.units[0]) { v -= p.units[0]; j = 1; }
+      const int nch = p.nchunks[j], nst = p.nstrips[j];
+      const int c = (int)(v % nch);
+      const long long w = v / nch;
+      s.j = j;
+      s.b = (int)(w / nst);
+      s.x0 = (int)(w % nst) * TC_WO;
+      s.ny = p.job[j].ny;
+      s.nx = p.job[j].nx;
+      long long cnt = nch - c;
+      if (cnt > hi_u - u) cnt = hi_u - u;
+      s.ya = c * LS_R;
+      s.yb = s.ya + (int)cnt * LS_R;
+      if (s.yb > s.ny) s.yb = s.ny;
+      u += cnt;
+    }
+    const ll_lift_job& J = p.job[s.j];
+    const float* srcb = J.src.ptr + (long long)s.b * J.src.sb;
+    const int a1_lo = max(0, s.ya - 6), a1_hi = min(s.ny, s.yb + 6);
+    const int a2_lo = max(0, s.ya - 4), a2_hi = min(s.ny, s.yb + 4);
+    const int a3_lo = max(0, s.ya - 2), a3_hi = min(s.ny, s.yb + 2);
+    const int sk_lo = max(0, s.ya - 8), sk_hi = min(s.ny, s.yb + 8);
+
+    auto skip_row = [&](int rr, int j) {   // skip ring row rr, column j (plane column x0 - 8 + j)
+      const int c = s.x0 - 8 + j;
+      float v = 0.f;
+      if (c >= 0 && c < s.nx) {
+        const float* q = srcb + (long long)rr * J.src.sy + (long long)c * J.src.sx;
+        const float s0 = rr > 0 ? q[-J.src.sy] : 0.f;
+        const float s1 = q[0];
+        const float s2 = rr + 1 < s.ny ? q[J.src.sy] : 0.f;
+        v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
+      }
+      SK[(rr & (TC_RS - 1)) * TC_PS + j] = v;
+    };
+
+    // prologue: skip rows ya-8 .. ya-4 (row ya-3 is produced by the first step)
+    if (warp < 8) {
+      for (int e = tid; e < 5 * 68; e += 256) {
+        const int rr = s.ya - 8 + e / 68;
+        if (rr >= sk_lo && rr < sk_hi) skip_row(rr, e % 68);
+      }
+    }
+    __syncthreads();
+
+    for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+      const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
+      const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
+      const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
+      if (warp == 8) {
+        // ======================= MMA warp =======================
+        mbar_wait(bar_free, n & 1);
+        tc_fence_after();
+        const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
+        if (elect_one()) {
+          if (m2 && !(p.dbg & 1)) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+              const int rr = r2m + dy - 2;
+              if (rr >= 0 && rr < s.ny) {
+                const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
+                tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
+                tc_mma_tf32_ts(tmem + TM_ACC2, al, bd, idesc, 1u);                        // lo * hi
+                tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
+                tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
+                tc_mma_tf32_ts(tmem + TM_ACC2, al + 8, bd + (2048 >> 4), idesc, 1u);
+                tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                acc = 1;
+              }
+            }
+          }
+          if (m3 && !(p.dbg & 1)) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+              const int rr = r3m + dy - 2;
+              if (rr >= 0 && rr < s.ny) {
+                const uint64_t bd = desc_ra2 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                const uint32_t ah = tmem + TM_W + 1 * 160 + dy * 16, al = ah + 80;
+                tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
+                tc_mma_tf32_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
+                tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd + (4096 >> 4), idesc, 1u);
+                tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + (2048 >> 4), idesc, 1u);
+                tc_mma_tf32_ts(tmem + TM_ACC3, al + 8, bd + (2048 >> 4), idesc, 1u);
+                tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                acc = 1;
+              }
+            }
+          }
+          tc_commit(bar_mma);
+        }
+        __syncwarp();
+      } else {
+        // ======================= workers =======================
+        // ---- E-A: accumulators of the previous step -> partial planes ----
+        if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
+        tc_fence_after();
+        {
+          const int q = warp & 3, hs = warp >> 2, m = q * 32 + lane;
+          if (q < 3 && !(p.dbg & 16)) {
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + 32 * hs;
+            uint32_t v[32];
+            if (e2) {
+              tc_ld32(ta + TM_ACC2, v);
+              tc_wait_ld();
+              if (m < 80) {
+                float* o = P2 + m * TC_PP + 32 * hs;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                  *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+              }
+            }
+            if (e3) {
+              tc_ld32(ta + TM_ACC3, v);
+              tc_wait_ld();
+              if (m < 80) {
+                float* o = P3 + m * TC_PP + 32 * hs;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                  *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+
+        // ---- E-B: conv2 row r2e -> a2 ring; conv3 row r3e -> a3 ring ----
+        {
+          const int co = tid >> 4, xq = tid & 15, i0 = 4 * xq;
+          if (e2 && !(p.dbg & 2)) {
+            float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+              const float* pr = P2 + (dx * 16 + co) * TC_PP + i0;
+              const float4 a = *reinterpret_cast<const float4*>(pr), b = *reinterpret_cast<const float4*>(pr + 4);
+              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sacc[k] = __fadd_rn(sacc[k], win[k + dx]);
+            }
+            const float bias = SW[SW_B2 + co];
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = s.x0 - 4 + i0 + k;
+              float x = __fadd_rn(sacc[k], bias);
+              if (!p.linear) x = tanhf(x);
+              v[k] = (c >= 0 && c < s.nx && i0 + k < 60) ? x : 0.f;
+            }
+            split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
+          }
+          if (e3 && xq < 14 && !(p.dbg & 2)) {
+            float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+              const float* pr = P3 + (dx * 16 + co) * TC_PP + i0;
+              const float4 a = *reinterpret_cast<const float4*>(pr), b = *reinterpret_cast<const float4*>(pr + 4);
+              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sacc[k] = __fadd_rn(sacc[k], win[k + dx]);
+            }
+            const float bias = SW[SW_B3 + co];
+            const float4 o1 = *reinterpret_cast<const float4*>(O1 + ((r3e % TC_RO) * 16 + co) * TC_P3 + i0);
+            const float o1v[4] = {o1.x, o1.y, o1.z, o1.w};
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = s.x0 - 2 + i0 + k;
+              const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
+              v[k] = (c >= 0 && c < s.nx) ? x : 0.f;
+            }
+            *reinterpret_cast<float4*>(A3 + ((r3e % TC_R3) * 16 + co) * TC_P3 + i0) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+
+        // ---- S: skip row t+3 (warps 4-7) ----
+        {
+          const int rr = t + 3;
+          if (tid >= 128 && tid < 128 + 68 && rr >= sk_lo && rr < sk_hi) skip_row(rr, tid - 128);
+        }
+        // ---- S: conv1 row t -> a1 ring (hi/lo) and o1 ring ----
+        if (t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
+          const int co = tid & 15, i1 = 4 * (tid >> 4);
+          const float b1 = SW[SW_B1 + co];
+          float acc[4] = {b1, b1, b1, b1};
+#pragma unroll
+          for (int dy = 0; dy < 5; ++dy) {
+            const int rr = t + dy - 2;
+            if (rr >= 0 && rr < s.ny) {
+              const float* sr = SK + (rr & (TC_RS - 1)) * TC_PS + i1;
+              const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
+              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int dx = 0; dx < 5; ++dx) {
+                const float w = SW[SW_W1 + (dy * 5 + dx) * 16 + co];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] = fmaf(win[k + dx], w, acc[k]);
+              }
+            }
+          }
+          float av[4], ov[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = s.x0 - 6 + i1 + k;
+            const bool in = c >= 0 && c < s.nx;
+            ov[k] = in ? acc[k] : 0.f;
+            av[k] = in ? (p.linear ? acc[k] : tanhf(acc[k])) : 0.f;
+          }
+          split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
+          if (i1 >= 4 && i1 < 60)
+            *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        }
+        // ---- S: conv4 + output row t-11 (warps 0-3) ----
+        {
+          const int r4 = t - 11;
+          if (r4 >= s.ya && r4 < s.yb && tid < 128 && !(p.dbg & 8)) {
+            const bool active = tid < 104;
+            const int pq = tid >> 3, cp = tid & 7;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (active) {
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const int ci = 2 * cp + cc;
+#pragma unroll
+                for (int dy = 0; dy < 5; ++dy) {
+                  const int rr = r4 + dy - 2;
+                  if (rr >= 0 && rr < s.ny) {
+                    const float* ar = A3 + ((rr % TC_R3) * 16 + ci) * TC_P3 + 4 * pq;
+                    const float4 a = *reinterpret_cast<const float4*>(ar), b = *reinterpret_cast<const float4*>(ar + 4);
+                    const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx) {
+                      const float w = SW[SW_W4 + ci * 25 + dy * 5 + dx];
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) acc[k] = fmaf(win[k + dx], w, acc[k]);
+                    }
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+              acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+              acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4);
+            }
+            if (active && cp == 0) {
+              const float b4 = SW[SW_B4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int jx = 4 * pq + k, c = s.x0 + jx;
+                if (c < s.nx) {
+                  const float net = __fadd_rn(acc[k], b4);
+                  const float sk = SK[(r4 & (TC_RS - 1)) * TC_PS + jx + 8];
+                  const float d = J.din.ptr[(long long)s.b * J.din.sb + (long long)r4 * J.din.sy + (long long)c * J.din.sx];
+                  const float tn = __fmul_rn(net, p.rw);
+                  const float o = p.sign > 0.f ? __fadd_rn(__fadd_rn(d, sk), tn)
+                                               : p.sign < 0.f ? __fadd_rn(__fadd_rn(d, -sk), -tn) : net;
+                  J.dout.ptr[(long long)s.b * J.dout.sb + (long long)r4 * J.dout.sy + (long long)c * J.dout.sx] = o;
+                }
+              }
+            }
+          }
+        }
+        fence_proxy_async();   // a1 / a2 ring writes -> visible to the tensor core's operand reads
+      }
+      __syncthreads();
+    }
+  }
+
+  // drain: the last step's commit must have landed before tensor memory is released
+  if (warp < 8 && n > 0) mbar_wait(bar_mma, (n - 1) & 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// (region = layer*2 + term, row m = dx*16 + co, col = dy*16 + ci) of the tensor-core weight block
+__global__ void pack_lift_tc_kernel(const float* __restrict__ w2, const float* __restrict__ w3, float* __restrict__ blob) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * 80 * 80; i += gridDim.x * blockDim.x) {
+    const int col = i % 80, m = (i / 80) % 80, reg = i / 6400;
+    const int dy = col / 16, ci = col % 16, dx = m / 16, co = m % 16;
+    const float w = ((reg >> 1) ? w3 : w2)[(co * 16 + ci) * 25 + dy * 5 + dx];
+    const float hi = tf32_rna(w);
+    blob[BL_TC + i] = (reg & 1) ? tf32_rna(w - hi) : hi;
+  }
+}
+
+int launch_lift_step_tc(const LiftParams& p0, cudaStream_t stream) {
+  LiftParams p = p0;
+  p.total_units = 0;
+  for (int j = 0; j < 2; ++j) {
+    if (j < p.njobs) {
+      p.nstrips[j] = (p.job[j].nx + TC_WO - 1) / TC_WO;
+      p.nchunks[j] = (p.job[j].ny + LS_R - 1) / LS_R;
+      p.units[j] = (long long)p.job[j].nb * p.nstrips[j] * p.nchunks[j];
+    } else {
+      p.units[j] = 0;
+      p.nstrips[j] = p.nchunks[j] = 1;
+    }
+    p.total_units += p.units[j];
+  }
+  if (p.total_units == 0) return LL_OK;
+  static thread_local bool attr_set[64] = {false};
+  int dev = 0;
+  LL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  long long grid = sm_count_cached();
+  if (grid > p.total_units) grid = p.total_units;
+  lift_step_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+  LL_LAUNCH_OK("lift_step_tc_kernel");
+  return LL_OK;
+}
+
+int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream) {
+  pack_lift_tc_kernel<<<100, 256, 0, stream>>>(w2, w3, blob);
+  LL_LAUNCH_OK("pack_lift_tc_kernel");
+  return LL_OK;
+}
+
+}  // namespace ll

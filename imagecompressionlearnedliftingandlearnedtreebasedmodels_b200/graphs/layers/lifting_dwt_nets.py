@@ -163,6 +163,9 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
         self.waveletInverse = nn.ModuleList()
         self.Yh_ae = nn.ModuleList()
         self.config = config
+        # new optional key (default keeps reference configs valid): "tc" = conv2/conv3 of every lifting step
+        # on tcgen05 with the 3xTF32 split (fp32-level accuracy), "fp32" = all layers on the FP32 FMA pipe
+        self.lift_precision = config.get("lift_precision", "tc") if hasattr(config, "get") else getattr(config, "lift_precision", "tc")
         self.depth_scale = config.depth_scale * 8
         self.preProcessingList = self.preProcessBlock(config.clrch, config.filtersize)
         if config.autoencoder == "SubbandAutoEncoder":
@@ -202,6 +205,7 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
 
     def transform(self, input):
         """The lifting levels alone: x -> (LL, [Yh_l (B,3,h,w)])."""
+        ops.set_lift_mode(self.lift_precision)
         Yh = []
         ll = input
         for lvl in range(self.waveletLevel):
@@ -210,6 +214,7 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
         return ll, Yh
 
     def inverse_transform(self, Yl, Yh):
+        ops.set_lift_mode(self.lift_precision)
         ll = Yl
         for lvl in range(self.waveletLevel - 1, -1, -1):
             ll = self.waveletInverse[lvl].level(ll, Yh[lvl])

@@ -23,7 +23,7 @@ def _count(n):
     _LAUNCHES += n
 
 
-LIFT_BLOB_FLOATS = 13656
+LIFT_BLOB_FLOATS = 39256
 AE1_BLOB_FLOATS = 2212
 
 
@@ -34,6 +34,22 @@ def _f32c(t, name):
 
 
 # ----------------------------------------------------------------------------- learned lifting
+LIFT_FP32, LIFT_TC = 0, 1
+
+
+def set_lift_mode(mode):
+    """Arithmetic of the learned-lifting kernels: ``"tc"`` (default: conv2/conv3 on tcgen05, 3xTF32 split,
+    fp32-level accuracy) or ``"fp32"`` (everything on the FP32 FMA pipe)."""
+    m = {"tc": LIFT_TC, "3xtf32": LIFT_TC, "fp32": LIFT_FP32, LIFT_TC: LIFT_TC, LIFT_FP32: LIFT_FP32}.get(mode)
+    if m is None:
+        raise ValueError(f"set_lift_mode: unknown mode {mode!r}")
+    check(_lib.load().ll_lift_set_mode(m))
+
+
+def get_lift_mode():
+    return "tc" if _lib.load().ll_lift_get_mode() == LIFT_TC else "fp32"
+
+
 def pack_lift_step(pre_w, conv):
     """``pre_w``: convBlock[k].weight (1,1,3,1); ``conv``: dict conv1..conv4 -> (weight, bias).
     Returns the device blob of one lifting step (ll_pack_lift_step)."""
@@ -51,7 +67,7 @@ def pack_lift_step(pre_w, conv):
     blob = torch.empty(LIFT_BLOB_FLOATS, dtype=torch.float32, device=pre_w.device)
     with torch.cuda.device(pre_w.device):
         check(lib.ll_pack_lift_step(*[ptr(a) for a in args], ptr(blob), stream_ptr()))
-    _count(1)
+    _count(2)
     return blob
 
 

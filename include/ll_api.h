@@ -56,7 +56,7 @@ typedef struct ll_lift_job {
   int32_t nb, ny, nx;
 } ll_lift_job;
 
-#define LL_LIFT_BLOB_FLOATS 13656
+#define LL_LIFT_BLOB_FLOATS 39256
 
 /* Packs one lifting step's parameters into the kernel's blob layout (device to
  * device, on `stream`).  pre_w: (3,) taps of convBlock[k] (lifting_dwt_nets.py:784-827);
@@ -114,6 +114,15 @@ int ll_dwt97_fwd(const float* x, float* yl, float* const* yh, float* scratch, in
                  ll_stream_t stream);
 int ll_dwt97_inv(const float* yl, const float* const* yh, float* x, float* scratch, int N, int h, int w, int J,
                  ll_stream_t stream);
+
+/* Arithmetic of the learned-lifting step kernels (process-wide, default LL_LIFT_TC):
+ *   LL_LIFT_FP32  every layer on the FP32 FMA pipe (exact, ~45 % of the FFMA2 peak);
+ *   LL_LIFT_TC    conv2 / conv3 (94 % of the MACs) on tcgen05 with the 3xTF32 hi/lo split and FP32
+ *                 accumulation in tensor memory (fp32-level accuracy, see lift_tc.cu), the rest FP32. */
+#define LL_LIFT_FP32 0
+#define LL_LIFT_TC 1
+int ll_lift_set_mode(int mode);
+int ll_lift_get_mode(void);
 
 /* ------------------------------------------------------------------------- */
 /* Pointwise subband auto-encoder (v1) fused with the quantiser               */
