@@ -178,6 +178,11 @@ def run_own(args):
     launches = timed.launches
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup))
+    for net in nets:                      # the exact FP32-FMA kernels, for the record (same results to ~1e-6)
+        net.lift_precision = "fp32"
+    ms_fp32 = timed(step_resident, max(1, args.steps // 2), 1) / max(1, args.steps // 2)
+    for net in nets:
+        net.lift_precision = "tc"
     with torch.no_grad():
         rec = torch.cat(step_resident(), dim=1)
     pr_err = float((rec - x_dev).abs().max().item())
@@ -203,6 +208,7 @@ def run_own(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "height": H, "width": W, "levels": LEVELS,
                    "weights": "random init (seed 1337), block_property=same, SubbandAutoEncoder not in the timed path",
+                   "lift_precision": "tc (conv2/conv3 on tcgen05, 3xTF32 split, fp32-level accuracy)",
                    "l2": "inputs+outputs+scratch per step (3 planes x 3 x 25 MB, read and rewritten 12x per level) exceed the 126 MB L2",
                    "parallelism": f"image-parallel x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": x_host.numel() * 4,
@@ -210,14 +216,26 @@ def run_own(args):
                 "api": "LiftingBasedNeuralWaveletv4.transform / .inverse_transform on pinned host tensors"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
-                     "kernel": "ll::lift_step_kernel",
-                     "note": "K2 is FP32-FMA-bound by design (13.6 kFLOP per algorithmic byte); see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32_fma", "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": fp32_peak,
-                          "unit": "TFLOP/s", "frac": flops / (ms_step * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+        # dominant kernel = ll::lift_step_tc_kernel: 94 % of its MACs (conv2/conv3) run on tcgen05 as 3xTF32
+        # (3 TF32 MMAs per product, M = 80 of 128 rows used), so the tensor pipe executes
+        # 3 * 128/80 * 0.94 = 4.5x the useful FLOPs; TF32 dense peak = half the measured BF16 peak.
+        "roofline": {"bound": "tensor", "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": pk["bf16_tflops"] / 2,
+                     "unit": "TFLOP/s", "frac": flops / (ms_step * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
+                     "traffic": None, "peak_kind": pk_kind + " bf16 burst / 2 (TF32)",
+                     "kernel": "ll::lift_step_tc_kernel",
+                     "issued_tflops": flops * 0.94 * 3 * 128 / 80 / (ms_step * 1e-3) / 1e12,
+                     "issued_frac": flops * 0.94 * 3 * 128 / 80 / (ms_step * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
+                     "note": "useful conv FLOPs (SURVEY.md 8d: 2 x 144532 per plane pixel, fwd+inv) / step time; "
+                             "issued = tensor-pipe FLOPs incl. the 3xTF32 split and M padding"},
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"],
+                         "note": "algorithmic 21.25 B per plane pixel; the learned lifting is compute-bound "
+                                 "(13.6 kFLOP per algorithmic byte), HBM is not its roofline"},
+        "roofline_fp32": {"bound": "fp32_fma", "achieved": flops / (ms_fp32 * 1e-3) / 1e12, "peak": fp32_peak,
+                          "unit": "TFLOP/s", "frac": flops / (ms_fp32 * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                          "ms_per_step": ms_fp32,
                           "peak_kind": "measured in this run: FFMA2 register-only loop, all SMs",
-                          "flops": "useful conv MACs x2 (SURVEY.md 8d), halo recompute not counted"},
+                          "note": "the same step with lift_precision='fp32' (ll::lift_step_kernel, every layer on the FP32 FMA pipe)"},
         "check": {"perfect_reconstruction_max_abs_err": pr_err},
     }
     line["dwt97"] = dwt97_probe(dev, pk)

@@ -20,13 +20,14 @@
 // layer, 32.5 cycles each when issued straight-line by one elected lane.
 //
 // Pipeline: the CTA marches down a strip of 52 output columns one row per step.  Per step t
-//   workers (8 warps):  [E-A] accumulators of the previous step: TMEM -> shared partial planes
+//   epilogue warps 0-7: [E-A] accumulators of the previous step: TMEM -> shared partial planes
 //                       [E-B] conv2 row t-4: sum dx, bias, tanh, hi/lo split -> a2 ring
 //                             conv3 row t-8: sum dx, bias, + o1 -> a3 ring (fp32)
-//                       [S]   skip row t+3; conv1 row t (FP32 SIMT) -> a1 ring (hi/lo) and o1 ring;
-//                             conv4 + output row t-11 (FP32 SIMT)
-//   MMA warp:           after the workers freed the accumulators: conv2 row t-3 and conv3 row t-7
-//                       (60 tcgen05.mma), one tcgen05.commit.
+//                       conv4 + output row t-11, pixel pairs 0..15 (FP32 FFMA2)
+//   SIMT warps 8-15:    conv1 row t (FP32 FFMA2) -> a1 ring (hi/lo) and o1 ring; conv4 + output
+//                       pixel pairs 16..25; skip row t+3; global loads issued first, used last
+//   MMA warp 16:        after the epilogue warps freed the accumulators: conv2 row t-3 and conv3
+//                       row t-7 (60 tcgen05.mma), one tcgen05.commit.
 // One block barrier per step; a row produced in step s is consumed in steps > s, ring depths follow.
 // Every intermediate is forced to 0 outside the plane (each conv zero-pads its own input).
 #include <stdint.h>
@@ -38,7 +39,8 @@
 
 namespace ll {
 
-constexpr int TC_THREADS = 288;  // 8 worker warps + 1 MMA warp
+constexpr int TC_THREADS = 544;  // 8 epilogue warps + 8 SIMT warps + 1 MMA warp
+constexpr int TC_MMA_WARP = 16;
 constexpr int TC_WO = 52;        // output columns per strip
 constexpr int TC_RA = 6;         // a1 / a2 ring rows
 constexpr int TC_R3 = 6;         // a3 ring rows
@@ -60,8 +62,10 @@ constexpr int TS_P2 = TS_O1 + TC_RO * 16 * TC_P3 * 4;
 constexpr int TS_P3 = TS_P2 + 80 * TC_PP * 4;
 constexpr int TS_SK = TS_P3 + 80 * TC_PP * 4;
 constexpr int TS_W = TS_SK + TC_RS * TC_PS * 4;
-// small weights (floats): pre[4] W1[25][16] b1[16] b2[16] b3[16] W4[16][25] b4[4]
-constexpr int SW_PRE = 0, SW_W1 = 4, SW_B1 = 404, SW_B2 = 420, SW_B3 = 436, SW_W4 = 452, SW_B4 = 852, SW_TOTAL = 856;
+// small weights (floats): pre[4] W1[tap 25][co 16] b1[16] b2[16] b3[16] W4[tap 25][ci 16] b4[4]
+// (channel-pair float2 loads feed packed FFMA2 with a broadcast activation)
+constexpr int SW_PRE = 0, SW_W1 = 4, SW_B1 = SW_W1 + 400, SW_B2 = SW_B1 + 16, SW_B3 = SW_B2 + 16, SW_W4 = SW_B3 + 16,
+              SW_B4 = SW_W4 + 400, SW_TOTAL = SW_B4 + 4;
 constexpr int TS_BAR = TS_W + SW_TOTAL * 4;
 constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -110,18 +114,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
     mbar_init(bar_free, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
   for (int i = tid; i < SW_TOTAL; i += TC_THREADS) {
     float v = 0.f;
     if (i < 4) v = p.blob[BL_PRE + i];
-    else if (i < SW_B1) v = p.blob[BL_W1 + (i - SW_W1)];
+    else if (i < SW_B1) v = p.blob[BL_W1 + (i - SW_W1)];                                  // [tap][co]
     else if (i < SW_B2) v = p.blob[BL_B1 + (i - SW_B1)];
     else if (i < SW_B3) v = p.blob[BL_B2 + (i - SW_B2)];
     else if (i < SW_W4) v = p.blob[BL_B3 + (i - SW_B3)];
-    else if (i < SW_B4) v = p.blob[BL_W4 + (i - SW_W4)];
+    else if (i < SW_B4) v = p.blob[BL_W4 + ((i - SW_W4) & 15) * 25 + ((i - SW_W4) >> 4)];   // blob [ci][tap] -> [tap][ci]
     else if (i == SW_B4) v = p.blob[BL_B4];
     SW[i] = v;
   }
@@ -198,9 +202,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
       SK[(rr & (TC_RS - 1)) * TC_PS + j] = v;
     };
 
+    // conv4 + output, 2 pixels x 2 input channels per thread (c4 in [0,208): ci pair = c4 & 7, pixel pair = c4 >> 3),
+    // packed FFMA2 over the channel pair, 8-lane shuffle reduction; dv = din of the two pixels (loaded early)
+    auto conv4_out = [&](int r4, int c4, bool active, const float (&dv)[2]) {
+      const int cp = c4 & 7, pp = c4 >> 3;
+      float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      if (active) {
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+          const int rr = r4 + dy - 2;
+          if (rr >= 0 && rr < s.ny) {
+            const float* ar = A3 + ((rr % TC_R3) * 16 + 2 * cp) * TC_P3 + 2 * pp;
+            float w0[6], w1[6];
+#pragma unroll
+            for (int k = 0; k < 6; k += 2) {
+              const float2 a = *reinterpret_cast<const float2*>(ar + k), b = *reinterpret_cast<const float2*>(ar + TC_P3 + k);
+              w0[k] = a.x; w0[k + 1] = a.y; w1[k] = b.x; w1[k + 1] = b.y;
+            }
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+              const float2 w = *reinterpret_cast<const float2*>(SW + SW_W4 + (dy * 5 + dx) * 16 + 2 * cp);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) acc[k] = __ffma2_rn(make_float2(w0[k + dx], w1[k + dx]), w, acc[k]);
+            }
+          }
+        }
+      }
+      float a2[2] = {acc[0].x + acc[0].y, acc[1].x + acc[1].y};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], 1);
+        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], 2);
+        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], 4);
+      }
+      if (active && cp == 0) {
+        const float b4 = SW[SW_B4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int jx = 2 * pp + k, c = s.x0 + jx;
+          if (c < s.nx) {
+            const float net = __fadd_rn(a2[k], b4);
+            const float sk = SK[(r4 & (TC_RS - 1)) * TC_PS + jx + 8];
+            const float tn = __fmul_rn(net, p.rw);
+            const float o = p.sign > 0.f ? __fadd_rn(__fadd_rn(dv[k], sk), tn)
+                                         : p.sign < 0.f ? __fadd_rn(__fadd_rn(dv[k], -sk), -tn) : net;
+            J.dout.ptr[(long long)s.b * J.dout.sb + (long long)r4 * J.dout.sy + (long long)c * J.dout.sx] = o;
+          }
+        }
+      }
+    };
+    auto load_din = [&](int r4, int c4, bool active, float (&dv)[2]) {
+      dv[0] = dv[1] = 0.f;
+      if (active && (c4 & 7) == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c = s.x0 + 2 * (c4 >> 3) + k;
+          if (c < s.nx) dv[k] = J.din.ptr[(long long)s.b * J.din.sb + (long long)r4 * J.din.sy + (long long)c * J.din.sx];
+        }
+      }
+    };
+
     // prologue: skip rows ya-8 .. ya-4 (row ya-3 is produced by the first step)
-    if (warp < 8) {
-      for (int e = tid; e < 5 * 68; e += 256) {
+    if (warp < 16) {
+      for (int e = tid; e < 5 * 68; e += 512) {
         const int rr = s.ya - 8 + e / 68;
         if (rr >= sk_lo && rr < sk_hi) skip_row(rr, e % 68);
       }
@@ -211,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
       const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
       const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
       const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
-      if (warp == 8) {
+      if (warp == TC_MMA_WARP) {
         // ======================= MMA warp =======================
         mbar_wait(bar_free, n & 1);
         tc_fence_after();
@@ -256,8 +320,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           tc_commit(bar_mma);
         }
         __syncwarp();
-      } else {
-        // ======================= workers =======================
+      } else if (warp < 8) {
+        // ======================= epilogue warps =======================
+        const int r4 = t - 11;
+        const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && tid < 128;   // warps 0-3: pixel pairs 0..15
+        float dv[2];
+        load_din(r4, tid, do4, dv);
         // ---- E-A: accumulators of the previous step -> partial planes ----
         if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
         tc_fence_after();
@@ -340,17 +408,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             *reinterpret_cast<float4*>(A3 + ((r3e % TC_R3) * 16 + co) * TC_P3 + i0) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
-
-        // ---- S: skip row t+3 (warps 4-7) ----
-        {
-          const int rr = t + 3;
-          if (tid >= 128 && tid < 128 + 68 && rr >= sk_lo && rr < sk_hi) skip_row(rr, tid - 128);
+        if (do4) conv4_out(r4, tid, true, dv);
+        fence_proxy_async();   // a2 ring writes -> visible to the tensor core's operand reads
+      } else {
+        // ======================= SIMT warps =======================
+        // warps 8-11 (st < 128): conv1; warps 12-14 (st 128..223): conv4 pixel pairs 16..25; st >= 188: skip row
+        const int st = tid - 256;
+        const int rs = t + 3, r4 = t - 11;
+        // global loads first (their latency hides behind the arithmetic)
+        const bool do_sk = st >= 188 && rs >= sk_lo && rs < sk_hi;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        bool sk_in = false;
+        if (do_sk) {
+          const int c = s.x0 - 8 + (st - 188);
+          sk_in = c >= 0 && c < s.nx;
+          if (sk_in) {
+            const float* q = srcb + (long long)rs * J.src.sy + (long long)c * J.src.sx;
+            s0 = rs > 0 ? q[-J.src.sy] : 0.f;
+            s1 = q[0];
+            s2 = rs + 1 < s.ny ? q[J.src.sy] : 0.f;
+          }
         }
-        // ---- S: conv1 row t -> a1 ring (hi/lo) and o1 ring ----
-        if (t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
-          const int co = tid & 15, i1 = 4 * (tid >> 4);
-          const float b1 = SW[SW_B1 + co];
-          float acc[4] = {b1, b1, b1, b1};
+        const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && st >= 128 && st < 224;
+        const bool act4 = st < 208;
+        float dv[2];
+        load_din(r4, st, do4 && act4, dv);     // c4 = 128 + (st - 128) = st
+        // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
+        if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
+          const int cp = st & 7, i1 = 4 * (st >> 3);
+          const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
+          float2 acc[4] = {b1, b1, b1, b1};
 #pragma unroll
           for (int dy = 0; dy < 5; ++dy) {
             const int rr = t + dy - 2;
@@ -360,77 +447,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
               for (int dx = 0; dx < 5; ++dx) {
-                const float w = SW[SW_W1 + (dy * 5 + dx) * 16 + co];
+                const float2 w = *reinterpret_cast<const float2*>(SW + SW_W1 + (dy * 5 + dx) * 16 + 2 * cp);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] = fmaf(win[k + dx], w, acc[k]);
+                for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), w, acc[k]);
               }
             }
           }
-          float av[4], ov[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = s.x0 - 6 + i1 + k;
-            const bool in = c >= 0 && c < s.nx;
-            ov[k] = in ? acc[k] : 0.f;
-            av[k] = in ? (p.linear ? acc[k] : tanhf(acc[k])) : 0.f;
-          }
-          split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
-          if (i1 >= 4 && i1 < 60)
-            *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        }
-        // ---- S: conv4 + output row t-11 (warps 0-3) ----
-        {
-          const int r4 = t - 11;
-          if (r4 >= s.ya && r4 < s.yb && tid < 128 && !(p.dbg & 8)) {
-            const bool active = tid < 104;
-            const int pq = tid >> 3, cp = tid & 7;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (active) {
-#pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const int ci = 2 * cp + cc;
-#pragma unroll
-                for (int dy = 0; dy < 5; ++dy) {
-                  const int rr = r4 + dy - 2;
-                  if (rr >= 0 && rr < s.ny) {
-                    const float* ar = A3 + ((rr % TC_R3) * 16 + ci) * TC_P3 + 4 * pq;
-                    const float4 a = *reinterpret_cast<const float4*>(ar), b = *reinterpret_cast<const float4*>(ar + 4);
-                    const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) {
-                      const float w = SW[SW_W4 + ci * 25 + dy * 5 + dx];
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) acc[k] = fmaf(win[k + dx], w, acc[k]);
-                    }
-                  }
-                }
-              }
-            }
+          for (int h = 0; h < 2; ++h) {
+            float av[4], ov[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
-              acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
-              acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 4);
+              const int c = s.x0 - 6 + i1 + k;
+              const bool in = c >= 0 && c < s.nx;
+              const float x = h ? acc[k].y : acc[k].x;
+              ov[k] = in ? x : 0.f;
+              av[k] = in ? (p.linear ? x : tanhf(x)) : 0.f;
             }
-            if (active && cp == 0) {
-              const float b4 = SW[SW_B4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int jx = 4 * pq + k, c = s.x0 + jx;
-                if (c < s.nx) {
-                  const float net = __fadd_rn(acc[k], b4);
-                  const float sk = SK[(r4 & (TC_RS - 1)) * TC_PS + jx + 8];
-                  const float d = J.din.ptr[(long long)s.b * J.din.sb + (long long)r4 * J.din.sy + (long long)c * J.din.sx];
-                  const float tn = __fmul_rn(net, p.rw);
-                  const float o = p.sign > 0.f ? __fadd_rn(__fadd_rn(d, sk), tn)
-                                               : p.sign < 0.f ? __fadd_rn(__fadd_rn(d, -sk), -tn) : net;
-                  J.dout.ptr[(long long)s.b * J.dout.sb + (long long)r4 * J.dout.sy + (long long)c * J.dout.sx] = o;
-                }
-              }
-            }
+            const int co = 2 * cp + h;
+            split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
+            if (i1 >= 4 && i1 < 60)
+              *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
           }
         }
-        fence_proxy_async();   // a1 / a2 ring writes -> visible to the tensor core's operand reads
+        // ---- conv4 + output row t-11, pixel pairs 16..25 ----
+        if (do4) conv4_out(r4, st, act4, dv);
+        // ---- skip row t+3 (values loaded at the top of the step) ----
+        if (do_sk) {
+          float v = 0.f;
+          if (sk_in) v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
+          SK[(rs & (TC_RS - 1)) * TC_PS + (st - 188)] = v;
+        }
+        fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
       }
       __syncthreads();
     }
@@ -440,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   if (warp < 8 && n > 0) mbar_wait(bar_mma, (n - 1) & 1);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

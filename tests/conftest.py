@@ -20,3 +20,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _reset_lift_mode(request):
+    """GPU tests may switch the process-wide arithmetic mode of the lifting kernels; restore the default."""
+    yield
+    if request.node.get_closest_marker("gpu") is not None:
+        from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+        ops.set_lift_mode("tc")

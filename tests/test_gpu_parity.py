@@ -103,9 +103,12 @@ def test_training_mode_noise_parity(prec):
     assert abs(tot - ref) <= 1e-3 * ref                    # bpp within 0.1 % in either precision
 
 
-def test_lifting_level_golden():
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_lifting_level_golden(mode):
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    ops.set_lift_mode(mode)
     m = META["lifting_one_level"]
-    model, cfg = product_model(m["config"])
+    model, cfg = product_model(dict(m["config"], lift_precision=mode))
     keyed_state(model)
     model = model.to(DEV).eval()
     g = load_case("lifting_one_level")
@@ -118,11 +121,17 @@ def test_lifting_level_golden():
     assert (rec.cpu() - g["x"]).abs().max().item() < 1e-5      # perfect reconstruction
 
 
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
 @pytest.mark.parametrize("shape,levels", [((2, 1, 48, 80), 3), ((1, 1, 128, 256), 4), ((3, 1, 16, 16), 2),
-                                          ((1, 1, 64, 1024), 1)])
-def test_learned_lifting_vs_oracle(shape, levels):
+                                          ((1, 1, 64, 1024), 1), ((2, 1, 104, 106), 1)])
+def test_learned_lifting_vs_oracle(shape, levels, mode):
+    """Both arithmetic modes of the lifting kernels against the CPU oracle: "tc" = conv2/conv3 on tcgen05
+    with the 3xTF32 split (default), "fp32" = every layer on the FP32 FMA pipe.  Same 1e-5 bar for both."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers import lifting_dwt_nets as ldn
-    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder", dwtlevels=levels)
+    ops.set_lift_mode(mode)
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder", dwtlevels=levels,
+                         lift_precision=mode)
     torch.manual_seed(1337)
     net = ldn.LiftingBasedNeuralWaveletv4(cfg)
     sd = om.keyed_weights({"m.autoencoder." + k: v for k, v in net.state_dict().items()})
@@ -146,6 +155,7 @@ def test_learned_lifting_vs_oracle(shape, levels):
         assert rel_err(L.cpu(), oL) < 1e-5 and rel_err(H.cpu(), oH) < 1e-5
         pb = net.P_blocks[0](x.to(DEV))
         assert rel_err(pb.cpu(), olift.p_block(x, sd, "m.autoencoder.P_blocks.0.")) < 1e-5
+    ops.set_lift_mode("tc")
 
 
 @pytest.mark.parametrize("shape,J", [((2, 3, 64, 96), 3), ((1, 1, 16, 24), 3), ((1, 2, 8, 8), 2), ((1, 1, 256, 256), 4),
