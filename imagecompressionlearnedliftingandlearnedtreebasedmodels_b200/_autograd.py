@@ -44,3 +44,16 @@ def run(fast_fn, ref_fn, tensors):
     if needs_grad(tensors):
         return RecomputeFn.apply(fast_fn, ref_fn, *tensors)
     return fast_fn(*tensors)
+
+
+def run_module(fast_fn, module, x):
+    """``fast_fn(x)`` on the kernels; differentiable by re-running the torch ``module`` (an nn.Sequential of
+    plain torch layers that defines the same function) functionally on the saved parameters."""
+    names, params = zip(*module.named_parameters())
+    if not needs_grad((x,) + params):
+        return fast_fn(x)
+
+    def ref(x, *ps):
+        return torch.func.functional_call(module, dict(zip(names, ps)), (x,))
+
+    return RecomputeFn.apply(lambda x, *ps: fast_fn(x), ref, x, *params)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "ll_lift_step": (c_int, [ctypes.POINTER(ll_lift_job), c_int, _P, c_float, c_float, c_int, _P]),
     "ll_lift_set_mode": (c_int, [c_int]),
     "ll_lift_get_mode": (c_int, []),
+    "ll_lift_set_debug_buffer": (c_int, [_P]),
     "ll_lift_level_scratch_floats": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "ll_lift_level_fwd": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, _P, c_int, c_int, c_int,
                                   ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, _P]),

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _autograd, _torch_ref, ops
 
 # --------------------------------------------------------------------------- bounds / GDN
 
@@ -135,6 +135,15 @@ class DWTForward(nn.Module):
         self.mode = mode
 
     def forward(self, x):
+        if _autograd.needs_grad([x]):
+            def ref(x):
+                yh, cur = [], x
+                for _ in range(self.J):
+                    cur, y = _torch_ref.dwt97_fwd_level(cur)
+                    yh.append(y)
+                return (cur, *yh)
+            out = _autograd.run(lambda x: (lambda r: (r[0], *r[1]))(ops.dwt97_forward(x, self.J)), ref, [x])
+            return out[0], list(out[1:])
         return ops.dwt97_forward(x, self.J)
 
 
@@ -153,6 +162,13 @@ class DWTInverse(nn.Module):
 
     def forward(self, coeffs):
         yl, yh = coeffs
+        if _autograd.needs_grad([yl] + list(yh)):
+            def ref(yl, *yh):
+                cur = yl
+                for y in yh[::-1]:
+                    cur = _torch_ref.dwt97_inv_level(cur, y)
+                return cur
+            return _autograd.run(lambda yl, *yh: ops.dwt97_inverse(yl, list(yh)), ref, [yl] + list(yh))
         return ops.dwt97_inverse(yl, yh)
 
 
@@ -183,7 +199,10 @@ class EntropyModel(nn.Module):
         if mode not in ("noise", "dequantize", "symbols"):
             raise ValueError(f'Invalid quantization mode: "{mode}"')
         if mode == "noise":
-            return ops.quantize(inputs, draw_noise(inputs))
+            noise = draw_noise(inputs)
+            if _autograd.needs_grad([inputs]):
+                return inputs + noise          # identity gradient, as compressai's additive-noise quantiser
+            return ops.quantize(inputs, noise)
         if means is not None:
             q = ops.quantize(inputs - means)
             return q + means if mode == "dequantize" else q.int()
@@ -211,6 +230,10 @@ class GaussianConditional(EntropyModel):
         if training is None:
             training = self.training
         noise = draw_noise(inputs) if training else None
+        if _autograd.needs_grad([inputs, ms]):
+            fast = lambda x, ms: ops.gauss_rate(x, ms, noise, want_y, acc)
+            ref = (lambda x, ms: _torch_ref.gauss_bits(x, ms, noise)) if want_y else (lambda x, ms: _torch_ref.gauss_bits(x, ms, noise)[0])
+            return _autograd.run(fast, ref, [inputs, ms])
         return ops.gauss_rate(inputs, ms, noise, want_y, acc)
 
     def forward(self, inputs, scales, means=None, training=None):
@@ -296,7 +319,15 @@ class EntropyBottleneck(EntropyModel):
         """(y, bits) through the fused CUDA kernel."""
         if training is None:
             training = self.training
-        noise = draw_noise(x) if training else None
+        noise = None
+        if training:
+            # compressai draws the noise on the channel-major (C, 1, B*H*W) view of x: same stream, that layout
+            B, C, H, W = x.shape
+            noise = draw_noise(x.new_empty(C, 1, B * H * W)).reshape(C, B, H, W).permute(1, 0, 2, 3).contiguous()
+        ps = self._param_list()
+        if _autograd.needs_grad([x] + ps):
+            return _autograd.run(lambda x, *p: ops.eb_rate(x, self._blob(), noise, acc),
+                                 lambda x, *p: _torch_ref.eb_bits(x, p, noise), [x] + ps)
         return ops.eb_rate(x, self._blob(), noise, acc)
 
     def forward(self, x, training=None):

@@ -9,6 +9,7 @@ int launch_lift_step_tc(const LiftParams& p, cudaStream_t stream);              
 int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream);         // lift_tc.cu
 static int g_lift_mode = LL_LIFT_TC;
 static int g_lift_dbg = 0;
+static long long* g_lift_dbg_buf = nullptr;
 
 __global__ void __launch_bounds__(LS_THREADS, 1) lift_step_kernel(const __grid_constant__ LiftParams p) {
   extern __shared__ __align__(16) float sm[];
@@ -77,6 +78,7 @@ static int launch_lift_step(const ll_lift_job* jobs, int njobs, const float* blo
   }
   if (p.total_units == 0) return LL_OK;  // empty input: nothing to do
   p.dbg = g_lift_dbg;
+  p.dbg_buf = g_lift_dbg_buf;
   if (g_lift_mode == LL_LIFT_TC) return launch_lift_step_tc(p, stream);
   static thread_local bool attr_set[64] = {false};
   int dev = 0;
@@ -143,6 +145,11 @@ int ll_lift_set_mode(int mode) {
 }
 
 int ll_lift_get_mode(void) { return g_lift_mode; }
+
+int ll_lift_set_debug_buffer(long long* buf) {   // undocumented: per-warp phase timestamps (17 x 8 int64)
+  g_lift_dbg_buf = buf;
+  return LL_OK;
+}
 
 int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float res_weight, int linear,
                  ll_stream_t stream) {

@@ -85,6 +85,7 @@ struct LiftParams {
   long long units[2];  // nb * nstrips * nchunks per job
   long long total_units;
   int dbg;             // timing experiments only (lift_tc.cu): bit 0 no MMA, 1 no E-B, 2 no conv1, 3 no conv4, 4 no E-A
+  long long* dbg_buf;  // optional [17 warps][8] clock64 stamps of CTA 0 at global step 40 (lift_tc.cu)
 };
 
 struct f2 {

@@ -89,6 +89,11 @@ __device__ __forceinline__ void split_store(uint8_t* row, int ci, int i, const f
   *reinterpret_cast<float4*>(q + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+#define TC_STAMP(k)                                                                      \
+  do {                                                                                   \
+    if (p.dbg_buf && blockIdx.x == 0 && n == 40 && lane == 0) p.dbg_buf[warp * 8 + (k)] = clock64(); \
+  } while (0)
+
 struct TcSeg {
   int j, b, x0, ya, yb, ny, nx;
 };
@@ -277,8 +282,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
       const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
       if (warp == TC_MMA_WARP) {
         // ======================= MMA warp =======================
+        TC_STAMP(0);
         mbar_wait(bar_free, n & 1);
         tc_fence_after();
+        TC_STAMP(1);
         const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
         if (elect_one()) {
           if (m2 && !(p.dbg & 1)) {
@@ -320,15 +327,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           tc_commit(bar_mma);
         }
         __syncwarp();
+        TC_STAMP(2);
       } else if (warp < 8) {
         // ======================= epilogue warps =======================
         const int r4 = t - 11;
         const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && tid < 128;   // warps 0-3: pixel pairs 0..15
         float dv[2];
         load_din(r4, tid, do4, dv);
+        TC_STAMP(0);
         // ---- E-A: accumulators of the previous step -> partial planes ----
         if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
         tc_fence_after();
+        TC_STAMP(1);
         {
           const int q = warp & 3, hs = warp >> 2, m = q * 32 + lane;
           if (q < 3 && !(p.dbg & 16)) {
@@ -359,7 +369,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_free);
         }
+        TC_STAMP(2);
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        TC_STAMP(3);
 
         // ---- E-B: conv2 row r2e -> a2 ring; conv3 row r3e -> a3 ring ----
         {
@@ -408,7 +420,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             *reinterpret_cast<float4*>(A3 + ((r3e % TC_R3) * 16 + co) * TC_P3 + i0) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
+        TC_STAMP(4);
         if (do4) conv4_out(r4, tid, true, dv);
+        TC_STAMP(5);
         fence_proxy_async();   // a2 ring writes -> visible to the tensor core's operand reads
       } else {
         // ======================= SIMT warps =======================
@@ -433,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         const bool act4 = st < 208;
         float dv[2];
         load_din(r4, st, do4 && act4, dv);     // c4 = 128 + (st - 128) = st
+        TC_STAMP(0);
         // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
         if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
           const int cp = st & 7, i1 = 4 * (st >> 3);
@@ -470,17 +485,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
           }
         }
+        TC_STAMP(1);
         // ---- conv4 + output row t-11, pixel pairs 16..25 ----
         if (do4) conv4_out(r4, st, act4, dv);
+        TC_STAMP(2);
         // ---- skip row t+3 (values loaded at the top of the step) ----
         if (do_sk) {
           float v = 0.f;
           if (sk_in) v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
           SK[(rs & (TC_RS - 1)) * TC_PS + (st - 188)] = v;
         }
+        TC_STAMP(3);
         fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
       }
+      TC_STAMP(6);
       __syncthreads();
+      TC_STAMP(7);
     }
   }
 

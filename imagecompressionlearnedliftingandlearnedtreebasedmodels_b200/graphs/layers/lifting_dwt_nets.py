@@ -8,7 +8,7 @@ constructors, sub-module names and parameter registration order as the reference
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import _autograd, ops
 from ...compat import GDN, DWTForward, DWTInverse
 from ._packing import PackCache
 from .P_block_v2 import P_block_v2
@@ -58,14 +58,14 @@ class SubbandAutoEncoder(nn.Module):
         return cache.get(flat, lambda: ops.pack_ae1(layers, self.in_ch, transposed))
 
     def encode(self, x):
-        return ops.ae1_apply(x, self._blob(self.ae_down, self._down_cache, False))
+        return _autograd.run_module(lambda x: ops.ae1_apply(x, self._blob(self.ae_down, self._down_cache, False)), self.ae_down, x)
 
     def encode_and_round(self, x):
         """(y, round(y)): the quantiser's rounding fused into the same pass."""
         return ops.ae1_apply(x, self._blob(self.ae_down, self._down_cache, False), want_round=True)
 
     def decode(self, y_hat):
-        return ops.ae1_apply(y_hat, self._blob(self.ae_up, self._up_cache, True))
+        return _autograd.run_module(lambda y: ops.ae1_apply(y, self._blob(self.ae_up, self._up_cache, True)), self.ae_up, y_hat)
 
 
 class SubbandAutoEncoderBerk(nn.Module):

@@ -5,7 +5,7 @@ Same parameters and ``mask`` buffer; like the reference, ``forward`` multiplies 
 """
 from torch import nn
 
-from ... import ops
+from ... import _autograd, _torch_ref, ops
 
 
 class MaskedConv2d(nn.Conv2d):
@@ -27,4 +27,8 @@ class MaskedConv2d(nn.Conv2d):
 
     def forward(self, x, lrelu=False, **remap):
         self.apply_mask()
+        if _autograd.needs_grad([x, self.weight, self.bias]) and not remap:
+            g = self.groups
+            return _autograd.run(lambda x, w, b: ops.conv2d(x, w, b, groups=g, lrelu=lrelu),
+                                 lambda x, w, b: _torch_ref.conv2d(x, w, b, g, lrelu, False), [x, self.weight, self.bias])
         return ops.conv2d(x, self.weight, self.bias, groups=self.groups, lrelu=lrelu, **remap)

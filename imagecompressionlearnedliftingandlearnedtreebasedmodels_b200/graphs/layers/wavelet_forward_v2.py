@@ -8,7 +8,7 @@ transpose or interleave copies), composed in C++ by ``ll_lift_level_fwd``.
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import _autograd, _torch_ref, ops
 from ._packing import PackCache
 
 lifting_coeff = [-1.586134342059924, -0.052980118572961, 0.882911075530934, 0.443506852043971, 0.869864451624781,
@@ -18,6 +18,18 @@ lifting_coeff = [-1.586134342059924, -0.052980118572961, 0.882911075530934, 0.44
 def step_sources(P, U, convBlock):
     """step k -> (pre-filter conv, CNN block): 1:P[0] 2:U[0] 3:P[1] 4:U[1] (wavelet_forward_v2.py:60-74)."""
     return [(convBlock[0], P[0]), (convBlock[1], U[0]), (convBlock[2], P[1]), (convBlock[3], U[1])]
+
+
+def step_params(P, U, convBlock, nh, nl, like):
+    """The 38 tensors ``_torch_ref.lift_level_*`` takes: per step (pre-filter, w1, b1, ..., w4, b4), then nh, nl."""
+    ts = []
+    for pre, blk in step_sources(P, U, convBlock):
+        ts.append(pre.weight)
+        for k in ("conv1", "conv2", "conv3", "conv4"):
+            ts += [getattr(blk, k).weight, getattr(blk, k).bias]
+    for n in (nh, nl):
+        ts.append(n if torch.is_tensor(n) else torch.zeros(1, 1, 1, 1, device=like.device, dtype=like.dtype))
+    return ts
 
 
 def pack_steps(cache, P, U, convBlock):
@@ -58,6 +70,13 @@ class wavelet_forward_v2(nn.Module):
     def level(self, x, ll_out=None, yh_out=None):
         """Same, returning (LL, Yh=(B,3,h/2,w/2) [LH,HL,HH]) without slicing."""
         scale = 1 if self.scale == 1 else 0
+        params = step_params(self.P, self.U, self.convBlock, self.nh, self.nl, x)
+        if _autograd.needs_grad([x] + params):
+            # training: forward on the fused kernels, backward by recomputation in torch (see _autograd.py)
+            fast = lambda x, *ps: ops.lift_level_fwd(x, self._blobs(), self.resnet_weight, self._linear(), scale,
+                                                     self.nh if scale else None, self.nl if scale else None)
+            ref = lambda x, *ps: _torch_ref.lift_level_fwd(x, ps, self.resnet_weight, self._linear(), scale)
+            return _autograd.run(fast, ref, [x] + params)
         return ops.lift_level_fwd(x, self._blobs(), self.resnet_weight, self._linear(), scale,
                                   self.nh if scale else None, self.nl if scale else None, ll_out, yh_out)
 

@@ -5,9 +5,9 @@ update of each half, not copies."""
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import _autograd, _torch_ref, ops
 from ._packing import PackCache
-from .wavelet_forward_v2 import lifting_coeff, pack_steps
+from .wavelet_forward_v2 import lifting_coeff, pack_steps, step_params
 
 
 class wavelet_inverse_v2(nn.Module):
@@ -37,8 +37,11 @@ class wavelet_inverse_v2(nn.Module):
 
     def level(self, LL, Yh):
         scale = 1 if self.scale == 1 else 0
-        return ops.lift_level_inv(LL, Yh, self._blobs(), self.resnet_coeff, self._linear(), scale,
-                                  self.nh if scale else None, self.nl if scale else None)
+        params = step_params(self.P, self.U, self.convBlock, self.nh, self.nl, LL)
+        fast = lambda ll, yh, *ps: ops.lift_level_inv(ll, yh, self._blobs(), self.resnet_coeff, self._linear(), scale,
+                                                      self.nh if scale else None, self.nl if scale else None)
+        ref = lambda ll, yh, *ps: _torch_ref.lift_level_inv(ll, yh, ps, self.resnet_coeff, self._linear(), scale)
+        return _autograd.run(fast, ref, [LL, Yh] + params)
 
     def reconstruct_fun(self, up, bot):
         """Interleave along dim 2, then transpose (wavelet_inverse_v2.py:40-56)."""

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from ... import compat
+from ... import _autograd, _torch_ref, compat
 from ...compat import EntropyBottleneck, GaussianConditional
 from ..layers._packing import PackCache
 from ..layers.lifting_dwt_nets import DWTPytorchWaveletsLayer, LiftingBasedNeuralWaveletv4
@@ -33,11 +33,18 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
     return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
 
 
-def _conv(seq_item, x, lrelu=False, **kw):
-    """nn.Conv2d / MaskedConv2d through the direct-conv kernel."""
+def _conv(seq_item, x, lrelu=False, upsample2=False, **kw):
+    """nn.Conv2d / MaskedConv2d through the direct-conv kernel (differentiable: backward recomputes the conv
+    with torch ops, see _autograd.py; the channel-remapped ``out=`` form is inference-only)."""
     if isinstance(seq_item, MaskedConv2d):
-        return seq_item(x, lrelu=lrelu, **kw)
-    return ops.conv2d(x, seq_item.weight, seq_item.bias, groups=seq_item.groups, lrelu=lrelu, **kw)
+        seq_item.apply_mask()
+    w, b, g = seq_item.weight, seq_item.bias, seq_item.groups
+    if _autograd.needs_grad([x, w, b]):
+        if kw:
+            raise RuntimeError("the channel-remapped conv output is not differentiable; use the plain form")
+        return _autograd.run(lambda x, w, b: ops.conv2d(x, w, b, groups=g, lrelu=lrelu, upsample2=upsample2),
+                             lambda x, w, b: _torch_ref.conv2d(x, w, b, g, lrelu, upsample2), [x, w, b])
+    return ops.conv2d(x, w, b, groups=g, lrelu=lrelu, upsample2=upsample2, **kw)
 
 
 def _chain(seq, x):
@@ -308,6 +315,17 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
             del h2
         return bits
 
+    def _level_grad(self, i, x, q, con):
+        """Differentiable form of ``_level`` (training): same kernels in the forward pass, the concat is a
+        torch op instead of a write pattern, every conv recomputes through torch in backward."""
+        plc, cgp, csc = self.plc_list[i], self.cgp_out_xo_list[i], self.csc_list[i]
+        c = _conv(csc, q)
+        t = _conv(plc[0], con, lrelu=True, upsample2=True)
+        pl = _conv(plc[2], t)
+        p0, p1, p2 = pl.chunk(3, dim=1)
+        c0, c1, c2 = c.chunk(3, dim=1)
+        return _chain(cgp, torch.cat((p0, c0, p1, c1, p2, c2), dim=1))
+
     def _level(self, i, x, q, con):
         """sigma/mu maps (B,6,h,w) of conditioned level i from the quantised child ``q`` and the
         half-resolution quantised parent ``con`` (:352-362) -- exact-fp32 SIMT path
@@ -342,7 +360,10 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         con = q
         for i in range(L - 2, -1, -1):
             q = self.ent_out_xo_list[i].quantize(out_xo_list[i], mode)
-            if self.ctx_precision == "bf16":
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                ms = self._level_grad(i, out_xo_list[i], q, con)
+                sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], ms, self.training, acc=acc))
+            elif self.ctx_precision == "bf16":
                 noise = compat.draw_noise(out_xo_list[i]) if self.training else None
                 sis.append(self._level_bits_tc(i, out_xo_list[i].contiguous(), q, con, noise, acc))
             else:
@@ -485,6 +506,9 @@ class onlyEZWT(nn.Module):
             # would move it by ~1e-3.  (cond2ZT returns plain round(x): there mu only feeds the rate.)
             for b0 in range(0, B, CTX_BATCH_CHUNK):
                 b1 = min(B, b0 + CTX_BATCH_CHUNK)
+                if torch.is_grad_enabled() and any(p.requires_grad for p in plc.parameters()):
+                    ms = _chain(plc[2:], _conv(plc[0], con, lrelu=True, upsample2=True))   # differentiable, whole batch
+                    break
                 t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
                 t = ops.conv2d(t, plc[2].weight, plc[2].bias, lrelu=True)
                 ops.conv2d(t, plc[4].weight, plc[4].bias, out=ms[b0:b1])

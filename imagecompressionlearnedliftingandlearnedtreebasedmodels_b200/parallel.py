@@ -44,3 +44,46 @@ def sum_over_ranks(values, device=None, group=None):
     t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [float(v) for v in t.tolist()]
+
+
+def allreduce_gradients(params, bucket_bytes=32 << 20, group=None):
+    """Data-parallel training (BASELINE config 4): average the gradients of ``params`` over ranks with
+    flat fp32 buckets (one ``all_reduce`` sum per bucket over NCCL / NVLink, or gloo in the CPU tests).
+    Parameters without a gradient on this rank (``nh``/``nl`` when ``scale: 0``) contribute zeros, so every
+    rank issues the same collectives.  Returns the number of collectives issued."""
+    params = [p for p in params if p.requires_grad]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    n_coll, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal n_coll, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        n_coll += 1
+        bucket, size = [], 0
+
+    seen = set()
+    for p in params:
+        if id(p) in seen:          # shared lifting blocks are registered under several names
+            continue
+        seen.add(id(p))
+        bucket.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return n_coll

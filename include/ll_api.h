@@ -123,6 +123,9 @@ int ll_dwt97_inv(const float* yl, const float* const* yh, float* x, float* scrat
 #define LL_LIFT_TC 1
 int ll_lift_set_mode(int mode);
 int ll_lift_get_mode(void);
+/* Profiling aid: device buffer of 17 x 8 int64 that receives per-warp clock64() stamps of one step of CTA 0
+ * of the tensor-core lifting kernel (NULL = off). */
+int ll_lift_set_debug_buffer(long long* buf);
 
 /* ------------------------------------------------------------------------- */
 /* Pointwise subband auto-encoder (v1) fused with the quantiser               */

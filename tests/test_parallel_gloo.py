@@ -56,3 +56,42 @@ def test_tiles_config5():
         assert (y1 - y0) % 32 == 0 and (x1 - x0) % 32 == 0           # 5 lifting levels divide evenly
         cover[y0:y1, x0:x1] += 1
     assert int(cover.min()) == 1 and int(cover.max()) == 1
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        shared = torch.nn.Parameter(torch.zeros(5))
+        ps = [torch.nn.Parameter(torch.zeros(3, 4)), shared, shared, torch.nn.Parameter(torch.zeros(7)),
+              torch.nn.Parameter(torch.zeros(2), requires_grad=False)]
+        ps[0].grad = torch.full((3, 4), float(rank + 1))
+        shared.grad = torch.arange(5.0) * (rank + 1)
+        # ps[3] has no gradient on rank 1 (an unused parameter there): treated as zeros
+        if rank == 0:
+            ps[3].grad = torch.ones(7)
+        n = parallel.allreduce_gradients(ps, bucket_bytes=40)   # tiny buckets: several collectives
+        if rank == 0:
+            out.put((n, ps[0].grad.tolist(), shared.grad.tolist(), ps[3].grad.tolist(), ps[4].grad))   # plain lists: no shm handles
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    n, g0, gs, g3, g4 = q.get()
+    assert n >= 2
+    assert torch.allclose(torch.tensor(g0), torch.full((3, 4), 1.5))
+    assert torch.allclose(torch.tensor(gs), torch.arange(5.0) * 1.5)
+    assert torch.allclose(torch.tensor(g3), torch.full((7,), 0.5))
+    assert g4 is None
