@@ -23,9 +23,9 @@
 //   epilogue warps 0-7: [E-A] accumulators of the previous step: TMEM -> shared partial planes
 //                       [E-B] conv2 row t-4: sum dx, bias, tanh, hi/lo split -> a2 ring
 //                             conv3 row t-8: sum dx, bias, + o1 -> a3 ring (fp32)
-//                       conv4 + output row t-11, pixel pairs 0..15 (FP32 FFMA2)
-//   SIMT warps 8-15:    conv1 row t (FP32 FFMA2) -> a1 ring (hi/lo) and o1 ring; conv4 + output
-//                       pixel pairs 16..25; skip row t+3; global loads issued first, used last
+//                       skip row t+3 (global loads issued first, stored last)
+//   SIMT warps 8-11:    conv1 row t (FP32 FFMA2, 4 px x 2 ch per thread) -> a1 ring (hi/lo) and o1 ring
+//   SIMT warps 12-15:   conv4 + output row t-11 (FP32 FFMA2, 4 px x 2 ch per thread, a3 channel pairs interleaved)
 //   MMA warp 16:        after the epilogue warps freed the accumulators: conv2 row t-3 and conv3
 //                       row t-7 (60 tcgen05.mma), one tcgen05.commit.
 // One block barrier per step; a row produced in step s is consumed in steps > s, ring depths follow.
@@ -109,14 +109,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   float* P3 = reinterpret_cast<float*>(gen + TS_P3);
   float* SK = reinterpret_cast<float*>(gen + TS_SK);
   float* SW = reinterpret_cast<float*>(gen + TS_W);
-  const uint32_t bar_mma = base + TS_BAR, bar_free = base + TS_BAR + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + TS_BAR + 16);
+  const uint32_t bar_mma = base + TS_BAR, bar_free = base + TS_BAR + 8, bar_free3 = base + TS_BAR + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + TS_BAR + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (tid == 0) {
     mbar_init(bar_mma, 1);
     mbar_init(bar_free, 8);
+    mbar_init(bar_free3, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -207,46 +208,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
       SK[(rr & (TC_RS - 1)) * TC_PS + j] = v;
     };
 
-    // conv4 + output, 2 pixels x 2 input channels per thread (c4 in [0,208): ci pair = c4 & 7, pixel pair = c4 >> 3),
-    // packed FFMA2 over the channel pair, 8-lane shuffle reduction; dv = din of the two pixels (loaded early)
-    auto conv4_out = [&](int r4, int c4, bool active, const float (&dv)[2]) {
-      const int cp = c4 & 7, pp = c4 >> 3;
-      float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    // conv4 + output, 4 pixels x 2 input channels per thread (c4 in [0,104): ci pair = c4 & 7, pixel quad = c4 >> 3).
+    // a3 is stored with the two channels of a pair interleaved ([row][pair][col][2]) so (a3[2cp], a3[2cp+1]) of a
+    // column is one aligned register pair: packed FFMA2 against the weight pair, no operand shuffling.
+    auto conv4_out = [&](int r4, int c4, bool active, const float (&dv)[4]) {
+      const int cp = c4 & 7, pq = c4 >> 3;
+      float2 acc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.f, 0.f);
       if (active) {
 #pragma unroll
         for (int dy = 0; dy < 5; ++dy) {
           const int rr = r4 + dy - 2;
           if (rr >= 0 && rr < s.ny) {
-            const float* ar = A3 + ((rr % TC_R3) * 16 + 2 * cp) * TC_P3 + 2 * pp;
-            float w0[6], w1[6];
-#pragma unroll
-            for (int k = 0; k < 6; k += 2) {
-              const float2 a = *reinterpret_cast<const float2*>(ar + k), b = *reinterpret_cast<const float2*>(ar + TC_P3 + k);
-              w0[k] = a.x; w0[k + 1] = a.y; w1[k] = b.x; w1[k + 1] = b.y;
-            }
+            const float* ar = A3 + ((rr % TC_R3) * 8 + cp) * (2 * TC_P3) + 8 * pq;     // columns 4pq .. 4pq+7, 2 channels each
+            const float4 v0 = *reinterpret_cast<const float4*>(ar), v1 = *reinterpret_cast<const float4*>(ar + 4),
+                         v2 = *reinterpret_cast<const float4*>(ar + 8), v3 = *reinterpret_cast<const float4*>(ar + 12);
+            const float2 col[8] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w),
+                                   make_float2(v2.x, v2.y), make_float2(v2.z, v2.w), make_float2(v3.x, v3.y), make_float2(v3.z, v3.w)};
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx) {
               const float2 w = *reinterpret_cast<const float2*>(SW + SW_W4 + (dy * 5 + dx) * 16 + 2 * cp);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) acc[k] = __ffma2_rn(make_float2(w0[k + dx], w1[k + dx]), w, acc[k]);
+              for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(col[k + dx], w, acc[k]);
             }
           }
         }
       }
-      float a2[2] = {acc[0].x + acc[0].y, acc[1].x + acc[1].y};
+      float a4[4];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], 1);
-        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], 2);
-        a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], 4);
+      for (int k = 0; k < 4; ++k) {
+        a4[k] = acc[k].x + acc[k].y;
+        a4[k] += __shfl_xor_sync(0xffffffffu, a4[k], 1);
+        a4[k] += __shfl_xor_sync(0xffffffffu, a4[k], 2);
+        a4[k] += __shfl_xor_sync(0xffffffffu, a4[k], 4);
       }
       if (active && cp == 0) {
         const float b4 = SW[SW_B4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int jx = 2 * pp + k, c = s.x0 + jx;
+        for (int k = 0; k < 4; ++k) {
+          const int jx = 4 * pq + k, c = s.x0 + jx;
           if (c < s.nx) {
-            const float net = __fadd_rn(a2[k], b4);
+            const float net = __fadd_rn(a4[k], b4);
             const float sk = SK[(r4 & (TC_RS - 1)) * TC_PS + jx + 8];
             const float tn = __fmul_rn(net, p.rw);
             const float o = p.sign > 0.f ? __fadd_rn(__fadd_rn(dv[k], sk), tn)
@@ -256,12 +259,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         }
       }
     };
-    auto load_din = [&](int r4, int c4, bool active, float (&dv)[2]) {
-      dv[0] = dv[1] = 0.f;
+    auto load_din = [&](int r4, int c4, bool active, float (&dv)[4]) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dv[k] = 0.f;
       if (active && (c4 & 7) == 0) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int c = s.x0 + 2 * (c4 >> 3) + k;
+        for (int k = 0; k < 4; ++k) {
+          const int c = s.x0 + 4 * (c4 >> 3) + k;
           if (c < s.nx) dv[k] = J.din.ptr[(long long)s.b * J.din.sb + (long long)r4 * J.din.sy + (long long)c * J.din.sx];
         }
       }
@@ -306,6 +310,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               }
             }
           }
+        }
+        mbar_wait(bar_free3, n & 1);
+        tc_fence_after();
+        if (elect_one()) {
           if (m3 && !(p.dbg & 1)) {
             uint32_t acc = 0;
 #pragma unroll
@@ -330,10 +338,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         TC_STAMP(2);
       } else if (warp < 8) {
         // ======================= epilogue warps =======================
-        const int r4 = t - 11;
-        const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && tid < 128;   // warps 0-3: pixel pairs 0..15
-        float dv[2];
-        load_din(r4, tid, do4, dv);
+        // skip row t+3 (threads 128..195): global loads first, shared-memory store at the end of the step
+        const int rs = t + 3;
+        const bool do_sk = tid >= 128 && tid < 196 && rs >= sk_lo && rs < sk_hi;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        bool sk_in = false;
+        if (do_sk) {
+          const int c = s.x0 - 8 + (tid - 128);
+          sk_in = c >= 0 && c < s.nx;
+          if (sk_in) {
+            const float* q = srcb + (long long)rs * J.src.sy + (long long)c * J.src.sx;
+            s0 = rs > 0 ? q[-J.src.sy] : 0.f;
+            s1 = q[0];
+            s2 = rs + 1 < s.ny ? q[J.src.sy] : 0.f;
+          }
+        }
         TC_STAMP(0);
         // ---- E-A: accumulators of the previous step -> partial planes ----
         if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
@@ -341,33 +360,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         TC_STAMP(1);
         {
           const int q = warp & 3, hs = warp >> 2, m = q * 32 + lane;
-          if (q < 3 && !(p.dbg & 16)) {
-            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + 32 * hs;
-            uint32_t v[32];
-            if (e2) {
-              tc_ld32(ta + TM_ACC2, v);
-              tc_wait_ld();
-              if (m < 80) {
-                float* o = P2 + m * TC_PP + 32 * hs;
+          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + 32 * hs;
+          uint32_t v[32];
+          if (q < 3 && e2 && !(p.dbg & 16)) {
+            tc_ld32(ta + TM_ACC2, v);
+            tc_wait_ld();
+            if (m < 80) {
+              float* o = P2 + m * TC_PP + 32 * hs;
 #pragma unroll
-                for (int k = 0; k < 32; k += 4)
-                  *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-              }
-            }
-            if (e3) {
-              tc_ld32(ta + TM_ACC3, v);
-              tc_wait_ld();
-              if (m < 80) {
-                float* o = P3 + m * TC_PP + 32 * hs;
-#pragma unroll
-                for (int k = 0; k < 32; k += 4)
-                  *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-              }
+              for (int k = 0; k < 32; k += 4)
+                *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
             }
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free);
+          if (lane == 0) mbar_arrive(bar_free);          // conv2 accumulator drained
+          if (q < 3 && e3 && !(p.dbg & 16)) {
+            tc_ld32(ta + TM_ACC3, v);
+            tc_wait_ld();
+            if (m < 80) {
+              float* o = P3 + m * TC_PP + 32 * hs;
+#pragma unroll
+              for (int k = 0; k < 32; k += 4)
+                *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free3);         // conv3 accumulator drained
         }
         TC_STAMP(2);
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -397,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             }
             split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
           }
-          if (e3 && xq < 14 && !(p.dbg & 2)) {
+          if (e3 && !(p.dbg & 2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
             float sacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx) {
@@ -417,36 +437,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
               v[k] = (c >= 0 && c < s.nx) ? x : 0.f;
             }
-            *reinterpret_cast<float4*>(A3 + ((r3e % TC_R3) * 16 + co) * TC_P3 + i0) = make_float4(v[0], v[1], v[2], v[3]);
+            // the partner lane (xor 16) holds the other channel of the pair for the same 4 columns
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __shfl_xor_sync(0xffffffffu, v[k], 16);
+            float* dst = A3 + ((r3e % TC_R3) * 8 + (co >> 1)) * (2 * TC_P3) + 2 * i0;
+            if (xq < 14) {
+              if (co & 1) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[2], v[2], o[3], v[3]);   // columns i0+2, i0+3
+              else *reinterpret_cast<float4*>(dst) = make_float4(v[0], o[0], v[1], o[1]);               // columns i0, i0+1
+            }
           }
         }
         TC_STAMP(4);
-        if (do4) conv4_out(r4, tid, true, dv);
+        if (do_sk) {
+          float v = 0.f;
+          if (sk_in) v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
+          SK[(rs & (TC_RS - 1)) * TC_PS + (tid - 128)] = v;
+        }
         TC_STAMP(5);
         fence_proxy_async();   // a2 ring writes -> visible to the tensor core's operand reads
       } else {
         // ======================= SIMT warps =======================
-        // warps 8-11 (st < 128): conv1; warps 12-14 (st 128..223): conv4 pixel pairs 16..25; st >= 188: skip row
+        // warps 8-11 (st < 128): conv1; warps 12-15 (st 128..255): conv4 + output (104 active threads)
         const int st = tid - 256;
-        const int rs = t + 3, r4 = t - 11;
-        // global loads first (their latency hides behind the arithmetic)
-        const bool do_sk = st >= 188 && rs >= sk_lo && rs < sk_hi;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        bool sk_in = false;
-        if (do_sk) {
-          const int c = s.x0 - 8 + (st - 188);
-          sk_in = c >= 0 && c < s.nx;
-          if (sk_in) {
-            const float* q = srcb + (long long)rs * J.src.sy + (long long)c * J.src.sx;
-            s0 = rs > 0 ? q[-J.src.sy] : 0.f;
-            s1 = q[0];
-            s2 = rs + 1 < s.ny ? q[J.src.sy] : 0.f;
-          }
-        }
-        const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && st >= 128 && st < 224;
-        const bool act4 = st < 208;
-        float dv[2];
-        load_din(r4, st, do4 && act4, dv);     // c4 = 128 + (st - 128) = st
+        const int r4 = t - 11;
+        const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && st >= 128;
+        const bool act4 = st - 128 < 104;
+        float dv[4];
+        load_din(r4, st - 128, do4 && act4, dv);     // global loads first; used at the end of conv4
         TC_STAMP(0);
         // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
         if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
@@ -486,16 +504,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           }
         }
         TC_STAMP(1);
-        // ---- conv4 + output row t-11, pixel pairs 16..25 ----
-        if (do4) conv4_out(r4, st, act4, dv);
+        // ---- conv4 + output row t-11 ----
+        if (do4) conv4_out(r4, st - 128, act4, dv);
         TC_STAMP(2);
-        // ---- skip row t+3 (values loaded at the top of the step) ----
-        if (do_sk) {
-          float v = 0.f;
-          if (sk_in) v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
-          SK[(rs & (TC_RS - 1)) * TC_PS + (st - 188)] = v;
-        }
-        TC_STAMP(3);
         fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
       }
       TC_STAMP(6);

@@ -147,6 +147,17 @@ tc_tf32_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
       for (int j = 0; j < 32; ++j) D[(long long)tid * TP_N + c * 32 + j] = __uint_as_float(v[j]);
     }
   }
+  if (split & 16) {
+    // debug: raw registers of 16x256b.x4 loads at lane offsets 0 / 16 of the warp's quarter, column offset 3:
+    // D is overwritten with [warp 4][half 2][lane 32][reg 16] (4096 floats of the 8192)
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[16];
+      tc_ld16x256b_x4(tmem + ((uint32_t)(warp * 32 + 16 * h) << 16) + 384 + 3, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[((warp * 2 + h) * 32 + lane) * 16 + j] = __uint_as_float(v[j]);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
