@@ -47,7 +47,8 @@ constexpr int TC_R3 = 6;         // a3 ring rows
 constexpr int TC_RO = 9;         // o1 ring rows
 constexpr int TC_RS = 16;        // skip ring rows
 constexpr int TC_SLOT = 8192;    // bytes per a1/a2 ring row: [term 2][cig 2][na 2][ka 2][4 ch][128 B]
-constexpr int TC_P3 = 60;        // a3 / o1 pitch (floats)
+constexpr int TC_P3 = 60;        // o1 pitch (floats)
+constexpr int TC_PA3 = 124;      // a3 channel-pair pitch: 60 columns x 2 channels (+4: pairs land on distinct bank groups)
 constexpr int TC_PP = 68;        // partial-plane pitch
 constexpr int TC_PS = 72;        // skip pitch
 // tensor-memory columns
@@ -57,7 +58,7 @@ constexpr int TM_ACC2 = 320, TM_ACC3 = 384;
 constexpr int TS_RA1 = 0;
 constexpr int TS_RA2 = TS_RA1 + TC_RA * TC_SLOT;
 constexpr int TS_A3 = TS_RA2 + TC_RA * TC_SLOT;
-constexpr int TS_O1 = TS_A3 + TC_R3 * 16 * TC_P3 * 4;
+constexpr int TS_O1 = TS_A3 + TC_R3 * 8 * TC_PA3 * 4;
 constexpr int TS_P2 = TS_O1 + TC_RO * 16 * TC_P3 * 4;
 constexpr int TS_P3 = TS_P2 + 80 * TC_PP * 4;
 constexpr int TS_SK = TS_P3 + 80 * TC_PP * 4;
@@ -75,6 +76,14 @@ static_assert(TS_RA2 % 1024 == 0 && TS_A3 % 16 == 0 && TS_O1 % 16 == 0 && TS_P2 
 __device__ __forceinline__ int ring_off(int ci, int i) {
   const int r = ci & 3;
   return (ci >> 3) * 2048 + (i >> 5) * 1024 + ((ci >> 2) & 1) * 512 + r * 128 + ((((i & 31) >> 3) ^ r) << 5) + ((i & 7) << 2);
+}
+
+// 128-bit shared load the compiler may not narrow (scalar loads at a 16-byte lane stride are 4-way bank conflicted)
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  asm volatile("" ::"f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));   // all four lanes stay live: ptxas keeps the 128-bit access
+  return v;
 }
 
 __device__ __forceinline__ void split_store(uint8_t* row, int ci, int i, const float (&v)[4]) {
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         for (int dy = 0; dy < 5; ++dy) {
           const int rr = r4 + dy - 2;
           if (rr >= 0 && rr < s.ny) {
-            const float* ar = A3 + ((rr % TC_R3) * 8 + cp) * (2 * TC_P3) + 8 * pq;     // columns 4pq .. 4pq+7, 2 channels each
+            const float* ar = A3 + ((rr % TC_R3) * 8 + cp) * TC_PA3 + 8 * pq;     // columns 4pq .. 4pq+7, 2 channels each
             const float4 v0 = *reinterpret_cast<const float4*>(ar), v1 = *reinterpret_cast<const float4*>(ar + 4),
                          v2 = *reinterpret_cast<const float4*>(ar + 8), v3 = *reinterpret_cast<const float4*>(ar + 12);
             const float2 col[8] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w),
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx) {
               const float* pr = P2 + (dx * 16 + co) * TC_PP + i0;
-              const float4 a = *reinterpret_cast<const float4*>(pr), b = *reinterpret_cast<const float4*>(pr + 4);
+              const float4 a = lds128(pr), b = lds128(pr + 4);
               const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) sacc[k] = __fadd_rn(sacc[k], win[k + dx]);
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx) {
               const float* pr = P3 + (dx * 16 + co) * TC_PP + i0;
-              const float4 a = *reinterpret_cast<const float4*>(pr), b = *reinterpret_cast<const float4*>(pr + 4);
+              const float4 a = lds128(pr), b = lds128(pr + 4);
               const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) sacc[k] = __fadd_rn(sacc[k], win[k + dx]);
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = __shfl_xor_sync(0xffffffffu, v[k], 16);
-            float* dst = A3 + ((r3e % TC_R3) * 8 + (co >> 1)) * (2 * TC_P3) + 2 * i0;
+            float* dst = A3 + ((r3e % TC_R3) * 8 + (co >> 1)) * TC_PA3 + 2 * i0;
             if (xq < 14) {
               if (co & 1) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[2], v[2], o[3], v[3]);   // columns i0+2, i0+3
               else *reinterpret_cast<float4*>(dst) = make_float4(v[0], o[0], v[1], o[1]);               // columns i0, i0+1
@@ -468,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         TC_STAMP(0);
         // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
         if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
-          const int cp = st & 7, i1 = 4 * (st >> 3);
+          const int cp = st >> 4, i1 = 4 * (st & 15);   // 16 consecutive lanes = the 16 pixel quads of one channel pair
           const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
           float2 acc[4] = {b1, b1, b1, b1};
 #pragma unroll
