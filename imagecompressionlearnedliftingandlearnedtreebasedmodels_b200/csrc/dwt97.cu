@@ -45,7 +45,7 @@ __device__ __forceinline__ void cp_wait() {
 // tile at sm + DFF_SM_IN and lo/hi at fixed offsets, so buffer b is presented by shifting the
 // base pointer: lo/hi live at the same absolute place for both (layout below).
 constexpr int DFF_IN_FLOATS = DWF_R * DFF_PI;
-constexpr int DFF_PIPE_TOTAL = 2 * DFF_IN_FLOATS + 2 * DWF_R * DFF_PM;
+constexpr int DFF_PIPE_TOTAL = 2 * DFF_IN_FLOATS + DWF_R * DFF_PM;
 
 __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];

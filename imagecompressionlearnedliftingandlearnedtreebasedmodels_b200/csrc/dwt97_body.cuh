@@ -257,11 +257,17 @@ LL_HD void dwti_rows(const DwtParams& p, const DwtTile& t, const float* sm, int 
 namespace ll {
 
 constexpr int DFF_PI = 2 * DW_TX + 12;   // 140: input tile pitch (== 12 mod 32)
-constexpr int DFF_PM = DW_TX + 16;       // 80:  mid pitch (== 16 mod 32)
+constexpr int DFF_PM = 2 * DW_TX + 8;    // 136: mid pitch; a mid row holds (lo, hi) pairs interleaved per column
 constexpr int DFF_SM_IN = 0;
-constexpr int DFF_SM_LO = DFF_SM_IN + DWF_R * DFF_PI;
-constexpr int DFF_SM_HI = DFF_SM_LO + DWF_R * DFF_PM;
-constexpr int DFF_SM_TOTAL = DFF_SM_HI + DWF_R * DFF_PM;
+constexpr int DFF_SM_LO = DFF_SM_IN + DWF_R * DFF_PI;   // mid base
+constexpr int DFF_SM_TOTAL = DFF_SM_LO + DWF_R * DFF_PM;
+
+// analysis / synthesis tap pairs for packed FFMA2: one broadcast sample feeds the low-pass and the
+// high-pass (or the even and the odd polyphase) accumulator in one instruction.  A zero tap leaves its
+// accumulator untouched (fma(0, v, acc) == acc), so the results equal the scalar tap loops bit for bit.
+#define LL_DEC_PAIR(k) (f2{LL_DEC_LO(k), LL_DEC_HI(k)})
+#define LL_RECL_PAIR(t) (f2{LL_REC_LO(2 * (t)), LL_REC_LO(2 * (t) + 1)})
+#define LL_RECH_PAIR(t) (f2{LL_REC_HI(2 * (t)), LL_REC_HI(2 * (t) + 1)})
 
 // fast wrap for indices that are at most a few extents out of range
 LL_HD int wrapf(int a, int n) {
@@ -282,16 +288,18 @@ struct CopySync16 {  // host emulation / generic: plain 16-byte copy
 template <class CP>
 LL_HD void dwtff_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, CP cp) {
   const float* base = p.x + (long long)t.n * p.x_sn;
-  constexpr int C4 = DWF_C / 4;
-  for (int e = tid; e < DWF_R * C4; e += DW_THREADS) {
-    const int rr = e / C4, c4 = e % C4;
+  constexpr int C4 = DWF_C / 4;                   // 34 column groups, 7 rows in flight per pass
+  constexpr int RPP = DW_THREADS / C4;
+  if (tid >= C4 * RPP) return;
+  const int c4 = tid % C4, r0 = tid / C4;
+  const float* col = base + wrapf(2 * t.x0 - 4 + 4 * c4, p.w);
+  for (int rr = r0; rr < DWF_R; rr += RPP) {
     const int gr = wrapf(2 * t.y0 - 4 + rr, p.h);
-    const int gc = wrapf(2 * t.x0 - 4 + 4 * c4, p.w);
-    cp(&sm[DFF_SM_IN + rr * DFF_PI + 4 * c4], base + (long long)gr * p.w + gc);
+    cp(&sm[DFF_SM_IN + rr * DFF_PI + 4 * c4], col + (long long)gr * p.w);
   }
 }
 
-// ``in`` / ``mid`` are view bases: the input tile is at in + DFF_SM_IN, lo/hi at mid + DFF_SM_LO/HI
+// ``in`` / ``mid`` are view bases: the input tile is at in + DFF_SM_IN, the mid rows at mid + DFF_SM_LO
 // (same base in the single-buffer layout, different bases in the double-buffered kernel).
 LL_HD void dwtff_rows(const float* in, float* mid, int tid) {
   // item = (row pair, 16 groups of 4 outputs); a warp covers 2 rows x 16 groups
@@ -310,18 +318,16 @@ LL_HD void dwtff_rows(const float* in, float* mid, int tid) {
       v[i + 2] = f.z;
       v[i + 3] = f.w;
     }
-    float lo[4], hi[4];
+    f2 acc[4];   // (lo, hi) of output 4g + i
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      lo[i] = LL_DEC_LO(1) * v[2 * i + 8];
-      hi[i] = LL_DEC_HI(1) * v[2 * i + 8];
+      acc[i] = f2{0.f, 0.f};
 #pragma unroll
-      for (int k = 2; k <= 9; ++k) lo[i] = fmaf(LL_DEC_LO(k), v[2 * i + 9 - k], lo[i]);
-#pragma unroll
-      for (int k = 2; k <= 7; ++k) hi[i] = fmaf(LL_DEC_HI(k), v[2 * i + 9 - k], hi[i]);
+      for (int k = 1; k <= 9; ++k) LL_FMA2(acc[i], v[2 * i + 9 - k], LL_DEC_PAIR(k));
     }
-    *reinterpret_cast<float4*>(&mid[DFF_SM_LO + rr * DFF_PM + 4 * g]) = float4{lo[0], lo[1], lo[2], lo[3]};
-    *reinterpret_cast<float4*>(&mid[DFF_SM_HI + rr * DFF_PM + 4 * g]) = float4{hi[0], hi[1], hi[2], hi[3]};
+    float* o = &mid[DFF_SM_LO + rr * DFF_PM + 8 * g];
+    *reinterpret_cast<float4*>(o) = float4{acc[0].x, acc[0].y, acc[1].x, acc[1].y};
+    *reinterpret_cast<float4*>(o + 4) = float4{acc[2].x, acc[2].y, acc[3].x, acc[3].y};
   }
 }
 
@@ -331,35 +337,26 @@ LL_HD void dwtff_cols(const DwtParams& p, const DwtTile& t, const float* sm, int
   const int nl = tid % DW_TX, mg = tid / DW_TX;   // 64 columns x 4 groups of 4 output rows
   const int gx = t.x0 + nl;
   if (gx >= w2) return;
-  float a[15], b[15];
+  f2 ab[15];   // (row-lo, row-hi) of this column over the 15-row window
 #pragma unroll
-  for (int i = 0; i < 15; ++i) {
-    a[i] = sm[DFF_SM_LO + (8 * mg + i) * DFF_PM + nl];
-    b[i] = sm[DFF_SM_HI + (8 * mg + i) * DFF_PM + nl];
-  }
+  for (int i = 0; i < 15; ++i) ab[i] = *reinterpret_cast<const f2*>(&sm[DFF_SM_LO + (8 * mg + i) * DFF_PM + 2 * nl]);
   float* llp = p.llo + (long long)t.n * p.ll_sn;
   float* yh = p.yho + (long long)t.n * p.yh_sn;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gy = t.y0 + 4 * mg + i;
     if (gy >= h2) break;
-    float LLv = LL_DEC_LO(1) * a[2 * i + 8], LHv = LL_DEC_HI(1) * a[2 * i + 8];
-    float HLv = LL_DEC_LO(1) * b[2 * i + 8], HHv = LL_DEC_HI(1) * b[2 * i + 8];
+    f2 A = f2{0.f, 0.f}, B = f2{0.f, 0.f};   // A = (LL, LH) from the row-low samples, B = (HL, HH) from the row-high ones
 #pragma unroll
-    for (int k = 2; k <= 9; ++k) {
-      LLv = fmaf(LL_DEC_LO(k), a[2 * i + 9 - k], LLv);
-      HLv = fmaf(LL_DEC_LO(k), b[2 * i + 9 - k], HLv);
-    }
-#pragma unroll
-    for (int k = 2; k <= 7; ++k) {
-      LHv = fmaf(LL_DEC_HI(k), a[2 * i + 9 - k], LHv);
-      HHv = fmaf(LL_DEC_HI(k), b[2 * i + 9 - k], HHv);
+    for (int k = 1; k <= 9; ++k) {
+      LL_FMA2(A, ab[2 * i + 9 - k].x, LL_DEC_PAIR(k));
+      LL_FMA2(B, ab[2 * i + 9 - k].y, LL_DEC_PAIR(k));
     }
     const long long o = (long long)gy * w2 + gx;
-    llp[o] = LLv;
-    yh[o] = LHv;
-    yh[sub + o] = HLv;
-    yh[2 * sub + o] = HHv;
+    llp[o] = A.x;
+    yh[o] = A.y;
+    yh[sub + o] = B.x;
+    yh[2 * sub + o] = B.y;
   }
 }
 
@@ -374,15 +371,18 @@ template <class CP>
 LL_HD void dwtif_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, CP cp) {
   const int h2 = p.h / 2, w2 = p.w / 2;
   const long long sub = (long long)h2 * w2;
-  constexpr int C4 = DIF_P / 4;   // 18
-  for (int e = tid; e < 4 * DWI_R * C4; e += DW_THREADS) {
-    const int s = e / (DWI_R * C4);
-    const int i = (e / C4) % DWI_R, c4 = e % C4;
-    const int gy = wrapf(t.y0 - 2 + i, h2), gx = wrapf(t.x0 - 4 + 4 * c4, w2);
-    const long long o = (long long)gy * w2 + gx;
-    const float* src = (s == 0) ? p.ll + (long long)t.n * p.ll_sn + o
-                                : p.yh + (long long)t.n * p.yh_sn + (s == 1 ? 0 : s == 2 ? sub : 2 * sub) + o;
-    cp(&sm[DIF_SM_SB + (s * DWI_R + i) * DIF_P + 4 * c4], src);
+  constexpr int C4 = DIF_P / 4;                   // 18 column groups, 14 (subband,row) lines in flight per pass
+  constexpr int RPP = DW_THREADS / C4;
+  if (tid >= C4 * RPP) return;
+  const int c4 = tid % C4, r0 = tid / C4;
+  const int gx = wrapf(t.x0 - 4 + 4 * c4, w2);
+  const float* b0 = p.ll + (long long)t.n * p.ll_sn + gx;
+  const float* b1 = p.yh + (long long)t.n * p.yh_sn + gx;
+  for (int rs = r0; rs < 4 * DWI_R; rs += RPP) {
+    const int s = rs / DWI_R, i = rs % DWI_R;
+    const int gy = wrapf(t.y0 - 2 + i, h2);
+    const float* src = (s == 0 ? b0 : b1 + (s - 1) * sub) + (long long)gy * w2;
+    cp(&sm[DIF_SM_SB + rs * DIF_P + 4 * c4], src);
   }
 }
 
@@ -401,16 +401,14 @@ LL_HD void dwtif_cols(const float* sb, float* mid, int tid) {
     float* o = &mid[(which ? DIF_SM_HI : DIF_SM_LO) + (8 * jg) * DIF_P + c];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float el = 0.f, eh = 0.f, ol = 0.f, oh = 0.f;
+      f2 al = f2{0.f, 0.f}, ah = f2{0.f, 0.f};   // (even, odd) partial sums of the low / high branch
 #pragma unroll
       for (int tt = 0; tt < 5; ++tt) {
-        el = fmaf(LL_REC_LO(2 * tt), l[j + 4 - tt], el);
-        eh = fmaf(LL_REC_HI(2 * tt), h[j + 4 - tt], eh);
-        ol = fmaf(LL_REC_LO(2 * tt + 1), l[j + 4 - tt], ol);
-        oh = fmaf(LL_REC_HI(2 * tt + 1), h[j + 4 - tt], oh);
+        LL_FMA2(al, l[j + 4 - tt], LL_RECL_PAIR(tt));
+        LL_FMA2(ah, h[j + 4 - tt], LL_RECH_PAIR(tt));
       }
-      o[(2 * j) * DIF_P] = el + eh;
-      o[(2 * j + 1) * DIF_P] = ol + oh;
+      o[(2 * j) * DIF_P] = al.x + ah.x;
+      o[(2 * j + 1) * DIF_P] = al.y + ah.y;
     }
   }
 }
@@ -434,16 +432,14 @@ LL_HD void dwtif_rows(const DwtParams& p, const DwtTile& t, const float* sm, int
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // output pair jl = 4 jg + j needs subband cols jl-2..jl+2 -> tile index c = jl + 2 .. jl + 6 -> local j + 2 .. j + 6
-      float el = 0.f, eh = 0.f, ol = 0.f, oh = 0.f;
+      f2 al = f2{0.f, 0.f}, ah = f2{0.f, 0.f};
 #pragma unroll
       for (int tt = 0; tt < 5; ++tt) {
-        el = fmaf(LL_REC_LO(2 * tt), l[j + 6 - tt], el);
-        eh = fmaf(LL_REC_HI(2 * tt), h[j + 6 - tt], eh);
-        ol = fmaf(LL_REC_LO(2 * tt + 1), l[j + 6 - tt], ol);
-        oh = fmaf(LL_REC_HI(2 * tt + 1), h[j + 6 - tt], oh);
+        LL_FMA2(al, l[j + 6 - tt], LL_RECL_PAIR(tt));
+        LL_FMA2(ah, h[j + 6 - tt], LL_RECH_PAIR(tt));
       }
-      out[2 * j] = el + eh;
-      out[2 * j + 1] = ol + oh;
+      out[2 * j] = al.x + ah.x;
+      out[2 * j + 1] = al.y + ah.y;
     }
     float* o = p.xo + (long long)t.n * p.x_sn + (long long)gy * p.w + 2 * gx;
     *reinterpret_cast<float4*>(o) = float4{out[0], out[1], out[2], out[3]};
