@@ -43,7 +43,7 @@ constexpr int IG_STAGE_BYTES = IG_A_BYTES + IG_B_BYTES;
 constexpr int IG_THREADS = 192;
 constexpr int IG_TMEM_COLS = 512;
 constexpr int IG_MAXG = 3;       // channel groups per launch (the cgp MLP has groups = 3)
-constexpr int IG_MAXSLOTS = 12;  // k-blocks per (group, tap)
+constexpr int IG_MAXSLOTS = 24;  // k-blocks per (group, tap); the 3xTF32 chain of a 192-channel layer needs 18
 constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXG * IG_MAXN * 4;
 
 struct IgemmParams {
@@ -58,9 +58,16 @@ struct IgemmParams {
   long long ntiles;                       // tiles x groups
   int groups, out_gstride;                // NHWC channel stride between groups
   int a_koff[IG_MAXG][IG_MAXSLOTS];       // input-channel coordinate of each k-block, per group
+  int b_koff[IG_MAXSLOTS];                // K coordinate of each k-block in the packed weights
+  // TF32 chain (SubbandAutoEncoderBerk): epi 1 = conv -> Y (raw) + S (hi|lo of y^2); 2 = GDN -> Z (hi|lo of
+  // y * rsqrt(acc + beta), or * sqrt for the inverse GDN), reading Y; 3 = conv -> Y only
+  int epi, inverse;
+  float* y;                               // NHWC fp32 (B,H,W,Cout)
+  float* sz;                              // NHWC fp32 (B,H,W,2*Cout)
 };
 
 // ---------------------------------------------------------------------------------------- kernel
+template <bool TF32>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ IgemmParams p) {
@@ -128,7 +135,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_expect_tx(full_bar(stage), stage_tx);
             const uint32_t sa = base + stage * IG_STAGE_BYTES;
             tma_load_4d(sa, &tmA, full_bar(stage), p.a_koff[g][kb], x0 + dx, y0 + dy, b);
-            tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), kb * IG_BK, 0, g * p.taps + tap);
+            tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), p.b_koff[kb], 0, g * p.taps + tap);
             if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -138,7 +145,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = Npad, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(IG_BM >> 4) << 24);
+      const uint32_t fmt = TF32 ? 2u : 1u;   // operand format: TF32 (fp32 containers) or BF16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(IG_BM >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -151,8 +159,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t sa = base + stage * IG_STAGE_BYTES;
           const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + IG_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < IG_BK / 16; ++k)   // 32 bytes (16 bf16) per MMA along K: +2 in 16-byte units
-            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          for (int k = 0; k < IG_BK / 16; ++k) {  // 32 bytes (16 bf16 / 8 tf32) per MMA along K: +2 in 16-byte units
+            if (TF32) tc_mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
+            else tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          }
           tc_commit(empty_bar(stage));           // smem stage reusable once these MMAs have read it
           if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -187,7 +197,42 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v[32];
         tc_ld32(taddr + c * 32, v);
         tc_wait_ld();
-        if (valid) {
+        if (TF32) {
+          if (valid && c * 32 < p.Cout) {
+            const long long px = ((long long)b * p.H + y) * p.W + x;
+            float* yp = p.y + px * p.Cout + c * 32;
+            float* zp = p.sz + px * (2 * p.Cout) + c * 32;
+            float o[32];
+            if (p.epi == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(yp + j);
+                o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
+              }
+            }
+            float hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(v[j]) + gb[c * 32 + j];
+              float r;
+              if (p.epi == 2) r = o[j] * (p.inverse ? sqrtf(a) : rsqrtf(a));   // GDN / inverse GDN
+              else { o[j] = a; r = a * a; }                                       // conv: raw output, square for the GDN norm
+              hi[j] = tf32_rna(r);
+              lo[j] = tf32_rna(r - hi[j]);
+            }
+            if (p.epi != 2) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+            if (p.epi != 3) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                *reinterpret_cast<float4*>(zp + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                *reinterpret_cast<float4*>(zp + p.Cout + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+              }
+            }
+          }
+        } else if (valid) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -383,6 +428,49 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, long long 
   }
 }
 
+// (Co, Ci, R, S) fp32 -> [R*S][Npad][2*Kpad] fp32: [hi | lo] TF32 halves along K, zero padded.  ``transposed``:
+// the source is a ConvTranspose2d weight (Ci_t = Co of the equivalent conv ... stored (in, out, R, S)); stride 1,
+// padding 1: equivalent conv weight w'[o][i][tap] = w[i][o][8 - tap].
+__global__ void pack_tf32_weight_kernel(const float* __restrict__ w, float* __restrict__ wp, int Co, int Ci, int taps,
+                                        int Npad, int Kpad, int transposed) {
+  const long long total = (long long)taps * Npad * Kpad;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(e % Kpad), co = (int)((e / Kpad) % Npad), tap = (int)(e / ((long long)Kpad * Npad));
+    float v = 0.f;
+    if (co < Co && ci < Ci) v = transposed ? w[((long long)ci * Co + co) * taps + (taps - 1 - tap)] : w[((long long)co * Ci + ci) * taps + tap];
+    const float hi = tf32_rna(v);
+    float* row = wp + ((long long)tap * Npad + co) * (2 * Kpad);
+    row[ci] = hi;
+    row[Kpad + ci] = tf32_rna(v - hi);
+  }
+}
+
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ sz, int B, int C,
+                                          int H, int W, int mode) {
+  const long long hw = (long long)H * W, total = (long long)B * hw * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const long long px = e / C;
+    const float v = x[((px / hw) * C + c) * hw + px % hw];
+    if (y) y[e] = v;
+    const float r = mode ? v : v * v;
+    const float hi = tf32_rna(r);
+    sz[px * (2 * C) + c] = hi;
+    sz[px * (2 * C) + C + c] = tf32_rna(r - hi);
+  }
+}
+
+__global__ void nhwc_split_to_nchw_kernel(const float* __restrict__ z, float* __restrict__ out, int B, int C, int H, int W) {
+  const long long hw = (long long)H * W, total = (long long)B * hw * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = e % hw;
+    const int c = (int)((e / hw) % C);
+    const long long b = e / (hw * C);
+    const float* q = z + (b * hw + s) * (2 * C);
+    out[e] = q[c] + q[C + c];
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -536,13 +624,122 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 64 && !attr[dev]) {
-    LL_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_BYTES));
+    attr[dev] = true;
+  }
+  for (int k = 0; k < p.kblocks; ++k) p.b_koff[k] = k * IG_BK;
+  const long long sms = sm_count_cached();
+  const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
+  igemm_conv_kernel<false><<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
+  LL_LAUNCH_OK("igemm_conv_kernel");
+  return LL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3xTF32 chain for SubbandAutoEncoderBerk (conv3x3 / GDN 1x1 with fp32-level accuracy)
+// ------------------------------------------------------------------------------------------------
+int ll_pack_tf32_weight(const float* w, float* wp, int Co, int Ci, int taps, int Npad, int Kpad, int transposed,
+                        ll_stream_t stream) {
+  if (Co < 1 || Ci < 1 || (taps != 1 && taps != 9) || Npad < Co || Kpad < Ci || Npad % 16 || Npad > IG_MAXN || Kpad % 32)
+    return fail(LL_EINVAL, "ll_pack_tf32_weight: bad extents (taps 1|9, Npad %%16 <= 256, Kpad %%32)");
+  if (!w || !wp) return fail(LL_EINVAL, "ll_pack_tf32_weight: null pointer");
+  const long long total = (long long)taps * Npad * Kpad;
+  pack_tf32_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(w, wp, Co, Ci, taps, Npad, Kpad, transposed);
+  LL_LAUNCH_OK("pack_tf32_weight_kernel");
+  return LL_OK;
+}
+
+int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B, int H, int W, int C, int Npad, int Cout,
+                  int taps, int epi, int inverse, float* y, float* sz, ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || C < 32 || C % 32 || Npad < 16 || Npad % 16 || Npad > IG_MAXN || Cout < 32 || Cout % 32 ||
+      Cout > Npad || (taps != 1 && taps != 9) || epi < 1 || epi > 3)
+    return fail(LL_EINVAL, "ll_igemm_tf32: bad extents (C, Cout multiples of 32, Npad %%16 <= 256, taps 1|9, epi 1..3)");
+  if (3 * (C / 32) > IG_MAXSLOTS) return fail(LL_EINVAL, "ll_igemm_tf32: at most %d input channels", IG_MAXSLOTS / 3 * 32);
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!a_nhwc || !wp || !y || (epi != 3 && !sz)) return fail(LL_EINVAL, "ll_igemm_tf32: null pointer");
+  if (((uintptr_t)a_nhwc & 15) || ((uintptr_t)wp & 15) || ((uintptr_t)y & 15) || ((uintptr_t)sz & 15))
+    return fail(LL_EINVAL, "ll_igemm_tf32: buffers must be 16-byte aligned");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmA, tmB;
+  {
+    const int Ca = 2 * C;   // [hi | lo]
+    cuuint64_t gdim[4] = {(cuuint64_t)Ca, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Ca * 4, (cuuint64_t)W * Ca * 4, (cuuint64_t)H * W * Ca * 4};
+    cuuint32_t box[4] = {32, IG_TW, IG_TH, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_nhwc), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    const int Kw = 2 * C;   // packed weights: [hi | lo] along K
+    cuuint64_t gdim[3] = {(cuuint64_t)Kw, (cuuint64_t)Npad, (cuuint64_t)taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kw * 4, (cuuint64_t)Npad * Kw * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)Npad, 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wp), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  IgemmParams p = {};
+  p.bias = bias;
+  p.co_group = 1 << 30;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Npad = Npad; p.taps = taps;
+  p.tiles_x = (W + IG_TW - 1) / IG_TW;
+  p.tiles_y = (H + IG_TH - 1) / IG_TH;
+  p.ntiles = (long long)B * p.tiles_x * p.tiles_y;
+  p.groups = 1;
+  // per 32-channel block: A_lo*B_hi, A_hi*B_lo (the small terms first), then A_hi*B_hi
+  const int kb = C / 32;
+  p.kblocks = 3 * kb;
+  for (int k = 0; k < kb; ++k) {
+    p.a_koff[0][3 * k + 0] = C + 32 * k; p.b_koff[3 * k + 0] = 32 * k;
+    p.a_koff[0][3 * k + 1] = 32 * k;     p.b_koff[3 * k + 1] = C + 32 * k;
+    p.a_koff[0][3 * k + 2] = 32 * k;     p.b_koff[3 * k + 2] = 32 * k;
+  }
+  p.epi = epi; p.inverse = inverse; p.y = y; p.sz = sz;
+  static thread_local bool attr[64] = {false};
+  int dev = 0;
+  LL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr[dev]) {
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_BYTES));
     attr[dev] = true;
   }
   const long long sms = sm_count_cached();
   const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
-  igemm_conv_kernel<<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
-  LL_LAUNCH_OK("igemm_conv_kernel");
+  igemm_conv_kernel<true><<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
+  LL_LAUNCH_OK("igemm_conv_kernel<tf32>");
+  return LL_OK;
+}
+
+// fp32 NCHW (B,C,H,W) -> Y NHWC (B,H,W,C) raw and S NHWC (B,H,W,2C) = [hi | lo] of x^2 (mode 0) or of x (mode 1)
+int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int H, int W, int mode, ll_stream_t stream) {
+  if (B < 0 || C < 1 || H < 0 || W < 0) return fail(LL_EINVAL, "ll_nchw_to_nhwc_split: bad extents");
+  const long long total = (long long)B * H * W * C;
+  if (total == 0) return LL_OK;
+  if (!x || !sz) return fail(LL_EINVAL, "ll_nchw_to_nhwc_split: null pointer");
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count_cached() * 16;
+  if (blocks > cap) blocks = cap;
+  nchw_to_nhwc_split_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, y, sz, B, C, H, W, mode);
+  LL_LAUNCH_OK("nchw_to_nhwc_split_kernel");
+  return LL_OK;
+}
+
+// Z NHWC (B,H,W,2C) [hi | lo] -> fp32 NCHW (B,C,H,W) = hi + lo
+int ll_nhwc_split_to_nchw(const float* z, float* out, int B, int C, int H, int W, ll_stream_t stream) {
+  if (B < 0 || C < 1 || H < 0 || W < 0) return fail(LL_EINVAL, "ll_nhwc_split_to_nchw: bad extents");
+  const long long total = (long long)B * H * W * C;
+  if (total == 0) return LL_OK;
+  if (!z || !out) return fail(LL_EINVAL, "ll_nhwc_split_to_nchw: null pointer");
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count_cached() * 16;
+  if (blocks > cap) blocks = cap;
+  nhwc_split_to_nchw_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(z, out, B, C, H, W);
+  LL_LAUNCH_OK("nhwc_split_to_nchw_kernel");
   return LL_OK;
 }
 

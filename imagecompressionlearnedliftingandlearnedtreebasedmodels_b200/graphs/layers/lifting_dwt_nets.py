@@ -86,6 +86,9 @@ class SubbandAutoEncoderBerk(nn.Module):
             nn.ConvTranspose2d(iC * H // 2, iC * H, kernel_size=K, stride=1, padding=P), GDN(iC * H, inverse=True),
             nn.ConvTranspose2d(iC * H, iC * H // 2, kernel_size=K, stride=1, padding=P), GDN(iC * H // 2, inverse=True),
             nn.ConvTranspose2d(iC * H // 2, iC * 1, kernel_size=K, stride=1, padding=P))
+        # "tc": 3xTF32 tensor-core chain (default, inference); "torch": torch fp32 convs (also used whenever autograd is on)
+        self.ae_precision = "tc"
+        self._down_cache, self._up_cache = PackCache(), PackCache()
 
     @staticmethod
     def _exact(fn, x):
@@ -99,10 +102,60 @@ class SubbandAutoEncoderBerk(nn.Module):
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
 
+    # ---- tensor-core path: convs 2-3 and the three GDN norms as 3xTF32 implicit GEMMs (fp32-level accuracy) ----
+    AE_BATCH_CHUNK = 8     # images per launch group: bounds the channels-last fp32 intermediates
+
+    def _pack(self, seq, transposed, cache):
+        convs = [seq[0], seq[2], seq[4], seq[6]]
+        gdns = [seq[1], seq[3], seq[5]]
+        srcs = [c.weight for c in convs] + [g.beta for g in gdns] + [g.gamma for g in gdns]
+
+        def build():
+            eq = (lambda w: w.detach().transpose(0, 1).flip(2, 3).contiguous()) if transposed else (lambda w: w.detach())
+            pk = {"w0": eq(convs[0].weight), "w3": eq(convs[3].weight),
+                  "wp": [ops.pack_tf32_weight(convs[1].weight, transposed), ops.pack_tf32_weight(convs[2].weight, transposed)],
+                  "gdn": []}
+            for g in gdns:
+                C = g.beta.numel()
+                beta = g.beta_reparam(g.beta.detach()).contiguous()
+                gamma = g.gamma_reparam(g.gamma.detach()).reshape(C, C, 1, 1).contiguous()
+                pk["gdn"].append((ops.pack_tf32_weight(gamma), beta))
+            return pk
+
+        return cache.get(srcs, build)
+
+    def _run_tc(self, seq, x, transposed, cache):
+        pk = self._pack(seq, transposed, cache)
+        convs = [seq[0], seq[2], seq[4], seq[6]]
+        inv = seq[1].inverse
+        outs = []
+        for b0 in range(0, x.shape[0], self.AE_BATCH_CHUNK):
+            xb = x[b0:b0 + self.AE_BATCH_CHUNK].contiguous()
+            c1 = ops.conv2d(xb, pk["w0"], convs[0].bias)                                   # exact fp32 SIMT (K = 9 * iC)
+            y, s = ops.nchw_to_nhwc_split(c1, squares=True)
+            del c1
+            _, z = ops.igemm_tf32(s, pk["gdn"][0][0], pk["gdn"][0][1], y.shape[3], epi=2, inverse=inv, y=y)
+            for k in (0, 1):
+                y, s = ops.igemm_tf32(z, pk["wp"][k], convs[1 + k].bias, convs[1 + k].weight.shape[1 if transposed else 0], epi=1)
+                _, z = ops.igemm_tf32(s, pk["gdn"][1 + k][0], pk["gdn"][1 + k][1], y.shape[3], epi=2, inverse=inv, y=y)
+            del y, s
+            t = ops.nhwc_split_to_nchw(z)
+            del z
+            outs.append(ops.conv2d(t, pk["w3"], convs[3].bias))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def _use_tc(self, x):
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        return self.ae_precision == "tc" and not need_grad
+
     def encode(self, x):
+        if self._use_tc(x):
+            return self._run_tc(self.ae_down, x, False, self._down_cache)
         return self._exact(self.ae_down, x)
 
     def decode(self, y_hat):
+        if self._use_tc(y_hat):
+            return self._run_tc(self.ae_up, y_hat, True, self._up_cache)
         return self._exact(self.ae_up, y_hat)
 
 

@@ -359,6 +359,73 @@ def igemm_conv(x_nhwc, wp, bias, cout, lrelu=False, out=None, co_group=0, co_str
     return out if out is not None else out_nhwc
 
 
+# ----------------------------------------------------------------------------- 3xTF32 chain (SubbandAutoEncoderBerk)
+def pack_tf32_weight(weight, transposed=False):
+    """(Co,Ci,R,S) conv weight -- or a ConvTranspose2d weight (in,out,R,S) when ``transposed`` -- -> fp32
+    (taps, Npad, 2*Kpad) blob of [hi | lo] TF32 halves for ``igemm_tf32``."""
+    require_device(weight)
+    w = _f32c(weight.detach(), "weight")
+    if transposed:
+        Ci, Co, R, S = w.shape
+    else:
+        Co, Ci, R, S = w.shape
+    taps, npad, kpad = R * S, _pad_to(Co, 16), _pad_to(Ci, 32)
+    wp = torch.empty(taps, npad, 2 * kpad, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check(_lib.load().ll_pack_tf32_weight(ptr(w), ptr(wp), Co, Ci, taps, npad, kpad, int(bool(transposed)), stream_ptr()))
+    _count(1)
+    return wp
+
+
+def igemm_tf32(a_split, wp, bias, cout, epi, inverse=False, y=None):
+    """3xTF32 implicit-GEMM conv of a channels-last fp32 split tensor (B,H,W,2C).  epi 1: returns (y, split(y^2));
+    epi 2 (GDN): returns (y, split(y * rsqrt(acc + bias))) with ``y`` given; epi 3: returns (y, None)."""
+    require_device(a_split)
+    if a_split.dtype != torch.float32 or not a_split.is_contiguous() or a_split.dim() != 4:
+        raise TypeError("igemm_tf32: a_split must be a contiguous fp32 (B,H,W,2C) tensor")
+    B, H, W, c2 = a_split.shape
+    C = c2 // 2
+    taps, npad, k2 = wp.shape
+    if k2 != 2 * C:
+        raise ValueError(f"igemm_tf32: packed weight has K={k2 // 2}, input has {C} channels")
+    b = _f32c(bias.detach(), "bias")
+    if epi == 2:
+        if y is None or tuple(y.shape) != (B, H, W, cout):
+            raise ValueError("igemm_tf32: the GDN epilogue needs the raw conv output y (B,H,W,Cout)")
+    else:
+        y = torch.empty(B, H, W, cout, dtype=torch.float32, device=a_split.device)
+    sz = torch.empty(B, H, W, 2 * cout, dtype=torch.float32, device=a_split.device) if epi != 3 else None
+    with torch.cuda.device(a_split.device):
+        check(_lib.load().ll_igemm_tf32(ptr(a_split), ptr(wp), ptr(b), B, H, W, C, npad, cout, taps, epi, int(bool(inverse)),
+                                        ptr(y), ptr(sz), stream_ptr()))
+    _count(1)
+    return y, sz
+
+
+def nchw_to_nhwc_split(x, squares=True, want_y=True):
+    """fp32 NCHW -> (y NHWC raw | None, split NHWC (B,H,W,2C) of x^2 (``squares``) or x)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, C, dtype=torch.float32, device=x.device) if want_y else None
+    sz = torch.empty(B, H, W, 2 * C, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_nchw_to_nhwc_split(ptr(x), ptr(y), ptr(sz), B, C, H, W, 0 if squares else 1, stream_ptr()))
+    _count(1)
+    return y, sz
+
+
+def nhwc_split_to_nchw(z):
+    """split NHWC (B,H,W,2C) -> fp32 NCHW (B,C,H,W) = hi + lo."""
+    require_device(z)
+    B, H, W, c2 = z.shape
+    out = torch.empty(B, c2 // 2, H, W, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        check(_lib.load().ll_nhwc_split_to_nchw(ptr(z), ptr(out), B, c2 // 2, H, W, stream_ptr()))
+    _count(1)
+    return out
+
+
 def cgp_tail_rate(h2, w3, b3, w4, b4, x, noise=None, want_y=False, want_ms=False, acc=None):
     """Last two grouped 1x1 layers of the cgp MLP + Gaussian rate (ll_cgp_tail_rate).  h2 (B,G*C2,H,W)
     fp32; w3 (G*C3,C2,1,1); w4 (2G,C3,1,1); x (B,G,H,W).  Returns bits (+ y, + ms (B,2G,H,W))."""

@@ -204,6 +204,25 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
                   int co_group, int co_stride, int co_off, void* out_bf16, int out_cstride, int out_coff,
                   int out_gstride, ll_stream_t stream);
 
+/* ---- 3xTF32 tensor-core chain for SubbandAutoEncoderBerk (lifting_dwt_nets.py:126-165): 3x3 convs and the 1x1
+ * GDN / inverse-GDN norms with fp32-level accuracy (the network feeds the quantiser).  Activations travel
+ * channels-last in fp32 as [hi | lo] TF32 halves (hi = rna_tf32(v), lo = rna_tf32(v - hi)); every product is
+ * A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with FP32 accumulation in tensor memory. ---- */
+
+/* (Co,Ci,R,S) fp32 -> [taps][Npad][2*Kpad] fp32 ([hi | lo] along K).  transposed != 0: w is a ConvTranspose2d weight
+ * (stored (in, out, R, S); stride 1, padding 1) and is flipped / swapped into the equivalent conv weight. */
+int ll_pack_tf32_weight(const float* w, float* wp, int Co, int Ci, int taps, int Npad, int Kpad, int transposed,
+                        ll_stream_t stream);
+/* a_nhwc (B,H,W,2C) [hi | lo]; wp from ll_pack_tf32_weight with Kpad == C; bias[Cout].  epi 1: conv -> y (B,H,W,Cout)
+ * raw output and sz (B,H,W,2*Cout) = split of y^2 (the GDN norm input); epi 2: GDN -> sz = split of
+ * y * rsqrt(acc + bias) (inverse != 0: * sqrt), y is READ; epi 3: conv -> y only.  C, Cout multiples of 32. */
+int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B, int H, int W, int C, int Npad, int Cout,
+                  int taps, int epi, int inverse, float* y, float* sz, ll_stream_t stream);
+/* fp32 NCHW (B,C,H,W) -> y NHWC raw (optional) and sz NHWC (B,H,W,2C) = split of x^2 (mode 0) or of x (mode 1). */
+int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int H, int W, int mode, ll_stream_t stream);
+/* z NHWC (B,H,W,2C) [hi | lo] -> fp32 NCHW (B,C,H,W) = hi + lo. */
+int ll_nhwc_split_to_nchw(const float* z, float* out, int B, int C, int H, int W, ll_stream_t stream);
+
 /* Tail of the cgp MLP fused with the rate: per group g (= child subband) and pixel,
  * h = LeakyReLU(W3[g] h2 + b3[g]) (C2 -> C3), (sigma, mu) = W4[g] h + b4[g], then exactly
  * ll_gauss_rate on x[:, g] (:286-290,361-365).  h2 fp32 (B, G*C2, hw) batch stride h2_sb; w3

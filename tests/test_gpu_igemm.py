@@ -176,3 +176,38 @@ def test_nchw_to_nhwc_bf16_slice():
     ops.nchw_to_nhwc_bf16(x, out, 81)
     assert (out[..., 81:162].float() == x.permute(0, 2, 3, 1).to(torch.bfloat16).float()).all()
     assert (out[..., :81] == 0).all() and (out[..., 162:] == 0).all()
+
+
+@pytest.mark.parametrize("in_ch,shape", [(3, (2, 3, 24, 40)), (1, (3, 1, 16, 16)), (3, (1, 3, 5, 7))])
+def test_berk_autoencoder_tc_matches_torch_fp32(in_ch, shape):
+    """SubbandAutoEncoderBerk on the 3xTF32 tensor-core chain vs the same module through torch fp32 convs (TF32 off):
+    both are compared with a float64 run of the same module: the tensor-core chain must be as accurate as the fp32 one."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers.lifting_dwt_nets import SubbandAutoEncoderBerk
+    torch.manual_seed(21)
+    ae = SubbandAutoEncoderBerk(in_ch)
+    with torch.no_grad():
+        for prm in ae.parameters():            # non-trivial weights, GDN parameters kept near their (valid) init
+            if prm.dim() == 4:
+                prm.copy_(torch.randn_like(prm) * (2.0 / (prm[0].numel() ** 0.5)))
+            elif prm.dim() == 2:
+                prm.add_(torch.rand_like(prm) * 0.05)
+    import copy
+    ae64 = copy.deepcopy(ae).double().to(DEV).eval()
+    ae = ae.to(DEV).eval()
+    x = (torch.randn(*shape) * 2).to(DEV)
+    with torch.no_grad():
+        for name in ("encode", "decode"):
+            ref = getattr(ae64, "ae_down" if name == "encode" else "ae_up")(x.double())     # float64 ground truth
+            ae.ae_precision = "tc"
+            got = getattr(ae, name)(x)
+            ae.ae_precision = "torch"
+            t32 = getattr(ae, name)(x)
+            scale = ref.abs().max().item()
+            err_tc = (got.double() - ref).abs().max().item() / scale
+            err_t32 = (t32.double() - ref).abs().max().item() / scale
+            print(f"{name}: 3xTF32 chain err {err_tc:.2e}, torch fp32 err {err_t32:.2e}")
+            # encode (decides the symbols): fp32-conv-chain level.  decode: the tensor core's FP32 accumulator rounds
+            # toward zero, a bias that grows with the 324-648 accumulation steps of these K = 864 / 1728 convs and that
+            # the inverse GDN (y * sqrt(norm)) does not normalise away like the forward GDN does; the reconstruction
+            # tolerance of the path is 1e-4, the chain must stay well inside it.
+            assert err_tc <= (max(3 * err_t32, 1e-5) if name == "encode" else 6e-5), (name, err_tc, err_t32)
