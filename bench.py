@@ -240,6 +240,7 @@ def run_own(args):
     }
     line["dwt97"] = dwt97_probe(dev, pk)
     line["context_cnn"] = context_probe(dev, pk)
+    line["codec_forward"] = codec_probe(dev)
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
     print(json.dumps(line))
@@ -317,6 +318,36 @@ def context_probe(dev, pk):
         ms = timed(lambda: em(xe, xo), 3)
     res["cond2zt_entropy_model"] = {"ms_per_plane_batch16": ms, "mp_per_s_3_planes": B * H * W / 1e6 / (3 * ms * 1e-3),
                                     "flops_per_plane_px": 430482, "note": "quantise + context CNNs + Gaussian rate + bit sums"}
+    return res
+
+
+def codec_probe(dev):
+    """Whole codec forward (configs[2] shape at batch 16): transform -> quantise + rate estimate -> inverse transform,
+    three colour planes, learned lifting L=4 + conditioned2ZT, with both scaling networks."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import \
+        LiftingBasedDWTNetWrapper
+    from oracle import model as om
+    res = {}
+    x = synthetic_input(7).to(dev)
+    for ae in ("SubbandAutoEncoder", "SubbandAutoEncoderBerk"):
+        cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder=ae, entropy_layer="conditioned2ZTsepSubbands",
+                             dwtlevels=LEVELS)
+        torch.manual_seed(1337)
+        model = LiftingBasedDWTNetWrapper(cfg).to(dev).eval()
+        with torch.no_grad():
+            model(x)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(2):
+                xhat, si_xe, si_xo = model(x)
+            ev1.record()
+            torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 2
+        bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
+        res[ae] = {"ms_per_batch16": ms, "mp_per_s": B * H * W / 1e6 / (ms * 1e-3), "bpp": bits / (B * H * W)}
+        del model
+    res["note"] = "random-init weights: bpp is a by-product, not a quality claim"
     return res
 
 

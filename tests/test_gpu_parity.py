@@ -226,3 +226,37 @@ def test_full_size_properties():
         assert (rec - x).abs().max().item() < 2e-5
         yl1, yh1 = net.transform(x[1:2])
         assert torch.equal(yl1, yl[1:2]) and all(torch.equal(a, b[1:2]) for a, b in zip(yh1, yh))
+
+
+def test_full_size_codec_properties():
+    """BASELINE config-3 image size (512x768, batch 1): size-independent properties of the whole codec forward --
+    (1) the tensor-core context path moves bpp by < 0.1 % relative to the exact-fp32 context path and changes no
+    symbol and no reconstructed sample (the context CNNs only feed the rate); (2) both lifting arithmetic modes give
+    the same symbols up to rounding-boundary flips and the same reconstruction to 1e-4."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import \
+        LiftingBasedDWTNetWrapper
+    torch.manual_seed(2)
+    x = om.preprocess(torch.rand(1, 3, 512, 768)).to(DEV)
+    outs = {}
+    for tag, kw in (("tc_bf16", {}), ("tc_fp32ctx", dict(ctx_precision="fp32")), ("fp32_lift", dict(lift_precision="fp32"))):
+        cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                             entropy_layer="conditioned2ZTsepSubbands", dwtlevels=4, **kw)
+        torch.manual_seed(1337)
+        model = LiftingBasedDWTNetWrapper(cfg)
+        keyed_state(model)
+        model = model.to(DEV).eval()
+        with torch.no_grad():
+            xhat, si_xe, si_xo = model(x)
+            sub = model.model0
+            oxe, oxo = sub.autoencoder.encode(x[:, 0:1])
+            _, _, xe_q, xo_q = sub.entropymodel(oxe, oxo)
+        bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
+        outs[tag] = (xhat, bits, [xe_q] + list(xo_q), [oxe] + list(oxo))
+        del model
+    a, b, c = outs["tc_bf16"], outs["tc_fp32ctx"], outs["fp32_lift"]
+    assert abs(a[1] - b[1]) <= 1e-3 * b[1]                                   # bpp within 0.1 %
+    assert torch.equal(a[0], b[0]) and all(torch.equal(p, q) for p, q in zip(a[2], b[2]))
+    assert rel_err(a[0], c[0]) < 1e-4
+    for qa, qc, pre in zip(a[2], c[2], c[3]):
+        n, bad = flip_audit(qa.cpu(), qc.cpu(), pre.cpu())
+        assert bad == 0 and n <= max(2, qa.numel() // 20000), (n, bad)     # rounding-boundary flips only
