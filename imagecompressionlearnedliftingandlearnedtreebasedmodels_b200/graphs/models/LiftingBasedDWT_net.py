@@ -71,6 +71,11 @@ class LiftingBasedDWTNetWrapper(nn.Module):
             self.model0 = LiftingBasedDWTNet(config)
             self.model1 = LiftingBasedDWTNet(config)
             self.model2 = LiftingBasedDWTNet(config)
+        # (the Berk scaling network streams multi-GB channels-last intermediates per plane: three of them in flight
+        # only fight over HBM and the allocator, measured 250 -> 279 ms; the lighter configurations gain 5 %)
+        ae = config.get("autoencoder", "") if hasattr(config, "get") else getattr(config, "autoencoder", "")
+        self.plane_streams = not (config.netType == "LiftingBasedNeuralWaveletv4" and ae == "SubbandAutoEncoderBerk")
+        self._streams = None
 
     def planes(self):
         return [self.model] if self.clrch == 3 else [self.model0, self.model1, self.model2]
@@ -80,10 +85,31 @@ class LiftingBasedDWTNetWrapper(nn.Module):
         for m in self.planes():
             m.entropymodel.bit_acc = acc
 
+    def _forward_planes(self, x):
+        """The three colour planes are independent networks (:52-54): in inference each one runs on its own CUDA
+        stream, so the many small launches of the deep levels of one plane overlap the kernels of another."""
+        if torch.is_grad_enabled() or not x.is_cuda or not self.plane_streams:
+            return [m(x[:, c:c + 1, :, :]) for c, m in enumerate(self.planes())]
+        if self._streams is None or self._streams[0].device != x.device:
+            self._streams = [torch.cuda.Stream(device=x.device) for _ in range(3)]
+        cur = torch.cuda.current_stream(x.device)
+        outs = [None] * 3
+        for c, m in enumerate(self.planes()):
+            st = self._streams[c]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs[c] = m(x[:, c:c + 1, :, :].contiguous())
+        for st in self._streams:
+            cur.wait_stream(st)
+        for o in outs:
+            for t in [o[0], o[1]] + list(o[2]):
+                t.record_stream(cur)
+        return outs
+
     def forward(self, x):
         if self.clrch == 3:
             return self.model.forward(x)
-        outs = [m(x[:, c:c + 1, :, :]) for c, m in enumerate(self.planes())]
+        outs = self._forward_planes(x)
         xhat = torch.cat([o[0] for o in outs], dim=1)
         si_xe = torch.cat([o[1] for o in outs], dim=1)
         si_xo = []
