@@ -62,6 +62,10 @@ struct IgemmParams {
   // TF32 chain (SubbandAutoEncoderBerk): epi 1 = conv -> Y (raw) + S (hi|lo of y^2); 2 = GDN -> Z (hi|lo of
   // y * rsqrt(acc + beta), or * sqrt for the inverse GDN), reading Y; 3 = conv -> Y only
   int epi, inverse;
+  // accumulator plan: nstages accumulator stages of stage_cols TMEM columns; a k-block goes to accumulator
+  // acc_sel[k] (0 main, 1 small terms) at column offset acc_sel * acc_cols inside the stage
+  int nstages, stage_cols, nacc, acc_cols;
+  int acc_sel[IG_MAXSLOTS];
   float* y;                               // NHWC fp32 (B,H,W,Cout)
   float* sz;                              // NHWC fp32 (B,H,W,2*Cout)
 };
@@ -152,22 +156,27 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * IG_MAXN;
+        uint32_t started = 0;                    // bit s: accumulator s of this tile already holds a partial sum
         for (int it = 0; it < iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          const int sel = p.acc_sel[it % p.kblocks];
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.stage_cols + sel * p.acc_cols);
+          const uint32_t first = ((started >> sel) & 1u) ^ 1u;
           const uint32_t sa = base + stage * IG_STAGE_BYTES;
           const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + IG_A_BYTES);
 #pragma unroll
           for (int k = 0; k < IG_BK / 16; ++k) {  // 32 bytes (16 bf16 / 8 tf32) per MMA along K: +2 in 16-byte units
-            if (TF32) tc_mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
-            else tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
+            const uint32_t accum = (uint32_t)(k != 0) | (first ^ 1u);
+            if (TF32) tc_mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            else tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
           }
+          started |= 1u << sel;
           tc_commit(empty_bar(stage));           // smem stage reusable once these MMAs have read it
           if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar(acc));               // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.nstages) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
@@ -189,7 +198,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool valid = y < p.H && x < p.W;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * IG_MAXN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.stage_cols);
       float* of = p.out_f32 ? p.out_f32 + (long long)b * p.out_sb + (long long)y * p.W + x : nullptr;
       __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff + g * p.out_gstride : nullptr;
       const long long plane = (long long)p.H * p.W;
@@ -197,6 +206,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v[32];
         tc_ld32(taddr + c * 32, v);
         tc_wait_ld();
+        if (TF32 && p.nacc == 2) {                 // main + small-term accumulators, summed here in round-to-nearest fp32
+          uint32_t w[32];
+          tc_ld32(taddr + p.acc_cols + c * 32, w);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
         if (TF32) {
           if (valid && c * 32 < p.Cout) {
             const long long px = ((long long)b * p.H + y) * p.W + x;
@@ -268,7 +284,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.nstages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -628,6 +644,7 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
     attr[dev] = true;
   }
   for (int k = 0; k < p.kblocks; ++k) p.b_koff[k] = k * IG_BK;
+  p.nstages = 2; p.stage_cols = IG_MAXN; p.nacc = 1; p.acc_cols = 0;
   const long long sms = sm_count_cached();
   const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
   igemm_conv_kernel<false><<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
@@ -700,6 +717,13 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
     p.a_koff[0][3 * k + 1] = 32 * k;     p.b_koff[3 * k + 1] = C + 32 * k;
     p.a_koff[0][3 * k + 2] = 32 * k;     p.b_koff[3 * k + 2] = 32 * k;
   }
+  // The tensor core's FP32 accumulator rounds toward zero: every accumulation step costs up to one ulp of the
+  // running sum, in one direction.  The two small-term products of each block go to a second accumulator (whose
+  // magnitude, hence ulp, is 2^-11 of the main one) so that the main accumulator takes one step per block, not three.
+  p.nacc = 2; p.acc_cols = (Npad + 31) / 32 * 32;
+  if (2 * p.acc_cols <= IG_MAXN) { p.nstages = 2; p.stage_cols = IG_MAXN; }
+  else { p.nstages = 1; p.stage_cols = IG_TMEM_COLS; }
+  for (int k = 0; k < kb; ++k) { p.acc_sel[3 * k + 0] = 1; p.acc_sel[3 * k + 1] = 1; p.acc_sel[3 * k + 2] = 0; }
   p.epi = epi; p.inverse = inverse; p.y = y; p.sz = sz;
   static thread_local bool attr[64] = {false};
   int dev = 0;

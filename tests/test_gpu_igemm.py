@@ -210,4 +210,5 @@ def test_berk_autoencoder_tc_matches_torch_fp32(in_ch, shape):
             # toward zero, a bias that grows with the 324-648 accumulation steps of these K = 864 / 1728 convs and that
             # the inverse GDN (y * sqrt(norm)) does not normalise away like the forward GDN does; the reconstruction
             # tolerance of the path is 1e-4, the chain must stay well inside it.
-            assert err_tc <= (max(3 * err_t32, 1e-5) if name == "encode" else 6e-5), (name, err_tc, err_t32)
+            # (the small-term products go to a second accumulator, which cut this bias 3x: decode measures 0.4-1.4e-5)
+            assert err_tc <= (max(3 * err_t32, 1e-5) if name == "encode" else 2.5e-5), (name, err_tc, err_t32)
