@@ -47,10 +47,17 @@ __device__ __forceinline__ void cp_wait() {
 constexpr int DFF_IN_FLOATS = DWF_R * DFF_PI;
 constexpr int DFF_PIPE_TOTAL = 2 * DFF_IN_FLOATS + DWF_R * DFF_PM;
 
+__device__ float g_dwt_taps[18];   // (dec_lo[k], dec_hi[k]) pairs, k = 1..9; written once by the host wrapper
+
+__global__ void dwt97_taps_kernel() { dwt_taps_init(g_dwt_taps); }
+
 __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
-  // layout: [in0][in1][lo][hi]
+  // layout: [in0][in1][mid]
   const int tid = threadIdx.x;
+  DwtTaps tp;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) tp.d[k] = f2{g_dwt_taps[2 * k], g_dwt_taps[2 * k + 1]};
   const long long ntiles = (long long)p.N * p.tiles_x * p.tiles_y;
   long long t = blockIdx.x;
   if (t >= ntiles) return;
@@ -67,9 +74,9 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid
     cp_commit();
     cp_wait<1>();
     __syncthreads();
-    dwtff_rows(cur, mid, tid);
+    dwtff_rows(cur, mid, tid, tp);
     __syncthreads();
-    dwtff_cols(p, dwt_tile(p, t), mid, tid);
+    dwtff_cols(p, dwt_tile(p, t), mid, tid, tp);
     __syncthreads();
     if (tn >= ntiles) break;
     t = tn;
@@ -144,6 +151,7 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 64 && !attr[dev]) {
+    dwt97_taps_kernel<<<1, 1, 0, as_stream(stream)>>>();
     LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
     attr[dev] = true;

@@ -285,78 +285,104 @@ struct CopySync16 {  // host emulation / generic: plain 16-byte copy
   }
 };
 
+// The nine analysis tap pairs live in registers for the whole (persistent) kernel: passing them in from memory the
+// compiler cannot see through keeps it from re-materialising two 32-bit immediates in front of every FFMA2.
+struct DwtTaps {
+  f2 d[9];   // d[k-1] = (dec_lo[k], dec_hi[k]), k = 1..9
+};
+LL_HD void dwt_taps_init(float* t18) {
+  const float lo[9] = {LL_DEC_LO(1), LL_DEC_LO(2), LL_DEC_LO(3), LL_DEC_LO(4), LL_DEC_LO(5), LL_DEC_LO(6), LL_DEC_LO(7), LL_DEC_LO(8), LL_DEC_LO(9)};
+  const float hi[9] = {LL_DEC_HI(1), LL_DEC_HI(2), LL_DEC_HI(3), LL_DEC_HI(4), LL_DEC_HI(5), LL_DEC_HI(6), LL_DEC_HI(7), LL_DEC_HI(8), LL_DEC_HI(9)};
+  for (int k = 0; k < 9; ++k) {
+    t18[2 * k] = lo[k];
+    t18[2 * k + 1] = hi[k];
+  }
+}
+
 template <class CP>
 LL_HD void dwtff_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, CP cp) {
-  const float* base = p.x + (long long)t.n * p.x_sn;
   constexpr int C4 = DWF_C / 4;                   // 34 column groups, 7 rows in flight per pass
   constexpr int RPP = DW_THREADS / C4;
   if (tid >= C4 * RPP) return;
   const int c4 = tid % C4, r0 = tid / C4;
-  const float* col = base + wrapf(2 * t.x0 - 4 + 4 * c4, p.w);
-  for (int rr = r0; rr < DWF_R; rr += RPP) {
-    const int gr = wrapf(2 * t.y0 - 4 + rr, p.h);
-    cp(&sm[DFF_SM_IN + rr * DFF_PI + 4 * c4], col + (long long)gr * p.w);
+  const float* col = p.x + (long long)t.n * p.x_sn + wrapf(2 * t.x0 - 4 + 4 * c4, p.w);
+  int gr = wrapf(2 * t.y0 - 4 + r0, p.h);       // rows advance by RPP < h: one conditional subtraction per step
+  float* dst = sm + DFF_SM_IN + r0 * DFF_PI + 4 * c4;
+#pragma unroll
+  for (int k = 0; k < (DWF_R + RPP - 1) / RPP; ++k) {
+    if (r0 + RPP * k < DWF_R) cp(dst, col + (long long)gr * p.w);
+    dst += RPP * DFF_PI;
+    gr += RPP;
+    if (gr >= p.h) gr -= p.h;
   }
 }
 
 // ``in`` / ``mid`` are view bases: the input tile is at in + DFF_SM_IN, the mid rows at mid + DFF_SM_LO
 // (same base in the single-buffer layout, different bases in the double-buffered kernel).
-LL_HD void dwtff_rows(const float* in, float* mid, int tid) {
+LL_HD void dwtff_rows(const float* in, float* mid, int tid, const DwtTaps& tp) {
   // item = (row pair, 16 groups of 4 outputs); a warp covers 2 rows x 16 groups
   const int warp = tid >> 5, lane = tid & 31;
   const int g = (lane & 3) | ((lane >> 3) << 2);
   const int r = (lane >> 2) & 1;
-  for (int rp = warp; rp < DWF_R / 2; rp += DW_THREADS / 32) {
-    const int rr = 2 * rp + r;
-    const float* q = &in[DFF_SM_IN + rr * DFF_PI + 8 * g];
-    float v[16];
+  const float* q = &in[DFF_SM_IN + (2 * warp + r) * DFF_PI + 8 * g];
+  float* o = &mid[DFF_SM_LO + (2 * warp + r) * DFF_PM + 8 * g];
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 f = *reinterpret_cast<const float4*>(q + i);
-      v[i] = f.x;
-      v[i + 1] = f.y;
-      v[i + 2] = f.z;
-      v[i + 3] = f.w;
+  for (int rp = 0; rp < (DWF_R / 2 + DW_THREADS / 32 - 1) / (DW_THREADS / 32); ++rp) {
+    if (warp + rp * (DW_THREADS / 32) < DWF_R / 2) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(q + i);
+        v[i] = f.x;
+        v[i + 1] = f.y;
+        v[i + 2] = f.z;
+        v[i + 3] = f.w;
+      }
+      f2 acc[4];   // (lo, hi) of output 4g + i
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i] = f2{0.f, 0.f};
+#pragma unroll
+        for (int k = 1; k <= 9; ++k) LL_FMA2(acc[i], v[2 * i + 9 - k], tp.d[k - 1]);
+      }
+      *reinterpret_cast<float4*>(o) = float4{acc[0].x, acc[0].y, acc[1].x, acc[1].y};
+      *reinterpret_cast<float4*>(o + 4) = float4{acc[2].x, acc[2].y, acc[3].x, acc[3].y};
     }
-    f2 acc[4];   // (lo, hi) of output 4g + i
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[i] = f2{0.f, 0.f};
-#pragma unroll
-      for (int k = 1; k <= 9; ++k) LL_FMA2(acc[i], v[2 * i + 9 - k], LL_DEC_PAIR(k));
-    }
-    float* o = &mid[DFF_SM_LO + rr * DFF_PM + 8 * g];
-    *reinterpret_cast<float4*>(o) = float4{acc[0].x, acc[0].y, acc[1].x, acc[1].y};
-    *reinterpret_cast<float4*>(o + 4) = float4{acc[2].x, acc[2].y, acc[3].x, acc[3].y};
+    q += 2 * (DW_THREADS / 32) * DFF_PI;
+    o += 2 * (DW_THREADS / 32) * DFF_PM;
   }
 }
 
-LL_HD void dwtff_cols(const DwtParams& p, const DwtTile& t, const float* sm, int tid) {
+LL_HD void dwtff_cols(const DwtParams& p, const DwtTile& t, const float* sm, int tid, const DwtTaps& tp) {
   const int h2 = p.h / 2, w2 = p.w / 2;
   const long long sub = (long long)h2 * w2;
   const int nl = tid % DW_TX, mg = tid / DW_TX;   // 64 columns x 4 groups of 4 output rows
-  const int gx = t.x0 + nl;
-  if (gx >= w2) return;
+  const int gx = t.x0 + nl, gy0 = t.y0 + 4 * mg;
+  if (gx >= w2 || gy0 >= h2) return;
   f2 ab[15];   // (row-lo, row-hi) of this column over the 15-row window
+  const float* q = &sm[DFF_SM_LO + (8 * mg) * DFF_PM + 2 * nl];
 #pragma unroll
-  for (int i = 0; i < 15; ++i) ab[i] = *reinterpret_cast<const f2*>(&sm[DFF_SM_LO + (8 * mg + i) * DFF_PM + 2 * nl]);
-  float* llp = p.llo + (long long)t.n * p.ll_sn;
-  float* yh = p.yho + (long long)t.n * p.yh_sn;
+  for (int i = 0; i < 15; ++i) ab[i] = *reinterpret_cast<const f2*>(q + i * DFF_PM);
+  const long long o0 = (long long)gy0 * w2 + gx;
+  float* pl = p.llo + (long long)t.n * p.ll_sn + o0;
+  float* ph = p.yho + (long long)t.n * p.yh_sn + o0;
+  const int nrow = h2 - gy0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int gy = t.y0 + 4 * mg + i;
-    if (gy >= h2) break;
-    f2 A = f2{0.f, 0.f}, B = f2{0.f, 0.f};   // A = (LL, LH) from the row-low samples, B = (HL, HH) from the row-high ones
+    if (i < nrow) {
+      f2 A = f2{0.f, 0.f}, B = f2{0.f, 0.f};   // A = (LL, LH) from the row-low samples, B = (HL, HH) from the row-high ones
 #pragma unroll
-    for (int k = 1; k <= 9; ++k) {
-      LL_FMA2(A, ab[2 * i + 9 - k].x, LL_DEC_PAIR(k));
-      LL_FMA2(B, ab[2 * i + 9 - k].y, LL_DEC_PAIR(k));
+      for (int k = 1; k <= 9; ++k) {
+        LL_FMA2(A, ab[2 * i + 9 - k].x, tp.d[k - 1]);
+        LL_FMA2(B, ab[2 * i + 9 - k].y, tp.d[k - 1]);
+      }
+      pl[0] = A.x;
+      ph[0] = A.y;
+      ph[sub] = B.x;
+      ph[2 * sub] = B.y;
     }
-    const long long o = (long long)gy * w2 + gx;
-    llp[o] = A.x;
-    yh[o] = A.y;
-    yh[sub + o] = B.x;
-    yh[2 * sub + o] = B.y;
+    pl += w2;
+    ph += w2;
   }
 }
 

@@ -117,8 +117,14 @@ int ll_emul_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll
     const DwtTile t = dwt_tile(p, b);
     if (dwt_fast_ok(p)) {
       for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_load(p, t, sm, tid, CopySync16());
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_rows(sm, sm, tid);
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_cols(p, t, sm, tid);
+      DwtTaps tp;
+      {
+        float t18[18];
+        dwt_taps_init(t18);
+        for (int k = 0; k < 9; ++k) tp.d[k] = f2{t18[2 * k], t18[2 * k + 1]};
+      }
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_rows(sm, sm, tid, tp);
+      for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_cols(p, t, sm, tid, tp);
       continue;
     }
     for (int tid = 0; tid < DW_THREADS; ++tid) dwtf_load(p, t, sm, tid);
