@@ -47,10 +47,19 @@ __device__ __forceinline__ void cp_wait() {
 constexpr int DFF_IN_FLOATS = DWF_R * DFF_PI;
 constexpr int DFF_PIPE_TOTAL = 2 * DFF_IN_FLOATS + DWF_R * DFF_PM;
 
-__device__ float g_dwt_taps[18];   // (dec_lo[k], dec_hi[k]) pairs, k = 1..9; written once by the host wrapper
+// Tap table in global memory, statically initialised at module load and deliberately not const: the kernels load
+// it into registers once, and the compiler cannot fold the values back into per-instruction immediates.
+// analysis (dec_lo[k], dec_hi[k]) pairs k = 1..9, then rec_lo[0..9], rec_hi[0..9]
+#define LL_DP(k) LL_DEC_LO(k), LL_DEC_HI(k)
+__device__ float g_dwt_taps[18 + 20] = {
+    LL_DP(1), LL_DP(2), LL_DP(3), LL_DP(4), LL_DP(5), LL_DP(6), LL_DP(7), LL_DP(8), LL_DP(9),
+    LL_REC_LO(0), LL_REC_LO(1), LL_REC_LO(2), LL_REC_LO(3), LL_REC_LO(4), LL_REC_LO(5), LL_REC_LO(6), LL_REC_LO(7), LL_REC_LO(8), LL_REC_LO(9),
+    LL_REC_HI(0), LL_REC_HI(1), LL_REC_HI(2), LL_REC_HI(3), LL_REC_HI(4), LL_REC_HI(5), LL_REC_HI(6), LL_REC_HI(7), LL_REC_HI(8), LL_REC_HI(9)};
+#undef LL_DP
 
-__global__ void dwt97_taps_kernel() { dwt_taps_init(g_dwt_taps); }
-
+// Tile t is decoded once and carried into the next iteration; three phases, two block barriers per tile: the next
+// load into a buffer and the next row pass into ``mid`` are both issued behind a barrier every thread only reaches
+// after it finished reading them.
 __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
   // layout: [in0][in1][mid]
@@ -58,59 +67,73 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid
   DwtTaps tp;
 #pragma unroll
   for (int k = 0; k < 9; ++k) tp.d[k] = f2{g_dwt_taps[2 * k], g_dwt_taps[2 * k + 1]};
-  const long long ntiles = (long long)p.N * p.tiles_x * p.tiles_y;
-  long long t = blockIdx.x;
+  const unsigned ntiles = (unsigned)p.N * p.tiles_x * p.tiles_y;
+  unsigned t = blockIdx.x;
   if (t >= ntiles) return;
   float* in0 = sm;
   float* in1 = sm + DFF_IN_FLOATS;
-  float* mid = sm + 2 * DFF_IN_FLOATS - DFF_SM_LO;  // so that mid + DFF_SM_LO / DFF_SM_HI land after both inputs
-  dwtff_load(p, dwt_tile(p, t), in0, tid, CopyAsync16());
+  float* mid = sm + 2 * DFF_IN_FLOATS - DFF_SM_LO;  // so that mid + DFF_SM_LO lands after both inputs
+  DwtTile cur_t = dwt_tile32(p, t), nxt_t = cur_t;
+  dwtff_load(p, cur_t, in0, tid, CopyAsync16());
   cp_commit();
   for (int it = 0;; ++it) {
     float* cur = (it & 1) ? in1 : in0;
     float* nxt = (it & 1) ? in0 : in1;
-    const long long tn = t + gridDim.x;
-    if (tn < ntiles) dwtff_load(p, dwt_tile(p, tn), nxt, tid, CopyAsync16());
+    const unsigned tn = t + gridDim.x;
+    if (tn < ntiles) {
+      nxt_t = dwt_tile32(p, tn);
+      dwtff_load(p, nxt_t, nxt, tid, CopyAsync16());
+    }
     cp_commit();
     cp_wait<1>();
     __syncthreads();
     dwtff_rows(cur, mid, tid, tp);
     __syncthreads();
-    dwtff_cols(p, dwt_tile(p, t), mid, tid, tp);
-    __syncthreads();
+    dwtff_cols(p, cur_t, mid, tid, tp);
     if (tn >= ntiles) break;
     t = tn;
+    cur_t = nxt_t;
   }
 }
 
 constexpr int DIF_SB_FLOATS = 4 * DWI_R * DIF_P;
 constexpr int DIF_PIPE_TOTAL = 2 * DIF_SB_FLOATS + 2 * 2 * DW_TY * DIF_P;
 
-__global__ void __launch_bounds__(DW_THREADS) dwt97_inv_fast_kernel(const __grid_constant__ DwtParams p) {
+__global__ void __launch_bounds__(DIF_THREADS) dwt97_inv_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
-  const long long ntiles = (long long)p.N * p.tiles_x * p.tiles_y;
-  long long t = blockIdx.x;
+  DwtSynTaps tp;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    tp.l[k] = f2{g_dwt_taps[18 + 2 * k], g_dwt_taps[18 + 2 * k + 1]};
+    tp.h[k] = f2{g_dwt_taps[28 + 2 * k], g_dwt_taps[28 + 2 * k + 1]};
+  }
+  const unsigned ntiles = (unsigned)p.N * p.tiles_x * p.tiles_y;
+  unsigned t = blockIdx.x;
   if (t >= ntiles) return;
   float* sb0 = sm;
   float* sb1 = sm + DIF_SB_FLOATS;
   float* mid = sm + 2 * DIF_SB_FLOATS - DIF_SM_LO;
-  dwtif_load(p, dwt_tile(p, t), sb0, tid, CopyAsync16());
+  DwtTile cur_t = dwt_tile32(p, t), nxt_t = cur_t;
+  dwtif_load(p, cur_t, sb0, tid, CopyAsync16());
   cp_commit();
   for (int it = 0;; ++it) {
     float* cur = (it & 1) ? sb1 : sb0;
     float* nxt = (it & 1) ? sb0 : sb1;
-    const long long tn = t + gridDim.x;
-    if (tn < ntiles) dwtif_load(p, dwt_tile(p, tn), nxt, tid, CopyAsync16());
+    const unsigned tn = t + gridDim.x;
+    if (tn < ntiles) {
+      nxt_t = dwt_tile32(p, tn);
+      dwtif_load(p, nxt_t, nxt, tid, CopyAsync16());
+    }
     cp_commit();
     cp_wait<1>();
     __syncthreads();
-    dwtif_cols(cur, mid, tid);
+    dwtif_cols(cur, mid, tid, tp);
     __syncthreads();
-    dwtif_rows(p, dwt_tile(p, t), mid, tid);
-    __syncthreads();
+    dwtif_rows(p, cur_t, mid, tid, tp);
     if (tn >= ntiles) break;
     t = tn;
+    cur_t = nxt_t;
   }
 }
 
@@ -151,7 +174,6 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 64 && !attr[dev]) {
-    dwt97_taps_kernel<<<1, 1, 0, as_stream(stream)>>>();
     LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
     attr[dev] = true;
@@ -189,7 +211,7 @@ int ll_dwt97_inv_level(const float* llp, int64_t ll_sn, const float* yh, int64_t
     attr[dev] = true;
   }
   const long long pgrid = (long long)sm_count_cached() * 3;
-  if (dwt_fast_ok(p)) dwt97_inv_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream)>>>(p);
+  if (dwt_fast_ok(p)) dwt97_inv_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DIF_THREADS, smem_fast, as_stream(stream)>>>(p);
   else dwt97_inv_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_inv_kernel");
   return LL_OK;

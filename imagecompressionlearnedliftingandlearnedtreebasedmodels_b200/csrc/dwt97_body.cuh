@@ -266,17 +266,25 @@ constexpr int DFF_SM_TOTAL = DFF_SM_LO + DWF_R * DFF_PM;
 // high-pass (or the even and the odd polyphase) accumulator in one instruction.  A zero tap leaves its
 // accumulator untouched (fma(0, v, acc) == acc), so the results equal the scalar tap loops bit for bit.
 #define LL_DEC_PAIR(k) (f2{LL_DEC_LO(k), LL_DEC_HI(k)})
-#define LL_RECL_PAIR(t) (f2{LL_REC_LO(2 * (t)), LL_REC_LO(2 * (t) + 1)})
-#define LL_RECH_PAIR(t) (f2{LL_REC_HI(2 * (t)), LL_REC_HI(2 * (t) + 1)})
 
-// fast wrap for indices that are at most a few extents out of range
-LL_HD int wrapf(int a, int n) {
-  if (a < 0) a += n;
-  if (a >= n) {
-    a -= n;
-    if (a >= n) a %= n;
-  }
-  return a < 0 ? wrapi(a, n) : a;
+// One fold.  The fast path runs on extents >= 10, where a tile's halo reaches at most 4 samples past either
+// end; indices further out only occur in the unused part of a partial tile and may map to any valid sample.
+LL_HD int wrap1(int a, int n) {
+  a += (a < 0) ? n : 0;
+  a -= (a >= n) ? n : 0;
+  return (unsigned)a < (unsigned)n ? a : 0;
+}
+
+// 32-bit tile decode (the launchers reject grids of 2^31 tiles or more)
+LL_HD DwtTile dwt_tile32(const DwtParams& p, unsigned t) {
+  DwtTile d;
+  const unsigned tx = (unsigned)p.tiles_x, ty = (unsigned)p.tiles_y;
+  const unsigned q = t / tx;
+  d.x0 = int(t - q * tx) * DW_TX;
+  const unsigned n = q / ty;
+  d.y0 = int(q - n * ty) * DW_TY;
+  d.n = int(n);
+  return d;
 }
 
 struct CopySync16 {  // host emulation / generic: plain 16-byte copy
@@ -305,8 +313,8 @@ LL_HD void dwtff_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, 
   constexpr int RPP = DW_THREADS / C4;
   if (tid >= C4 * RPP) return;
   const int c4 = tid % C4, r0 = tid / C4;
-  const float* col = p.x + (long long)t.n * p.x_sn + wrapf(2 * t.x0 - 4 + 4 * c4, p.w);
-  int gr = wrapf(2 * t.y0 - 4 + r0, p.h);       // rows advance by RPP < h: one conditional subtraction per step
+  const float* col = p.x + (long long)t.n * p.x_sn + wrap1(2 * t.x0 - 4 + 4 * c4, p.w);
+  int gr = wrap1(2 * t.y0 - 4 + r0, p.h);       // rows advance by RPP < h: one conditional subtraction per step
   float* dst = sm + DFF_SM_IN + r0 * DFF_PI + 4 * c4;
 #pragma unroll
   for (int k = 0; k < (DWF_R + RPP - 1) / RPP; ++k) {
@@ -387,65 +395,86 @@ LL_HD void dwtff_cols(const DwtParams& p, const DwtTile& t, const float* sm, int
 }
 
 // ---- inverse fast path ----
+constexpr int DIF_THREADS = 288;          // 9 warps: 288 column-synthesis items, 80 subband lines = 5 x 16 load passes
 constexpr int DIF_P = DW_TX + 8;          // 72: subband tile / mid pitch; column c <-> subband col x0 - 4 + c
 constexpr int DIF_SM_SB = 0;              // [4][DWI_R][DIF_P]
 constexpr int DIF_SM_LO = DIF_SM_SB + 4 * DWI_R * DIF_P;   // [2 TY][DIF_P]
 constexpr int DIF_SM_HI = DIF_SM_LO + 2 * DW_TY * DIF_P;
 constexpr int DIF_SM_TOTAL = DIF_SM_HI + 2 * DW_TY * DIF_P;
 
+// synthesis tap pairs, register-resident like DwtTaps: l[t] = (rec_lo[2t], rec_lo[2t+1]), h[t] = (rec_hi[2t], rec_hi[2t+1])
+struct DwtSynTaps {
+  f2 l[5], h[5];
+};
+LL_HD void dwt_syn_taps_init(float* t20) {
+  const float lo[10] = {LL_REC_LO(0), LL_REC_LO(1), LL_REC_LO(2), LL_REC_LO(3), LL_REC_LO(4), LL_REC_LO(5), LL_REC_LO(6), LL_REC_LO(7), LL_REC_LO(8), LL_REC_LO(9)};
+  const float hi[10] = {LL_REC_HI(0), LL_REC_HI(1), LL_REC_HI(2), LL_REC_HI(3), LL_REC_HI(4), LL_REC_HI(5), LL_REC_HI(6), LL_REC_HI(7), LL_REC_HI(8), LL_REC_HI(9)};
+  for (int k = 0; k < 10; ++k) {
+    t20[k] = lo[k];
+    t20[10 + k] = hi[k];
+  }
+}
+
 template <class CP>
 LL_HD void dwtif_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, CP cp) {
   const int h2 = p.h / 2, w2 = p.w / 2;
   const long long sub = (long long)h2 * w2;
-  constexpr int C4 = DIF_P / 4;                   // 18 column groups, 14 (subband,row) lines in flight per pass
-  constexpr int RPP = DW_THREADS / C4;
-  if (tid >= C4 * RPP) return;
+  constexpr int C4 = DIF_P / 4;                   // 18 column groups, 16 (subband,row) lines in flight per pass
+  constexpr int RPP = DIF_THREADS / C4;
   const int c4 = tid % C4, r0 = tid / C4;
-  const int gx = wrapf(t.x0 - 4 + 4 * c4, w2);
+  const int gx = wrap1(t.x0 - 4 + 4 * c4, w2);
   const float* b0 = p.ll + (long long)t.n * p.ll_sn + gx;
   const float* b1 = p.yh + (long long)t.n * p.yh_sn + gx;
-  for (int rs = r0; rs < 4 * DWI_R; rs += RPP) {
-    const int s = rs / DWI_R, i = rs % DWI_R;
-    const int gy = wrapf(t.y0 - 2 + i, h2);
+  float* dst = sm + DIF_SM_SB + r0 * DIF_P + 4 * c4;
+#pragma unroll
+  for (int k = 0; k < 4 * DWI_R / RPP; ++k) {
+    const int rs = r0 + RPP * k, s = rs / DWI_R, i = rs - s * DWI_R;
+    const int gy = wrap1(t.y0 - 2 + i, h2);
     const float* src = (s == 0 ? b0 : b1 + (s - 1) * sub) + (long long)gy * w2;
-    cp(&sm[DIF_SM_SB + rs * DIF_P + 4 * c4], src);
+    cp(dst, src);
+    dst += RPP * DIF_P;
   }
 }
+static_assert((4 * DWI_R) % (DIF_THREADS / (DIF_P / 4)) == 0, "inverse load passes cover the subband lines exactly");
 
-LL_HD void dwtif_cols(const float* sb, float* mid, int tid) {
-  // item = (lo|hi, group of 4 j's, column): 2 x 4 x 72 = 576
-  for (int e = tid; e < 2 * (DW_TY / 4) * DIF_P; e += DW_THREADS) {
-    const int c = e % DIF_P, jg = (e / DIF_P) % (DW_TY / 4), which = e / (DIF_P * (DW_TY / 4));
-    const float* lo = &sb[DIF_SM_SB + ((which ? 2 : 0) * DWI_R + 4 * jg) * DIF_P + c];
-    const float* hi = &sb[DIF_SM_SB + ((which ? 3 : 1) * DWI_R + 4 * jg) * DIF_P + c];
-    float l[8], h[8];
+LL_HD void dwtif_cols(const float* sb, float* mid, int tid, const DwtSynTaps& tp) {
+  // item = (lo|hi, group of 4 j's, column pair): 2 x 4 x 36 = one per thread
+  const int cp = tid % (DIF_P / 2), jg = (tid / (DIF_P / 2)) & 3, which = tid / (2 * DIF_P);
+  const float* lo = &sb[DIF_SM_SB + ((which ? 2 : 0) * DWI_R + 4 * jg) * DIF_P + 2 * cp];
+  const float* hi = lo + DWI_R * DIF_P;          // lh follows ll, hh follows hl
+  f2 l[8], h[8];                                 // (column 2cp, column 2cp+1) of the 8-row window
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      l[i] = lo[i * DIF_P];
-      h[i] = hi[i * DIF_P];
+  for (int i = 0; i < 8; ++i) {
+    l[i] = *reinterpret_cast<const f2*>(lo + i * DIF_P);
+    h[i] = *reinterpret_cast<const f2*>(hi + i * DIF_P);
+  }
+  float* o = &mid[(which ? DIF_SM_HI : DIF_SM_LO) + (8 * jg) * DIF_P + 2 * cp];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f2 al0 = f2{0.f, 0.f}, ah0 = f2{0.f, 0.f}, al1 = f2{0.f, 0.f}, ah1 = f2{0.f, 0.f};   // (even, odd) partial sums
+#pragma unroll
+    for (int tt = 0; tt < 5; ++tt) {
+      LL_FMA2(al0, l[j + 4 - tt].x, tp.l[tt]);
+      LL_FMA2(ah0, h[j + 4 - tt].x, tp.h[tt]);
+      LL_FMA2(al1, l[j + 4 - tt].y, tp.l[tt]);
+      LL_FMA2(ah1, h[j + 4 - tt].y, tp.h[tt]);
     }
-    float* o = &mid[(which ? DIF_SM_HI : DIF_SM_LO) + (8 * jg) * DIF_P + c];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      f2 al = f2{0.f, 0.f}, ah = f2{0.f, 0.f};   // (even, odd) partial sums of the low / high branch
-#pragma unroll
-      for (int tt = 0; tt < 5; ++tt) {
-        LL_FMA2(al, l[j + 4 - tt], LL_RECL_PAIR(tt));
-        LL_FMA2(ah, h[j + 4 - tt], LL_RECH_PAIR(tt));
-      }
-      o[(2 * j) * DIF_P] = al.x + ah.x;
-      o[(2 * j + 1) * DIF_P] = al.y + ah.y;
-    }
+    *reinterpret_cast<f2*>(o + (2 * j) * DIF_P) = f2{al0.x + ah0.x, al1.x + ah1.x};
+    *reinterpret_cast<f2*>(o + (2 * j + 1) * DIF_P) = f2{al0.y + ah0.y, al1.y + ah1.y};
   }
 }
+static_assert(2 * (DW_TY / 4) * (DIF_P / 2) == DIF_THREADS, "one column-synthesis item per thread");
 
-LL_HD void dwtif_rows(const DwtParams& p, const DwtTile& t, const float* sm, int tid) {
+LL_HD void dwtif_rows(const DwtParams& p, const DwtTile& t, const float* sm, int tid, const DwtSynTaps& tp) {
   const int w2 = p.w / 2;
+  float* plane = p.xo + (long long)t.n * p.x_sn;
   // item = (output row, group of 4 output pairs): 32 x 16 = 512
-  for (int e = tid; e < 2 * DW_TY * (DW_TX / 4); e += DW_THREADS) {
+#pragma unroll
+  for (int k = 0; k < (2 * DW_TY * (DW_TX / 4) + DIF_THREADS - 1) / DIF_THREADS; ++k) {
+    const int e = tid + k * DIF_THREADS;
     const int jg = e % (DW_TX / 4), r = e / (DW_TX / 4);
     const int gy = 2 * t.y0 + r, gx = t.x0 + 4 * jg;
-    if (gy >= p.h || gx >= w2) continue;
+    if (e >= 2 * DW_TY * (DW_TX / 4) || gy >= p.h || gx >= w2) continue;
     float l[12], h[12];
 #pragma unroll
     for (int i = 0; i < 12; i += 4) {
@@ -461,13 +490,13 @@ LL_HD void dwtif_rows(const DwtParams& p, const DwtTile& t, const float* sm, int
       f2 al = f2{0.f, 0.f}, ah = f2{0.f, 0.f};
 #pragma unroll
       for (int tt = 0; tt < 5; ++tt) {
-        LL_FMA2(al, l[j + 6 - tt], LL_RECL_PAIR(tt));
-        LL_FMA2(ah, h[j + 6 - tt], LL_RECH_PAIR(tt));
+        LL_FMA2(al, l[j + 6 - tt], tp.l[tt]);
+        LL_FMA2(ah, h[j + 6 - tt], tp.h[tt]);
       }
       out[2 * j] = al.x + ah.x;
       out[2 * j + 1] = al.y + ah.y;
     }
-    float* o = p.xo + (long long)t.n * p.x_sn + (long long)gy * p.w + 2 * gx;
+    float* o = plane + (long long)gy * p.w + 2 * gx;
     *reinterpret_cast<float4*>(o) = float4{out[0], out[1], out[2], out[3]};
     *reinterpret_cast<float4*>(o + 4) = float4{out[4], out[5], out[6], out[7]};
   }

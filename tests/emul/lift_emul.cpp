@@ -113,8 +113,8 @@ int ll_emul_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll
   float* sm = (float*)(((uintptr_t)smv.data() + 15) & ~(uintptr_t)15);
   const long long tiles = (long long)N * p.tiles_x * p.tiles_y;
   for (long long b = 0; b < tiles; ++b) {
-    for (int i = 0; i < DWF_SM_TOTAL; ++i) sm[i] = __builtin_nanf("");
-    const DwtTile t = dwt_tile(p, b);
+    for (int i = 0; i < (DWF_SM_TOTAL > DFF_SM_TOTAL ? DWF_SM_TOTAL : DFF_SM_TOTAL); ++i) sm[i] = __builtin_nanf("");
+    const DwtTile t = dwt_fast_ok(p) ? dwt_tile32(p, (unsigned)b) : dwt_tile(p, b);
     if (dwt_fast_ok(p)) {
       for (int tid = 0; tid < DW_THREADS; ++tid) dwtff_load(p, t, sm, tid, CopySync16());
       DwtTaps tp;
@@ -145,12 +145,21 @@ int ll_emul_dwt97_inv_level(const float* llp, int64_t ll_sn, const float* yh, in
   float* sm = (float*)(((uintptr_t)smv.data() + 15) & ~(uintptr_t)15);
   const long long tiles = (long long)N * p.tiles_x * p.tiles_y;
   for (long long b = 0; b < tiles; ++b) {
-    for (int i = 0; i < DWI_SM_TOTAL; ++i) sm[i] = __builtin_nanf("");
-    const DwtTile t = dwt_tile(p, b);
+    for (int i = 0; i < (DWI_SM_TOTAL > DIF_SM_TOTAL ? DWI_SM_TOTAL : DIF_SM_TOTAL); ++i) sm[i] = __builtin_nanf("");
+    const DwtTile t = dwt_fast_ok(p) ? dwt_tile32(p, (unsigned)b) : dwt_tile(p, b);
     if (dwt_fast_ok(p)) {
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_load(p, t, sm, tid, CopySync16());
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_cols(sm, sm, tid);
-      for (int tid = 0; tid < DW_THREADS; ++tid) dwtif_rows(p, t, sm, tid);
+      DwtSynTaps tp;
+      {
+        float t20[20];
+        dwt_syn_taps_init(t20);
+        for (int k = 0; k < 5; ++k) {
+          tp.l[k] = f2{t20[2 * k], t20[2 * k + 1]};
+          tp.h[k] = f2{t20[10 + 2 * k], t20[10 + 2 * k + 1]};
+        }
+      }
+      for (int tid = 0; tid < DIF_THREADS; ++tid) dwtif_load(p, t, sm, tid, CopySync16());
+      for (int tid = 0; tid < DIF_THREADS; ++tid) dwtif_cols(sm, sm, tid, tp);
+      for (int tid = 0; tid < DIF_THREADS; ++tid) dwtif_rows(p, t, sm, tid, tp);
       continue;
     }
     for (int tid = 0; tid < DW_THREADS; ++tid) dwti_load(p, t, sm, tid);
