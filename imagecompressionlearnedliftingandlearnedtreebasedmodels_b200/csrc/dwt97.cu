@@ -1,4 +1,6 @@
 // dwt97.cu -- CDF 9/7 fixed-filter DWT (K1): kernels + C ABI.
+#include <stdlib.h>
+
 #include "dwt97_body.cuh"
 #include "ll_common.cuh"
 
@@ -26,21 +28,6 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_inv_kernel(const __grid_cons
   dwti_rows(p, t, sm, tid);
 }
 
-// 16-byte asynchronous global->shared copy (LDGSTS), used to prefetch the next tile while the
-// current one is being filtered: without it every CTA of a wave loads, filters and stores in
-// lock-step and DRAM idles during the compute phases (ncu: long-scoreboard stall 4.0 per issue).
-struct CopyAsync16 {
-  __device__ __forceinline__ void operator()(float* dst, const float* src) const {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-  }
-};
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // Persistent, double-buffered: smem = in[2] | lo | hi.  The phase functions address the input
 // tile at sm + DFF_SM_IN and lo/hi at fixed offsets, so buffer b is presented by shifting the
 // base pointer: lo/hi live at the same absolute place for both (layout below).
@@ -57,9 +44,51 @@ __device__ float g_dwt_taps[18 + 20] = {
     LL_REC_HI(0), LL_REC_HI(1), LL_REC_HI(2), LL_REC_HI(3), LL_REC_HI(4), LL_REC_HI(5), LL_REC_HI(6), LL_REC_HI(7), LL_REC_HI(8), LL_REC_HI(9)};
 #undef LL_DP
 
-// Tile t is decoded once and carried into the next iteration; three phases, two block barriers per tile: the next
-// load into a buffer and the next row pass into ``mid`` are both issued behind a barrier every thread only reaches
-// after it finished reading them.
+// ---- persistent fast kernels ------------------------------------------------------------------------------------
+// Double-buffered: the next tile is prefetched with 16-byte LDGSTS copies while the current one is filtered (without
+// it every CTA of a wave loads, filters and stores in lock-step and DRAM idles during the compute phases).  Bulk
+// copies (UBLKCP) were tried and rejected: one per tile row is needed, each is a uniform-datapath instruction that the
+// compiler serialises over the issuing lanes (~25 issue slots per row against ~10 for the row's 34 LDGSTS lanes).
+// The tile index advances incrementally (no division per tile); three phases, two block barriers per tile -- the next
+// copy into a buffer and the next first-pass write into ``mid`` are both issued behind a barrier that every thread
+// only reaches after it finished reading them.
+struct CopyAsync16 {
+  __device__ __forceinline__ void operator()(float* dst, const float* src) const {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  }
+};
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct TileWalk {   // tile coordinates advanced by gridDim.x tiles per iteration without dividing
+  int x, y, n, sx, sy, sn;
+  __device__ __forceinline__ TileWalk(const DwtParams& p, unsigned t, unsigned step) {
+    const unsigned tx = p.tiles_x, ty = p.tiles_y;
+    unsigned q = t / tx;
+    x = t - q * tx;
+    n = q / ty;
+    y = q - n * ty;
+    q = step / tx;
+    sx = step - q * tx;
+    sn = q / ty;
+    sy = q - sn * ty;
+  }
+  __device__ __forceinline__ void advance(const DwtParams& p) {
+    x += sx;
+    int c = x >= p.tiles_x;
+    x -= c ? p.tiles_x : 0;
+    y += sy + c;
+    c = y >= p.tiles_y;
+    y -= c ? p.tiles_y : 0;
+    n += sn + c;
+  }
+  __device__ __forceinline__ DwtTile tile() const { return DwtTile{n, y * DW_TY, x * DW_TX}; }
+};
+
 __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
   // layout: [in0][in1][mid]
@@ -69,30 +98,54 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid
   for (int k = 0; k < 9; ++k) tp.d[k] = f2{g_dwt_taps[2 * k], g_dwt_taps[2 * k + 1]};
   const unsigned ntiles = (unsigned)p.N * p.tiles_x * p.tiles_y;
   unsigned t = blockIdx.x;
-  if (t >= ntiles) return;
-  float* in0 = sm;
-  float* in1 = sm + DFF_IN_FLOATS;
   float* mid = sm + 2 * DFF_IN_FLOATS - DFF_SM_LO;  // so that mid + DFF_SM_LO lands after both inputs
-  DwtTile cur_t = dwt_tile32(p, t), nxt_t = cur_t;
-  dwtff_load(p, cur_t, in0, tid, CopyAsync16());
+  TileWalk cur(p, t, gridDim.x), nxt = cur;
+  dwtff_load(p, cur.tile(), sm, tid, CopyAsync16());
   cp_commit();
-  for (int it = 0;; ++it) {
-    float* cur = (it & 1) ? in1 : in0;
-    float* nxt = (it & 1) ? in0 : in1;
+  for (unsigned it = 0;; ++it) {
+    const unsigned b = it & 1;
     const unsigned tn = t + gridDim.x;
-    if (tn < ntiles) {
-      nxt_t = dwt_tile32(p, tn);
-      dwtff_load(p, nxt_t, nxt, tid, CopyAsync16());
-    }
+    nxt.advance(p);
+    if (tn < ntiles) dwtff_load(p, nxt.tile(), sm + (b ^ 1) * DFF_IN_FLOATS, tid, CopyAsync16());
     cp_commit();
     cp_wait<1>();
     __syncthreads();
-    dwtff_rows(cur, mid, tid, tp);
+    dwtff_rows(sm + b * DFF_IN_FLOATS, mid, tid, tp);
     __syncthreads();
-    dwtff_cols(p, cur_t, mid, tid, tp);
+    dwtff_cols(p, cur.tile(), mid, tid, tp);
     if (tn >= ntiles) break;
     t = tn;
-    cur_t = nxt_t;
+    cur = nxt;
+  }
+}
+
+// Single-buffer variant (experiment): 44 KB per CTA -> 4 resident CTAs; the next tile's copy is issued after the row
+// pass released the input buffer and lands while the column pass runs.
+__global__ void __launch_bounds__(DW_THREADS, 4) dwt97_fwd_fast1_kernel(const __grid_constant__ DwtParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  DwtTaps tp;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) tp.d[k] = f2{g_dwt_taps[2 * k], g_dwt_taps[2 * k + 1]};
+  const unsigned ntiles = (unsigned)p.N * p.tiles_x * p.tiles_y;
+  unsigned t = blockIdx.x;
+  float* mid = sm + DFF_IN_FLOATS - DFF_SM_LO;
+  TileWalk cur(p, t, gridDim.x), nxt = cur;
+  dwtff_load(p, cur.tile(), sm, tid, CopyAsync16());
+  cp_commit();
+  for (;;) {
+    const unsigned tn = t + gridDim.x;
+    nxt.advance(p);
+    cp_wait<0>();
+    __syncthreads();
+    dwtff_rows(sm, mid, tid, tp);
+    __syncthreads();
+    if (tn < ntiles) dwtff_load(p, nxt.tile(), sm, tid, CopyAsync16());
+    cp_commit();
+    dwtff_cols(p, cur.tile(), mid, tid, tp);
+    if (tn >= ntiles) break;
+    t = tn;
+    cur = nxt;
   }
 }
 
@@ -110,30 +163,24 @@ __global__ void __launch_bounds__(DIF_THREADS) dwt97_inv_fast_kernel(const __gri
   }
   const unsigned ntiles = (unsigned)p.N * p.tiles_x * p.tiles_y;
   unsigned t = blockIdx.x;
-  if (t >= ntiles) return;
-  float* sb0 = sm;
-  float* sb1 = sm + DIF_SB_FLOATS;
   float* mid = sm + 2 * DIF_SB_FLOATS - DIF_SM_LO;
-  DwtTile cur_t = dwt_tile32(p, t), nxt_t = cur_t;
-  dwtif_load(p, cur_t, sb0, tid, CopyAsync16());
+  TileWalk cur(p, t, gridDim.x), nxt = cur;
+  dwtif_load(p, cur.tile(), sm, tid, CopyAsync16());
   cp_commit();
-  for (int it = 0;; ++it) {
-    float* cur = (it & 1) ? sb1 : sb0;
-    float* nxt = (it & 1) ? sb0 : sb1;
+  for (unsigned it = 0;; ++it) {
+    const unsigned b = it & 1;
     const unsigned tn = t + gridDim.x;
-    if (tn < ntiles) {
-      nxt_t = dwt_tile32(p, tn);
-      dwtif_load(p, nxt_t, nxt, tid, CopyAsync16());
-    }
+    nxt.advance(p);
+    if (tn < ntiles) dwtif_load(p, nxt.tile(), sm + (b ^ 1) * DIF_SB_FLOATS, tid, CopyAsync16());
     cp_commit();
     cp_wait<1>();
     __syncthreads();
-    dwtif_cols(cur, mid, tid, tp);
+    dwtif_cols(sm + b * DIF_SB_FLOATS, mid, tid, tp);
     __syncthreads();
-    dwtif_rows(p, cur_t, mid, tid, tp);
+    dwtif_rows(p, cur.tile(), mid, tid, tp);
     if (tn >= ntiles) break;
     t = tn;
-    cur_t = nxt_t;
+    cur = nxt;
   }
 }
 
@@ -179,6 +226,14 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
     attr[dev] = true;
   }
   const long long pgrid = (long long)sm_count_cached() * 3;   // 3 resident CTAs per SM (70 KB each)
+  static const bool sb = getenv("LL_DWT_SB") != nullptr;
+  if (dwt_fast_ok(p) && sb) {
+    const long long g4 = (long long)sm_count_cached() * 4;
+    constexpr size_t smem1 = (DFF_IN_FLOATS + DWF_R * DFF_PM) * sizeof(float);
+    static bool a1 = false;
+    if (!a1) { LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_fast1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); a1 = true; }
+    dwt97_fwd_fast1_kernel<<<(unsigned)(tiles < g4 ? tiles : g4), DW_THREADS, smem1, as_stream(stream)>>>(p);
+  } else
   if (dwt_fast_ok(p)) dwt97_fwd_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream)>>>(p);
   else dwt97_fwd_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_fwd_kernel");

@@ -313,15 +313,18 @@ LL_HD void dwtff_load(const DwtParams& p, const DwtTile& t, float* sm, int tid, 
   constexpr int RPP = DW_THREADS / C4;
   if (tid >= C4 * RPP) return;
   const int c4 = tid % C4, r0 = tid / C4;
-  const float* col = p.x + (long long)t.n * p.x_sn + wrap1(2 * t.x0 - 4 + 4 * c4, p.w);
-  int gr = wrap1(2 * t.y0 - 4 + r0, p.h);       // rows advance by RPP < h: one conditional subtraction per step
+  int gr = wrap1(2 * t.y0 - 4 + r0, p.h);       // rows advance by RPP < h: one conditional fold per step
+  const float* src = p.x + (long long)t.n * p.x_sn + wrap1(2 * t.x0 - 4 + 4 * c4, p.w) + (long long)gr * p.w;
+  const long long step = (long long)RPP * p.w, fold = step - (long long)p.h * p.w;
   float* dst = sm + DFF_SM_IN + r0 * DFF_PI + 4 * c4;
 #pragma unroll
   for (int k = 0; k < (DWF_R + RPP - 1) / RPP; ++k) {
-    if (r0 + RPP * k < DWF_R) cp(dst, col + (long long)gr * p.w);
+    if (r0 + RPP * k < DWF_R) cp(dst, src);
     dst += RPP * DFF_PI;
     gr += RPP;
-    if (gr >= p.h) gr -= p.h;
+    const bool f = gr >= p.h;
+    gr -= f ? p.h : 0;
+    src += f ? fold : step;
   }
 }
 
@@ -372,25 +375,26 @@ LL_HD void dwtff_cols(const DwtParams& p, const DwtTile& t, const float* sm, int
 #pragma unroll
   for (int i = 0; i < 15; ++i) ab[i] = *reinterpret_cast<const f2*>(q + i * DFF_PM);
   const long long o0 = (long long)gy0 * w2 + gx;
-  float* pl = p.llo + (long long)t.n * p.ll_sn + o0;
-  float* ph = p.yho + (long long)t.n * p.yh_sn + o0;
+  float* pLL = p.llo + (long long)t.n * p.ll_sn + o0;
+  float* pLH = p.yho + (long long)t.n * p.yh_sn + o0;
+  float* pHL = pLH + sub;
+  float* pHH = pHL + sub;
   const int nrow = h2 - gy0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i < nrow) {
-      f2 A = f2{0.f, 0.f}, B = f2{0.f, 0.f};   // A = (LL, LH) from the row-low samples, B = (HL, HH) from the row-high ones
+    f2 A = f2{0.f, 0.f}, B = f2{0.f, 0.f};   // A = (LL, LH) from the row-low samples, B = (HL, HH) from the row-high ones
 #pragma unroll
-      for (int k = 1; k <= 9; ++k) {
-        LL_FMA2(A, ab[2 * i + 9 - k].x, tp.d[k - 1]);
-        LL_FMA2(B, ab[2 * i + 9 - k].y, tp.d[k - 1]);
-      }
-      pl[0] = A.x;
-      ph[0] = A.y;
-      ph[sub] = B.x;
-      ph[2 * sub] = B.y;
+    for (int k = 1; k <= 9; ++k) {
+      LL_FMA2(A, ab[2 * i + 9 - k].x, tp.d[k - 1]);
+      LL_FMA2(B, ab[2 * i + 9 - k].y, tp.d[k - 1]);
     }
-    pl += w2;
-    ph += w2;
+    if (i < nrow) {                          // rows below the plane (partial tile) are computed on unused samples and dropped
+      const unsigned off = (unsigned)(i * w2);
+      pLL[off] = A.x;
+      pLH[off] = A.y;
+      pHL[off] = B.x;
+      pHH[off] = B.y;
+    }
   }
 }
 

@@ -60,8 +60,8 @@ constexpr int TS_RA2 = TS_RA1 + TC_RA * TC_SLOT;
 constexpr int TS_A3 = TS_RA2 + TC_RA * TC_SLOT;
 constexpr int TS_O1 = TS_A3 + TC_R3 * 8 * TC_PA3 * 4;
 constexpr int TS_P2 = TS_O1 + TC_RO * 16 * TC_P3 * 4;
-constexpr int TS_P3 = TS_P2 + 80 * TC_PP * 4;
-constexpr int TS_SK = TS_P3 + 80 * TC_PP * 4;
+constexpr int TS_P3 = TS_P2 + 48 * TC_PP * 4;   // partial planes: [dx pair 3][co 16][TC_PP]
+constexpr int TS_SK = TS_P3 + 48 * TC_PP * 4;
 constexpr int TS_W = TS_SK + TC_RS * TC_PS * 4;
 // small weights (floats): pre[4] W1[tap 25][co 16] b1[16] b2[16] b3[16] W4[tap 25][ci 16] b4[4]
 // (channel-pair float2 loads feed packed FFMA2 with a broadcast activation)
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   // ---- one-time setup -------------------------------------------------------------------------
   if (tid == 0) {
     mbar_init(bar_mma, 1);
-    mbar_init(bar_free, 8);
-    mbar_init(bar_free3, 8);
+    mbar_init(bar_free, 4);
+    mbar_init(bar_free3, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -289,238 +289,249 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
     }
     __syncthreads();
 
-    for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
-      const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
-      const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
-      const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
-      if (warp == TC_MMA_WARP) {
-        // ======================= MMA warp =======================
-        TC_STAMP(0);
-        mbar_wait(bar_free, n & 1);
-        tc_fence_after();
-        TC_STAMP(1);
-        const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
-        if (elect_one()) {
-          if (m2 && !(p.dbg & 1)) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int dy = 0; dy < 5; ++dy) {
-              const int rr = r2m + dy - 2;
-              if (rr >= 0 && rr < s.ny) {
-                const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
-                const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
-                tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
-                tc_mma_tf32_ts(tmem + TM_ACC2, al, bd, idesc, 1u);                        // lo * hi
-                tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
-                tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
-                tc_mma_tf32_ts(tmem + TM_ACC2, al + 8, bd + (2048 >> 4), idesc, 1u);
-                tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
-                acc = 1;
+    // One step loop per warp role (instead of one loop with a role switch inside): each role keeps only its own
+    // loop invariants in registers.  All three loops run the same steps and meet at barrier 0 once per step.
+    if (warp == TC_MMA_WARP) {
+      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+        const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
+        const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
+        const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
+          // ======================= MMA warp =======================
+          TC_STAMP(0);
+          mbar_wait(bar_free, n & 1);
+          tc_fence_after();
+          TC_STAMP(1);
+          const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
+          if (elect_one()) {
+            if (m2 && !(p.dbg & 1)) {
+              uint32_t acc = 0;
+  #pragma unroll
+              for (int dy = 0; dy < 5; ++dy) {
+                const int rr = r2m + dy - 2;
+                if (rr >= 0 && rr < s.ny) {
+                  const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                  const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
+                  tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
+                  tc_mma_tf32_ts(tmem + TM_ACC2, al, bd, idesc, 1u);                        // lo * hi
+                  tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
+                  tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
+                  tc_mma_tf32_ts(tmem + TM_ACC2, al + 8, bd + (2048 >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                  acc = 1;
+                }
               }
             }
           }
-        }
-        mbar_wait(bar_free3, n & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          if (m3 && !(p.dbg & 1)) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int dy = 0; dy < 5; ++dy) {
-              const int rr = r3m + dy - 2;
-              if (rr >= 0 && rr < s.ny) {
-                const uint64_t bd = desc_ra2 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
-                const uint32_t ah = tmem + TM_W + 1 * 160 + dy * 16, al = ah + 80;
-                tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
-                tc_mma_tf32_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
-                tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd + (4096 >> 4), idesc, 1u);
-                tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + (2048 >> 4), idesc, 1u);
-                tc_mma_tf32_ts(tmem + TM_ACC3, al + 8, bd + (2048 >> 4), idesc, 1u);
-                tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
-                acc = 1;
+          mbar_wait(bar_free3, n & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            if (m3 && !(p.dbg & 1)) {
+              uint32_t acc = 0;
+  #pragma unroll
+              for (int dy = 0; dy < 5; ++dy) {
+                const int rr = r3m + dy - 2;
+                if (rr >= 0 && rr < s.ny) {
+                  const uint64_t bd = desc_ra2 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                  const uint32_t ah = tmem + TM_W + 1 * 160 + dy * 16, al = ah + 80;
+                  tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
+                  tc_mma_tf32_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
+                  tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd + (4096 >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + (2048 >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(tmem + TM_ACC3, al + 8, bd + (2048 >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                  acc = 1;
+                }
               }
             }
+            tc_commit(bar_mma);
           }
-          tc_commit(bar_mma);
-        }
-        __syncwarp();
-        TC_STAMP(2);
-      } else if (warp < 8) {
-        // ======================= epilogue warps =======================
-        // skip row t+3 (threads 128..195): global loads first, shared-memory store at the end of the step
-        const int rs = t + 3;
-        const bool do_sk = tid >= 128 && tid < 196 && rs >= sk_lo && rs < sk_hi;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        bool sk_in = false;
-        if (do_sk) {
-          const int c = s.x0 - 8 + (tid - 128);
-          sk_in = c >= 0 && c < s.nx;
-          if (sk_in) {
-            const float* q = srcb + (long long)rs * J.src.sy + (long long)c * J.src.sx;
-            s0 = rs > 0 ? q[-J.src.sy] : 0.f;
-            s1 = q[0];
-            s2 = rs + 1 < s.ny ? q[J.src.sy] : 0.f;
-          }
-        }
-        TC_STAMP(0);
-        // ---- E-A: accumulators of the previous step -> partial planes ----
-        if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
-        tc_fence_after();
-        TC_STAMP(1);
-        {
-          const int q = warp & 3, hs = warp >> 2, m = q * 32 + lane;
-          const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + 32 * hs;
-          uint32_t v[32];
-          if (q < 3 && e2 && !(p.dbg & 16)) {
-            tc_ld32(ta + TM_ACC2, v);
-            tc_wait_ld();
-            if (m < 80) {
-              float* o = P2 + m * TC_PP + 32 * hs;
-#pragma unroll
-              for (int k = 0; k < 32; k += 4)
-                *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-            }
-          }
-          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free);          // conv2 accumulator drained
-          if (q < 3 && e3 && !(p.dbg & 16)) {
-            tc_ld32(ta + TM_ACC3, v);
-            tc_wait_ld();
-            if (m < 80) {
-              float* o = P3 + m * TC_PP + 32 * hs;
-#pragma unroll
-              for (int k = 0; k < 32; k += 4)
-                *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-            }
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_free3);         // conv3 accumulator drained
-        }
-        TC_STAMP(2);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        TC_STAMP(3);
-
-        // ---- E-B: conv2 row r2e -> a2 ring; conv3 row r3e -> a3 ring ----
-        {
-          const int co = tid >> 4, xq = tid & 15, i0 = 4 * xq;
-          if (e2 && !(p.dbg & 2)) {
-            float sacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-              const float* pr = P2 + (dx * 16 + co) * TC_PP + i0;
-              const float4 a = lds128(pr), b = lds128(pr + 4);
-              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) sacc[k] = __fadd_rn(sacc[k], win[k + dx]);
-            }
-            const float bias = SW[SW_B2 + co];
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = s.x0 - 4 + i0 + k;
-              float x = __fadd_rn(sacc[k], bias);
-              if (!p.linear) x = tanhf(x);
-              v[k] = (c >= 0 && c < s.nx && i0 + k < 60) ? x : 0.f;
-            }
-            split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
-          }
-          if (e3 && !(p.dbg & 2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
-            float sacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-              const float* pr = P3 + (dx * 16 + co) * TC_PP + i0;
-              const float4 a = lds128(pr), b = lds128(pr + 4);
-              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) sacc[k] = __fadd_rn(sacc[k], win[k + dx]);
-            }
-            const float bias = SW[SW_B3 + co];
-            const float4 o1 = *reinterpret_cast<const float4*>(O1 + ((r3e % TC_RO) * 16 + co) * TC_P3 + i0);
-            const float o1v[4] = {o1.x, o1.y, o1.z, o1.w};
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = s.x0 - 2 + i0 + k;
-              const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
-              v[k] = (c >= 0 && c < s.nx) ? x : 0.f;
-            }
-            // the partner lane (xor 16) holds the other channel of the pair for the same 4 columns
-            float o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = __shfl_xor_sync(0xffffffffu, v[k], 16);
-            float* dst = A3 + ((r3e % TC_R3) * 8 + (co >> 1)) * TC_PA3 + 2 * i0;
-            if (xq < 14) {
-              if (co & 1) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[2], v[2], o[3], v[3]);   // columns i0+2, i0+3
-              else *reinterpret_cast<float4*>(dst) = make_float4(v[0], o[0], v[1], o[1]);               // columns i0, i0+1
-            }
-          }
-        }
-        TC_STAMP(4);
-        if (do_sk) {
-          float v = 0.f;
-          if (sk_in) v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
-          SK[(rs & (TC_RS - 1)) * TC_PS + (tid - 128)] = v;
-        }
-        TC_STAMP(5);
-        fence_proxy_async();   // a2 ring writes -> visible to the tensor core's operand reads
-      } else {
-        // ======================= SIMT warps =======================
-        // warps 8-11 (st < 128): conv1; warps 12-15 (st 128..255): conv4 + output (104 active threads)
-        const int st = tid - 256;
-        const int r4 = t - 11;
-        const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && st >= 128;
-        const bool act4 = st - 128 < 104;
-        float dv[4];
-        load_din(r4, st - 128, do4 && act4, dv);     // global loads first; used at the end of conv4
-        TC_STAMP(0);
-        // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
-        if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
-          const int cp = st >> 4, i1 = 4 * (st & 15);   // 16 consecutive lanes = the 16 pixel quads of one channel pair
-          const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
-          float2 acc[4] = {b1, b1, b1, b1};
-#pragma unroll
-          for (int dy = 0; dy < 5; ++dy) {
-            const int rr = t + dy - 2;
-            if (rr >= 0 && rr < s.ny) {
-              const float* sr = SK + (rr & (TC_RS - 1)) * TC_PS + i1;
-              const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
-              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int dx = 0; dx < 5; ++dx) {
-                const float2 w = *reinterpret_cast<const float2*>(SW + SW_W1 + (dy * 5 + dx) * 16 + 2 * cp);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), w, acc[k]);
-              }
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float av[4], ov[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = s.x0 - 6 + i1 + k;
-              const bool in = c >= 0 && c < s.nx;
-              const float x = h ? acc[k].y : acc[k].x;
-              ov[k] = in ? x : 0.f;
-              av[k] = in ? (p.linear ? x : tanhf(x)) : 0.f;
-            }
-            const int co = 2 * cp + h;
-            split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
-            if (i1 >= 4 && i1 < 60)
-              *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-          }
-        }
-        TC_STAMP(1);
-        // ---- conv4 + output row t-11 ----
-        if (do4) conv4_out(r4, st - 128, act4, dv);
-        TC_STAMP(2);
-        fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
+          TC_STAMP(2);
+        TC_STAMP(6);
+        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_STAMP(7);
       }
-      TC_STAMP(6);
-      __syncthreads();
-      TC_STAMP(7);
+    } else if (warp < 8) {
+      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+        const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
+        const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
+        const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
+          // ======================= epilogue warps =======================
+          // skip row t+3 (threads 128..195): global loads first, shared-memory store at the end of the step
+          const int rs = t + 3;
+          const bool do_sk = tid >= 128 && tid < 196 && rs >= sk_lo && rs < sk_hi;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+          bool sk_in = false;
+          if (do_sk) {
+            const int c = s.x0 - 8 + (tid - 128);
+            sk_in = c >= 0 && c < s.nx;
+            if (sk_in) {
+              const float* q = srcb + (long long)rs * J.src.sy + (long long)c * J.src.sx;
+              s0 = rs > 0 ? q[-J.src.sy] : 0.f;
+              s1 = q[0];
+              s2 = rs + 1 < s.ny ? q[J.src.sy] : 0.f;
+            }
+          }
+          TC_STAMP(0);
+          // ---- E-A: accumulators of the previous step -> partial planes ----
+          if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
+          tc_fence_after();
+          TC_STAMP(1);
+          // Warps 0-3 drain the conv2 accumulator, warps 4-7 the conv3 one; warp quarter q owns accumulator lanes
+          // 32q .. 32q+31 = the rows of dx = 2q (lanes 0-15) and dx = 2q+1 (lanes 16-31).  A 16-lane load
+          // (16x32bx2: threads 0-15 <- columns c .. c+31 of lane t, threads 16-31 <- columns c+32 .. c+63 of lane t-16)
+          // at column offset dx hands every thread the dx-shifted samples of ITS (co, column) positions, so the two
+          // taps of a quarter are summed in registers and only 3 pair-sum planes go through shared memory.
+          {
+            const int q = warp & 3, l3 = warp >> 2;
+            const bool on = (l3 ? e3 : e2) && q < 3 && !(p.dbg & 16);
+            if (on) {
+              const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (l3 ? TM_ACC3 : TM_ACC2) + 2 * q;
+              float* o = (l3 ? P3 : P2) + (q * 16 + (lane & 15)) * TC_PP + 32 * (lane >> 4);
+  #pragma unroll
+              for (int r = 0; r < 4; ++r) {            // four rounds of 8 columns per half keep 16 registers live
+                uint32_t va[8], vb[8];
+                tc_ld16x32bx2_x8(ta + 8 * r, va);
+                if (q < 2) tc_ld16x32bx2_x8(ta + (16u << 16) + 1 + 8 * r, vb);
+                tc_wait_ld();
+  #pragma unroll
+                for (int k = 0; k < 8; k += 4) {
+                  float4 f = make_float4(__uint_as_float(va[k]), __uint_as_float(va[k + 1]), __uint_as_float(va[k + 2]), __uint_as_float(va[k + 3]));
+                  if (q < 2) {
+                    f.x = __fadd_rn(f.x, __uint_as_float(vb[k]));
+                    f.y = __fadd_rn(f.y, __uint_as_float(vb[k + 1]));
+                    f.z = __fadd_rn(f.z, __uint_as_float(vb[k + 2]));
+                    f.w = __fadd_rn(f.w, __uint_as_float(vb[k + 3]));
+                  }
+                  *reinterpret_cast<float4*>(o + 8 * r + k) = f;
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(l3 ? bar_free3 : bar_free);   // this warp's share of the accumulator is drained
+          }
+          TC_STAMP(2);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          TC_STAMP(3);
+
+          // ---- E-B: conv2 row r2e -> a2 ring; conv3 row r3e -> a3 ring ----
+          {
+            const int co = tid >> 4, xq = tid & 15, i0 = 4 * xq;
+            if (e2 && !(p.dbg & 2)) {
+              const float* pr = P2 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
+              const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
+              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x), __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y),
+                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z), __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w)};
+              const float bias = SW[SW_B2 + co];
+              float v[4];
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = s.x0 - 4 + i0 + k;
+                float x = __fadd_rn(sacc[k], bias);
+                if (!p.linear) x = tanhf(x);
+                v[k] = (c >= 0 && c < s.nx && i0 + k < 60) ? x : 0.f;
+              }
+              split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
+            }
+            if (e3 && !(p.dbg & 2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
+              const float* pr = P3 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
+              const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
+              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x), __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y),
+                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z), __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w)};
+              const float bias = SW[SW_B3 + co];
+              const float4 o1 = *reinterpret_cast<const float4*>(O1 + ((r3e % TC_RO) * 16 + co) * TC_P3 + i0);
+              const float o1v[4] = {o1.x, o1.y, o1.z, o1.w};
+              float v[4];
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = s.x0 - 2 + i0 + k;
+                const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
+                v[k] = (c >= 0 && c < s.nx) ? x : 0.f;
+              }
+              // the partner lane (xor 16) holds the other channel of the pair for the same 4 columns
+              float o[4];
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = __shfl_xor_sync(0xffffffffu, v[k], 16);
+              float* dst = A3 + ((r3e % TC_R3) * 8 + (co >> 1)) * TC_PA3 + 2 * i0;
+              if (xq < 14) {
+                if (co & 1) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[2], v[2], o[3], v[3]);   // columns i0+2, i0+3
+                else *reinterpret_cast<float4*>(dst) = make_float4(v[0], o[0], v[1], o[1]);               // columns i0, i0+1
+              }
+            }
+          }
+          TC_STAMP(4);
+          if (do_sk) {
+            float v = 0.f;
+            if (sk_in) v = fmaf(SW[SW_PRE + 2], s2, fmaf(SW[SW_PRE + 1], s1, __fmul_rn(SW[SW_PRE + 0], s0)));
+            SK[(rs & (TC_RS - 1)) * TC_PS + (tid - 128)] = v;
+          }
+          TC_STAMP(5);
+          fence_proxy_async();   // a2 ring writes -> visible to the tensor core's operand reads
+        TC_STAMP(6);
+        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_STAMP(7);
+      }
+    } else {
+      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+        const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
+        const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
+        const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
+          // ======================= SIMT warps =======================
+          // warps 8-11 (st < 128): conv1; warps 12-15 (st 128..255): conv4 + output (104 active threads)
+          const int st = tid - 256;
+          const int r4 = t - 11;
+          const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && st >= 128;
+          const bool act4 = st - 128 < 104;
+          float dv[4];
+          load_din(r4, st - 128, do4 && act4, dv);     // global loads first; used at the end of conv4
+          TC_STAMP(0);
+          // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
+          if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
+            const int cp = st >> 4, i1 = 4 * (st & 15);   // 16 consecutive lanes = the 16 pixel quads of one channel pair
+            const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
+            float2 acc[4] = {b1, b1, b1, b1};
+  #pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+              const int rr = t + dy - 2;
+              if (rr >= 0 && rr < s.ny) {
+                const float* sr = SK + (rr & (TC_RS - 1)) * TC_PS + i1;
+                const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
+                const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  #pragma unroll
+                for (int dx = 0; dx < 5; ++dx) {
+                  const float2 w = *reinterpret_cast<const float2*>(SW + SW_W1 + (dy * 5 + dx) * 16 + 2 * cp);
+  #pragma unroll
+                  for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), w, acc[k]);
+                }
+              }
+            }
+  #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float av[4], ov[4];
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = s.x0 - 6 + i1 + k;
+                const bool in = c >= 0 && c < s.nx;
+                const float x = h ? acc[k].y : acc[k].x;
+                ov[k] = in ? x : 0.f;
+                av[k] = in ? (p.linear ? x : tanhf(x)) : 0.f;
+              }
+              const int co = 2 * cp + h;
+              split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
+              if (i1 >= 4 && i1 < 60)
+                *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            }
+          }
+          TC_STAMP(1);
+          // ---- conv4 + output row t-11 ----
+          if (do4) conv4_out(r4, st - 128, act4, dv);
+          TC_STAMP(2);
+          fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
+        TC_STAMP(6);
+        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_STAMP(7);
+      }
     }
   }
 

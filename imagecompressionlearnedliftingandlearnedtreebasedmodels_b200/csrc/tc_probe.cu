@@ -158,6 +158,18 @@ tc_tf32_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
       for (int j = 0; j < 16; ++j) D[((warp * 2 + h) * 32 + lane) * 16 + j] = __uint_as_float(v[j]);
     }
   }
+  if (split & 32) {
+    // debug: raw registers of 16x32bx2.x32 loads (second half 32 columns further) at lane offsets 0 / 16 of the
+    // warp's quarter, column offset (split >> 8) & 15: D is overwritten with [warp 4][half 2][lane 32][reg 32]
+    const uint32_t coff = (split >> 8) & 15;
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      tc_ld16x32bx2_x32(tmem + ((uint32_t)(warp * 32 + 16 * h) << 16) + 384 + coff, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) D[((warp * 2 + h) * 32 + lane) * 32 + j] = __uint_as_float(v[j]);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {

@@ -22,6 +22,16 @@ for (h, w) in [(512, 768), (256, 384), (128, 192), (64, 96)]:
     mf, mi = t(f), t(g)
     by = 8.0 * N * h * w
     print(f"level {h}x{w}: fwd {mf*1e3:7.1f} us {by/mf/1e6:7.0f} GB/s | inv {mi*1e3:7.1f} us {by/mi/1e6:7.0f} GB/s | PR {(xr-x).abs().max().item():.2e}")
+# config-3 sized batch (64 images x 3 planes) at level 0
+N = 192; h, w = 512, 768
+x = torch.rand(N, h, w, device=dev)
+ll = torch.empty(N, h // 2, w // 2, device=dev); yh = torch.empty(N, 3, h // 2, w // 2, device=dev)
+xr = torch.empty_like(x)
+mf, mi = t(f), t(g)
+by = 8.0 * N * h * w
+print(f"batch-192 level {h}x{w}: fwd {mf*1e3:7.1f} us {by/mf/1e6:7.0f} GB/s | inv {mi*1e3:7.1f} us {by/mi/1e6:7.0f} GB/s | PR {(xr-x).abs().max().item():.2e}")
+mc = t(lambda: xr.copy_(x))
+print(f"torch copy 302MB: {mc*1e3:.1f} us {2*x.numel()*4/mc/1e6:.0f} GB/s")
 # plain device copy for reference
 a = torch.rand(N, 512, 768, device=dev); b = torch.empty_like(a)
 mc = t(lambda: b.copy_(a))
