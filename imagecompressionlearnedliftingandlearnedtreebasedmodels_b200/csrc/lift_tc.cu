@@ -52,8 +52,9 @@ constexpr int TC_PA3 = 124;      // a3 channel-pair pitch: 60 columns x 2 channe
 constexpr int TC_PP = 68;        // partial-plane pitch
 constexpr int TC_PS = 72;        // skip pitch
 // tensor-memory columns
-constexpr int TM_W = 0;          // [layer 2][term 2][dy 5][ci 16]
-constexpr int TM_ACC2 = 320, TM_ACC3 = 384;
+constexpr int TM_W = 192;        // [layer 2][term 2][dy 5][ci 16] (320 columns, behind the accumulators: the dx-shifted drains
+                                 // read up to 4 columns past an accumulator, which must stay inside the allocation)
+constexpr int TM_ACC2 = 0, TM_ACC3 = 64, TM_ACC2B = 128;   // conv2 accumulator double-buffered (steps alternate)
 // shared memory (bytes from the 1024-aligned base)
 constexpr int TS_RA1 = 0;
 constexpr int TS_RA2 = TS_RA1 + TC_RA * TC_SLOT;
@@ -66,7 +67,7 @@ constexpr int TS_W = TS_SK + TC_RS * TC_PS * 4;
 // small weights (floats): pre[4] W1[tap 25][co 16] b1[16] b2[16] b3[16] W4[tap 25][ci 16] b4[4]
 // (channel-pair float2 loads feed packed FFMA2 with a broadcast activation)
 constexpr int SW_PRE = 0, SW_W1 = 4, SW_B1 = SW_W1 + 400, SW_B2 = SW_B1 + 16, SW_B3 = SW_B2 + 16, SW_W4 = SW_B3 + 16,
-              SW_B4 = SW_W4 + 400, SW_TOTAL = SW_B4 + 4;
+              SW_B4 = SW_W4 + 400, SW_ZERO = SW_B4 + 4, SW_TOTAL = SW_ZERO + 16;   // SW_ZERO: 64 B of zeros = "row outside the plane"
 constexpr int TS_BAR = TS_W + SW_TOTAL * 4;
 constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -118,14 +119,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   float* P3 = reinterpret_cast<float*>(gen + TS_P3);
   float* SK = reinterpret_cast<float*>(gen + TS_SK);
   float* SW = reinterpret_cast<float*>(gen + TS_W);
-  const uint32_t bar_mma = base + TS_BAR, bar_free = base + TS_BAR + 8, bar_free3 = base + TS_BAR + 16;
+  const uint32_t bar_mma = base + TS_BAR, bar_free3 = base + TS_BAR + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + TS_BAR + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (tid == 0) {
     mbar_init(bar_mma, 1);
-    mbar_init(bar_free, 4);
     mbar_init(bar_free3, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -228,19 +228,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
       if (active) {
 #pragma unroll
         for (int dy = 0; dy < 5; ++dy) {
+          // rows outside the plane read a block of zeros instead of being skipped: no branch, so all the row and
+          // weight loads of the 5 taps can be in flight together (the loop used to pay 5 shared-memory round trips)
           const int rr = r4 + dy - 2;
-          if (rr >= 0 && rr < s.ny) {
-            const float* ar = A3 + ((rr % TC_R3) * 8 + cp) * TC_PA3 + 8 * pq;     // columns 4pq .. 4pq+7, 2 channels each
-            const float4 v0 = *reinterpret_cast<const float4*>(ar), v1 = *reinterpret_cast<const float4*>(ar + 4),
-                         v2 = *reinterpret_cast<const float4*>(ar + 8), v3 = *reinterpret_cast<const float4*>(ar + 12);
-            const float2 col[8] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w),
-                                   make_float2(v2.x, v2.y), make_float2(v2.z, v2.w), make_float2(v3.x, v3.y), make_float2(v3.z, v3.w)};
+          const float* ar = (rr >= 0 && rr < s.ny) ? A3 + ((rr % TC_R3) * 8 + cp) * TC_PA3 + 8 * pq : SW + SW_ZERO;   // columns 4pq .. 4pq+7, 2 channels each
+          const float4 v0 = *reinterpret_cast<const float4*>(ar), v1 = *reinterpret_cast<const float4*>(ar + 4),
+                       v2 = *reinterpret_cast<const float4*>(ar + 8), v3 = *reinterpret_cast<const float4*>(ar + 12);
+          const float2 col[8] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w),
+                                 make_float2(v2.x, v2.y), make_float2(v2.z, v2.w), make_float2(v3.x, v3.y), make_float2(v3.z, v3.w)};
 #pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-              const float2 w = *reinterpret_cast<const float2*>(SW + SW_W4 + (dy * 5 + dx) * 16 + 2 * cp);
+          for (int dx = 0; dx < 5; ++dx) {
+            const float2 w = *reinterpret_cast<const float2*>(SW + SW_W4 + (dy * 5 + dx) * 16 + 2 * cp);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(col[k + dx], w, acc[k]);
-            }
+            for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(col[k + dx], w, acc[k]);
           }
         }
       }
@@ -297,10 +297,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
         const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
           // ======================= MMA warp =======================
+          // conv2 alternates between two accumulators: the one of step n was drained in step n-1 (behind the
+          // end-of-step barrier), so its MMAs start at once; only conv3 waits for this step's drain.
           TC_STAMP(0);
-          mbar_wait(bar_free, n & 1);
           tc_fence_after();
-          TC_STAMP(1);
+          const uint32_t acc2 = tmem + TM_ACC2 + (n & 1) * (TM_ACC2B - TM_ACC2);
           const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
           if (elect_one()) {
             if (m2 && !(p.dbg & 1)) {
@@ -311,17 +312,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                 if (rr >= 0 && rr < s.ny) {
                   const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
                   const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
-                  tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
-                  tc_mma_tf32_ts(tmem + TM_ACC2, al, bd, idesc, 1u);                        // lo * hi
-                  tc_mma_tf32_ts(tmem + TM_ACC2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
-                  tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
-                  tc_mma_tf32_ts(tmem + TM_ACC2, al + 8, bd + (2048 >> 4), idesc, 1u);
-                  tc_mma_tf32_ts(tmem + TM_ACC2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(acc2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
+                  tc_mma_tf32_ts(acc2, al, bd, idesc, 1u);                        // lo * hi
+                  tc_mma_tf32_ts(acc2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
+                  tc_mma_tf32_ts(acc2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
+                  tc_mma_tf32_ts(acc2, al + 8, bd + (2048 >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(acc2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
                   acc = 1;
                 }
               }
             }
           }
+          TC_STAMP(1);
           mbar_wait(bar_free3, n & 1);
           tc_fence_after();
           if (elect_one()) {
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             const int q = warp & 3, l3 = warp >> 2;
             const bool on = (l3 ? e3 : e2) && q < 3 && !(p.dbg & 16);
             if (on) {
-              const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (l3 ? TM_ACC3 : TM_ACC2) + 2 * q;
+              const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (l3 ? TM_ACC3 : ((n & 1) ? TM_ACC2 : TM_ACC2B)) + 2 * q;   // conv2: buffer of step n-1
               float* o = (l3 ? P3 : P2) + (q * 16 + (lane & 15)) * TC_PP + 32 * (lane >> 4);
   #pragma unroll
               for (int r = 0; r < 4; ++r) {            // four rounds of 8 columns per half keep 16 registers live
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(l3 ? bar_free3 : bar_free);   // this warp's share of the accumulator is drained
+            if (l3 && lane == 0) mbar_arrive(bar_free3);   // this warp's share of the conv3 accumulator is drained
           }
           TC_STAMP(2);
           asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -493,17 +495,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             float2 acc[4] = {b1, b1, b1, b1};
   #pragma unroll
             for (int dy = 0; dy < 5; ++dy) {
-              const int rr = t + dy - 2;
-              if (rr >= 0 && rr < s.ny) {
-                const float* sr = SK + (rr & (TC_RS - 1)) * TC_PS + i1;
-                const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
-                const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+              const int rr = t + dy - 2;            // rows outside the plane: zeros, no branch (see conv4_out)
+              const float* sr = (rr >= 0 && rr < s.ny) ? SK + (rr & (TC_RS - 1)) * TC_PS + i1 : SW + SW_ZERO;
+              const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
+              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   #pragma unroll
-                for (int dx = 0; dx < 5; ++dx) {
-                  const float2 w = *reinterpret_cast<const float2*>(SW + SW_W1 + (dy * 5 + dx) * 16 + 2 * cp);
+              for (int dx = 0; dx < 5; ++dx) {
+                const float2 w = *reinterpret_cast<const float2*>(SW + SW_W1 + (dy * 5 + dx) * 16 + 2 * cp);
   #pragma unroll
-                  for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), w, acc[k]);
-                }
+                for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), w, acc[k]);
               }
             }
   #pragma unroll
