@@ -99,15 +99,19 @@ __device__ __forceinline__ void split_store(uint8_t* row, int ci, int i, const f
   *reinterpret_cast<float4*>(q + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// Timing hooks (scripts/gpu_lift_tc_time.py, gpu_lift_tc_timeline.py) only exist in the DBG instantiation of the
+// kernel, which the launcher picks when a debug mode or stamp buffer is set; the product kernel carries none of it.
 #define TC_STAMP(k)                                                                      \
   do {                                                                                   \
-    if (p.dbg_buf && blockIdx.x == 0 && n == 40 && lane == 0) p.dbg_buf[warp * 8 + (k)] = clock64(); \
+    if (DBG && p.dbg_buf && blockIdx.x == 0 && n == 40 && lane == 0) p.dbg_buf[warp * 8 + (k)] = clock64(); \
   } while (0)
+#define TC_OFF(bit) (DBG && (p.dbg & (bit)))
 
 struct TcSeg {
   int j, b, x0, ya, yb, ny, nx;
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __grid_constant__ LiftParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           const uint32_t acc2 = tmem + TM_ACC2 + (n & 1) * (TM_ACC2B - TM_ACC2);
           const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
           if (elect_one()) {
-            if (m2 && !(p.dbg & 1)) {
+            if (m2 && !TC_OFF(1)) {
               uint32_t acc = 0;
   #pragma unroll
               for (int dy = 0; dy < 5; ++dy) {
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           mbar_wait(bar_free3, n & 1);
           tc_fence_after();
           if (elect_one()) {
-            if (m3 && !(p.dbg & 1)) {
+            if (m3 && !TC_OFF(1)) {
               uint32_t acc = 0;
   #pragma unroll
               for (int dy = 0; dy < 5; ++dy) {
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           // taps of a quarter are summed in registers and only 3 pair-sum planes go through shared memory.
           {
             const int q = warp & 3, l3 = warp >> 2;
-            const bool on = (l3 ? e3 : e2) && q < 3 && !(p.dbg & 16);
+            const bool on = (l3 ? e3 : e2) && q < 3 && !TC_OFF(16);
             if (on) {
               const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (l3 ? TM_ACC3 : ((n & 1) ? TM_ACC2 : TM_ACC2B)) + 2 * q;   // conv2: buffer of step n-1
               float* o = (l3 ? P3 : P2) + (q * 16 + (lane & 15)) * TC_PP + 32 * (lane >> 4);
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           // ---- E-B: conv2 row r2e -> a2 ring; conv3 row r3e -> a3 ring ----
           {
             const int co = tid >> 4, xq = tid & 15, i0 = 4 * xq;
-            if (e2 && !(p.dbg & 2)) {
+            if (e2 && !TC_OFF(2)) {
               const float* pr = P2 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
               const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
               const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x), __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y),
@@ -436,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               }
               split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
             }
-            if (e3 && !(p.dbg & 2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
+            if (e3 && !TC_OFF(2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
               const float* pr = P3 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
               const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
               const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x), __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y),
@@ -483,13 +487,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           // warps 8-11 (st < 128): conv1; warps 12-15 (st 128..255): conv4 + output (104 active threads)
           const int st = tid - 256;
           const int r4 = t - 11;
-          const bool do4 = r4 >= s.ya && r4 < s.yb && !(p.dbg & 8) && st >= 128;
+          const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8) && st >= 128;
           const bool act4 = st - 128 < 104;
           float dv[4];
           load_din(r4, st - 128, do4 && act4, dv);     // global loads first; used at the end of conv4
           TC_STAMP(0);
           // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
-          if (st < 128 && t >= a1_lo && t < a1_hi && !(p.dbg & 4)) {
+          if (st < 128 && t >= a1_lo && t < a1_hi && !TC_OFF(4)) {
             const int cp = st >> 4, i1 = 4 * (st & 15);   // 16 consecutive lanes = the 16 pixel quads of one channel pair
             const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
             float2 acc[4] = {b1, b1, b1, b1};
@@ -575,12 +579,14 @@ int launch_lift_step_tc(const LiftParams& p0, cudaStream_t stream) {
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set[dev] = true;
   }
   long long grid = sm_count_cached();
   if (grid > p.total_units) grid = p.total_units;
-  lift_step_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+  if (p.dbg || p.dbg_buf) lift_step_tc_kernel<true><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+  else lift_step_tc_kernel<false><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
   LL_LAUNCH_OK("lift_step_tc_kernel");
   return LL_OK;
 }
