@@ -294,7 +294,36 @@ def dwt97_probe(dev, pk):
         ms = ev0.elapsed_time(ev1) / n
         gbs = 8.0 * sum(4.0 ** -l for l in range(LEVELS)) * 3 * B * H * W / (ms * 1e-3) / 1e9
         res[name] = {"ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"]}
-    res["note"] = "150 MB in+out per level-0 launch (> L2 126 MB); back-to-back launches, CUDA events"
+    res["note"] = "4-level call; 150 MB in+out per level-0 launch (> L2 126 MB); back-to-back launches, CUDA events"
+    # the dominant launch alone (level 0 = 75 % of the bytes), at this batch and at the config-3 batch (64 images):
+    # 8 B per input sample, straight through the C ABI on preallocated buffers
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import _lib
+    lib = _lib.load()
+    sp = torch.cuda.current_stream().cuda_stream
+    for nb in (B, 4 * B):
+        n = 3 * nb
+        xi = torch.rand(n, H, W, device=dev) - 0.5
+        ll = torch.empty(n, H // 2, W // 2, device=dev)
+        hh = torch.empty(n, 3, H // 2, W // 2, device=dev)
+        xr = torch.empty_like(xi)
+        f = lambda: _lib.check(lib.ll_dwt97_fwd_level(xi.data_ptr(), H * W, ll.data_ptr(), H * W // 4, hh.data_ptr(), 3 * H * W // 4, n, H, W, sp))
+        g = lambda: _lib.check(lib.ll_dwt97_inv_level(ll.data_ptr(), H * W // 4, hh.data_ptr(), 3 * H * W // 4, xr.data_ptr(), H * W, n, H, W, sp))
+        for name, fn in (("fwd", f), ("inv", g)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(20):
+                fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / 20
+            gbs = 8.0 * n * H * W / (ms * 1e-3) / 1e9
+            res[f"level0_{name}_batch{nb}"] = {"ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"],
+                                               "kernel": f"ll::dwt97_{name}_fast_kernel"}
+        res[f"level0_batch{nb}_perfect_reconstruction_max_abs_err"] = float((xr - xi).abs().max().item())
+        del xi, ll, hh, xr
     return res
 
 

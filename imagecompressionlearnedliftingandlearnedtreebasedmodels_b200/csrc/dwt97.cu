@@ -1,6 +1,4 @@
 // dwt97.cu -- CDF 9/7 fixed-filter DWT (K1): kernels + C ABI.
-#include <stdlib.h>
-
 #include "dwt97_body.cuh"
 #include "ll_common.cuh"
 
@@ -49,6 +47,7 @@ __device__ float g_dwt_taps[18 + 20] = {
 // it every CTA of a wave loads, filters and stores in lock-step and DRAM idles during the compute phases).  Bulk
 // copies (UBLKCP) were tried and rejected: one per tile row is needed, each is a uniform-datapath instruction that the
 // compiler serialises over the issuing lanes (~25 issue slots per row against ~10 for the row's 34 LDGSTS lanes).
+// A single-buffer variant (44 KB, 4 resident CTAs, next copy issued behind the row pass) measured the same.
 // The tile index advances incrementally (no division per tile); three phases, two block barriers per tile -- the next
 // copy into a buffer and the next first-pass write into ``mid`` are both issued behind a barrier that every thread
 // only reaches after it finished reading them.
@@ -112,36 +111,6 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid
     __syncthreads();
     dwtff_rows(sm + b * DFF_IN_FLOATS, mid, tid, tp);
     __syncthreads();
-    dwtff_cols(p, cur.tile(), mid, tid, tp);
-    if (tn >= ntiles) break;
-    t = tn;
-    cur = nxt;
-  }
-}
-
-// Single-buffer variant (experiment): 44 KB per CTA -> 4 resident CTAs; the next tile's copy is issued after the row
-// pass released the input buffer and lands while the column pass runs.
-__global__ void __launch_bounds__(DW_THREADS, 4) dwt97_fwd_fast1_kernel(const __grid_constant__ DwtParams p) {
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
-  DwtTaps tp;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) tp.d[k] = f2{g_dwt_taps[2 * k], g_dwt_taps[2 * k + 1]};
-  const unsigned ntiles = (unsigned)p.N * p.tiles_x * p.tiles_y;
-  unsigned t = blockIdx.x;
-  float* mid = sm + DFF_IN_FLOATS - DFF_SM_LO;
-  TileWalk cur(p, t, gridDim.x), nxt = cur;
-  dwtff_load(p, cur.tile(), sm, tid, CopyAsync16());
-  cp_commit();
-  for (;;) {
-    const unsigned tn = t + gridDim.x;
-    nxt.advance(p);
-    cp_wait<0>();
-    __syncthreads();
-    dwtff_rows(sm, mid, tid, tp);
-    __syncthreads();
-    if (tn < ntiles) dwtff_load(p, nxt.tile(), sm, tid, CopyAsync16());
-    cp_commit();
     dwtff_cols(p, cur.tile(), mid, tid, tp);
     if (tn >= ntiles) break;
     t = tn;
@@ -226,14 +195,6 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
     attr[dev] = true;
   }
   const long long pgrid = (long long)sm_count_cached() * 3;   // 3 resident CTAs per SM (70 KB each)
-  static const bool sb = getenv("LL_DWT_SB") != nullptr;
-  if (dwt_fast_ok(p) && sb) {
-    const long long g4 = (long long)sm_count_cached() * 4;
-    constexpr size_t smem1 = (DFF_IN_FLOATS + DWF_R * DFF_PM) * sizeof(float);
-    static bool a1 = false;
-    if (!a1) { LL_CUDA_OK(cudaFuncSetAttribute(dwt97_fwd_fast1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); a1 = true; }
-    dwt97_fwd_fast1_kernel<<<(unsigned)(tiles < g4 ? tiles : g4), DW_THREADS, smem1, as_stream(stream)>>>(p);
-  } else
   if (dwt_fast_ok(p)) dwt97_fwd_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream)>>>(p);
   else dwt97_fwd_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_fwd_kernel");

@@ -87,6 +87,28 @@ __device__ __forceinline__ float4 lds128(const float* p) {
   return v;
 }
 
+// tanh of two values on the packed FP32 pipe (FMUL2 / FFMA2 / FADD2): |x| < 0.625 -> x + x^3 P(x^2) with the Cephes
+// tanhf coefficients (< 2 ulp), else 1 - 2 / (exp(2|x|) + 1) on ex2.approx / rcp.approx (absolute error < 1e-7; the
+// scalar tanhf of the CUDA math library has the same structure at twice the instruction count).
+__device__ __forceinline__ float2 tanh2(float2 x) {
+  const float2 z = __fmul2_rn(x, x);
+  float2 q = __ffma2_rn(z, make_float2(-5.70498872745e-3f, -5.70498872745e-3f), make_float2(2.06390887954e-2f, 2.06390887954e-2f));
+  q = __ffma2_rn(q, z, make_float2(-5.37397155531e-2f, -5.37397155531e-2f));
+  q = __ffma2_rn(q, z, make_float2(1.33314422036e-1f, 1.33314422036e-1f));
+  q = __ffma2_rn(q, z, make_float2(-3.33332819422e-1f, -3.33332819422e-1f));
+  q = __ffma2_rn(q, __fmul2_rn(z, x), x);
+  const float ax = fabsf(x.x), ay = fabsf(x.y);
+  float ex, ey;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(ax * 2.885390081777927f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(ay * 2.885390081777927f));
+  const float2 e1 = __fadd2_rn(make_float2(ex, ey), make_float2(1.f, 1.f));
+  float rx, ry;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(e1.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(e1.y));
+  const float2 b = __ffma2_rn(make_float2(rx, ry), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
+  return make_float2(ax < 0.625f ? q.x : copysignf(b.x, x.x), ay < 0.625f ? q.y : copysignf(b.y, x.y));
+}
+
 __device__ __forceinline__ void split_store(uint8_t* row, int ci, int i, const float (&v)[4]) {
   float hi[4], lo[4];
 #pragma unroll
@@ -272,15 +294,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         }
       }
     };
+    // Branch-free: lanes that have nothing to load read the plane's first sample instead (a divergent region around
+    // the loads makes the warp wait for them at its reconvergence point, ~650 cycles at the start of every step).
+    const float* din_b = J.din.ptr + (long long)s.b * J.din.sb;
     auto load_din = [&](int r4, int c4, bool active, float (&dv)[4]) {
+      const float* row = din_b + (long long)r4 * J.din.sy;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dv[k] = 0.f;
-      if (active && (c4 & 7) == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = s.x0 + 4 * (c4 >> 3) + k;
-          if (c < s.nx) dv[k] = J.din.ptr[(long long)s.b * J.din.sb + (long long)r4 * J.din.sy + (long long)c * J.din.sx];
-        }
+      for (int k = 0; k < 4; ++k) {
+        const int c = s.x0 + 4 * (c4 >> 3) + k;
+        const bool ok = active && (c4 & 7) == 0 && c < s.nx;
+        dv[k] = *(ok ? row + (long long)c * J.din.sx : din_b);
       }
     };
 
@@ -431,12 +454,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                                      __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z), __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w)};
               const float bias = SW[SW_B2 + co];
               float v[4];
+              {
+                float2 x01 = make_float2(__fadd_rn(sacc[0], bias), __fadd_rn(sacc[1], bias));
+                float2 x23 = make_float2(__fadd_rn(sacc[2], bias), __fadd_rn(sacc[3], bias));
+                if (!p.linear) {
+                  x01 = tanh2(x01);
+                  x23 = tanh2(x23);
+                }
+                const float x[4] = {x01.x, x01.y, x23.x, x23.y};
   #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = s.x0 - 4 + i0 + k;
-                float x = __fadd_rn(sacc[k], bias);
-                if (!p.linear) x = tanhf(x);
-                v[k] = (c >= 0 && c < s.nx && i0 + k < 60) ? x : 0.f;
+                for (int k = 0; k < 4; ++k) {
+                  const int c = s.x0 - 4 + i0 + k;
+                  v[k] = (c >= 0 && c < s.nx && i0 + k < 60) ? x[k] : 0.f;
+                }
               }
               split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
             }
@@ -489,8 +519,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           const int r4 = t - 11;
           const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8) && st >= 128;
           const bool act4 = st - 128 < 104;
-          float dv[4];
-          load_din(r4, st - 128, do4 && act4, dv);     // global loads first; used at the end of conv4
+          float dv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (st >= 128) load_din(r4, st - 128, do4 && act4, dv);     // (warp-uniform) global loads first; used at the end of conv4
           TC_STAMP(0);
           // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
           if (st < 128 && t >= a1_lo && t < a1_hi && !TC_OFF(4)) {
@@ -511,15 +541,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               }
             }
   #pragma unroll
+            float2 th[4];                       // tanh of the channel pair, two values per packed instruction
+  #pragma unroll
+            for (int k = 0; k < 4; ++k) th[k] = p.linear ? acc[k] : tanh2(acc[k]);
+  #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float av[4], ov[4];
   #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int c = s.x0 - 6 + i1 + k;
                 const bool in = c >= 0 && c < s.nx;
-                const float x = h ? acc[k].y : acc[k].x;
-                ov[k] = in ? x : 0.f;
-                av[k] = in ? (p.linear ? x : tanhf(x)) : 0.f;
+                ov[k] = in ? (h ? acc[k].y : acc[k].x) : 0.f;
+                av[k] = in ? (h ? th[k].y : th[k].x) : 0.f;
               }
               const int co = 2 * cp + h;
               split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
