@@ -135,6 +135,69 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Last 3x3 conv of SubbandAutoEncoderBerk (lifting_dwt_nets.py:133,143: C = 96 -> 3 or 32 -> 1, the output feeds
+// the quantiser / the inverse transform) straight from the tensor-core chain's activations: z is channels-last
+// fp32 [hi | lo] (B,H,W,2C); the kernel forms hi + lo on load and writes fp32 NCHW.  Replaces the
+// NHWC -> NCHW conversion + generic NCHW conv pair (2.45 ms -> one HBM-bound pass over z).
+// CTA = 8x32 pixels, thread = 1 pixel x CO outputs, 16 input channels per stage ([py][px][20] floats: the 80-byte
+// pixel pitch makes the 16-byte channel-quad reads of 8 neighbouring pixels hit 8 distinct bank groups).
+constexpr int TL_TH = 8, TL_TW = 32, TL_CC = 16, TL_PITCH = 20;
+
+template <int CO>
+__global__ void __launch_bounds__(256) nhwc_split_conv3_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                               int B, int C, int H, int W, int tiles_x) {
+  __shared__ __align__(16) float tile[(TL_TH + 2) * (TL_TW + 2) * TL_PITCH];
+  __shared__ __align__(16) float wsm[9 * CO * TL_CC];   // [tap][co][16 ch]
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int x0 = (blockIdx.x % tiles_x) * TL_TW, y0 = (blockIdx.x / tiles_x) * TL_TH, b = blockIdx.y;
+  const float* zb = z + (long long)b * H * W * 2 * C;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = bias ? bias[o] : 0.f;
+  for (int c0 = 0; c0 < C; c0 += TL_CC) {
+    __syncthreads();
+    for (int e = tid; e < (TL_TH + 2) * (TL_TW + 2) * (TL_CC / 4); e += 256) {
+      const int q = e & 3, px = (e >> 2) % (TL_TW + 2), py = (e >> 2) / (TL_TW + 2);
+      const int gy = y0 + py - 1, gx = x0 + px - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const float* s = zb + ((long long)gy * W + gx) * (2 * C) + c0 + 4 * q;
+        const float4 hi = *reinterpret_cast<const float4*>(s), lo = *reinterpret_cast<const float4*>(s + C);
+        v = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+      }
+      *reinterpret_cast<float4*>(&tile[(py * (TL_TW + 2) + px) * TL_PITCH + 4 * q]) = v;
+    }
+    for (int e = tid; e < 9 * CO * TL_CC; e += 256) {
+      const int c = e % TL_CC, o = (e / TL_CC) % CO, t = e / (TL_CC * CO);
+      wsm[e] = w[((long long)o * C + c0 + c) * 9 + t];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float* a = &tile[((ty + t / 3) * (TL_TW + 2) + tx + t % 3) * TL_PITCH];
+#pragma unroll
+      for (int q = 0; q < TL_CC / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(a + 4 * q);
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          const float4 k = *reinterpret_cast<const float4*>(&wsm[(t * CO + o) * TL_CC + 4 * q]);
+          acc[o] = fmaf(v.x, k.x, acc[o]);
+          acc[o] = fmaf(v.y, k.y, acc[o]);
+          acc[o] = fmaf(v.z, k.z, acc[o]);
+          acc[o] = fmaf(v.w, k.w, acc[o]);
+        }
+      }
+    }
+  }
+  const int gy = y0 + ty, gx = x0 + tx;
+  if (gy < H && gx < W) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o) out[(((long long)b * CO + o) * H + gy) * W + gx] = acc[o];
+  }
+}
+
 }  // namespace ll
 
 using namespace ll;
@@ -171,6 +234,22 @@ int ll_conv2d(const float* x, int64_t x_sb, const float* w, const float* b, floa
   else if (K == 3) conv2d_kernel<3><<<grid, CV_THREADS, 0, st>>>(p);
   else conv2d_kernel<5><<<grid, CV_THREADS, 0, st>>>(p);
   LL_LAUNCH_OK("conv2d_kernel");
+  return LL_OK;
+}
+
+int ll_nhwc_split_conv3(const float* z, const float* w, const float* bias, float* out, int B, int C, int Cout, int H, int W,
+                        ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || C <= 0 || (C % TL_CC)) return fail(LL_EINVAL, "ll_nhwc_split_conv3: C must be a positive multiple of %d (got %d)", TL_CC, C);
+  if (Cout != 1 && Cout != 3) return fail(LL_EINVAL, "ll_nhwc_split_conv3: Cout must be 1 or 3 (got %d)", Cout);
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!z || !w || !out) return fail(LL_EINVAL, "ll_nhwc_split_conv3: null pointer");
+  if (reinterpret_cast<uintptr_t>(z) & 15) return fail(LL_EINVAL, "ll_nhwc_split_conv3: z must be 16-byte aligned");
+  const int tiles_x = (W + TL_TW - 1) / TL_TW, tiles_y = (H + TL_TH - 1) / TL_TH;
+  if (B > 65535) return fail(LL_EINVAL, "ll_nhwc_split_conv3: batch too large");
+  dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)B);
+  if (Cout == 1) nhwc_split_conv3_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
+  else nhwc_split_conv3_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
+  LL_LAUNCH_OK("nhwc_split_conv3_kernel");
   return LL_OK;
 }
 

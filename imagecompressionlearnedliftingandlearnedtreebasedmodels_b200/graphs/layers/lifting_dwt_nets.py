@@ -139,9 +139,8 @@ class SubbandAutoEncoderBerk(nn.Module):
                 y, s = ops.igemm_tf32(z, pk["wp"][k], convs[1 + k].bias, convs[1 + k].weight.shape[1 if transposed else 0], epi=1)
                 _, z = ops.igemm_tf32(s, pk["gdn"][1 + k][0], pk["gdn"][1 + k][1], y.shape[3], epi=2, inverse=inv, y=y)
             del y, s
-            t = ops.nhwc_split_to_nchw(z)
+            outs.append(ops.nhwc_split_conv3(z, pk["w3"], convs[3].bias))     # exact fp32, straight from the chain's layout
             del z
-            outs.append(ops.conv2d(t, pk["w3"], convs[3].bias))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def _use_tc(self, x):

@@ -426,6 +426,22 @@ def nhwc_split_to_nchw(z):
     return out
 
 
+def nhwc_split_conv3(z, w, bias):
+    """split NHWC (B,H,W,2C) -> 3x3 conv (zero padding 1, cross-correlation, exact fp32) -> fp32 NCHW (B,Cout,H,W)."""
+    require_device(z)
+    B, H, W, c2 = z.shape
+    w = _f32c(w, "w")
+    cout = w.shape[0]
+    if w.shape[1] * 2 != c2 or tuple(w.shape[2:]) != (3, 3):
+        raise ValueError(f"nhwc_split_conv3: weight {tuple(w.shape)} does not match {c2 // 2} input channels, 3x3")
+    b = _f32c(bias, "bias") if bias is not None else None
+    out = torch.empty(B, cout, H, W, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        check(_lib.load().ll_nhwc_split_conv3(ptr(z), ptr(w), ptr(b), ptr(out), B, c2 // 2, cout, H, W, stream_ptr()))
+    _count(1)
+    return out
+
+
 def cgp_tail_rate(h2, w3, b3, w4, b4, x, noise=None, want_y=False, want_ms=False, acc=None):
     """Last two grouped 1x1 layers of the cgp MLP + Gaussian rate (ll_cgp_tail_rate).  h2 (B,G*C2,H,W)
     fp32; w3 (G*C3,C2,1,1); w4 (2G,C3,1,1); x (B,G,H,W).  Returns bits (+ y, + ms (B,2G,H,W))."""

@@ -222,6 +222,12 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
 int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int H, int W, int mode, ll_stream_t stream);
 /* z NHWC (B,H,W,2C) [hi | lo] -> fp32 NCHW (B,C,H,W) = hi + lo. */
 int ll_nhwc_split_to_nchw(const float* z, float* out, int B, int C, int H, int W, ll_stream_t stream);
+/* Last 3x3 conv of SubbandAutoEncoderBerk.ae_down / ae_up (nn.Conv2d / ConvTranspose2d(iC*32, iC, 3, padding=1),
+ * lifting_dwt_nets.py:133,143) on the chain's own activations: z NHWC (B,H,W,2C) [hi | lo], w (Cout,C,3,3) in
+ * cross-correlation layout (ConvTranspose weights flipped / transposed by the caller), bias (Cout) or NULL ->
+ * out fp32 NCHW (B,Cout,H,W).  Exact fp32 FMA (feeds the quantiser).  C % 16 == 0, Cout in {1, 3}. */
+int ll_nhwc_split_conv3(const float* z, const float* w, const float* bias, float* out, int B, int C, int Cout, int H, int W,
+                        ll_stream_t stream);
 
 /* Tail of the cgp MLP fused with the rate: per group g (= child subband) and pixel,
  * h = LeakyReLU(W3[g] h2 + b3[g]) (C2 -> C3), (sigma, mu) = W4[g] h + b4[g], then exactly

@@ -212,3 +212,25 @@ def test_berk_autoencoder_tc_matches_torch_fp32(in_ch, shape):
             # tolerance of the path is 1e-4, the chain must stay well inside it.
             # (the small-term products go to a second accumulator, which cut this bias 3x: decode measures 0.4-1.4e-5)
             assert err_tc <= (max(3 * err_t32, 1e-5) if name == "encode" else 2.5e-5), (name, err_tc, err_t32)
+
+
+@pytest.mark.parametrize("C,Cout,shape", [(96, 3, (2, 24, 40)), (32, 1, (3, 16, 16)), (96, 3, (1, 5, 7)), (32, 1, (1, 9, 33))])
+def test_nhwc_split_tail_conv_matches_torch(C, Cout, shape):
+    """Last conv of SubbandAutoEncoderBerk straight from the chain's [hi | lo] channels-last layout (ll_nhwc_split_conv3)
+    against torch conv2d on hi + lo in float64; fp32 FMA accumulation over K = 9 C: a few 1e-7 of the output scale."""
+    ops = _ops()
+    torch.manual_seed(C + Cout)
+    B, H, W = shape
+    v = torch.randn(B, H, W, C, device=DEV)
+    hi = (v.view(torch.int32) & ~0x1FFF).view(torch.float32)        # a TF32-representable high half and the rest
+    z = torch.cat([hi, v - hi], dim=3).contiguous()
+    w = torch.randn(Cout, C, 3, 3, device=DEV) * 0.1
+    b = torch.randn(Cout, device=DEV)
+    got = ops.nhwc_split_conv3(z, w, b)
+    ref = F.conv2d((hi.double() + (v - hi).double()).permute(0, 3, 1, 2), w.double(), b.double(), padding=1)
+    assert got.shape == (B, Cout, H, W)
+    assert (got.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    nob = ops.nhwc_split_conv3(z, w, None)
+    assert (nob.double() - (ref - b.double().view(1, -1, 1, 1))).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    with pytest.raises(Exception):
+        ops.nhwc_split_conv3(z[..., :2 * C - 2].contiguous(), w, b)

@@ -260,3 +260,55 @@ def test_full_size_codec_properties():
     for qa, qc, pre in zip(a[2], c[2], c[3]):
         n, bad = flip_audit(qa.cpu(), qc.cpu(), pre.cpu())
         assert bad == 0 and n <= max(2, qa.numel() // 20000), (n, bad)     # rounding-boundary flips only
+
+
+def test_config5_tile_five_levels_vs_oracle():
+    """BASELINE config 5: a 2048x2048 image cut into 8 independent (3, 2048, 256) tiles, 5-level learned lifting +
+    conditioned2ZT.  One tile, one colour plane's networks: (1) the 5-level transform against the CPU oracle (coefficients
+    1e-5, reconstruction 2e-5); (2) the whole codec forward on the tile: symbols bit-exact up to rounding-boundary flips,
+    bits within 0.1 % (exact-fp32 context path), reconstruction 1e-4."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import parallel
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import \
+        LiftingBasedDWTNetWrapper
+    boxes = parallel.tiles_of(2048, 2048, 8)
+    y0, y1, x0, x1 = boxes[3]
+    assert ((y1 - y0) % 32 == 0) and ((x1 - x0) % 32 == 0)
+    torch.manual_seed(5)
+    img = om.preprocess(torch.rand(1, 3, 2048, 2048))
+    tile = img[:, :, y0:y1, x0:x1].contiguous()
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                         entropy_layer="conditioned2ZTsepSubbands", dwtlevels=5, ctx_precision="fp32")
+    torch.manual_seed(1337)
+    model = LiftingBasedDWTNetWrapper(cfg)
+    sd = keyed_state(model)
+    model = model.to(DEV).eval()
+    x = tile[:, 0:1]
+    with torch.no_grad():
+        pre = "model0.autoencoder."
+        yl, yh = olift.transform_forward(x, sd, pre, cfg)
+        ae = model.model0.autoencoder
+        gl, gh = ae.transform(x.to(DEV))
+        assert len(gh) == 5 and gl.shape[-2:] == ((y1 - y0) // 32, (x1 - x0) // 32)
+        assert rel_err(gl.cpu(), yl) < 1e-5
+        for a, b in zip(gh, yh):
+            assert rel_err(a.cpu(), b) < 1e-5
+        rec = ae.inverse_transform(gl, gh)
+        assert (rec.cpu() - x).abs().max().item() < 2e-5
+        # whole codec forward of this plane on the tile against the oracle
+        oxhat, osi_xe, osi_xo, oxe_q, oxo_q, o_xe, o_xo = om.net_forward(x, sd, "model0.", cfg)
+        oxe, oxo = ae.encode(x.to(DEV))
+        si_xe, si_xo, xe_q, xo_q = model.model0.entropymodel(oxe, oxo)
+        flips = 0
+        for q, oq, pre_q in zip([xe_q] + list(xo_q), [oxe_q] + list(oxo_q), [o_xe] + list(o_xo)):
+            n, bad = flip_audit(q.cpu(), oq, pre_q)
+            assert bad == 0 and n <= max(2, q.numel() // 20000), (n, bad)
+            flips += n
+        # decoder parity on the oracle's own symbols (a rounding-boundary flip legitimately moves the reconstruction
+        # by a quantisation step), and the end-to-end reconstruction when no symbol flipped
+        xhat = ae.decode(oxe_q.to(DEV), [t.to(DEV) for t in oxo_q])
+        if flips == 0:
+            assert rel_err(ae.decode(xe_q, xo_q).cpu(), oxhat) < 1e-4
+        bits = float(si_xe.double().sum() + sum(t.double().sum() for t in si_xo))
+        obits = float(osi_xe.double().sum() + sum(t.double().sum() for t in osi_xo))
+        assert abs(bits - obits) <= 1e-3 * obits
+        assert rel_err(xhat.cpu(), oxhat) < 1e-4
