@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           const float2 col[8] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w),
                                  make_float2(v2.x, v2.y), make_float2(v2.z, v2.w), make_float2(v3.x, v3.y), make_float2(v3.z, v3.w)};
 #pragma unroll
-          for (int dx = 0; dx < 5; ++dx) {
+          for (int dx = 0; dx < 5; ++dx) {    // (the 25 weight pairs do not fit this role's registers next to the 5x16 window)
             const float2 w = *reinterpret_cast<const float2*>(SW + SW_W4 + (dy * 5 + dx) * 16 + 2 * cp);
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(col[k + dx], w, acc[k]);
@@ -508,63 +508,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
         TC_STAMP(7);
       }
-    } else {
+    } else if (warp < 12) {
+      // ======================= conv1 warps 8-11 =======================
+      // conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2); 16 consecutive lanes = the
+      // 16 pixel quads of one channel pair.  The 25 tap weights of the pair live in registers for the whole segment.
+      const int st = tid - 256;
+      const int cp = st >> 4, i1 = 4 * (st & 15);
+      float2 wr[25];
+#pragma unroll
+      for (int k = 0; k < 25; ++k) wr[k] = *reinterpret_cast<const float2*>(SW + SW_W1 + k * 16 + 2 * cp);
+      const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
       for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
-        const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
-        const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
-        const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
-          // ======================= SIMT warps =======================
-          // warps 8-11 (st < 128): conv1; warps 12-15 (st 128..255): conv4 + output (104 active threads)
-          const int st = tid - 256;
-          const int r4 = t - 11;
-          const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8) && st >= 128;
-          const bool act4 = st - 128 < 104;
-          float dv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (st >= 128) load_din(r4, st - 128, do4 && act4, dv);     // (warp-uniform) global loads first; used at the end of conv4
-          TC_STAMP(0);
-          // ---- conv1 row t -> a1 ring (hi/lo) and o1 ring: thread = 4 pixels x 2 channels (FFMA2) ----
-          if (st < 128 && t >= a1_lo && t < a1_hi && !TC_OFF(4)) {
-            const int cp = st >> 4, i1 = 4 * (st & 15);   // 16 consecutive lanes = the 16 pixel quads of one channel pair
-            const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
-            float2 acc[4] = {b1, b1, b1, b1};
-  #pragma unroll
-            for (int dy = 0; dy < 5; ++dy) {
-              const int rr = t + dy - 2;            // rows outside the plane: zeros, no branch (see conv4_out)
-              const float* sr = (rr >= 0 && rr < s.ny) ? SK + (rr & (TC_RS - 1)) * TC_PS + i1 : SW + SW_ZERO;
-              const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
-              const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  #pragma unroll
-              for (int dx = 0; dx < 5; ++dx) {
-                const float2 w = *reinterpret_cast<const float2*>(SW + SW_W1 + (dy * 5 + dx) * 16 + 2 * cp);
-  #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), w, acc[k]);
-              }
-            }
-  #pragma unroll
-            float2 th[4];                       // tanh of the channel pair, two values per packed instruction
-  #pragma unroll
-            for (int k = 0; k < 4; ++k) th[k] = p.linear ? acc[k] : tanh2(acc[k]);
-  #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float av[4], ov[4];
-  #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = s.x0 - 6 + i1 + k;
-                const bool in = c >= 0 && c < s.nx;
-                ov[k] = in ? (h ? acc[k].y : acc[k].x) : 0.f;
-                av[k] = in ? (h ? th[k].y : th[k].x) : 0.f;
-              }
-              const int co = 2 * cp + h;
-              split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
-              if (i1 >= 4 && i1 < 60)
-                *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        TC_STAMP(0);
+        if (t >= a1_lo && t < a1_hi && !TC_OFF(4)) {
+          float2 acc[4] = {b1, b1, b1, b1};
+#pragma unroll
+          for (int dy = 0; dy < 5; ++dy) {
+            const int rr = t + dy - 2;            // rows outside the plane: zeros, no branch (see conv4_out)
+            const float* sr = (rr >= 0 && rr < s.ny) ? SK + (rr & (TC_RS - 1)) * TC_PS + i1 : SW + SW_ZERO;
+            const float4 a = *reinterpret_cast<const float4*>(sr), b = *reinterpret_cast<const float4*>(sr + 4);
+            const float win[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(make_float2(win[k + dx], win[k + dx]), wr[dy * 5 + dx], acc[k]);
             }
           }
-          TC_STAMP(1);
-          // ---- conv4 + output row t-11 ----
-          if (do4) conv4_out(r4, st - 128, act4, dv);
-          TC_STAMP(2);
-          fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
+          float2 th[4];                       // tanh of the channel pair, two values per packed instruction
+#pragma unroll
+          for (int k = 0; k < 4; ++k) th[k] = p.linear ? acc[k] : tanh2(acc[k]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float av[4], ov[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = s.x0 - 6 + i1 + k;
+              const bool in = c >= 0 && c < s.nx;
+              ov[k] = in ? (h ? acc[k].y : acc[k].x) : 0.f;
+              av[k] = in ? (h ? th[k].y : th[k].x) : 0.f;
+            }
+            const int co = 2 * cp + h;
+            split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
+            if (i1 >= 4 && i1 < 60)
+              *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+          }
+        }
+        TC_STAMP(1);
+        fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
+        TC_STAMP(6);
+        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_STAMP(7);
+      }
+    } else {
+      // ======================= conv4 + output warps 12-15 (104 active threads) =======================
+      const int c4 = tid - 384;
+      const bool act4 = c4 < 104;
+      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+        const int r4 = t - 11;
+        const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8);
+        float dv[4];
+        load_din(r4, c4, do4 && act4, dv);     // global loads first; used at the end of conv4
+        TC_STAMP(0);
+        if (do4) conv4_out(r4, c4, act4, dv);
+        TC_STAMP(2);
         TC_STAMP(6);
         asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
         TC_STAMP(7);
