@@ -388,16 +388,18 @@ def codec_probe(dev):
                              dwtlevels=LEVELS)
         torch.manual_seed(1337)
         model = LiftingBasedDWTNetWrapper(cfg).to(dev).eval()
+        torch.cuda.empty_cache()
         with torch.no_grad():
-            model(x)
+            for _ in range(2):                     # weight packing, allocator growth
+                model(x)
             torch.cuda.synchronize()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-            for _ in range(2):
+            for _ in range(3):
                 xhat, si_xe, si_xo = model(x)
             ev1.record()
             torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / 2
+        ms = ev0.elapsed_time(ev1) / 3
         bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
         res[ae] = {"ms_per_batch16": ms, "mp_per_s": B * H * W / 1e6 / (ms * 1e-3), "bpp": bits / (B * H * W)}
         del model
