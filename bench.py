@@ -266,6 +266,7 @@ def run_own(args):
     line["dwt97"] = dwt97_probe(dev, pk)
     line["context_cnn"] = context_probe(dev, pk)
     line["codec_forward"] = codec_probe(dev)
+    line["agent_pointwise"] = colour_probe(dev, pk)
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
     print(json.dumps(line))
@@ -404,6 +405,33 @@ def codec_probe(dev):
         res[ae] = {"ms_per_batch16": ms, "mp_per_s": B * H * W / 1e6 / (ms * 1e-3), "bpp": bits / (B * H * W)}
         del model
     res["note"] = "random-init weights: bpp is a by-product, not a quality claim"
+    return res
+
+
+def colour_probe(dev, pk):
+    """Agent-side pointwise kernels on batch 64 of 512x768 RGB (302 MB per tensor > L2): RGB->YCbCr with
+    Y-0.5 (24 B per pixel) and Y+0.5 / YCbCr->RGB / -0.5 / clamp / squared error (36 B per pixel with the reconstruction
+    written, 24 B without)."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    x = torch.rand(4 * B, 3, H, W, device=dev)
+    y = ops.rgb_to_ycbcr_shift(x)
+    res = {}
+    px = 4 * B * H * W
+    for name, fn, bpp in (("rgb_to_ycbcr_shift", lambda: ops.rgb_to_ycbcr_shift(x), 24.0),
+                          ("ycbcr_to_rgb_sse", lambda: ops.ycbcr_to_rgb_sse(y, x, want_xhat=True), 36.0),
+                          ("ycbcr_to_rgb_sse_no_xhat", lambda: ops.ycbcr_to_rgb_sse(y, x, want_xhat=False), 24.0)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(10):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 10
+        gbs = bpp * px / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "bytes_per_pixel": bpp}
     return res
 
 

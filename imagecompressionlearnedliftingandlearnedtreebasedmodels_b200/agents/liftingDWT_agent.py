@@ -1,0 +1,122 @@
+"""``LiftingBasedDWTAgent``: the reference agent's data path (agents/liftingDWT_agent.py:14-190) on the B200 kernels.
+
+Scope: the agent's *computation* -- pre-processing, model forward, post-processing, the R-D scalars of
+``validate`` (:157-197) and one optimisation step of ``train_one_epoch`` (:78-125) -- behind the reference's constructor
+and method names.  The reference's loggers, Visdom, checkpoint bookkeeping of ``BaseAgent``, the image data loaders and the
+post-processing networks stay out of scope: ``data_loader`` is any iterable of RGB batches in [0, 1] handed in by the caller.
+
+What changes on the B200 path: RGB->YCbCr / Y-0.5 is one pass (``ll_rgb_to_ycbcr_shift``); Y+0.5 /
+YCbCr->RGB / -0.5 / clamp / squared error is one pass (``ll_ycbcr_to_rgb_sse``) that leaves the per-image squared error
+in a double on the device; the bit sums are accumulated inside the rate kernels, so a validated batch costs one host
+synchronisation instead of four ``.item()`` calls and ~25 elementwise launches.
+"""
+import math
+
+import torch
+from torch import optim
+
+from .. import ops
+from ..graphs.losses.rate_dist import TrainDLoss, TrainRDLoss
+from ..graphs.models.LiftingBasedDWT_net import LiftingBasedDWTNetWrapper
+
+
+def _cfg(config, key, default):
+    """Optional config key (EasyDict raises AttributeError, dict-backed configs KeyError)."""
+    try:
+        return getattr(config, key)
+    except (AttributeError, KeyError):
+        return default
+
+
+def configure_optimizers(model, lr):
+    """Adam on every parameter (the reference's helper at the bottom of agents/liftingDWT_agent.py)."""
+    return optim.Adam((p for p in model.parameters() if p.requires_grad), lr=lr)
+
+
+class LiftingBasedDWTAgent:
+    def __init__(self, config, data_loader=None, device=None):
+        self.config = config
+        self.clrch = config.clrch
+        self.device = torch.device(device if device is not None else "cuda:0")
+        self.lr = _cfg(config, "learning_rate", 1e-4)
+        self.model = LiftingBasedDWTNetWrapper(config).to(self.device)
+        self.optimizer = configure_optimizers(self.model, self.lr)
+        self.scheduler = optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, factor=0.5, patience=5, threshold=0.0001,
+                                                              threshold_mode='rel', cooldown=0, min_lr=1e-06, eps=1e-08)
+        self.grad_acc_iters = _cfg(config, "grad_acc_iters", 1)
+        self.lambda_ = config.lambda_
+        self.training_loss_switch = _cfg(config, "training_loss_switch", 1)
+        self.train_loss = TrainDLoss(config.lambda_) if self.training_loss_switch == 0 else TrainRDLoss(config.lambda_)
+        self.valid_loss = TrainRDLoss(config.lambda_)
+        self.data_loader = data_loader
+        self.current_epoch = 0
+        self.current_iteration = 0
+
+    # ---- pre / post processing (:100-105, :164-181) ----
+    def preprocess(self, x):
+        """RGB in [0,1] -> model input.  clrch == 3: x - 0.5; clrch == 1: YCbCr (BT.709) with Y - 0.5."""
+        if self.clrch == 3:
+            return x - 0.5
+        return ops.rgb_to_ycbcr_shift(x)
+
+    def postprocess(self, yhat, x=None):
+        """Model output -> (xhat in [-0.5, 0.5], per-image squared error against x - 0.5 | None)."""
+        if self.clrch == 3:
+            xhat = yhat.clamp(-0.5, 0.5)
+            sse = ((x - 0.5 - xhat).double() ** 2).sum(dim=(1, 2, 3)) if x is not None else None
+            return xhat, sse
+        return ops.ycbcr_to_rgb_sse(yhat, x, want_xhat=True)
+
+    # ---- validate (:157-197) ----
+    @torch.no_grad()
+    def validate_batch(self, x):
+        """One batch of ``validate``: returns a dict of python floats (rd_loss, mse, psnr, rate1, rate2, bpp) with one
+        device->host transfer."""
+        self.model.eval()
+        x = x.to(self.device)
+        yhat, si_xe, si_xo = self.model(self.preprocess(x))
+        _, sse = self.postprocess(yhat, x)
+        n = x.numel()
+        vals = torch.stack([sse.sum(), si_xe.double().sum(), sum(s.double().sum() for s in si_xo)]).cpu()
+        mse = float(vals[0]) / n
+        rate1, rate2 = float(vals[1]) / n * 3, float(vals[2]) / n * 3          # rate_dist.py:37-41
+        return {"rd_loss": rate1 + rate2 + self.lambda_ * mse, "mse": mse, "psnr": 10.0 * math.log10(1.0 / mse) if mse > 0 else float("inf"),
+                "rate1": rate1, "rate2": rate2, "bpp": rate1 + rate2}
+
+    @torch.no_grad()
+    def validate(self):
+        if self.data_loader is None:
+            raise RuntimeError("LiftingBasedDWTAgent.validate: no data_loader was given")
+        rows = [self.validate_batch(x) for x in self.data_loader]
+        if not rows:
+            raise RuntimeError("LiftingBasedDWTAgent.validate: the data_loader is empty")
+        avg = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
+        self.scheduler.step(avg["rd_loss"])
+        return avg
+
+    # ---- one optimisation step of train_one_epoch (:78-125) ----
+    def train_batch(self, x):
+        self.model.train()
+        x = x.to(self.device)
+        y = self.preprocess(x)
+        yhat, si_xe, si_xo = self.model(y)
+        if self.clrch == 3:
+            xs, xhat = y, yhat
+        else:   # the colour transform back is linear: autograd runs through the torch expression of it
+            from ..compat import YCbCr2RGB
+            shift = torch.tensor([[[0.5]], [[0.0]], [[0.0]]], device=self.device)
+            xs, xhat = x - 0.5, YCbCr2RGB()(yhat + shift) - 0.5
+        rd_loss, mse_loss, rate1, rate2 = self.train_loss.forward3(xs, xhat, si_xe, si_xo)
+        (rd_loss / self.grad_acc_iters).backward()
+        self.current_iteration += 1
+        if self.current_iteration % self.grad_acc_iters == 0:
+            self.optimizer.step()
+            self.optimizer.zero_grad()
+        return rd_loss.detach(), mse_loss.detach(), rate1.detach(), torch.as_tensor(rate2).detach()
+
+    def train_one_epoch(self):
+        if self.data_loader is None:
+            raise RuntimeError("LiftingBasedDWTAgent.train_one_epoch: no data_loader was given")
+        out = [self.train_batch(x) for x in self.data_loader]
+        self.current_epoch += 1
+        return out

@@ -426,6 +426,39 @@ def nhwc_split_to_nchw(z):
     return out
 
 
+def rgb_to_ycbcr_shift(rgb):
+    """Agent pre-processing (agents/liftingDWT_agent.py:170-171): RGB (B,3,H,W) in [0,1] -> YCbCr (BT.709) with Y - 0.5."""
+    require_device(rgb)
+    rgb = _f32c(rgb, "rgb")
+    if rgb.dim() != 4 or rgb.shape[1] != 3:
+        raise ValueError(f"rgb_to_ycbcr_shift: expected (B,3,H,W), got {tuple(rgb.shape)}")
+    out = torch.empty_like(rgb)
+    with torch.cuda.device(rgb.device):
+        check(_lib.load().ll_rgb_to_ycbcr_shift(ptr(rgb), ptr(out), rgb.shape[0], rgb.shape[2] * rgb.shape[3], stream_ptr()))
+    _count(1)
+    return out
+
+
+def ycbcr_to_rgb_sse(ycc_hat, rgb_ref=None, want_xhat=True):
+    """Agent post-processing (:174-186): xhat = clamp(YCbCr2RGB(yhat + (0.5,0,0)) - 0.5, +-0.5) and, with ``rgb_ref``,
+    the per-image sum of squared errors against ``rgb_ref - 0.5`` (float64 (B,)).  Returns (xhat | None, sse | None)."""
+    require_device(ycc_hat)
+    y = _f32c(ycc_hat, "ycc_hat")
+    if y.dim() != 4 or y.shape[1] != 3:
+        raise ValueError(f"ycbcr_to_rgb_sse: expected (B,3,H,W), got {tuple(y.shape)}")
+    ref = _f32c(rgb_ref, "rgb_ref") if rgb_ref is not None else None
+    if ref is not None and ref.shape != y.shape:
+        raise ValueError("ycbcr_to_rgb_sse: reference and reconstruction shapes differ")
+    if ref is None and not want_xhat:
+        raise ValueError("ycbcr_to_rgb_sse: nothing to compute")
+    xhat = torch.empty_like(y) if want_xhat else None
+    sse = torch.zeros(y.shape[0], dtype=torch.float64, device=y.device) if ref is not None else None
+    with torch.cuda.device(y.device):
+        check(_lib.load().ll_ycbcr_to_rgb_sse(ptr(y), ptr(ref), ptr(xhat), y.shape[0], y.shape[2] * y.shape[3], ptr(sse), stream_ptr()))
+    _count(1)
+    return xhat, sse
+
+
 def nhwc_split_conv3(z, w, bias):
     """split NHWC (B,H,W,2C) -> 3x3 conv (zero padding 1, cross-correlation, exact fp32) -> fp32 NCHW (B,Cout,H,W)."""
     require_device(z)

@@ -238,6 +238,22 @@ int ll_cgp_tail_rate(const float* h2, int64_t h2_sb, const float* w3, const floa
                      const float* x, int64_t x_sb, const float* noise, float* bits, int64_t bits_sb, float* y,
                      float* ms_out, int B, int G, int C2, int C3, int64_t hw, double* sum_out, ll_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* Agent-side pointwise work around the codec                */
+/* ------------------------------------------------------------------------- */
+
+/* agents/liftingDWT_agent.py:170-171 (also :104-105 in the training loop), clrch == 1:
+ * y = compressai.transforms.RGB2YCbCr()(x) (BT.709, full range, chroma offset +0.5); y[:, 0] -= 0.5.
+ * rgb, ycc: planar fp32 (B, 3, hw). */
+int ll_rgb_to_ycbcr_shift(const float* rgb, float* ycc, int B, int64_t hw, ll_stream_t stream);
+
+/* agents/liftingDWT_agent.py:174-181 + the MSE of TrainRDLoss.forward3 (graphs/losses/rate_dist.py:36):
+ * xhat = clamp(YCbCr2RGB(yhat + (0.5, 0, 0)) - 0.5, -0.5, 0.5) written to xhat (optional), and
+ * sse[b] += sum over the image of ((rgb_ref - 0.5) - xhat)^2 (optional, double, one entry per image; the caller
+ * zeroes it): mse = sum(sse) / (3 B hw), PSNR = 10 log10(1 / mse) (:186).  Planar fp32 (B, 3, hw). */
+int ll_ycbcr_to_rgb_sse(const float* ycc_hat, const float* rgb_ref, float* xhat, int B, int64_t hw, double* sse,
+                        ll_stream_t stream);
+
 /* EntropyModel.quantize (compressai 1.2.1; call sites :330,341,352,719): q = round-half-even(x)
  * when noise == NULL ("dequantize"), else q = x + noise ("noise"; the caller draws U(-1/2,1/2)). */
 int ll_quantize(const float* x, const float* noise, float* q, int64_t n, ll_stream_t stream);

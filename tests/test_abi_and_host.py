@@ -180,3 +180,21 @@ def test_oracle_known_answers():
     v = (y - mu).abs().double().numpy()
     want = norm.cdf((0.5 - v) / s2) - norm.cdf((-0.5 - v) / s2)
     assert abs(lik.double().numpy() - want).max() < 1e-6
+
+
+def test_agent_mirrors_are_importable_and_refuse_to_run_unconfigured():
+    """``LiftingBasedDWTAgent(config)`` / ``CompressionAgent(config)`` keep the reference's names; without
+    a loader (or, for CompressionAgent, a model -- the reference leaves it None) they raise instead of doing CPU work."""
+    import pytest
+    from oracle import model as om
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.agents import CompressionAgent, LiftingBasedDWTAgent
+    cfg = om.default_cfg(dwtlevels=2, autoencoder="SubbandAutoEncoder")
+    agent = LiftingBasedDWTAgent(cfg, device="cpu")
+    assert agent.clrch == 1 and agent.lambda_ == cfg.lambda_ and len(list(agent.model.parameters())) > 0
+    with pytest.raises(RuntimeError):
+        agent.validate()
+    with pytest.raises(RuntimeError):
+        CompressionAgent(cfg, device="cpu").train_one_epoch()
+    import torch
+    with pytest.raises(RuntimeError):
+        agent.preprocess(torch.rand(1, 3, 8, 8))          # CPU tensor: the kernels have no CPU fallback

@@ -1,0 +1,106 @@
+"""GPU tests (``-m gpu``) of the agent-side pointwise kernels and of the ``LiftingBasedDWTAgent`` mirror:
+colour transform, clamp and squared error against the oracle's restatement of compressai.transforms (BT.709) and of
+agents/liftingDWT_agent.py:164-186; the agent's validate scalars against the oracle pipeline on the same weights."""
+import math
+
+import pytest
+import torch
+
+from oracle import model as om, thirdparty as tp
+
+from common import keyed_state
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 7, 9), (3, 3, 1, 5), (1, 3, 512, 768)])
+def test_colour_kernels_match_oracle(shape):
+    ops = _ops()
+    torch.manual_seed(sum(shape))
+    x = torch.rand(*shape)
+    ref = om.preprocess(x)                                   # RGB2YCbCr, Y - 0.5 (agents/liftingDWT_agent.py:170-171)
+    got = ops.rgb_to_ycbcr_shift(x.to(DEV)).cpu()
+    assert (got - ref).abs().max().item() <= 2e-7            # same IEEE operations: at most an ulp
+    # post-processing of a perturbed "reconstruction": + (0.5,0,0), YCbCr2RGB, - 0.5, clamp, squared error (:174-186)
+    yhat = ref + 0.3 * torch.randn(*shape)                   # large enough to hit the clamp
+    shift = torch.tensor([[[0.5]], [[0.0]], [[0.0]]])
+    oxhat = (tp.ycbcr2rgb(yhat + shift) - 0.5).clamp(-0.5, 0.5)
+    osse = ((x - 0.5 - oxhat).double() ** 2).sum(dim=(1, 2, 3))
+    xhat, sse = ops.ycbcr_to_rgb_sse(yhat.to(DEV), x.to(DEV))
+    assert (xhat.cpu() - oxhat).abs().max().item() <= 4e-7
+    assert ((xhat.cpu() == 0.5) | (xhat.cpu() == -0.5)).any()       # the clamp was exercised
+    assert torch.allclose(sse.cpu(), osse, rtol=2e-5, atol=1e-9)
+    _, sse2 = ops.ycbcr_to_rgb_sse(yhat.to(DEV), x.to(DEV), want_xhat=False)
+    assert torch.allclose(sse2.cpu(), osse, rtol=2e-5, atol=1e-9)
+    xh3, none = ops.ycbcr_to_rgb_sse(yhat.to(DEV))
+    assert none is None and torch.equal(xh3, xhat)
+    # exact inverse pair up to rounding
+    back, _ = ops.ycbcr_to_rgb_sse(ops.rgb_to_ycbcr_shift(x.to(DEV)))
+    assert (back.cpu() - (x - 0.5)).abs().max().item() <= 1e-6
+
+
+def test_colour_kernel_errors():
+    ops = _ops()
+    with pytest.raises(RuntimeError):
+        ops.rgb_to_ycbcr_shift(torch.rand(1, 3, 4, 4))                       # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        ops.rgb_to_ycbcr_shift(torch.rand(1, 1, 4, 4, device=DEV))
+    with pytest.raises(ValueError):
+        ops.ycbcr_to_rgb_sse(torch.rand(1, 3, 4, 4, device=DEV), torch.rand(1, 3, 4, 5, device=DEV))
+    assert ops.rgb_to_ycbcr_shift(torch.rand(0, 3, 4, 4, device=DEV)).shape == (0, 3, 4, 4)
+
+
+def test_agent_validate_batch_matches_oracle_pipeline():
+    """``LiftingBasedDWTAgent.validate_batch`` (pre-processing, codec forward, post-processing, R-D scalars) against the
+    oracle: preprocess -> wrapper_forward -> ycbcr2rgb / clamp -> TrainRDLoss.forward3, same synthetic weights."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.agents import CompressionAgent, LiftingBasedDWTAgent
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                         entropy_layer="conditioned2ZTsepSubbands", dwtlevels=2, ctx_precision="fp32")
+    cfg.learning_rate, cfg.lambda_ = 1e-4, 0.01
+    torch.manual_seed(1337)
+    agent = LiftingBasedDWTAgent(cfg, device=DEV)
+    sd = keyed_state(agent.model.cpu())
+    agent.model.to(DEV)
+    torch.manual_seed(4)
+    x = torch.rand(2, 3, 64, 96)
+    got = agent.validate_batch(x)
+    with torch.no_grad():
+        y = om.preprocess(x)
+        oyhat, osi_xe, osi_xo = om.wrapper_forward(y, sd, cfg)
+        shift = torch.tensor([[[0.5]], [[0.0]], [[0.0]]])
+        oxhat = (tp.ycbcr2rgb(oyhat + shift) - 0.5).clamp(-0.5, 0.5)
+        loss, mse, r1, r2 = om.rd_loss(x - 0.5, oxhat, osi_xe, osi_xo, cfg.lambda_)
+    assert abs(got["bpp"] - float(r1 + r2)) <= 1e-3 * float(r1 + r2)            # bpp within 0.1 %
+    assert abs(got["mse"] - float(mse)) <= 1e-3 * float(mse)
+    assert abs(got["psnr"] - 10.0 * math.log10(1.0 / float(mse))) <= 0.01
+    assert abs(got["rd_loss"] - float(loss)) <= 1e-3 * float(loss)
+    # loaders: validate() averages the batches; the CompressionAgent skeleton refuses to run without a model
+    agent.data_loader = [x, x]
+    avg = agent.validate()
+    assert abs(avg["bpp"] - got["bpp"]) <= 1e-9 * max(1.0, got["bpp"])
+    with pytest.raises(RuntimeError):
+        CompressionAgent(cfg, device=DEV).validate()
+
+
+def test_agent_train_batch_steps():
+    """One optimisation step of ``train_one_epoch`` (:78-125): finite losses, parameters move."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.agents import LiftingBasedDWTAgent
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                         entropy_layer="conditioned2ZTsepSubbands", dwtlevels=2)
+    cfg.learning_rate, cfg.lambda_ = 1e-4, 0.01
+    torch.manual_seed(1337)
+    agent = LiftingBasedDWTAgent(cfg, device=DEV)
+    keyed_state(agent.model.cpu())
+    agent.model.to(DEV)
+    before = [p.detach().clone() for p in agent.model.parameters()]
+    torch.manual_seed(6)
+    rd, mse, r1, r2 = agent.train_batch(torch.rand(2, 3, 32, 32))
+    assert all(torch.isfinite(v).all() for v in (rd, mse, r1, r2))
+    moved = sum(int(not torch.equal(a, b.detach())) for a, b in zip(before, agent.model.parameters()))
+    assert moved > 0
