@@ -404,6 +404,26 @@ def codec_probe(dev):
         bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
         res[ae] = {"ms_per_batch16": ms, "mp_per_s": B * H * W / 1e6 / (ms * 1e-3), "bpp": bits / (B * H * W)}
         del model
+    # configs[2] end to end through the agent mirror: pinned host RGB batch -> H2D -> RGB->YCbCr -> codec forward ->
+    # YCbCr->RGB, clamp, squared error -> one D2H of the three scalars (bpp, PSNR)
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.agents import LiftingBasedDWTAgent
+    cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                         entropy_layer="conditioned2ZTsepSubbands", dwtlevels=LEVELS)
+    torch.manual_seed(1337)
+    agent = LiftingBasedDWTAgent(cfg, device=dev)
+    rgb = torch.rand(B, 3, H, W).pin_memory()
+    for _ in range(2):
+        out = agent.validate_batch(rgb)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out = agent.validate_batch(rgb)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 3 * 1e3
+    res["agent_validate_batch"] = {"ms_per_batch16": ms, "mp_per_s": B * H * W / 1e6 / (ms * 1e-3), "bpp": out["bpp"], "psnr": out["psnr"],
+                                   "h2d_bytes": rgb.numel() * 4, "d2h_bytes": 24,
+                                   "note": "wall clock around LiftingBasedDWTAgent.validate_batch (host RGB in, python floats out), SubbandAutoEncoder"}
+    del agent
     res["note"] = "random-init weights: bpp is a by-product, not a quality claim"
     return res
 
