@@ -1,0 +1,285 @@
+// rans.cu -- parallel entropy coding of the quantised subbands (SURVEY.md 8f "next #3").
+//
+// The reference only has a serial, per-coefficient Python coder, and only for its autoregressive model
+// (LiftingBasedDWT_net.py:374-556, compress_ar / decompress_ar around compressai.ans).  The entropy layers whose
+// contexts depend on *already decoded levels only* (factorized :182-231, onlyEZWT :759-840) can be decoded a whole
+// subband at a time, so their symbols are coded here with interleaved rANS streams, one GPU thread per stream:
+//   * state 32 bit, renormalisation by 16-bit words, probabilities quantised to 2^16 (ryg_rans word variant);
+//   * image b of a (B, C, hw) tensor owns S streams; stream s codes samples s, s+S, s+2S, ... of the image, so a warp
+//     reads 32 consecutive samples per step (coalesced) and every image's bytes are separable;
+//   * the distribution of a sample is never tabulated: the coder evaluates the model's own CDF -- the Gaussian of
+//     GaussianConditional (sigma clamped at 0.11, mean mu; compressai 1.2.1 entropy_models.py) or the factorized
+//     logistic-mixture CDF of EntropyBottleneck -- at the symbol's edges, with the same device code in the encoder and
+//     the decoder (bit-identical on the same architecture):
+//         C(a) = 2a + floor(F(a - K - 1/2) * (2^16 - 2(2K+2))),   a = k + K in [0, 2K], a = 2K+1 escape
+//     (the 2a term guarantees every symbol a frequency >= 1 even if F glitches by an ulp; K = clamp(ceil(6 sigma),
+//     15, 2047) for the Gaussian, 255 for the factorized model); |k| > K is an escape followed by 16 raw bits.
+// The symbol is k = round(y - mu) of the *dequantised* value y = round(x - mu) + mu the forward pass returns, and the
+// decoder returns k + mu computed the same way, so decode(encode(y)) == y bit for bit.
+#include <stdint.h>
+
+#include "ll_common.cuh"
+
+namespace ll {
+
+constexpr int RN_THREADS = 128;
+constexpr uint32_t RN_L = 1u << 16;
+constexpr int RN_EB_BLOB = 64;   // == EB_BLOB of rate.cu (ll_pack_eb)
+
+// EntropyBottleneck logits (same arithmetic as rate.cu::eb_logits; blob layout of ll_pack_eb)
+__device__ __forceinline__ float rn_eb_logits(const float* __restrict__ w, float v) {
+  float h[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float t = __fadd_rn(__fmul_rn(w[i], v), w[3 + i]);
+    h[i] = __fadd_rn(t, __fmul_rn(w[6 + i], tanhf(t)));
+  }
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const float* q = w + 9 + 15 * l;
+    float g[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float t = __fmul_rn(q[3 * i], h[0]);
+      t = fmaf(q[3 * i + 1], h[1], t);
+      t = fmaf(q[3 * i + 2], h[2], t);
+      t = __fadd_rn(t, q[9 + i]);
+      g[i] = __fadd_rn(t, __fmul_rn(q[12 + i], tanhf(t)));
+    }
+    h[0] = g[0];
+    h[1] = g[1];
+    h[2] = g[2];
+  }
+  float t = __fmul_rn(w[54], h[0]);
+  t = fmaf(w[55], h[1], t);
+  t = fmaf(w[56], h[2], t);
+  return __fadd_rn(t, w[57]);
+}
+
+// A sample's distribution: cumulative frequency of alphabet index a in [0, 2K+2] (2K+2 -> 2^16).
+struct GaussDist {
+  float s, mu;
+  int K;
+  __device__ __forceinline__ GaussDist(float sigma, float mean) : s(fmaxf(sigma, 0.11f)), mu(mean) {
+    const int k = (int)ceilf(6.f * s);
+    K = k < 15 ? 15 : (k > 2047 ? 2047 : k);
+  }
+  __device__ __forceinline__ float centre() const { return mu; }
+  __device__ __forceinline__ uint32_t C(int a) const {
+    if (a <= 0) return 0u;
+    if (a >= 2 * K + 2) return 65536u;
+    const uint32_t M = 65536u - 2u * (2 * K + 2);
+    const float t = (float)(a - K) - 0.5f;
+    const float F = 0.5f * erfcf(-0.70710678118654752440f * __fdiv_rn(t, s));
+    const uint32_t q = (uint32_t)fminf(floorf(F * (float)M), (float)M);
+    return 2u * a + q;
+  }
+};
+
+struct EbDist {
+  const float* w;
+  float med;
+  int K;
+  __device__ __forceinline__ EbDist(const float* blob_c) : w(blob_c), med(blob_c[58]), K(255) {}
+  __device__ __forceinline__ float centre() const { return med; }
+  __device__ __forceinline__ uint32_t C(int a) const {
+    if (a <= 0) return 0u;
+    if (a >= 2 * K + 2) return 65536u;
+    const uint32_t M = 65536u - 2u * (2 * K + 2);
+    const float t = __fadd_rn(med, (float)(a - K) - 0.5f);
+    const float F = 1.f / (1.f + expf(-rn_eb_logits(w, t)));
+    const uint32_t q = (uint32_t)fminf(floorf(F * (float)M), (float)M);
+    return 2u * a + q;
+  }
+};
+
+struct RansEnc {   // writes 16-bit words backwards from the end of the stream's scratch region
+  uint32_t x;
+  uint16_t* buf;
+  int pos;
+  __device__ __forceinline__ RansEnc(uint16_t* b, int cap) : x(RN_L), buf(b), pos(cap) {}
+  __device__ __forceinline__ void put(uint32_t start, uint32_t freq) {
+    if (x >= (freq << 16)) {
+      buf[--pos] = (uint16_t)(x & 0xffffu);
+      x >>= 16;
+    }
+    x = ((x / freq) << 16) + (x % freq) + start;
+  }
+  __device__ __forceinline__ int finish(int cap) {
+    buf[--pos] = (uint16_t)(x & 0xffffu);
+    buf[--pos] = (uint16_t)(x >> 16);
+    return cap - pos;
+  }
+};
+
+struct RansDec {
+  uint32_t x;
+  const uint16_t* buf;
+  __device__ __forceinline__ RansDec(const uint16_t* b) : x(((uint32_t)b[0] << 16) | b[1]), buf(b + 2) {}
+  __device__ __forceinline__ uint32_t slot() const { return x & 0xffffu; }
+  __device__ __forceinline__ void advance(uint32_t start, uint32_t freq) {
+    x = freq * (x >> 16) + (x & 0xffffu) - start;
+    if (x < RN_L) x = (x << 16) | *buf++;
+  }
+};
+
+template <class D>
+__device__ __forceinline__ void enc_sample(RansEnc& e, const D& d, float y) {
+  const float kf = rintf(__fsub_rn(y, d.centre()));
+  const int K = d.K;
+  if (fabsf(kf) <= (float)K) {
+    const int a = (int)kf + K;
+    const uint32_t c0 = d.C(a);
+    e.put(c0, d.C(a + 1) - c0);
+  } else {   // escape: the decoder pops the escape symbol first, so the raw word is pushed first
+    const float kc = fminf(fmaxf(kf, -32768.f), 32767.f);
+    e.put((uint32_t)((int)kc + 32768), 1u);
+    const uint32_t c0 = d.C(2 * K + 1);
+    e.put(c0, 65536u - c0);
+  }
+}
+
+template <class D>
+__device__ __forceinline__ float dec_sample(RansDec& r, const D& d) {
+  const uint32_t sl = r.slot();
+  const int K = d.K;
+  int lo = 0, hi = 2 * K + 1;            // largest a with C(a) <= slot
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (d.C(mid) <= sl) lo = mid;
+    else hi = mid - 1;
+  }
+  const uint32_t c0 = d.C(lo);
+  r.advance(c0, d.C(lo + 1) - c0);
+  float kf;
+  if (lo <= 2 * K) kf = (float)(lo - K);
+  else {
+    const uint32_t v = r.slot();
+    r.advance(v, 1u);
+    kf = (float)((int)v - 32768);
+  }
+  return __fadd_rn(kf, d.centre());
+}
+
+// MODE 0: Gaussian, ms (B, 2C, hw) with channel 2c = sigma, 2c+1 = mu.  MODE 1: factorized, blob (C, 64).
+template <int MODE>
+__global__ void __launch_bounds__(RN_THREADS) rans_encode_kernel(const float* __restrict__ y, const float* __restrict__ par, int B,
+                                                                int C, long long hw, int S, uint16_t* __restrict__ scratch,
+                                                                int cap, int* __restrict__ counts) {
+  const long long st = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (st >= (long long)B * S) return;
+  const long long b = st / S;
+  const int s = (int)(st % S);
+  const long long N = (long long)C * hw;
+  const float* yb = y + b * N;
+  RansEnc enc(scratch + st * cap, cap);
+  const long long ns = s < N ? (N - s + S - 1) / S : 0;
+  for (long long j = ns - 1; j >= 0; --j) {
+    const long long e = s + j * S;
+    const int c = (int)(e / hw);
+    if (MODE == 0) {
+      const long long pix = e - c * hw;
+      const float* m = par + (b * 2 * C + 2 * c) * hw + pix;
+      enc_sample(enc, GaussDist(m[0], m[hw]), yb[e]);
+    } else {
+      enc_sample(enc, EbDist(par + (size_t)c * RN_EB_BLOB), yb[e]);
+    }
+  }
+  counts[st] = enc.finish(cap);
+}
+
+__global__ void rans_pack_kernel(const uint16_t* __restrict__ scratch, const int* __restrict__ counts, const long long* __restrict__ offsets,
+                                 long long nstreams, int cap, uint16_t* __restrict__ packed) {
+  // one warp per stream
+  const long long st = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (st >= nstreams) return;
+  const int n = counts[st];
+  const uint16_t* src = scratch + st * cap + (cap - n);
+  uint16_t* dst = packed + offsets[st];
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RN_THREADS) rans_decode_kernel(const uint16_t* __restrict__ packed, const long long* __restrict__ offsets,
+                                                                const float* __restrict__ par, int B, int C, long long hw, int S,
+                                                                float* __restrict__ y) {
+  const long long st = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (st >= (long long)B * S) return;
+  const long long b = st / S;
+  const int s = (int)(st % S);
+  const long long N = (long long)C * hw;
+  float* yb = y + b * N;
+  RansDec dec(packed + offsets[st]);
+  for (long long e = s; e < N; e += S) {
+    const int c = (int)(e / hw);
+    if (MODE == 0) {
+      const long long pix = e - c * hw;
+      const float* m = par + (b * 2 * C + 2 * c) * hw + pix;
+      yb[e] = dec_sample(dec, GaussDist(m[0], m[hw]));
+    } else {
+      yb[e] = dec_sample(dec, EbDist(par + (size_t)c * RN_EB_BLOB));
+    }
+  }
+}
+
+}  // namespace ll
+
+using namespace ll;
+
+extern "C" {
+
+int64_t ll_rans_stream_cap(int64_t n_per_image, int S) {
+  if (n_per_image < 0 || S <= 0) return -1;
+  const int64_t per = (n_per_image + S - 1) / S;
+  return 2 * per + 4;   // <= 2 words per sample (escape + raw), 2 words of final state, slack
+}
+
+static int rans_args(const char* who, const void* a, const void* b, const void* c, const void* d, int B, int C, int64_t hw, int S) {
+  if (B < 0 || C <= 0 || hw < 0 || S <= 0) return fail(LL_EINVAL, "%s: bad extents", who);
+  if ((long long)B * hw > 0 && (!a || !b || !c || !d)) return fail(LL_EINVAL, "%s: null pointer", who);
+  if ((long long)B * S > 0x7fffffffLL) return fail(LL_EINVAL, "%s: too many streams", who);
+  return LL_OK;
+}
+
+int ll_rans_encode(int mode, const float* y, const float* par, int B, int C, int64_t hw, int S, uint16_t* scratch,
+                   int32_t* counts, ll_stream_t stream) {
+  int rc = rans_args("ll_rans_encode", y, par, scratch, counts, B, C, hw, S);
+  if (rc) return rc;
+  if (mode != 0 && mode != 1) return fail(LL_EINVAL, "ll_rans_encode: mode must be 0 (gaussian) or 1 (factorized)");
+  const long long nst = (long long)B * S;
+  if (nst == 0 || hw == 0) return LL_OK;
+  const int cap = (int)ll_rans_stream_cap((int64_t)C * hw, S);
+  const unsigned blocks = (unsigned)((nst + RN_THREADS - 1) / RN_THREADS);
+  if (mode == 0) rans_encode_kernel<0><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
+  else rans_encode_kernel<1><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
+  LL_LAUNCH_OK("rans_encode_kernel");
+  return LL_OK;
+}
+
+int ll_rans_pack(const uint16_t* scratch, const int32_t* counts, const int64_t* offsets, int64_t nstreams, int cap,
+                 uint16_t* packed, ll_stream_t stream) {
+  if (nstreams < 0 || cap <= 0) return fail(LL_EINVAL, "ll_rans_pack: bad extents");
+  if (nstreams == 0) return LL_OK;
+  if (!scratch || !counts || !offsets || !packed) return fail(LL_EINVAL, "ll_rans_pack: null pointer");
+  const unsigned blocks = (unsigned)((nstreams * 32 + 255) / 256);
+  rans_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(scratch, counts, reinterpret_cast<const long long*>(offsets), nstreams, cap, packed);
+  LL_LAUNCH_OK("rans_pack_kernel");
+  return LL_OK;
+}
+
+int ll_rans_decode(int mode, const uint16_t* packed, const int64_t* offsets, const float* par, int B, int C, int64_t hw, int S,
+                   float* y, ll_stream_t stream) {
+  int rc = rans_args("ll_rans_decode", packed, offsets, par, y, B, C, hw, S);
+  if (rc) return rc;
+  if (mode != 0 && mode != 1) return fail(LL_EINVAL, "ll_rans_decode: mode must be 0 (gaussian) or 1 (factorized)");
+  const long long nst = (long long)B * S;
+  if (nst == 0 || hw == 0) return LL_OK;
+  const unsigned blocks = (unsigned)((nst + RN_THREADS - 1) / RN_THREADS);
+  if (mode == 0) rans_decode_kernel<0><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
+  else rans_decode_kernel<1><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
+  LL_LAUNCH_OK("rans_decode_kernel");
+  return LL_OK;
+}
+
+}  // extern "C"

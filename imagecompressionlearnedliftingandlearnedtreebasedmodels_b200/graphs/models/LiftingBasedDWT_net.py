@@ -124,8 +124,27 @@ class LiftingBasedDWTNetWrapper(nn.Module):
         return sum(m.aux_loss() for m in self.planes())
 
     def compress(self, x):
-        raise NotImplementedError("compress(): the serial per-coefficient rANS coder (LiftingBasedDWT_net.py:374-556) "
-                                  "is outside the data-parallel hot path this package implements")
+        """(:76-99) x (B,3,H,W) -> (xhat, len_xe, len_xo): bits per pixel actually spent on the LL band and on the detail
+        subbands, summed over the colour planes (per-stream length tables included); the bitstreams themselves are kept
+        in ``self.last_bitstreams`` (one list per plane) for :meth:`decompress`."""
+        if self.clrch != 1:
+            xhat, streams = self.model.compress(x)
+            per_plane = [streams]
+        else:
+            outs = [m.compress(x[:, c:c + 1].contiguous()) for c, m in enumerate(self.planes())]
+            xhat = torch.cat([o[0] for o in outs], dim=1)
+            per_plane = [o[1] for o in outs]
+        self.last_bitstreams = per_plane
+        B, _, H, W = x.shape
+        len_xe = sum(st[0].nbytes() for st in per_plane) * 8 / (B * H * W)
+        len_xo = sum(sum(t.nbytes() for t in st[1:]) for st in per_plane) * 8 / (B * H * W)
+        return xhat, len_xe, len_xo
+
+    def decompress(self, per_plane=None):
+        per_plane = self.last_bitstreams if per_plane is None else per_plane
+        if self.clrch != 1:
+            return self.model.decompress(per_plane[0])
+        return torch.cat([m.decompress(st) for m, st in zip(self.planes(), per_plane)], dim=1)
 
 
 class LiftingBasedDWTNet(nn.Module):
@@ -152,7 +171,26 @@ class LiftingBasedDWTNet(nn.Module):
             self.entropymodel = DWTConditioned2EntropyLayerZTBlock(config)
 
     def compress(self, x):
-        raise NotImplementedError("compress(): serial coder out of scope (see module docstring)")
+        """x (B,C,H,W) -> (xhat, streams): real bitstreams for the entropy layers that decode a subband at a time
+        (``factorized``, ``onlyEZWT``; interleaved rANS, ``coding.py``).  The reference's ``compress`` (:136-152) calls
+        ``entropymodel.test``, which only exists for ``conditioned2ZTsepSubbands`` (its serial per-coefficient coder,
+        :374-556) -- that one stays out of scope."""
+        if not hasattr(self.entropymodel, "compress"):
+            raise NotImplementedError(f"compress(): no parallel coder for entropy_layer={self.entropy_layer!r} "
+                                      "(the serial per-coefficient coder of the reference is out of scope)")
+        with torch.no_grad():
+            out_xe, out_xo_list = self.autoencoder.encode(x)
+            streams, xe_q, qs = self.entropymodel.compress(out_xe, out_xo_list)
+            xhat = self.autoencoder.decode(xe_q, qs)
+        return xhat, streams
+
+    def decompress(self, streams):
+        """Inverse of :meth:`compress`: bitstreams -> reconstruction (B,C,H,W)."""
+        if not hasattr(self.entropymodel, "decompress"):
+            raise NotImplementedError(f"decompress(): no parallel coder for entropy_layer={self.entropy_layer!r}")
+        with torch.no_grad():
+            xe_q, qs = self.entropymodel.decompress(streams)
+            return self.autoencoder.decode(xe_q, qs)
 
     def forward(self, x):
         """x (B,C,H,W) -> (xhat, si_xe, si_xo_list) (:154-170)."""
@@ -222,6 +260,26 @@ class DWTFactorizedEntropyLayer(nn.Module):
             qs.append(q)
         xe_q, si_xe = self.ent_out_xe.rate(out_xe, self.training, self.bit_acc)
         return si_xe, sis, xe_q, qs
+
+    @torch.no_grad()
+    def compress(self, out_xe, out_xo_list):
+        """Real bitstreams (interleaved rANS, ``coding.py``): returns (streams, xe_q, qs); ``streams[0]`` codes the LL
+        band, ``streams[1 + l]`` level l (finest first)."""
+        from ... import coding
+        was = self.training
+        self.eval()
+        si_xe, sis, xe_q, qs = self.forward(out_xe, out_xo_list)
+        self.train(was)
+        streams = [coding.encode_factorized(self.ent_out_xe, xe_q)]
+        streams += [coding.encode_factorized(self.ent_out_xo_list[i], qs[i]) for i in range(self.num_lifting_layers)]
+        return streams, xe_q, qs
+
+    @torch.no_grad()
+    def decompress(self, streams):
+        from ... import coding
+        xe_q = coding.decode_factorized(self.ent_out_xe, streams[0])
+        qs = [coding.decode_factorized(self.ent_out_xo_list[i], streams[1 + i]) for i in range(self.num_lifting_layers)]
+        return xe_q, qs
 
 
 class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
@@ -401,6 +459,7 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         sis.reverse()
         return si_xe, sis, xe_q, qs
 
+
     def test(self, out_xe, out_xo_list):
         raise NotImplementedError("serial coder (test/compress_ar/decompress_ar) is out of scope")
 
@@ -523,22 +582,8 @@ class onlyEZWT(nn.Module):
         sis.append(si)
         con = q
         for i in range(L - 2, -1, -1):
-            plc = self.plc_list[i]
             x = out_xo_list[i]
-            B = x.shape[0]
-            ms = torch.empty(B, 6, x.shape[2], x.shape[3], dtype=torch.float32, device=x.device)
-            # exact fp32 on purpose: this layer's mu is part of the *dequantised* output
-            # (round(x - mu) + mu, :832) and so of the reconstruction (1e-4 tolerance); BF16 operands
-            # would move it by ~1e-3.  (cond2ZT returns plain round(x): there mu only feeds the rate.)
-            for b0 in range(0, B, CTX_BATCH_CHUNK):
-                b1 = min(B, b0 + CTX_BATCH_CHUNK)
-                if torch.is_grad_enabled() and any(p.requires_grad for p in plc.parameters()):
-                    ms = _chain(plc[2:], _conv(plc[0], con, lrelu=True, upsample2=True))   # differentiable, whole batch
-                    break
-                t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
-                t = ops.conv2d(t, plc[2].weight, plc[2].bias, lrelu=True)
-                ops.conv2d(t, plc[4].weight, plc[4].bias, out=ms[b0:b1])
-                del t
+            ms = self._ms(i, con)
             bits, q = self.ent_out_xo_list[i].bits(x, ms, self.training, want_y=True, acc=acc)
             sis.append(bits)
             qs.append(q)
@@ -546,3 +591,51 @@ class onlyEZWT(nn.Module):
         qs.reverse()
         sis.reverse()
         return si_xe, sis, xe_q, qs
+
+    def _ms(self, i, con):
+        """(sigma, mu) of level i from the dequantised parent level ``con`` (B,3,h/2,w/2) -> (B,6,h,w) (:826-831)."""
+        plc = self.plc_list[i]
+        B = con.shape[0]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in plc.parameters()):
+            return _chain(plc[2:], _conv(plc[0], con, lrelu=True, upsample2=True))   # differentiable, whole batch
+        ms = torch.empty(B, 6, 2 * con.shape[2], 2 * con.shape[3], dtype=torch.float32, device=con.device)
+        # exact fp32 on purpose: this layer's mu is part of the *dequantised* output
+        # (round(x - mu) + mu, :832) and so of the reconstruction (1e-4 tolerance); BF16 operands
+        # would move it by ~1e-3.  (cond2ZT returns plain round(x): there mu only feeds the rate.)
+        for b0 in range(0, B, CTX_BATCH_CHUNK):
+            b1 = min(B, b0 + CTX_BATCH_CHUNK)
+            t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
+            t = ops.conv2d(t, plc[2].weight, plc[2].bias, lrelu=True)
+            ops.conv2d(t, plc[4].weight, plc[4].bias, out=ms[b0:b1])
+            del t
+        return ms
+
+    @torch.no_grad()
+    def compress(self, out_xe, out_xo_list):
+        """Real bitstreams (interleaved rANS, ``coding.py``): LL and the coarsest level under their factorized models,
+        every finer level under the Gaussian conditioned on its decoded parent.  Returns (streams, xe_q, qs) with
+        ``streams[0]`` = LL, ``streams[1 + l]`` = level l (finest first)."""
+        from ... import coding
+        L = self.num_lifting_layers
+        was = self.training
+        self.eval()
+        si_xe, sis, xe_q, qs = self.forward(out_xe, out_xo_list)
+        self.train(was)
+        streams = [None] * (L + 1)
+        streams[0] = coding.encode_factorized(self.ent_out_xe, xe_q)
+        streams[L] = coding.encode_factorized(self.ent_out_xo, qs[L - 1])
+        for i in range(L - 2, -1, -1):
+            streams[1 + i] = coding.encode_gaussian(qs[i], self._ms(i, qs[i + 1]))
+        return streams, xe_q, qs
+
+    @torch.no_grad()
+    def decompress(self, streams):
+        """Coarse to fine: a level's (sigma, mu) come from the level decoded just before it."""
+        from ... import coding
+        L = self.num_lifting_layers
+        xe_q = coding.decode_factorized(self.ent_out_xe, streams[0])
+        qs = [None] * L
+        qs[L - 1] = coding.decode_factorized(self.ent_out_xo, streams[L])
+        for i in range(L - 2, -1, -1):
+            qs[i] = coding.decode_gaussian(streams[1 + i], self._ms(i, qs[i + 1]))
+        return xe_q, qs

@@ -426,6 +426,55 @@ def nhwc_split_to_nchw(z):
     return out
 
 
+RANS_GAUSS, RANS_EB = 0, 1
+
+
+def rans_streams_per_image(n_per_image, target=2048):
+    """Streams per image: ~``target`` samples per stream (the 4-byte flush of a stream stays < 0.1 bit per ~60 samples),
+    at least 32 so that a warp reads a contiguous run."""
+    return int(max(32, min(4096, (int(n_per_image) + target - 1) // target)))
+
+
+def rans_encode(mode, y, par, streams=None):
+    """Entropy-code the dequantised tensor ``y`` (B,C,H,W) under the model's own distribution (``mode`` RANS_GAUSS:
+    ``par`` = ms (B,2C,H,W); RANS_EB: ``par`` = ll_pack_eb blob).  Returns (words uint16 (n,), counts int32 (B*S,), S):
+    stream b*S+s of image b occupies ``counts[b*S+s]`` consecutive words."""
+    require_device(y)
+    y = _f32c(y, "y")
+    par = _f32c(par, "par")
+    B, C, H, W = y.shape
+    hw = H * W
+    S = int(streams) if streams else rans_streams_per_image(C * hw)
+    lib = _lib.load()
+    cap = int(lib.ll_rans_stream_cap(C * hw, S))
+    scratch = torch.empty(B * S * cap, dtype=torch.int16, device=y.device)
+    counts = torch.zeros(B * S, dtype=torch.int32, device=y.device)
+    with torch.cuda.device(y.device):
+        check(lib.ll_rans_encode(int(mode), ptr(y), ptr(par), B, C, hw, S, ptr(scratch), ptr(counts), stream_ptr()))
+        offsets = torch.cumsum(counts.to(torch.int64), 0) - counts
+        total = int(offsets[-1] + counts[-1]) if B * S else 0
+        words = torch.empty(total, dtype=torch.int16, device=y.device)
+        check(lib.ll_rans_pack(ptr(scratch), ptr(counts), ptr(offsets), B * S, cap, ptr(words), stream_ptr()))
+    _count(2)
+    return words, counts, S
+
+
+def rans_decode(mode, words, counts, par, shape, S):
+    """Inverse of :func:`rans_encode`: returns the dequantised tensor of ``shape`` (B,C,H,W) bit for bit."""
+    require_device(words)
+    par = _f32c(par, "par")
+    B, C, H, W = shape
+    if counts.numel() != B * S:
+        raise ValueError(f"rans_decode: {counts.numel()} stream lengths for {B} images x {S} streams")
+    counts = counts.to(device=words.device, dtype=torch.int32)
+    offsets = (torch.cumsum(counts.to(torch.int64), 0) - counts).contiguous()
+    y = torch.empty(B, C, H, W, dtype=torch.float32, device=words.device)
+    with torch.cuda.device(words.device):
+        check(_lib.load().ll_rans_decode(int(mode), ptr(words), ptr(offsets), ptr(par), B, C, H * W, int(S), ptr(y), stream_ptr()))
+    _count(1)
+    return y
+
+
 def rgb_to_ycbcr_shift(rgb):
     """Agent pre-processing (agents/liftingDWT_agent.py:170-171): RGB (B,3,H,W) in [0,1] -> YCbCr (BT.709) with Y - 0.5."""
     require_device(rgb)

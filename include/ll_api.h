@@ -254,6 +254,28 @@ int ll_rgb_to_ycbcr_shift(const float* rgb, float* ycc, int B, int64_t hw, ll_st
 int ll_ycbcr_to_rgb_sse(const float* ycc_hat, const float* rgb_ref, float* xhat, int B, int64_t hw, double* sse,
                         ll_stream_t stream);
 
+/* ------------------------------------------------------------------------- */
+/* Parallel entropy coding of the quantised subbands         */
+/* ------------------------------------------------------------------------- */
+
+/* Interleaved rANS (32-bit state, 16-bit words, 2^16 probability resolution), one GPU thread per stream.  Replaces,
+ * for the entropy layers whose contexts depend on already decoded levels only (factorized :182-231, onlyEZWT
+ * :759-840), the serial per-coefficient Python coder the reference has for its autoregressive model
+ * (compress_ar / decompress_ar, LiftingBasedDWT_net.py:458-556, around compressai.ans BufferedRansEncoder /
+ * RansDecoder).  y (B, C, hw) holds the DEQUANTISED values the forward pass returns (round(x - mu) + mu); image b owns
+ * S streams, stream s codes samples s, s+S, ... of the image.  mode 0: GaussianConditional, par = ms (B, 2C, hw) with
+ * channel 2c = sigma, 2c+1 = mu; mode 1: EntropyBottleneck, par = blob of ll_pack_eb (C, 64).
+ * ll_rans_encode writes stream st = b*S + s backwards into scratch[st*cap .. (st+1)*cap) (cap = ll_rans_stream_cap)
+ * and its length in 16-bit words into counts[st]; ll_rans_pack gathers the streams at offsets[st] (exclusive scan of
+ * counts, computed by the caller); ll_rans_decode reads the packed words and returns y bit for bit. */
+int64_t ll_rans_stream_cap(int64_t n_per_image, int S);
+int ll_rans_encode(int mode, const float* y, const float* par, int B, int C, int64_t hw, int S, uint16_t* scratch,
+                   int32_t* counts, ll_stream_t stream);
+int ll_rans_pack(const uint16_t* scratch, const int32_t* counts, const int64_t* offsets, int64_t nstreams, int cap,
+                 uint16_t* packed, ll_stream_t stream);
+int ll_rans_decode(int mode, const uint16_t* packed, const int64_t* offsets, const float* par, int B, int C, int64_t hw,
+                   int S, float* y, ll_stream_t stream);
+
 /* EntropyModel.quantize (compressai 1.2.1; call sites :330,341,352,719): q = round-half-even(x)
  * when noise == NULL ("dequantize"), else q = x + noise ("noise"; the caller draws U(-1/2,1/2)). */
 int ll_quantize(const float* x, const float* noise, float* q, int64_t n, ll_stream_t stream);
