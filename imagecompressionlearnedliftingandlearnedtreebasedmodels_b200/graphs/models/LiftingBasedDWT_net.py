@@ -572,11 +572,12 @@ class onlyEZWT(nn.Module):
         self.ent_out_xo = EntropyBottleneck(channels=3)
         self.bit_acc = None
 
-    def forward(self, out_xe, out_xo_list):
+    def forward(self, out_xe, out_xo_list, keep_ms=None):
+        """``keep_ms``: optional list that receives the (sigma, mu) tensor of every conditioned level (finest first)."""
         L = self.num_lifting_layers
         acc = self.bit_acc
         xe_q, si_xe = self.ent_out_xe.rate(out_xe, self.training, acc)
-        qs, sis = [], []
+        qs, sis, mss = [], [], []
         q, si = self.ent_out_xo.rate(out_xo_list[L - 1], self.training, acc)
         qs.append(q)
         sis.append(si)
@@ -587,9 +588,12 @@ class onlyEZWT(nn.Module):
             bits, q = self.ent_out_xo_list[i].bits(x, ms, self.training, want_y=True, acc=acc)
             sis.append(bits)
             qs.append(q)
+            mss.append(ms)
             con = q
         qs.reverse()
         sis.reverse()
+        if keep_ms is not None:
+            keep_ms.extend(reversed(mss))
         return si_xe, sis, xe_q, qs
 
     def _ms(self, i, con):
@@ -619,13 +623,14 @@ class onlyEZWT(nn.Module):
         L = self.num_lifting_layers
         was = self.training
         self.eval()
-        si_xe, sis, xe_q, qs = self.forward(out_xe, out_xo_list)
+        mss = []
+        si_xe, sis, xe_q, qs = self.forward(out_xe, out_xo_list, keep_ms=mss)
         self.train(was)
         streams = [None] * (L + 1)
         streams[0] = coding.encode_factorized(self.ent_out_xe, xe_q)
         streams[L] = coding.encode_factorized(self.ent_out_xo, qs[L - 1])
         for i in range(L - 2, -1, -1):
-            streams[1 + i] = coding.encode_gaussian(qs[i], self._ms(i, qs[i + 1]))
+            streams[1 + i] = coding.encode_gaussian(qs[i], mss[i])
         return streams, xe_q, qs
 
     @torch.no_grad()
