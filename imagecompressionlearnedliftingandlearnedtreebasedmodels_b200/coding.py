@@ -62,11 +62,13 @@ def decode_factorized(eb, bs):
     return ops.rans_decode(ops.RANS_EB, bs.words, bs.counts, eb._blob(), bs.shape, bs.S)
 
 
-def encode_gaussian(q, ms, streams=None):
-    """``q`` = dequantised output of ``GaussianConditional`` (round(x - mu) + mu); ``ms`` (B,2C,H,W): sigma, mu."""
-    words, counts, S = ops.rans_encode(ops.RANS_GAUSS, q, ms, streams)
-    return SubbandBitstream(ops.RANS_GAUSS, tuple(q.shape), S, counts, words)
+def encode_gaussian(q, ms, streams=None, integer_grid=False):
+    """``ms`` (B,2C,H,W): sigma, mu.  ``q`` = dequantised output of ``GaussianConditional`` (round(x - mu) + mu), or,
+    with ``integer_grid``, the plain round(x) the ZTBlock layer decodes (Gaussian discretised on the integers)."""
+    mode = ops.RANS_GAUSS_GRID if integer_grid else ops.RANS_GAUSS
+    words, counts, S = ops.rans_encode(mode, q, ms, streams)
+    return SubbandBitstream(mode, tuple(q.shape), S, counts, words)
 
 
 def decode_gaussian(bs, ms):
-    return ops.rans_decode(ops.RANS_GAUSS, bs.words, bs.counts, ms, bs.shape, bs.S)
+    return ops.rans_decode(bs.mode, bs.words, bs.counts, ms, bs.shape, bs.S)

@@ -2,8 +2,8 @@
 //
 // The reference only has a serial, per-coefficient Python coder, and only for its autoregressive model
 // (LiftingBasedDWT_net.py:374-556, compress_ar / decompress_ar around compressai.ans).  The entropy layers whose
-// contexts depend on *already decoded levels only* (factorized :182-231, onlyEZWT :759-840) can be decoded a whole
-// subband at a time, so their symbols are coded here with interleaved rANS streams, one GPU thread per stream:
+// contexts depend on *already decoded samples of other levels / phases only* (factorized :182-231, onlyEZWT :759-840,
+// ZTBlock :558-757 with its four 2x2 phases) can be decoded a whole subband (phase) at a time, so their symbols are coded here with interleaved rANS streams, one GPU thread per stream:
 //   * state 32 bit, renormalisation by 16-bit words, probabilities quantised to 2^16 (ryg_rans word variant);
 //   * image b of a (B, C, hw) tensor owns S streams; stream s codes samples s, s+S, s+2S, ... of the image, so a warp
 //     reads 32 consecutive samples per step (coalesced) and every image's bytes are separable;
@@ -14,6 +14,8 @@
 //         C(a) = 2a + floor(F(a - K - 1/2) * (2^16 - 2(2K+2))),   a = k + K in [0, 2K], a = 2K+1 escape
 //     (the 2a term guarantees every symbol a frequency >= 1 even if F glitches by an ulp; K = clamp(ceil(6 sigma),
 //     15, 2047) for the Gaussian, 255 for the factorized model); |k| > K is an escape followed by 16 raw bits.
+// For the ZTBlock layer, which decodes and conditions on plain round(x), the same Gaussian is discretised on the
+// integer grid instead (GaussGridDist).
 // The symbol is k = round(y - mu) of the *dequantised* value y = round(x - mu) + mu the forward pass returns, and the
 // decoder returns k + mu computed the same way, so decode(encode(y)) == y bit for bit.
 #include <stdint.h>
@@ -70,6 +72,29 @@ struct GaussDist {
     if (a >= 2 * K + 2) return 65536u;
     const uint32_t M = 65536u - 2u * (2 * K + 2);
     const float t = (float)(a - K) - 0.5f;
+    const float F = 0.5f * erfcf(-0.70710678118654752440f * __fdiv_rn(t, s));
+    const uint32_t q = (uint32_t)fminf(floorf(F * (float)M), (float)M);
+    return 2u * a + q;
+  }
+};
+
+// Gaussian N(mu, sigma) discretised on the INTEGER grid: the symbol is the plain round(x) that
+// DWTConditioned2EntropyLayerZTBlock decodes and conditions on (:719-724,754), coded relative to c = round(mu);
+// P(k) = Phi((c + k + 1/2 - mu) / sigma) - Phi((c + k - 1/2 - mu) / sigma).
+struct GaussGridDist {
+  float s, c, delta;
+  int K;
+  __device__ __forceinline__ GaussGridDist(float sigma, float mean) : s(fmaxf(sigma, 0.11f)), c(rintf(mean)) {
+    delta = __fsub_rn(c, mean);
+    const int k = (int)ceilf(6.f * s) + 1;
+    K = k < 15 ? 15 : (k > 2047 ? 2047 : k);
+  }
+  __device__ __forceinline__ float centre() const { return c; }
+  __device__ __forceinline__ uint32_t C(int a) const {
+    if (a <= 0) return 0u;
+    if (a >= 2 * K + 2) return 65536u;
+    const uint32_t M = 65536u - 2u * (2 * K + 2);
+    const float t = __fadd_rn((float)(a - K) - 0.5f, delta);
     const float F = 0.5f * erfcf(-0.70710678118654752440f * __fdiv_rn(t, s));
     const uint32_t q = (uint32_t)fminf(floorf(F * (float)M), (float)M);
     return 2u * a + q;
@@ -161,7 +186,8 @@ __device__ __forceinline__ float dec_sample(RansDec& r, const D& d) {
   return __fadd_rn(kf, d.centre());
 }
 
-// MODE 0: Gaussian, ms (B, 2C, hw) with channel 2c = sigma, 2c+1 = mu.  MODE 1: factorized, blob (C, 64).
+// MODE 0: Gaussian centred on mu, ms (B, 2C, hw) with channel 2c = sigma, 2c+1 = mu.  MODE 1: factorized, blob (C, 64).
+// MODE 2: Gaussian on the integer grid (same ms layout).
 template <int MODE>
 __global__ void __launch_bounds__(RN_THREADS) rans_encode_kernel(const float* __restrict__ y, const float* __restrict__ par, int B,
                                                                 int C, long long hw, int S, uint16_t* __restrict__ scratch,
@@ -177,10 +203,11 @@ __global__ void __launch_bounds__(RN_THREADS) rans_encode_kernel(const float* __
   for (long long j = ns - 1; j >= 0; --j) {
     const long long e = s + j * S;
     const int c = (int)(e / hw);
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
       const long long pix = e - c * hw;
       const float* m = par + (b * 2 * C + 2 * c) * hw + pix;
-      enc_sample(enc, GaussDist(m[0], m[hw]), yb[e]);
+      if (MODE == 0) enc_sample(enc, GaussDist(m[0], m[hw]), yb[e]);
+      else enc_sample(enc, GaussGridDist(m[0], m[hw]), yb[e]);
     } else {
       enc_sample(enc, EbDist(par + (size_t)c * RN_EB_BLOB), yb[e]);
     }
@@ -213,10 +240,10 @@ __global__ void __launch_bounds__(RN_THREADS) rans_decode_kernel(const uint16_t*
   RansDec dec(packed + offsets[st]);
   for (long long e = s; e < N; e += S) {
     const int c = (int)(e / hw);
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 2) {
       const long long pix = e - c * hw;
       const float* m = par + (b * 2 * C + 2 * c) * hw + pix;
-      yb[e] = dec_sample(dec, GaussDist(m[0], m[hw]));
+      yb[e] = MODE == 0 ? dec_sample(dec, GaussDist(m[0], m[hw])) : dec_sample(dec, GaussGridDist(m[0], m[hw]));
     } else {
       yb[e] = dec_sample(dec, EbDist(par + (size_t)c * RN_EB_BLOB));
     }
@@ -246,12 +273,13 @@ int ll_rans_encode(int mode, const float* y, const float* par, int B, int C, int
                    int32_t* counts, ll_stream_t stream) {
   int rc = rans_args("ll_rans_encode", y, par, scratch, counts, B, C, hw, S);
   if (rc) return rc;
-  if (mode != 0 && mode != 1) return fail(LL_EINVAL, "ll_rans_encode: mode must be 0 (gaussian) or 1 (factorized)");
+  if (mode < 0 || mode > 2) return fail(LL_EINVAL, "ll_rans_encode: mode must be 0 (gaussian), 1 (factorized) or 2 (gaussian, integer grid)");
   const long long nst = (long long)B * S;
   if (nst == 0 || hw == 0) return LL_OK;
   const int cap = (int)ll_rans_stream_cap((int64_t)C * hw, S);
   const unsigned blocks = (unsigned)((nst + RN_THREADS - 1) / RN_THREADS);
   if (mode == 0) rans_encode_kernel<0><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
+  else if (mode == 2) rans_encode_kernel<2><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
   else rans_encode_kernel<1><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
   LL_LAUNCH_OK("rans_encode_kernel");
   return LL_OK;
@@ -272,11 +300,12 @@ int ll_rans_decode(int mode, const uint16_t* packed, const int64_t* offsets, con
                    float* y, ll_stream_t stream) {
   int rc = rans_args("ll_rans_decode", packed, offsets, par, y, B, C, hw, S);
   if (rc) return rc;
-  if (mode != 0 && mode != 1) return fail(LL_EINVAL, "ll_rans_decode: mode must be 0 (gaussian) or 1 (factorized)");
+  if (mode < 0 || mode > 2) return fail(LL_EINVAL, "ll_rans_decode: mode must be 0 (gaussian), 1 (factorized) or 2 (gaussian, integer grid)");
   const long long nst = (long long)B * S;
   if (nst == 0 || hw == 0) return LL_OK;
   const unsigned blocks = (unsigned)((nst + RN_THREADS - 1) / RN_THREADS);
   if (mode == 0) rans_decode_kernel<0><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
+  else if (mode == 2) rans_decode_kernel<2><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
   else rans_decode_kernel<1><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
   LL_LAUNCH_OK("rans_decode_kernel");
   return LL_OK;

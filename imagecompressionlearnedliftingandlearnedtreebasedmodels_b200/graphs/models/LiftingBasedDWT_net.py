@@ -509,7 +509,17 @@ class DWTConditioned2EntropyLayerZTBlock(nn.Module):
         self.ent_out_xo = EntropyBottleneck(channels=3)
         self.bit_acc = None
 
-    def forward(self, out_xe, out_xo_list):
+    _SLOTS = [(0, 0), (0, 1), (1, 0), (1, 1)]     # phases ee, eo, oe, oo
+
+    def _phase_ms(self, n, k, dep):
+        """(sigma, mu) of phase k (1..4) of conditioned subband n from its dependencies ``dep`` (B,k,h,w) -> (B,2,h,w)."""
+        mu = _chain(getattr(self, f"dep_{k}_list_mu")[n], dep)
+        sg = _chain(getattr(self, f"dep_{k}_list_sigma")[n], dep)
+        return torch.cat((sg, mu), dim=1)
+
+    def forward(self, out_xe, out_xo_list, keep_ms=None):
+        """``keep_ms``: optional list that receives, per conditioned level (coarse to fine) and subband, the full-resolution
+        (sigma, mu) tensor (B,2,H,W)."""
         L = self.dwtLevels
         acc = self.bit_acc
         mode = "noise" if self.training else "dequantize"
@@ -521,7 +531,7 @@ class DWTConditioned2EntropyLayerZTBlock(nn.Module):
         con = q
         for i in range(0, L - 1):
             lvl = L - i - 2
-            si_j, q_j = [], []
+            si_j, q_j, ms_j = [], [], []
             for j in range(3):
                 gc = self.ent_out_xo_list[(L - i - 1) * 3 - j - 1]
                 xin = out_xo_list[lvl][:, j:j + 1].contiguous()
@@ -532,18 +542,72 @@ class DWTConditioned2EntropyLayerZTBlock(nn.Module):
                 d1 = con[:, j:j + 1]
                 n = j + i * 3
                 deps = [d1, torch.cat((d1, ee), 1), torch.cat((d1, ee, eo), 1), torch.cat((d1, ee, eo, oe), 1)]
-                slots = [(0, 0), (0, 1), (1, 0), (1, 1)]
-                for k, (dep, (ry, rx)) in enumerate(zip(deps, slots), start=1):
+                for k, (dep, (ry, rx)) in enumerate(zip(deps, self._SLOTS), start=1):
                     ms[:, 1:2, ry::2, rx::2] = _chain(getattr(self, f"dep_{k}_list_mu")[n], dep)
                     ms[:, 0:1, ry::2, rx::2] = _chain(getattr(self, f"dep_{k}_list_sigma")[n], dep)
                 si_j.append(gc.bits(xin, ms, self.training, acc=acc))
                 q_j.append(qq)
+                ms_j.append(ms)
             sis.append(torch.cat(si_j, dim=1))
             con = torch.cat(q_j, dim=1)
             qs.append(con)
+            if keep_ms is not None:
+                keep_ms.append(ms_j)
         qs.reverse()
         sis.reverse()
         return si_xe, sis, xe_q, qs
+
+    @torch.no_grad()
+    def compress(self, out_xe, out_xo_list):
+        """Real bitstreams (interleaved rANS, ``coding.py``).  LL and the coarsest level under their factorized models;
+        every conditioned subband as four streams, one per 2x2 phase (ee, eo, oe, oo), under the Gaussian of its phase
+        discretised on the integer grid -- the layer decodes and conditions on plain round(x) (:719-724,754), while its
+        rate estimate is taken at round(x - mu) + mu (:747-749), so the coded size follows the estimate only
+        approximately.  Returns (streams, xe_q, qs); streams = [LL, coarsest, then per level (coarse to fine), subband
+        and phase]."""
+        from ... import coding
+        was = self.training
+        self.eval()
+        mss = []
+        si_xe, sis, xe_q, qs = self.forward(out_xe, out_xo_list, keep_ms=mss)
+        self.train(was)
+        L = self.dwtLevels
+        streams = [coding.encode_factorized(self.ent_out_xe, xe_q), coding.encode_factorized(self.ent_out_xo, qs[L - 1])]
+        for i in range(0, L - 1):
+            q = qs[L - i - 2]
+            for j in range(3):
+                for ry, rx in self._SLOTS:
+                    streams.append(coding.encode_gaussian(q[:, j:j + 1, ry::2, rx::2].contiguous(),
+                                                          mss[i][j][:, :, ry::2, rx::2].contiguous(), integer_grid=True))
+        return streams, xe_q, qs
+
+    @torch.no_grad()
+    def decompress(self, streams):
+        """Coarse to fine; inside a subband the four phases in order, each conditioned on the parent and on the phases
+        decoded before it."""
+        from ... import coding
+        L = self.dwtLevels
+        xe_q = coding.decode_factorized(self.ent_out_xe, streams[0])
+        con = coding.decode_factorized(self.ent_out_xo, streams[1])
+        qs = [con]
+        pos = 2
+        for i in range(0, L - 1):
+            q_j = []
+            for j in range(3):
+                d1 = con[:, j:j + 1]
+                B, _, h, w = d1.shape
+                qq = torch.empty(B, 1, 2 * h, 2 * w, dtype=torch.float32, device=d1.device)
+                dep = d1
+                for k, (ry, rx) in enumerate(self._SLOTS, start=1):
+                    ph = coding.decode_gaussian(streams[pos], self._phase_ms(j + i * 3, k, dep.contiguous()))
+                    pos += 1
+                    qq[:, :, ry::2, rx::2] = ph
+                    dep = torch.cat((dep, ph), 1)
+                q_j.append(qq)
+            con = torch.cat(q_j, dim=1)
+            qs.append(con)
+        qs.reverse()
+        return xe_q, qs
 
 
 class onlyEZWT(nn.Module):

@@ -426,7 +426,7 @@ def nhwc_split_to_nchw(z):
     return out
 
 
-RANS_GAUSS, RANS_EB = 0, 1
+RANS_GAUSS, RANS_EB, RANS_GAUSS_GRID = 0, 1, 2
 
 
 def rans_streams_per_image(n_per_image, target=8192):

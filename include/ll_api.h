@@ -260,11 +260,13 @@ int ll_ycbcr_to_rgb_sse(const float* ycc_hat, const float* rgb_ref, float* xhat,
 
 /* Interleaved rANS (32-bit state, 16-bit words, 2^16 probability resolution), one GPU thread per stream.  Replaces,
  * for the entropy layers whose contexts depend on already decoded levels only (factorized :182-231, onlyEZWT
- * :759-840), the serial per-coefficient Python coder the reference has for its autoregressive model
+ * :759-840, ZTBlock :558-757), the serial per-coefficient Python coder the reference has for its autoregressive model
  * (compress_ar / decompress_ar, LiftingBasedDWT_net.py:458-556, around compressai.ans BufferedRansEncoder /
  * RansDecoder).  y (B, C, hw) holds the DEQUANTISED values the forward pass returns (round(x - mu) + mu); image b owns
  * S streams, stream s codes samples s, s+S, ... of the image.  mode 0: GaussianConditional, par = ms (B, 2C, hw) with
- * channel 2c = sigma, 2c+1 = mu; mode 1: EntropyBottleneck, par = blob of ll_pack_eb (C, 64).
+ * channel 2c = sigma, 2c+1 = mu; mode 1: EntropyBottleneck, par = blob of ll_pack_eb (C, 64); mode 2: the same
+ * Gaussian discretised on the integer grid, y = round(x) (DWTConditioned2EntropyLayerZTBlock decodes and conditions
+ * on plain rounding, :719-724,754).
  * ll_rans_encode writes stream st = b*S + s backwards into scratch[st*cap .. (st+1)*cap) (cap = ll_rans_stream_cap)
  * and its length in 16-bit words into counts[st]; ll_rans_pack gathers the streams at offsets[st] (exclusive scan of
  * counts, computed by the caller); ll_rans_decode reads the packed words and returns y bit for bit. */
