@@ -40,7 +40,7 @@ constexpr int IG_MAXN = 256;
 constexpr int IG_A_BYTES = IG_BM * IG_BK * 2;     // 16 KB
 constexpr int IG_B_BYTES = IG_MAXN * IG_BK * 2;   // 32 KB
 constexpr int IG_STAGE_BYTES = IG_A_BYTES + IG_B_BYTES;
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter: even / odd 32-column chunks)
 constexpr int IG_TMEM_COLS = 512;
 constexpr int IG_MAXG = 3;       // channel groups per launch (the cgp MLP has groups = 3)
 constexpr int IG_MAXSLOTS = 24;  // k-blocks per (group, tap); the 3xTF32 chain of a 192-channel layer needs 18
@@ -104,7 +104,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), 8);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,7 +181,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    // Eight epilogue warps: the epilogue is a chain of global loads / stores per 32-column chunk (ncu: 4 warps left the
+    // GDN GEMMs latency bound at 9 % warp occupancy, tensor pipe 7-12 % active), so every TMEM lane quarter gets two
+    // warps that take the even and the odd chunks.
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read (warp id mod 4)
+    const int chunk0 = (warp - 2) >> 2;          // 0: even chunks, 1: odd chunks
     const int row = q * 32 + lane;
     const int ty = row / IG_TW, tx = row % IG_TW;
     int acc = 0;
@@ -202,7 +206,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float* of = p.out_f32 ? p.out_f32 + (long long)b * p.out_sb + (long long)y * p.W + x : nullptr;
       __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff + g * p.out_gstride : nullptr;
       const long long plane = (long long)p.H * p.W;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = chunk0; c < nchunks; c += 2) {
         uint32_t v[32];
         tc_ld32(taddr + c * 32, v);
         tc_wait_ld();
