@@ -51,6 +51,14 @@ __device__ float g_dwt_taps[18 + 20] = {
 // The tile index advances incrementally (no division per tile); three phases, two block barriers per tile -- the next
 // copy into a buffer and the next first-pass write into ``mid`` are both issued behind a barrier that every thread
 // only reaches after it finished reading them.
+// Programmatic dependent launch: the levels of a multi-level call are tiny launches in one stream (levels 2-3 of a 512x768
+// batch run ~6 us each, half of it launch latency).  Every fast kernel lets its successor be scheduled right away
+// (launch_dependents at entry) and itself waits for its predecessor's memory (wait) only after its own prologue, so the
+// next level's CTAs are resident and set up when the previous level drains.  Launched with the programmatic-stream-
+// serialization attribute; without it (or behind a kernel that never signals) both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct CopyAsync16 {
   __device__ __forceinline__ void operator()(float* dst, const float* src) const {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -92,6 +100,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid
   extern __shared__ __align__(16) float sm[];
   // layout: [in0][in1][mid]
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
   DwtTaps tp;
 #pragma unroll
   for (int k = 0; k < 9; ++k) tp.d[k] = f2{g_dwt_taps[2 * k], g_dwt_taps[2 * k + 1]};
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwt97_fwd_fast_kernel(const __grid
   unsigned t = blockIdx.x;
   float* mid = sm + 2 * DFF_IN_FLOATS - DFF_SM_LO;  // so that mid + DFF_SM_LO lands after both inputs
   TileWalk cur(p, t, gridDim.x), nxt = cur;
+  pdl_wait();
   dwtff_load(p, cur.tile(), sm, tid, CopyAsync16());
   cp_commit();
   for (unsigned it = 0;; ++it) {
@@ -124,6 +134,7 @@ constexpr int DIF_PIPE_TOTAL = 2 * DIF_SB_FLOATS + 2 * 2 * DW_TY * DIF_P;
 __global__ void __launch_bounds__(DIF_THREADS) dwt97_inv_fast_kernel(const __grid_constant__ DwtParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
   DwtSynTaps tp;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(DIF_THREADS) dwt97_inv_fast_kernel(const __gri
   unsigned t = blockIdx.x;
   float* mid = sm + 2 * DIF_SB_FLOATS - DIF_SM_LO;
   TileWalk cur(p, t, gridDim.x), nxt = cur;
+  pdl_wait();
   dwtif_load(p, cur.tile(), sm, tid, CopyAsync16());
   cp_commit();
   for (unsigned it = 0;; ++it) {
@@ -151,6 +163,21 @@ __global__ void __launch_bounds__(DIF_THREADS) dwt97_inv_fast_kernel(const __gri
     t = tn;
     cur = nxt;
   }
+}
+
+static int launch_pdl(void (*kernel)(const DwtParams), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, const DwtParams& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LL_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  return LL_OK;
 }
 
 static int fill(DwtParams& p, int N, int h, int w, const char* who) {
@@ -195,8 +222,10 @@ int ll_dwt97_fwd_level(const float* x, int64_t x_sn, float* llp, int64_t ll_sn, 
     attr[dev] = true;
   }
   const long long pgrid = (long long)sm_count_cached() * 3;   // 3 resident CTAs per SM (70 KB each)
-  if (dwt_fast_ok(p)) dwt97_fwd_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream)>>>(p);
-  else dwt97_fwd_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
+  if (dwt_fast_ok(p)) {
+    rc = launch_pdl(dwt97_fwd_fast_kernel, (unsigned)(tiles < pgrid ? tiles : pgrid), DW_THREADS, smem_fast, as_stream(stream), p);
+    if (rc) return rc;
+  } else dwt97_fwd_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_fwd_kernel");
   return LL_OK;
 }
@@ -227,8 +256,10 @@ int ll_dwt97_inv_level(const float* llp, int64_t ll_sn, const float* yh, int64_t
     attr[dev] = true;
   }
   const long long pgrid = (long long)sm_count_cached() * 3;
-  if (dwt_fast_ok(p)) dwt97_inv_fast_kernel<<<(unsigned)(tiles < pgrid ? tiles : pgrid), DIF_THREADS, smem_fast, as_stream(stream)>>>(p);
-  else dwt97_inv_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
+  if (dwt_fast_ok(p)) {
+    rc = launch_pdl(dwt97_inv_fast_kernel, (unsigned)(tiles < pgrid ? tiles : pgrid), DIF_THREADS, smem_fast, as_stream(stream), p);
+    if (rc) return rc;
+  } else dwt97_inv_kernel<<<(unsigned)tiles, DW_THREADS, smem, as_stream(stream)>>>(p);
   LL_LAUNCH_OK("dwt97_inv_kernel");
   return LL_OK;
 }
