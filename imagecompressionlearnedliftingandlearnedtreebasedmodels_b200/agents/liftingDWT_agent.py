@@ -38,6 +38,9 @@ class LiftingBasedDWTAgent:
         self.config = config
         self.clrch = config.clrch
         self.device = torch.device(device if device is not None else "cuda:0")
+        # the reference sets it in its entry point; the recompute backward of train_batch runs torch
+        # convolutions and gains 35 % from the autotuned algorithms (381 vs 516 ms per config-4 step)
+        torch.backends.cudnn.benchmark = True
         self.lr = _cfg(config, "learning_rate", 1e-4)
         self.model = LiftingBasedDWTNetWrapper(config).to(self.device)
         self.optimizer = configure_optimizers(self.model, self.lr)

@@ -14,6 +14,7 @@ from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.losses.
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
+torch.backends.cudnn.benchmark = os.environ.get("CUDNN_BENCHMARK", "1") == "1"   # the reference agent sets it too (main.py)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
