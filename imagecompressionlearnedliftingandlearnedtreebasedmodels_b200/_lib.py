@@ -70,6 +70,7 @@ SIGNATURES = {
     "ll_nchw_to_nhwc_split": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P]),
     "ll_nhwc_split_to_nchw": (c_int, [_P, _P] + [c_int] * 4 + [_P]),
     "ll_nhwc_split_conv3": (c_int, [_P, _P, _P, _P] + [c_int] * 5 + [_P]),
+    "ll_nhwc_lrelu_conv1": (c_int, [_P, _P, _P, _P, c_int, c_i64, c_int, c_int, c_int, c_int, _P]),
     "ll_rans_stream_cap": (c_i64, [c_i64, c_int]),
     "ll_rans_encode": (c_int, [c_int, _P, _P, c_int, c_int, c_i64, c_int, _P, _P, _P]),
     "ll_rans_pack": (c_int, [_P, _P, _P, c_i64, c_int, _P, _P]),

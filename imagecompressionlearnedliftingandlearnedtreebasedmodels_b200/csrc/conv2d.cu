@@ -198,6 +198,52 @@ __global__ void __launch_bounds__(256) nhwc_split_conv3_kernel(const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 1x1 head of onlyEZWT's parent context net (nn.Conv2d(243, 6, 1) behind a LeakyReLU, LiftingBasedDWT_net.py:
+// 792-794) on the raw channels-last output of the 3xTF32 tensor-core conv: out[b][o][pix] = bias[o] +
+// sum_c w[o][c] * lrelu(y[pix][c]).  y (B*hw, Cpad) fp32 with Cpad % 4 == 0 (channels >= C are ignored), out fp32
+// NCHW (B, Cout, hw), Cout <= 8.  One thread per pixel, weights broadcast from shared memory, exact fp32 FMA.
+constexpr int PW_MAXCO = 8, PW_MAXC = 256;
+
+__global__ void __launch_bounds__(256) nhwc_lrelu_conv1_kernel(const float* __restrict__ y, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                               long long npix, long long hw, int C, int Cpad, int Cout, int lrelu) {
+  __shared__ __align__(16) float wsm[PW_MAXCO * PW_MAXC];   // [c / 4][o][4]
+  const int c4n = (C + 3) / 4;
+  for (int e = threadIdx.x; e < c4n * PW_MAXCO * 4; e += 256) {
+    const int j = e & 3, o = (e >> 2) % PW_MAXCO, c = (e / (4 * PW_MAXCO)) * 4 + j;
+    wsm[e] = (o < Cout && c < C) ? w[(long long)o * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (long long pix = blockIdx.x * 256LL + threadIdx.x; pix < npix; pix += (long long)gridDim.x * 256) {
+    const float* yp = y + pix * Cpad;
+    float acc[PW_MAXCO];
+#pragma unroll
+    for (int o = 0; o < PW_MAXCO; ++o) acc[o] = (bias && o < Cout) ? bias[o] : 0.f;
+    for (int c4 = 0; c4 < c4n; ++c4) {
+      float4 v = *reinterpret_cast<const float4*>(yp + 4 * c4);
+      if (lrelu) {
+        v.x = v.x < 0.f ? v.x * 0.01f : v.x;
+        v.y = v.y < 0.f ? v.y * 0.01f : v.y;
+        v.z = v.z < 0.f ? v.z * 0.01f : v.z;
+        v.w = v.w < 0.f ? v.w * 0.01f : v.w;
+      }
+#pragma unroll
+      for (int o = 0; o < PW_MAXCO; ++o) {
+        const float4 k = *reinterpret_cast<const float4*>(&wsm[(c4 * PW_MAXCO + o) * 4]);
+        acc[o] = fmaf(v.x, k.x, acc[o]);
+        acc[o] = fmaf(v.y, k.y, acc[o]);
+        acc[o] = fmaf(v.z, k.z, acc[o]);
+        acc[o] = fmaf(v.w, k.w, acc[o]);
+      }
+    }
+    const long long b = pix / hw, p = pix - b * hw;
+#pragma unroll
+    for (int o = 0; o < PW_MAXCO; ++o)
+      if (o < Cout) out[(b * Cout + o) * hw + p] = acc[o];
+  }
+}
+
 }  // namespace ll
 
 using namespace ll;
@@ -250,6 +296,22 @@ int ll_nhwc_split_conv3(const float* z, const float* w, const float* bias, float
   if (Cout == 1) nhwc_split_conv3_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
   else nhwc_split_conv3_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
   LL_LAUNCH_OK("nhwc_split_conv3_kernel");
+  return LL_OK;
+}
+
+int ll_nhwc_lrelu_conv1(const float* y, const float* w, const float* bias, float* out, int B, int64_t hw, int C, int Cpad,
+                        int Cout, int lrelu, ll_stream_t stream) {
+  if (B < 0 || hw < 0 || C <= 0 || C > PW_MAXC || Cpad < C || (Cpad % 4) || Cout <= 0 || Cout > PW_MAXCO)
+    return fail(LL_EINVAL, "ll_nhwc_lrelu_conv1: bad extents (C <= %d, Cpad %% 4 == 0 and >= C, Cout <= %d)", PW_MAXC, PW_MAXCO);
+  const long long npix = (long long)B * hw;
+  if (npix == 0) return LL_OK;
+  if (!y || !w || !out) return fail(LL_EINVAL, "ll_nhwc_lrelu_conv1: null pointer");
+  if (reinterpret_cast<uintptr_t>(y) & 15) return fail(LL_EINVAL, "ll_nhwc_lrelu_conv1: y must be 16-byte aligned");
+  long long blocks = (npix + 255) / 256;
+  const long long cap = (long long)sm_count_cached() * 8;
+  if (blocks > cap) blocks = cap;
+  nhwc_lrelu_conv1_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(y, w, bias, out, npix, hw, C, Cpad, Cout, lrelu);
+  LL_LAUNCH_OK("nhwc_lrelu_conv1_kernel");
   return LL_OK;
 }
 

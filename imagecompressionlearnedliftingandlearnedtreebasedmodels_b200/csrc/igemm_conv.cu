@@ -465,18 +465,44 @@ __global__ void pack_tf32_weight_kernel(const float* __restrict__ w, float* __re
   }
 }
 
-__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ sz, int B, int C,
-                                          int H, int W, int mode) {
-  const long long hw = (long long)H * W, total = (long long)B * hw * C;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % C);
-    const long long px = e / C;
-    const float v = x[((px / hw) * C + c) * hw + px % hw];
-    if (y) y[e] = v;
-    const float r = mode ? v : v * v;
-    const float hi = tf32_rna(r);
-    sz[px * (2 * C) + c] = hi;
-    sz[px * (2 * C) + C + c] = tf32_rna(r - hi);
+// 32 pixels x 32 channels per CTA through a shared-memory tile: reads run along the pixels (contiguous in NCHW), writes
+// along the channels (contiguous in NHWC).  (The first version read with a stride of one plane per thread.)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                 float* __restrict__ sz, int B, int C, int H, int W, int mode) {
+  __shared__ float tile[32][33];
+  const long long hw = (long long)H * W;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  const long long ptiles = (hw + 31) / 32;
+  const int ctiles = (C + 31) / 32;
+  const long long ntiles = (long long)B * ptiles * ctiles;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int ct = (int)(t % ctiles);
+    const long long r = t / ctiles;
+    const long long pt = r % ptiles, b = r / ptiles;
+    const long long p0 = pt * 32;
+    const int c0 = ct * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k;
+      const long long pix = p0 + tx;
+      tile[ty + 8 * k][tx] = (c < C && pix < hw) ? x[(b * C + c) * hw + pix] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long pix = p0 + ty + 8 * k;
+      const int c = c0 + tx;
+      if (c < C && pix < hw) {
+        const float v = tile[tx][ty + 8 * k];
+        const long long px = b * hw + pix;
+        if (y) y[px * C + c] = v;
+        const float rr = mode ? v : v * v;
+        const float hi = tf32_rna(rr);
+        sz[px * (2 * C) + c] = hi;
+        sz[px * (2 * C) + C + c] = tf32_rna(rr - hi);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -749,7 +775,7 @@ int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int
   const long long total = (long long)B * H * W * C;
   if (total == 0) return LL_OK;
   if (!x || !sz) return fail(LL_EINVAL, "ll_nchw_to_nhwc_split: null pointer");
-  long long blocks = (total + 255) / 256;
+  long long blocks = (long long)B * (((long long)H * W + 31) / 32) * ((C + 31) / 32);
   const long long cap = (long long)sm_count_cached() * 16;
   if (blocks > cap) blocks = cap;
   nchw_to_nhwc_split_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, y, sz, B, C, H, W, mode);

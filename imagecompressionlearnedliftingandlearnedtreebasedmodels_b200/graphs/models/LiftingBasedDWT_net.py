@@ -635,6 +635,8 @@ class onlyEZWT(nn.Module):
         self.ent_out_xe = EntropyBottleneck(channels=1)
         self.ent_out_xo = EntropyBottleneck(channels=3)
         self.bit_acc = None
+        self.ctx_precision = _ctx_precision(config)      # "fp32": FP32 FMA kernels only; anything else: 3xTF32 chain
+        self._tc_cache = [PackCache() for _ in range(self.num_lifting_layers - 1)]
 
     def forward(self, out_xe, out_xo_list, keep_ms=None):
         """``keep_ms``: optional list that receives the (sigma, mu) tensor of every conditioned level (finest first)."""
@@ -667,16 +669,46 @@ class onlyEZWT(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in plc.parameters()):
             return _chain(plc[2:], _conv(plc[0], con, lrelu=True, upsample2=True))   # differentiable, whole batch
         ms = torch.empty(B, 6, 2 * con.shape[2], 2 * con.shape[3], dtype=torch.float32, device=con.device)
-        # exact fp32 on purpose: this layer's mu is part of the *dequantised* output
-        # (round(x - mu) + mu, :832) and so of the reconstruction (1e-4 tolerance); BF16 operands
-        # would move it by ~1e-3.  (cond2ZT returns plain round(x): there mu only feeds the rate.)
+        # fp32-level accuracy on purpose: this layer's mu is part of the *dequantised* output (round(x - mu) + mu, :832)
+        # and so of the reconstruction (1e-4 tolerance); BF16 operands would move it by ~1e-3.  (cond2ZT returns plain
+        # round(x): there mu only feeds the rate.)  Default: the 243 -> 243 conv (88 % of the layer's FLOPs) on the
+        # 3xTF32 tensor-core chain of SubbandAutoEncoderBerk; ``ctx_precision: "fp32"`` keeps everything on the FP32 FMA
+        # kernels.
+        tc = self.ctx_precision != "fp32" and plc[2].weight.shape[0] <= 256
+        if tc:
+            pk = self._tc_cache[i].get([plc[0].weight, plc[0].bias, plc[2].weight, plc[2].bias], lambda: self._tc_pack(plc))
         for b0 in range(0, B, CTX_BATCH_CHUNK):
             b1 = min(B, b0 + CTX_BATCH_CHUNK)
+            if tc:
+                t = ops.conv2d(con[b0:b1], pk["w0"], pk["b0"], lrelu=True, upsample2=True)     # (b,256,H,W), pad channels 0
+                _, sz = ops.nchw_to_nhwc_split(t, squares=False, want_y=False)
+                del t
+                y, _ = ops.igemm_tf32(sz, pk["wp2"], pk["b2"], pk["cpad"], epi=3)
+                del sz
+                ops.nhwc_lrelu_conv1(y, plc[4].weight, plc[4].bias, plc[4].weight.shape[1], out=ms[b0:b1])
+                del y
+                continue
             t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
             t = ops.conv2d(t, plc[2].weight, plc[2].bias, lrelu=True)
             ops.conv2d(t, plc[4].weight, plc[4].bias, out=ms[b0:b1])
             del t
         return ms
+
+    @staticmethod
+    def _tc_pack(plc):
+        """Weights of the first two convs zero-padded to a multiple of 32 channels for the 3xTF32 implicit GEMM."""
+        c = plc[2].weight.shape[0]
+        cpad = (c + 31) // 32 * 32
+        w0 = plc[0].weight.detach()
+        w0p = torch.zeros(cpad, *w0.shape[1:], dtype=torch.float32, device=w0.device)
+        w0p[:c] = w0
+        b0p = torch.zeros(cpad, dtype=torch.float32, device=w0.device)
+        b0p[:c] = plc[0].bias.detach()
+        w2p = torch.zeros(cpad, cpad, 3, 3, dtype=torch.float32, device=w0.device)
+        w2p[:c, :c] = plc[2].weight.detach()
+        b2p = torch.zeros(cpad, dtype=torch.float32, device=w0.device)
+        b2p[:c] = plc[2].bias.detach()
+        return {"w0": w0p, "b0": b0p, "wp2": ops.pack_tf32_weight(w2p), "b2": b2p, "cpad": cpad}
 
     @torch.no_grad()
     def compress(self, out_xe, out_xo_list):

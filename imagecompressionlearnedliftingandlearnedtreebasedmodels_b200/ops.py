@@ -426,6 +426,26 @@ def nhwc_split_to_nchw(z):
     return out
 
 
+def nhwc_lrelu_conv1(y, w, bias, cin, out=None, lrelu=True):
+    """Raw channels-last conv output y (B,H,W,Cpad) -> 1x1 conv of lrelu(y[..., :cin]) -> fp32 NCHW (B,Cout,H,W)."""
+    require_device(y)
+    if y.dtype != torch.float32 or not y.is_contiguous() or y.dim() != 4:
+        raise TypeError("nhwc_lrelu_conv1: y must be a contiguous fp32 (B,H,W,Cpad) tensor")
+    B, H, W, cpad = y.shape
+    w = _f32c(w.detach().reshape(w.shape[0], -1), "w")
+    if w.shape[1] != cin or cin > cpad:
+        raise ValueError(f"nhwc_lrelu_conv1: weight {tuple(w.shape)} does not match cin={cin} (Cpad={cpad})")
+    b = _f32c(bias.detach(), "bias") if bias is not None else None
+    if out is None:
+        out = torch.empty(B, w.shape[0], H, W, dtype=torch.float32, device=y.device)
+    elif tuple(out.shape) != (B, w.shape[0], H, W) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("nhwc_lrelu_conv1: out must be a contiguous fp32 (B,Cout,H,W) tensor")
+    with torch.cuda.device(y.device):
+        check(_lib.load().ll_nhwc_lrelu_conv1(ptr(y), ptr(w), ptr(b), ptr(out), B, H * W, cin, cpad, w.shape[0], int(bool(lrelu)), stream_ptr()))
+    _count(1)
+    return out
+
+
 RANS_GAUSS, RANS_EB, RANS_GAUSS_GRID = 0, 1, 2
 
 

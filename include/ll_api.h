@@ -228,6 +228,12 @@ int ll_nhwc_split_to_nchw(const float* z, float* out, int B, int C, int H, int W
  * out fp32 NCHW (B,Cout,H,W).  Exact fp32 FMA (feeds the quantiser).  C % 16 == 0, Cout in {1, 3}. */
 int ll_nhwc_split_conv3(const float* z, const float* w, const float* bias, float* out, int B, int C, int Cout, int H, int W,
                         ll_stream_t stream);
+/* 1x1 head of onlyEZWT's parent context net (LeakyReLU + nn.Conv2d(243, 6, 1), LiftingBasedDWT_net.py:792-794) on
+ * the raw channels-last output of ll_igemm_tf32 (epi 3): out[b][o][pix] = bias[o] + sum_c w[o][c] * lrelu(y[pix][c]).
+ * y (B*hw, Cpad) fp32 (channels >= C ignored), w (Cout, C), out fp32 NCHW (B, Cout, hw); exact fp32 FMA.
+ * C <= 256, Cpad % 4 == 0, Cout <= 8. */
+int ll_nhwc_lrelu_conv1(const float* y, const float* w, const float* bias, float* out, int B, int64_t hw, int C, int Cpad,
+                        int Cout, int lrelu, ll_stream_t stream);
 
 /* Tail of the cgp MLP fused with the rate: per group g (= child subband) and pixel,
  * h = LeakyReLU(W3[g] h2 + b3[g]) (C2 -> C3), (sigma, mu) = W4[g] h + b4[g], then exactly

@@ -180,3 +180,44 @@ def test_coder_errors():
     model = LiftingBasedDWTNetWrapper(cfg).to(DEV).eval()
     with pytest.raises(NotImplementedError):                 # conditioned2ZT: only the serial coder exists upstream
         model.compress(torch.zeros(1, 3, 32, 32, device=DEV))
+
+
+def test_onlyezwt_tensor_core_context_matches_fp32_path():
+    """onlyEZWT's parent context net on the 3xTF32 tensor-core chain (default) against the all-FP32-FMA kernels
+    (``ctx_precision: "fp32"``): (sigma, mu) of every level from the SAME parent to fp32-level accuracy (3e-6 of the
+    tensor's scale over K = 9 x 243 products), total bits of the whole layer within 0.1 %."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import onlyEZWT
+    mods = {}
+    torch.manual_seed(2)
+    xe = torch.randn(3, 1, 8, 12, device=DEV) * 4
+    xo = [torch.randn(3, 3, 64 >> l, 96 >> l, device=DEV) * (2 + l) for l in range(3)]
+    bits = {}
+    for prec in ("bf16", "fp32"):
+        cfg = om.default_cfg(entropy_layer="onlyEZWT", dwtlevels=3, ctx_precision=prec)
+        torch.manual_seed(1337)
+        em = onlyEZWT(cfg)
+        with torch.no_grad():
+            for prm in em.plc_list.parameters():
+                if prm.dim() == 4:
+                    prm.mul_(3.0)
+            for seq in em.plc_list:
+                seq[4].bias[0::2] += 2.0                  # sigma heads away from the 0.11 floor
+        mods[prec] = em.to(DEV).eval()
+        with torch.no_grad():
+            si_xe, sis, _, _ = mods[prec](xe, xo)
+        bits[prec] = float(si_xe.double().sum() + sum(t.double().sum() for t in sis))
+    with torch.no_grad():
+        for i in range(2):
+            parent = torch.round(xo[i + 1])
+            a, b = mods["bf16"]._ms(i, parent), mods["fp32"]._ms(i, parent)
+            assert a.shape == b.shape == (3, 6, 64 >> i, 96 >> i)
+            plc64 = __import__("copy").deepcopy(mods["fp32"].plc_list[i]).double()
+            up = parent.double().repeat_interleave(2, 2).repeat_interleave(2, 3)
+            ref = plc64(up)
+            scale = ref.abs().max().item()
+            err_tc, err_fp32 = (a.double() - ref).abs().max().item() / scale, (b.double() - ref).abs().max().item() / scale
+            print(f"level {i}: 3xTF32 chain err {err_tc:.2e}, FP32 FMA err {err_fp32:.2e} (of the tensor scale, vs float64)")
+            # K = 9 x 243 products per output and a tensor-core accumulator that rounds toward zero: ~5e-6; the path's
+            # tolerance on the dequantised output this mu enters is 1e-4
+            assert err_tc <= 1.5e-5 and err_fp32 <= 3e-6, i
+    assert abs(bits["bf16"] - bits["fp32"]) <= 1e-3 * bits["fp32"]
