@@ -246,7 +246,11 @@ def run_own(args):
         # 3 * 128/80 * 0.94 = 4.5x the useful FLOPs; TF32 dense peak = half the measured BF16 peak.
         "roofline": {"bound": "tensor", "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": pk["bf16_tflops"] / 2,
                      "unit": "TFLOP/s", "frac": flops / (ms_step * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
-                     "traffic": None, "peak_kind": pk_kind + " bf16 burst / 2 (TF32)",
+                     # DRAM bytes of one launch of the dominant kernel (level-0 step on a (16,256,768) view: 12.6 MB source +
+                     # 12.6 MB updated half read, 12.6 MB written) from the ncu --set full capture in
+                     # profiles/r01_ncu_lift_tc_final.json: 25.3 MB read + the 12.6 MB result still in L2 at kernel end
+                     "traffic": 25.3e6, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "peak_kind": pk_kind + " bf16 burst / 2 (TF32)",
                      "kernel": "ll::lift_step_tc_kernel",
                      "issued_tflops": flops * 0.94 * 3 * 128 / 80 / (ms_step * 1e-3) / 1e12,
                      "issued_frac": flops * 0.94 * 3 * 128 / 80 / (ms_step * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
