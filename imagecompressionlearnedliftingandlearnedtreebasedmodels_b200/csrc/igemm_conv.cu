@@ -207,6 +207,18 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff + g * p.out_gstride : nullptr;
       const long long plane = (long long)p.H * p.W;
       for (int c = chunk0; c < nchunks; c += 2) {
+        // GDN epilogue: the raw conv output y of this chunk is fetched first, so its global latency overlaps the
+        // tensor-memory loads below (it used to be issued behind them, one dependent round trip per chunk)
+        float o[32];
+        const bool chunk_on = TF32 && valid && c * 32 < p.Cout;
+        if (TF32 && p.epi == 2 && chunk_on) {
+          const float* yq = p.y + (((long long)b * p.H + y) * p.W + x) * p.Cout + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(yq + j);
+            o[j] = t4.x; o[j + 1] = t4.y; o[j + 2] = t4.z; o[j + 3] = t4.w;
+          }
+        }
         uint32_t v[32];
         tc_ld32(taddr + c * 32, v);
         tc_wait_ld();
@@ -222,14 +234,6 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const long long px = ((long long)b * p.H + y) * p.W + x;
             float* yp = p.y + px * p.Cout + c * 32;
             float* zp = p.sz + px * (2 * p.Cout) + c * 32;
-            float o[32];
-            if (p.epi == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(yp + j);
-                o[j] = t.x; o[j + 1] = t.y; o[j + 2] = t.z; o[j + 3] = t.w;
-              }
-            }
             float hi[32], lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
