@@ -378,6 +378,23 @@ def context_probe(dev, pk):
         ms = timed(lambda: em(xe, xo), 3)
     res["cond2zt_entropy_model"] = {"ms_per_plane_batch16": ms, "mp_per_s_3_planes": B * H * W / 1e6 / (3 * ms * 1e-3),
                                     "flops_per_plane_px": 430482, "note": "quantise + context CNNs + Gaussian rate + bit sums"}
+    del em
+    # the other three parallelisable entropy layers on the same subbands, eval forward of one plane
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import (
+        DWTConditioned2EntropyLayerZTBlock, DWTFactorizedEntropyLayer, onlyEZWT)
+    layers = {}
+    for name, cls, flop in (("onlyEZWT", onlyEZWT, 354023), ("ZTBlock", DWTConditioned2EntropyLayerZTBlock, 47315),
+                            ("factorized", DWTFactorizedEntropyLayer, 132)):
+        torch.manual_seed(1337)
+        layer = cls(cfg).to(dev).eval()
+        with torch.no_grad():
+            ms = timed(lambda: layer(xe, xo), 3)
+            out = layer(xe, xo)
+        bits = float(out[0].double().sum() + sum(s.double().sum() for s in out[1]))
+        layers[name] = {"ms_per_plane_batch16": ms, "mp_per_s_3_planes": B * H * W / 1e6 / (3 * ms * 1e-3),
+                        "flops_per_plane_px": flop, "bits_per_coefficient": bits / (B * H * W)}
+        del layer
+    res["other_entropy_layers"] = layers
     return res
 
 
@@ -428,7 +445,51 @@ def codec_probe(dev):
     res["agent_validate_batch"] = {"ms_per_batch16": ms, "mp_per_s": B * H * W / 1e6 / (ms * 1e-3), "bpp": out["bpp"], "psnr": out["psnr"],
                                    "h2d_bytes": rgb.numel() * 4, "d2h_bytes": 24,
                                    "note": "wall clock around LiftingBasedDWTAgent.validate_batch (host RGB in, python floats out), SubbandAutoEncoder"}
-    del agent
+    # the same call at configs[2]'s own batch: 64 images of 512x768 (302 MB of host RGB per call)
+    rgb64 = torch.rand(64, 3, H, W).pin_memory()
+    out = agent.validate_batch(rgb64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        out = agent.validate_batch(rgb64)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 2 * 1e3
+    res["agent_validate_batch64"] = {"ms_per_batch64": ms, "mp_per_s": 64 * H * W / 1e6 / (ms * 1e-3), "bpp": out["bpp"],
+                                     "psnr": out["psnr"], "h2d_bytes": rgb64.numel() * 4, "d2h_bytes": 24,
+                                     "note": "BASELINE configs[2] shape (batch 64 of 512x768), wall clock, host RGB in, bpp + PSNR out"}
+    del agent, rgb64
+    torch.cuda.empty_cache()
+    # configs[4]: one 2048x2048 image cut into 8 independent tiles of 2048x256 (parallel.tiles_of), 5-level learned
+    # lifting + conditioned2ZT.  One rank's share on 8 GPUs = one tile; on one GPU the 8 tiles run as a batch of 8.
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.parallel import tiles_of
+    cfg5 = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                          entropy_layer="conditioned2ZTsepSubbands", dwtlevels=5)
+    torch.manual_seed(1337)
+    model = LiftingBasedDWTNetWrapper(cfg5).to(dev).eval()
+    img = om.preprocess(torch.rand(1, 3, 2048, 2048)).to(dev)
+    boxes = tiles_of(2048, 2048, 8)
+    tiles = torch.cat([img[:, :, y0:y1, x0:x1] for (y0, y1, x0, x1) in boxes], dim=0).contiguous()
+    c5 = {"tile": [boxes[0][1] - boxes[0][0], boxes[0][3] - boxes[0][2]], "tiles": len(boxes), "levels": 5}
+    with torch.no_grad():
+        for key, xin in (("ms_one_tile", tiles[:1]), ("ms_eight_tiles_one_gpu", tiles)):
+            for _ in range(2):
+                model(xin)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(3):
+                xhat, si_xe, si_xo = model(xin)
+            ev1.record()
+            torch.cuda.synchronize()
+            c5[key] = ev0.elapsed_time(ev1) / 3
+    bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
+    c5["bpp_full_image"] = bits / (2048 * 2048)
+    c5["mp_per_s_one_gpu"] = 2048 * 2048 / 1e6 / (c5["ms_eight_tiles_one_gpu"] * 1e-3)
+    c5["mp_per_s_8_gpus_one_tile_each"] = 2048 * 2048 / 1e6 / (c5["ms_one_tile"] * 1e-3)
+    c5["note"] = ("8-GPU figure = image pixels / time of one rank's tile measured on this GPU (tiles are independent, "
+                  "no exchange; bpp = sum of the tiles' bits / full-image pixels)")
+    res["config5_tiles"] = c5
+    del model
     res["note"] = "random-init weights: bpp is a by-product, not a quality claim"
     return res
 

@@ -472,6 +472,10 @@ static_assert(2 * (DW_TY / 4) * (DIF_P / 2) == DIF_THREADS, "one column-synthesi
 LL_HD void dwtif_rows(const DwtParams& p, const DwtTile& t, const float* sm, int tid, const DwtSynTaps& tp) {
   const int w2 = p.w / 2;
   float* plane = p.xo + (long long)t.n * p.x_sn;
+  // an item's 8 outputs are 32 contiguous bytes; they are 32-byte aligned when the plane base and pitches are
+  // (w % 8 == 0 is a fast-path condition).  Uniform per launch.
+  const bool wide = ((reinterpret_cast<uintptr_t>(p.xo) & 31) == 0) && (p.x_sn % 8 == 0);
+  (void)wide;
   // item = (output row, group of 4 output pairs): 32 x 16 = 512
 #pragma unroll
   for (int k = 0; k < (2 * DW_TY * (DW_TX / 4) + DIF_THREADS - 1) / DIF_THREADS; ++k) {
@@ -501,6 +505,14 @@ LL_HD void dwtif_rows(const DwtParams& p, const DwtTile& t, const float* sm, int
       out[2 * j + 1] = al.y + ah.y;
     }
     float* o = plane + (long long)gy * p.w + 2 * gx;
+#if defined(__CUDA_ARCH__)
+    if (wide) {   // one 256-bit store per item: every store instruction writes whole 32-byte sectors
+      asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(out[0]), "f"(out[1]), "f"(out[2]),
+                   "f"(out[3]), "f"(out[4]), "f"(out[5]), "f"(out[6]), "f"(out[7])
+                   : "memory");
+      continue;
+    }
+#endif
     *reinterpret_cast<float4*>(o) = float4{out[0], out[1], out[2], out[3]};
     *reinterpret_cast<float4*>(o + 4) = float4{out[4], out[5], out[6], out[7]};
   }

@@ -175,6 +175,34 @@ def test_dwt97_vs_oracle(shape, J):
         assert (rec.cpu() - x).abs().max().item() < 1e-5
 
 
+def test_dwt97_inverse_output_alignment_paths():
+    """The fast inverse kernel writes an item's 8 outputs with one 256-bit store when the output plane is
+    32-byte aligned and with two 128-bit stores otherwise: both paths through the C ABI (ll_dwt97_inv_level,
+    include/ll_api.h) on the same subbands must give the same bits, and match the oracle."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import _lib, ops
+    lib = _lib.load()
+    torch.manual_seed(11)
+    N, h, w = 3, 64, 160
+    x = torch.rand(N, 1, h, w) - 0.5
+    yl, yh = tp.dwt97_forward(x, 1)
+    want = tp.dwt97_inverse(yl, yh).reshape(N, h, w)
+    gl, gh = yl.to(DEV).contiguous(), yh[0].to(DEV).contiguous()
+    sub = (h // 2) * (w // 2)
+    outs = []
+    for off in (0, 4):                       # floats: 0 -> 32-byte aligned base, 4 -> 16-byte aligned only
+        buf = torch.full((N * h * w + 8,), float("nan"), device=DEV)
+        out = buf[off:off + N * h * w]
+        assert out.data_ptr() % 32 == (16 if off else 0)
+        with torch.cuda.device(DEV):
+            ops.check(lib.ll_dwt97_inv_level(ops.ptr(gl), sub, ops.ptr(gh), 3 * sub, out.data_ptr(), h * w, N, h, w,
+                                             ops.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.isnan(buf[:off]).all() and torch.isnan(buf[off + N * h * w:]).all()   # nothing outside the plane
+        outs.append(out.view(N, h, w).cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert rel_err(outs[0], want) < 1e-5
+
+
 def test_pointwise_autoencoder_symbols_bit_exact():
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers.lifting_dwt_nets import SubbandAutoEncoder
     torch.manual_seed(1337)
