@@ -267,6 +267,34 @@ def run_own(args):
                           "note": "the same step with lift_precision='fp32' (ll::lift_step_kernel, every layer on the FP32 FMA pipe)"},
         "check": {"perfect_reconstruction_max_abs_err": pr_err},
     }
+    # the dominant kernel timed alone, per launch (CUDA events on the launching stream, back-to-back launches):
+    # one level-0 row step on a (16,256,768) view; 2 x 13 603 MAC per view pixel (3-tap pre-filter + the four 5x5 layers)
+    with torch.no_grad():
+        blobs = nets[0].waveletForward[0]._blobs()
+        vsrc = torch.rand(B, H // 2, W, device=dev) - 0.5
+        vdin = torch.rand(B, H // 2, W, device=dev) - 0.5
+        vout = torch.empty_like(vsrc)
+        for _ in range(3):
+            ops.lift_step([(vsrc, vdin, vout)], blobs[0], 1.0, 0.1, False)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(20):
+            ops.lift_step([(vsrc, vdin, vout)], blobs[0], 1.0, 0.1, False)
+        ev1.record()
+        torch.cuda.synchronize()
+        k_ms = ev0.elapsed_time(ev1) / 20
+        k_flop = 2.0 * 13603 * vsrc.numel()
+        tf32_peak = pk["bf16_tflops"] / 2
+        line["roofline"]["per_launch"] = {
+            "view": [B, H // 2, W], "ms": k_ms, "useful_tflops": k_flop / (k_ms * 1e-3) / 1e12,
+            "useful_frac": k_flop / (k_ms * 1e-3) / 1e12 / tf32_peak,
+            "issued_tflops": k_flop * 0.94 * 3 * 128 / 80 / (k_ms * 1e-3) / 1e12,
+            "issued_frac": k_flop * 0.94 * 3 * 128 / 80 / (k_ms * 1e-3) / 1e12 / tf32_peak,
+            "algorithmic_bytes": 12 * vsrc.numel(), "hbm_gbs": 12 * vsrc.numel() / (k_ms * 1e-3) / 1e9,
+            "note": "ll::lift_step_tc_kernel alone: 20 back-to-back launches between two CUDA events on the launching stream; "
+                    "25.2 MB read (src, din) + 12.6 MB written per launch; frac against the TF32 dense peak (measured BF16 burst / 2)"}
+        del vsrc, vdin, vout
     line["dwt97"] = dwt97_probe(dev, pk)
     line["context_cnn"] = context_probe(dev, pk)
     line["codec_forward"] = codec_probe(dev)

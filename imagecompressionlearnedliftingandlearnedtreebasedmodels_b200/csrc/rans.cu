@@ -165,17 +165,35 @@ __device__ __forceinline__ void enc_sample(RansEnc& e, const D& d, float y) {
 }
 
 template <class D>
-__device__ __forceinline__ float dec_sample(RansDec& r, const D& d) {
+__device__ __forceinline__ float dec_sample(RansDec& r, const D& d, int lane) {
+  // Wanted: the largest a in [0, 2K+1] with C(a) <= slot.  Every C() is an erfc (or logistic-mixture) evaluation on
+  // the stream's serial dependency chain, so the WARP that owns the stream searches cooperatively: each round the 32
+  // lanes probe 32 evenly spaced candidates at once and a ballot keeps the sub-interval that holds the answer --
+  // 1 round for the 32-symbol alphabets of small sigma, 3 for the widest (4096 symbols) instead of 7 .. 14 dependent
+  // evaluations of a bisection.  C(lo) and C(hi + 1) ride along, so no evaluation is repeated.  All state is
+  // warp-uniform (every lane runs the same rANS state machine).
   const uint32_t sl = r.slot();
-  const int K = d.K;
-  int lo = 0, hi = 2 * K + 1;            // largest a with C(a) <= slot
+  const int K = d.K, top = 2 * K + 1;
+  int lo = 0, hi = top;
+  uint32_t c_lo = 0u, c_up = 65536u;     // C(lo), C(hi + 1)
   while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (d.C(mid) <= sl) lo = mid;
-    else hi = mid - 1;
+    const int stepw = (hi - lo + 31) >> 5;
+    const int b = lo + (lane + 1) * stepw;
+    const uint32_t cb = b <= hi ? d.C(b) : 65536u;
+    const unsigned le = __ballot_sync(0xffffffffu, b <= hi && cb <= sl);   // C is increasing: a prefix of the lanes
+    const int cnt = __popc(le);
+    const uint32_t c_in = __shfl_sync(0xffffffffu, cb, cnt > 0 ? cnt - 1 : 0);
+    const uint32_t c_out = __shfl_sync(0xffffffffu, cb, cnt < 32 ? cnt : 31);
+    if (cnt < 32 && lo + (cnt + 1) * stepw <= hi) {
+      hi = lo + (cnt + 1) * stepw - 1;
+      c_up = c_out;
+    }
+    if (cnt > 0) {
+      lo += cnt * stepw;
+      c_lo = c_in;
+    }
   }
-  const uint32_t c0 = d.C(lo);
-  r.advance(c0, d.C(lo + 1) - c0);
+  r.advance(c_lo, c_up - c_lo);
   float kf;
   if (lo <= 2 * K) kf = (float)(lo - K);
   else {
@@ -200,17 +218,40 @@ __global__ void __launch_bounds__(RN_THREADS) rans_encode_kernel(const float* __
   const float* yb = y + b * N;
   RansEnc enc(scratch + st * cap, cap);
   const long long ns = s < N ? (N - s + S - 1) / S : 0;
-  for (long long j = ns - 1; j >= 0; --j) {
-    const long long e = s + j * S;
-    const int c = (int)(e / hw);
-    if (MODE == 0 || MODE == 2) {
-      const long long pix = e - c * hw;
-      const float* m = par + (b * 2 * C + 2 * c) * hw + pix;
-      if (MODE == 0) enc_sample(enc, GaussDist(m[0], m[hw]), yb[e]);
-      else enc_sample(enc, GaussGridDist(m[0], m[hw]), yb[e]);
-    } else {
-      enc_sample(enc, EbDist(par + (size_t)c * RN_EB_BLOB), yb[e]);
+  // samples s + j S, j = ns-1 .. 0 (rANS encodes backwards).  One thread = one serial chain with nothing to hide a
+  // DRAM round trip behind, so the next sample and its parameters are fetched before the current one is coded, and
+  // the (channel, pixel) split of the sample index is carried along instead of divided out per sample.
+  long long e = s + (ns - 1) * S;
+  int c = ns > 0 ? (int)(e / hw) : 0;
+  long long pix = e - c * hw;
+  const float* pb = par + b * 2 * C * hw;
+  float v = 0.f, sg = 1.f, mu = 0.f;
+  if (ns > 0) {
+    v = yb[e];
+    if (MODE != 1) {
+      sg = pb[2 * c * hw + pix];
+      mu = pb[(2 * c + 1) * hw + pix];
     }
+  }
+  for (long long j = ns - 1; j >= 0; --j) {
+    const int cc = c;
+    const float vc = v, sgc = sg, muc = mu;
+    if (j > 0) {
+      e -= S;
+      pix -= S;
+      while (pix < 0) {
+        pix += hw;
+        --c;
+      }
+      v = yb[e];
+      if (MODE != 1) {
+        sg = pb[2 * c * hw + pix];
+        mu = pb[(2 * c + 1) * hw + pix];
+      }
+    }
+    if (MODE == 0) enc_sample(enc, GaussDist(sgc, muc), vc);
+    else if (MODE == 2) enc_sample(enc, GaussGridDist(sgc, muc), vc);
+    else enc_sample(enc, EbDist(par + (size_t)cc * RN_EB_BLOB), vc);
   }
   counts[st] = enc.finish(cap);
 }
@@ -231,22 +272,43 @@ template <int MODE>
 __global__ void __launch_bounds__(RN_THREADS) rans_decode_kernel(const uint16_t* __restrict__ packed, const long long* __restrict__ offsets,
                                                                 const float* __restrict__ par, int B, int C, long long hw, int S,
                                                                 float* __restrict__ y) {
-  const long long st = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // one WARP per stream (see dec_sample); lane 0 writes the decoded samples
+  const long long st = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (st >= (long long)B * S) return;
   const long long b = st / S;
   const int s = (int)(st % S);
   const long long N = (long long)C * hw;
   float* yb = y + b * N;
   RansDec dec(packed + offsets[st]);
+  // same software pipeline as the encoder: parameters of the next sample are in flight while this one is decoded
+  int c = s < N ? (int)(s / hw) : 0;
+  long long pix = s - c * hw;
+  const float* pb = par + b * 2 * C * hw;
+  float sg = 1.f, mu = 0.f;
+  if (MODE != 1 && s < N) {
+    sg = pb[2 * c * hw + pix];
+    mu = pb[(2 * c + 1) * hw + pix];
+  }
   for (long long e = s; e < N; e += S) {
-    const int c = (int)(e / hw);
-    if (MODE == 0 || MODE == 2) {
-      const long long pix = e - c * hw;
-      const float* m = par + (b * 2 * C + 2 * c) * hw + pix;
-      yb[e] = MODE == 0 ? dec_sample(dec, GaussDist(m[0], m[hw])) : dec_sample(dec, GaussGridDist(m[0], m[hw]));
-    } else {
-      yb[e] = dec_sample(dec, EbDist(par + (size_t)c * RN_EB_BLOB));
+    const int cc = c;
+    const float sgc = sg, muc = mu;
+    if (e + S < N) {
+      pix += S;
+      while (pix >= hw) {
+        pix -= hw;
+        ++c;
+      }
+      if (MODE != 1) {
+        sg = pb[2 * c * hw + pix];
+        mu = pb[(2 * c + 1) * hw + pix];
+      }
     }
+    float out;
+    if (MODE == 0) out = dec_sample(dec, GaussDist(sgc, muc), lane);
+    else if (MODE == 2) out = dec_sample(dec, GaussGridDist(sgc, muc), lane);
+    else out = dec_sample(dec, EbDist(par + (size_t)cc * RN_EB_BLOB), lane);
+    if (lane == 0) yb[e] = out;
   }
 }
 
@@ -303,7 +365,7 @@ int ll_rans_decode(int mode, const uint16_t* packed, const int64_t* offsets, con
   if (mode < 0 || mode > 2) return fail(LL_EINVAL, "ll_rans_decode: mode must be 0 (gaussian), 1 (factorized) or 2 (gaussian, integer grid)");
   const long long nst = (long long)B * S;
   if (nst == 0 || hw == 0) return LL_OK;
-  const unsigned blocks = (unsigned)((nst + RN_THREADS - 1) / RN_THREADS);
+  const unsigned blocks = (unsigned)((nst * 32 + RN_THREADS - 1) / RN_THREADS);   // one warp per stream
   if (mode == 0) rans_decode_kernel<0><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
   else if (mode == 2) rans_decode_kernel<2><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
   else rans_decode_kernel<1><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(packed, reinterpret_cast<const long long*>(offsets), par, B, C, hw, S, y);
