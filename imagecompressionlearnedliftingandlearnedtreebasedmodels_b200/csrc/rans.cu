@@ -3,10 +3,11 @@
 // The reference only has a serial, per-coefficient Python coder, and only for its autoregressive model
 // (LiftingBasedDWT_net.py:374-556, compress_ar / decompress_ar around compressai.ans).  The entropy layers whose
 // contexts depend on *already decoded samples of other levels / phases only* (factorized :182-231, onlyEZWT :759-840,
-// ZTBlock :558-757 with its four 2x2 phases) can be decoded a whole subband (phase) at a time, so their symbols are coded here with interleaved rANS streams, one GPU thread per stream:
+// ZTBlock :558-757 with its four 2x2 phases) can be decoded a whole subband (phase) at a time, so their symbols are coded
+// here with interleaved rANS streams, one warp per stream (the lanes share the CDF evaluations, see the kernels):
 //   * state 32 bit, renormalisation by 16-bit words, probabilities quantised to 2^16 (ryg_rans word variant);
-//   * image b of a (B, C, hw) tensor owns S streams; stream s codes samples s, s+S, s+2S, ... of the image, so a warp
-//     reads 32 consecutive samples per step (coalesced) and every image's bytes are separable;
+//   * image b of a (B, C, hw) tensor owns S streams; stream s codes samples s, s+S, s+2S, ... of the image (neighbouring
+//     streams touch neighbouring samples, so their sectors are shared in L2) and every image's bytes are separable;
 //   * the distribution of a sample is never tabulated: the coder evaluates the model's own CDF -- the Gaussian of
 //     GaussianConditional (sigma clamped at 0.11, mean mu; compressai 1.2.1 entropy_models.py) or the factorized
 //     logistic-mixture CDF of EntropyBottleneck -- at the symbol's edges, with the same device code in the encoder and
@@ -122,17 +123,22 @@ struct RansEnc {   // writes 16-bit words backwards from the end of the stream's
   uint32_t x;
   uint16_t* buf;
   int pos;
-  __device__ __forceinline__ RansEnc(uint16_t* b, int cap) : x(RN_L), buf(b), pos(cap) {}
+  bool writer;   // every lane of the stream's warp runs the state machine, one of them stores the words
+  __device__ __forceinline__ RansEnc(uint16_t* b, int cap, bool w) : x(RN_L), buf(b), pos(cap), writer(w) {}
   __device__ __forceinline__ void put(uint32_t start, uint32_t freq) {
     if (x >= (freq << 16)) {
-      buf[--pos] = (uint16_t)(x & 0xffffu);
+      --pos;
+      if (writer) buf[pos] = (uint16_t)(x & 0xffffu);
       x >>= 16;
     }
     x = ((x / freq) << 16) + (x % freq) + start;
   }
   __device__ __forceinline__ int finish(int cap) {
-    buf[--pos] = (uint16_t)(x & 0xffffu);
-    buf[--pos] = (uint16_t)(x >> 16);
+    pos -= 2;
+    if (writer) {
+      buf[pos + 1] = (uint16_t)(x & 0xffffu);
+      buf[pos] = (uint16_t)(x >> 16);
+    }
     return cap - pos;
   }
 };
@@ -148,20 +154,28 @@ struct RansDec {
   }
 };
 
+// (start, freq) of a sample under its distribution -- independent of the coder state, so the warp evaluates 32 samples
+// at once.  Escape: ``raw`` is pushed (frequency 1) before the escape symbol, because the decoder pops the escape first.
+struct EncSym {
+  uint32_t start, freq, raw;
+  bool esc;
+};
 template <class D>
-__device__ __forceinline__ void enc_sample(RansEnc& e, const D& d, float y) {
+__device__ __forceinline__ EncSym enc_symbol(const D& d, float y) {
+  EncSym r;
   const float kf = rintf(__fsub_rn(y, d.centre()));
   const int K = d.K;
-  if (fabsf(kf) <= (float)K) {
-    const int a = (int)kf + K;
-    const uint32_t c0 = d.C(a);
-    e.put(c0, d.C(a + 1) - c0);
-  } else {   // escape: the decoder pops the escape symbol first, so the raw word is pushed first
+  r.esc = !(fabsf(kf) <= (float)K);
+  r.raw = 0u;
+  int a = (int)kf + K;
+  if (r.esc) {
     const float kc = fminf(fmaxf(kf, -32768.f), 32767.f);
-    e.put((uint32_t)((int)kc + 32768), 1u);
-    const uint32_t c0 = d.C(2 * K + 1);
-    e.put(c0, 65536u - c0);
+    r.raw = (uint32_t)((int)kc + 32768);
+    a = 2 * K + 1;
   }
+  r.start = d.C(a);
+  r.freq = d.C(a + 1) - r.start;      // C(2K + 2) = 2^16
+  return r;
 }
 
 template <class D>
@@ -210,50 +224,54 @@ template <int MODE>
 __global__ void __launch_bounds__(RN_THREADS) rans_encode_kernel(const float* __restrict__ y, const float* __restrict__ par, int B,
                                                                 int C, long long hw, int S, uint16_t* __restrict__ scratch,
                                                                 int cap, int* __restrict__ counts) {
-  const long long st = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // One WARP per stream.  The stream's samples s + j S are coded backwards (j = ns-1 .. 0), 32 at a time: lane l
+  // evaluates the CDF edges of sample j0 - l (the erfc work, which does not depend on the coder state, runs 32-wide),
+  // then every lane replays the 32 (start, freq) pairs through the serial rANS state machine (a compare, a 32-bit
+  // divide and an occasional 16-bit store per symbol).  The next chunk's loads are issued before the serial part.
+  const long long st = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (st >= (long long)B * S) return;
   const long long b = st / S;
   const int s = (int)(st % S);
   const long long N = (long long)C * hw;
   const float* yb = y + b * N;
-  RansEnc enc(scratch + st * cap, cap);
-  const long long ns = s < N ? (N - s + S - 1) / S : 0;
-  // samples s + j S, j = ns-1 .. 0 (rANS encodes backwards).  One thread = one serial chain with nothing to hide a
-  // DRAM round trip behind, so the next sample and its parameters are fetched before the current one is coded, and
-  // the (channel, pixel) split of the sample index is carried along instead of divided out per sample.
-  long long e = s + (ns - 1) * S;
-  int c = ns > 0 ? (int)(e / hw) : 0;
-  long long pix = e - c * hw;
   const float* pb = par + b * 2 * C * hw;
+  RansEnc enc(scratch + st * cap, cap, lane == 0);
+  const long long ns = s < N ? (N - s + S - 1) / S : 0;
   float v = 0.f, sg = 1.f, mu = 0.f;
-  if (ns > 0) {
+  int ch = 0;
+  auto fetch = [&](long long j) {
+    if (j < 0) return;
+    const long long e = s + j * S;
+    ch = (int)(e / hw);
+    const long long pix = e - ch * hw;
     v = yb[e];
     if (MODE != 1) {
-      sg = pb[2 * c * hw + pix];
-      mu = pb[(2 * c + 1) * hw + pix];
+      sg = pb[2 * ch * hw + pix];
+      mu = pb[(2 * ch + 1) * hw + pix];
+    }
+  };
+  fetch(ns - 1 - lane);
+  for (long long j0 = ns - 1; j0 >= 0; j0 -= 32) {
+    EncSym sym = {0u, 1u, 0u, false};
+    if (j0 - lane >= 0) {
+      if (MODE == 0) sym = enc_symbol(GaussDist(sg, mu), v);
+      else if (MODE == 2) sym = enc_symbol(GaussGridDist(sg, mu), v);
+      else sym = enc_symbol(EbDist(par + (size_t)ch * RN_EB_BLOB), v);
+    }
+    fetch(j0 - 32 - lane);
+    const int n = j0 + 1 < 32 ? (int)(j0 + 1) : 32;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t st_i = __shfl_sync(0xffffffffu, sym.start, i);
+      const uint32_t fr_i = __shfl_sync(0xffffffffu, sym.freq, i);
+      const uint32_t raw_i = __shfl_sync(0xffffffffu, sym.raw, i);
+      const bool esc_i = __shfl_sync(0xffffffffu, (int)sym.esc, i) != 0;
+      if (esc_i) enc.put(raw_i, 1u);
+      enc.put(st_i, fr_i);
     }
   }
-  for (long long j = ns - 1; j >= 0; --j) {
-    const int cc = c;
-    const float vc = v, sgc = sg, muc = mu;
-    if (j > 0) {
-      e -= S;
-      pix -= S;
-      while (pix < 0) {
-        pix += hw;
-        --c;
-      }
-      v = yb[e];
-      if (MODE != 1) {
-        sg = pb[2 * c * hw + pix];
-        mu = pb[(2 * c + 1) * hw + pix];
-      }
-    }
-    if (MODE == 0) enc_sample(enc, GaussDist(sgc, muc), vc);
-    else if (MODE == 2) enc_sample(enc, GaussGridDist(sgc, muc), vc);
-    else enc_sample(enc, EbDist(par + (size_t)cc * RN_EB_BLOB), vc);
-  }
-  counts[st] = enc.finish(cap);
+  const int words = enc.finish(cap);
+  if (lane == 0) counts[st] = words;
 }
 
 __global__ void rans_pack_kernel(const uint16_t* __restrict__ scratch, const int* __restrict__ counts, const long long* __restrict__ offsets,
@@ -339,7 +357,7 @@ int ll_rans_encode(int mode, const float* y, const float* par, int B, int C, int
   const long long nst = (long long)B * S;
   if (nst == 0 || hw == 0) return LL_OK;
   const int cap = (int)ll_rans_stream_cap((int64_t)C * hw, S);
-  const unsigned blocks = (unsigned)((nst + RN_THREADS - 1) / RN_THREADS);
+  const unsigned blocks = (unsigned)((nst * 32 + RN_THREADS - 1) / RN_THREADS);   // one warp per stream
   if (mode == 0) rans_encode_kernel<0><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
   else if (mode == 2) rans_encode_kernel<2><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
   else rans_encode_kernel<1><<<blocks, RN_THREADS, 0, as_stream(stream)>>>(y, par, B, C, hw, S, scratch, cap, counts);
