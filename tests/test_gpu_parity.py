@@ -340,3 +340,26 @@ def test_config5_tile_five_levels_vs_oracle():
         obits = float(osi_xe.double().sum() + sum(t.double().sum() for t in osi_xo))
         assert abs(bits - obits) <= 1e-3 * obits
         assert rel_err(xhat.cpu(), oxhat) < 1e-4
+
+
+@pytest.mark.parametrize("entropy_layer", ["conditioned2ZTsepSubbands", "onlyEZWT"])
+def test_cuda_graph_replay_matches_eager(entropy_layer):
+    """utils.cuda_graph.GraphedForward: the whole codec forward (three planes on three streams, every launch through
+    the C ABI) captured once and replayed must reproduce the eager call bit for bit, also on fresh input data."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils.cuda_graph import GraphedForward
+    cfg = dict(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder", entropy_layer=entropy_layer,
+               dwtlevels=3, clrch=1)
+    model, _ = product_model(cfg)
+    model = model.to(DEV).eval()
+    torch.manual_seed(3)
+    x0 = om.preprocess(torch.rand(2, 3, 64, 96)).to(DEV)
+    x1 = om.preprocess(torch.rand(2, 3, 64, 96)).to(DEV)
+    graphed = GraphedForward(model, x0)
+    for x in (x0, x1, x0):
+        with torch.no_grad():
+            want = model(x)
+        got = graphed(x)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert len(got[2]) == len(want[2]) and all(torch.equal(a, b) for a, b in zip(got[2], want[2]))
+    with pytest.raises(ValueError):
+        graphed(x0[:1])
