@@ -54,6 +54,10 @@ class LiftingBasedDWTAgent:
         self.data_loader = data_loader
         self.current_epoch = 0
         self.current_iteration = 0
+        # optional key (absent from the reference's JSON): replay the model forward of ``validate_batch`` as one CUDA graph
+        # per input shape -- worth it for launch-bound inputs (tiles, small crops); weights must not change in between
+        self.cuda_graph = bool(_cfg(config, "cuda_graph", False))
+        self._graphs = {}
 
     # ---- pre / post processing (:100-105, :164-181) ----
     def preprocess(self, x):
@@ -77,7 +81,15 @@ class LiftingBasedDWTAgent:
         device->host transfer."""
         self.model.eval()
         x = x.to(self.device)
-        yhat, si_xe, si_xo = self.model(self.preprocess(x))
+        y = self.preprocess(x)
+        if self.cuda_graph:
+            key = (tuple(y.shape), y.dtype)
+            if key not in self._graphs:
+                from ..utils.cuda_graph import GraphedForward
+                self._graphs[key] = GraphedForward(self.model, y)
+            yhat, si_xe, si_xo = self._graphs[key](y)
+        else:
+            yhat, si_xe, si_xo = self.model(y)
         _, sse = self.postprocess(yhat, x)
         n = x.numel()
         vals = torch.stack([sse.sum(), si_xe.double().sum(), sum(s.double().sum() for s in si_xo)]).cpu()
@@ -100,6 +112,7 @@ class LiftingBasedDWTAgent:
     # ---- one optimisation step of train_one_epoch (:78-125) ----
     def train_batch(self, x):
         self.model.train()
+        self._graphs.clear()          # captured graphs read packed copies of the weights this step is about to change
         x = x.to(self.device)
         y = self.preprocess(x)
         yhat, si_xe, si_xo = self.model(y)

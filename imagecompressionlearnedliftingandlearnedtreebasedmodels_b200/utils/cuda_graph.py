@@ -16,9 +16,9 @@ class GraphedForward:
     * inference only (captured under ``torch.no_grad()`` in the module's current train/eval mode);
     * the returned tensors are the graph's static output buffers: they are overwritten by the next
       call -- clone what must survive;
-    * weights are read in place, so ``load_state_dict`` / in-place updates are seen by later replays
-      as long as the packed-weight caches are refreshed by one eager call (the packers key on the
-      parameters' version counters and are not part of the graph).
+    * the kernels read *packed* copies of the weights (``ll_pack_*`` blobs made during the warm-up
+      calls); the graph keeps pointing at those blobs, so build a new ``GraphedForward`` after
+      ``load_state_dict`` or an optimiser step.
     """
 
     def __init__(self, module, example, warmup=3):

@@ -86,6 +86,11 @@ def test_agent_validate_batch_matches_oracle_pipeline():
     assert abs(avg["bpp"] - got["bpp"]) <= 1e-9 * max(1.0, got["bpp"])
     with pytest.raises(RuntimeError):
         CompressionAgent(cfg, device=DEV).validate()
+    # optional ``cuda_graph`` key: the same batch through a captured graph gives the same scalars, also on replay
+    agent.cuda_graph = True
+    for _ in range(2):
+        again = agent.validate_batch(x)
+        assert all(again[k] == got[k] for k in got), (again, got)
 
 
 def test_agent_train_batch_steps():
