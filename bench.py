@@ -406,6 +406,13 @@ def context_probe(dev, pk):
         ms = timed(lambda: em(xe, xo), 3)
     res["cond2zt_entropy_model"] = {"ms_per_plane_batch16": ms, "mp_per_s_3_planes": B * H * W / 1e6 / (3 * ms * 1e-3),
                                     "flops_per_plane_px": 430482, "note": "quantise + context CNNs + Gaussian rate + bit sums"}
+    try:
+        from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils.cuda_graph import GraphedForward
+        graphed = GraphedForward(em, xe, xo)
+        res["cond2zt_entropy_model"]["ms_per_plane_batch16_cuda_graph"] = timed(lambda: graphed(xe, xo), 3)
+        del graphed
+    except Exception as e:  # noqa: BLE001
+        res["cond2zt_entropy_model"]["cuda_graph_error"] = f"{type(e).__name__}: {e}"[:300]
     del em
     # the other three parallelisable entropy layers on the same subbands, eval forward of one plane
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import (
@@ -421,6 +428,16 @@ def context_probe(dev, pk):
         bits = float(out[0].double().sum() + sum(s.double().sum() for s in out[1]))
         layers[name] = {"ms_per_plane_batch16": ms, "mp_per_s_3_planes": B * H * W / 1e6 / (3 * ms * 1e-3),
                         "flops_per_plane_px": flop, "bits_per_coefficient": bits / (B * H * W)}
+        try:   # the same call replayed as one CUDA graph (ZTBlock is several hundred small launches)
+            from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils.cuda_graph import GraphedForward
+            graphed = GraphedForward(layer, xe, xo)
+            layers[name]["ms_per_plane_batch16_cuda_graph"] = timed(lambda: graphed(xe, xo), 3)
+            gout = graphed(xe, xo)
+            layers[name]["cuda_graph_matches_eager"] = bool(torch.equal(gout[0], out[0]) and
+                                                            all(torch.equal(a, b) for a, b in zip(gout[1], out[1])))
+            del graphed, gout
+        except Exception as e:  # noqa: BLE001
+            layers[name]["cuda_graph_error"] = f"{type(e).__name__}: {e}"[:300]
         del layer
     res["other_entropy_layers"] = layers
     return res
