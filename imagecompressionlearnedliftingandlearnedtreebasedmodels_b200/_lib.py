@@ -59,6 +59,7 @@ SIGNATURES = {
     "ll_pack_ae1": (c_int, [_P] * 8 + [c_int, c_int, _P, _P]),
     "ll_ae1_apply": (c_int, [_P, _P, _P, _P, c_int, c_int, c_i64, _P]),
     "ll_conv2d": (c_int, [_P, c_i64, _P, _P, _P, c_i64] + [c_int] * 12 + [_P]),
+    "ll_pw_mlp3": (c_int, [_P, c_i64, _P, _P, _P, _P, _P, _P, _P, c_i64, c_int, c_int, c_i64, _P]),
     "ll_ctx_conv_nhwc": (c_int, [_P, _P, _P, _P] + [c_int] * 15 + [_P]),
     "ll_cgp_tail_rate": (c_int, [_P, c_i64, _P, _P, _P, _P, _P, c_i64, _P, _P, c_i64, _P, _P, c_int, c_int, c_int, c_int, c_i64, _P, _P]),
     "ll_pack_igemm_weight": (c_int, [_P, _P] + [c_int] * 5 + [_P]),

@@ -59,6 +59,20 @@ def _chain(seq, x):
     return x
 
 
+def _dep_net(seq, x):
+    """A ZTBlock dependency CNN (:618-680): [Conv3x3, LReLU, Conv3x3, LReLU, Conv1x1, LReLU, Conv1x1, LReLU, Conv1x1].
+    Inference: the two 3x3 convs on the direct-conv kernel, the pointwise tail (32->32->32->1) in one fused pass;
+    with autograd on, the generic differentiable chain."""
+    mods = list(seq)
+    tail = len(mods) == 9 and all(isinstance(mods[i], nn.Conv2d) and mods[i].kernel_size == (1, 1) for i in (4, 6, 8)) \
+        and mods[4].in_channels == 32 and mods[4].out_channels == 32 and mods[6].out_channels == 32 and mods[8].out_channels == 1
+    if not tail or _autograd.needs_grad([x] + list(seq.parameters())):
+        return _chain(seq, x)
+    x = _conv(mods[0], x, lrelu=True)
+    x = _conv(mods[2], x, lrelu=True)
+    return ops.pw_mlp3(x, mods[4], mods[6], mods[8])
+
+
 class LiftingBasedDWTNetWrapper(nn.Module):
     """Per-colour-plane dispatch (:35-99): ``clrch == 1`` builds three independent nets."""
 
@@ -513,8 +527,8 @@ class DWTConditioned2EntropyLayerZTBlock(nn.Module):
 
     def _phase_ms(self, n, k, dep):
         """(sigma, mu) of phase k (1..4) of conditioned subband n from its dependencies ``dep`` (B,k,h,w) -> (B,2,h,w)."""
-        mu = _chain(getattr(self, f"dep_{k}_list_mu")[n], dep)
-        sg = _chain(getattr(self, f"dep_{k}_list_sigma")[n], dep)
+        mu = _dep_net(getattr(self, f"dep_{k}_list_mu")[n], dep)
+        sg = _dep_net(getattr(self, f"dep_{k}_list_sigma")[n], dep)
         return torch.cat((sg, mu), dim=1)
 
     def forward(self, out_xe, out_xo_list, keep_ms=None):
@@ -543,8 +557,8 @@ class DWTConditioned2EntropyLayerZTBlock(nn.Module):
                 n = j + i * 3
                 deps = [d1, torch.cat((d1, ee), 1), torch.cat((d1, ee, eo), 1), torch.cat((d1, ee, eo, oe), 1)]
                 for k, (dep, (ry, rx)) in enumerate(zip(deps, self._SLOTS), start=1):
-                    ms[:, 1:2, ry::2, rx::2] = _chain(getattr(self, f"dep_{k}_list_mu")[n], dep)
-                    ms[:, 0:1, ry::2, rx::2] = _chain(getattr(self, f"dep_{k}_list_sigma")[n], dep)
+                    ms[:, 1:2, ry::2, rx::2] = _dep_net(getattr(self, f"dep_{k}_list_mu")[n], dep)
+                    ms[:, 0:1, ry::2, rx::2] = _dep_net(getattr(self, f"dep_{k}_list_sigma")[n], dep)
                 si_j.append(gc.bits(xin, ms, self.training, acc=acc))
                 q_j.append(qq)
                 ms_j.append(ms)

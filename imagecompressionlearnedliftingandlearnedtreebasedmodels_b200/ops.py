@@ -249,6 +249,25 @@ def conv2d(x, weight, bias=None, groups=1, lrelu=False, upsample2=False, out=Non
     return out
 
 
+def pw_mlp3(x, conv1, conv2, conv3):
+    """Conv1x1(32->32), LeakyReLU, Conv1x1(32->32), LeakyReLU, Conv1x1(32->1) of a ZTBlock dependency net in one pass
+    (ll_pw_mlp3).  ``x`` (B,32,H,W); ``conv*`` the three nn.Conv2d modules.  Returns (B,1,H,W)."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, C, H, W = x.shape
+    ws = [_f32c(c.weight.detach(), "weight") for c in (conv1, conv2, conv3)]
+    bs = [_f32c(c.bias.detach(), "bias") if c.bias is not None else None for c in (conv1, conv2, conv3)]
+    if tuple(ws[0].shape) != (C, C, 1, 1) or tuple(ws[1].shape) != (C, C, 1, 1) or tuple(ws[2].shape) != (1, C, 1, 1) \
+            or bs[0] is None or bs[1] is None:
+        raise ValueError("pw_mlp3: expected biased 1x1 convs C->C, C->C, C->1")
+    out = torch.empty(B, 1, H, W, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_pw_mlp3(ptr(x), C * H * W, ptr(ws[0]), ptr(bs[0]), ptr(ws[1]), ptr(bs[1]), ptr(ws[2]), ptr(bs[2]),
+                                     ptr(out), H * W, B, C, H * W, stream_ptr()))
+    _count(1)
+    return out
+
+
 # ----------------------------------------------------------------------------- tcgen05 context CNNs
 IG_BK = 64      # input channels per k-block (one 128-byte swizzle row of bf16)
 

@@ -161,6 +161,15 @@ int ll_conv2d(const float* x, int64_t x_sb, const float* w, const float* b, floa
               int H, int W, int Cout, int K, int groups, int upsample2, int lrelu, int co_group, int co_stride,
               int co_off, ll_stream_t stream);
 
+/* Pointwise tail of a ZTBlock dependency CNN in one pass: out = W3 . lrelu(W2 . lrelu(W1 . x + b1) + b2) + b3 per
+ * pixel, LeakyReLU(0.01).  x (B,32,hw) fp32 with batch stride x_sb (elements) and channel stride hw; w1, w2 in torch
+ * layout (32,32,1,1), w3 (1,32,1,1), b3 may be NULL; out (B,1,hw) with batch stride out_sb.  C must be 32.
+ * Replaces the last three nn.Conv2d (1x1) + two nn.LeakyReLU of every dep_{1..4}_list_{mu,sigma}[n]
+ * (graphs/models/LiftingBasedDWT_net.py:618-680, applied at :727-740). */
+int ll_pw_mlp3(const float* x, int64_t x_sb, const float* w1, const float* b1, const float* w2, const float* b2,
+               const float* w3, const float* b3, float* out, int64_t out_sb, int B, int C, int64_t hw,
+               ll_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Dense context CNNs on the tcgen05 tensor cores (K3)                        */
 /* ------------------------------------------------------------------------- */

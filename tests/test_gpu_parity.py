@@ -363,3 +363,26 @@ def test_cuda_graph_replay_matches_eager(entropy_layer):
         assert len(got[2]) == len(want[2]) and all(torch.equal(a, b) for a, b in zip(got[2], want[2]))
     with pytest.raises(ValueError):
         graphed(x0[:1])
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 17, 23), (1, 32, 1, 1), (3, 32, 64, 96), (0, 32, 8, 8)])
+def test_pointwise_mlp_tail_matches_torch(shape):
+    """ll_pw_mlp3 (the fused 1x1 tail of the ZTBlock dependency CNNs, LiftingBasedDWT_net.py:618-680) against the same
+    three convs evaluated by torch in float64: fp32 rounding only (1e-5 relative), odd plane sizes included."""
+    import torch.nn as nn
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    torch.manual_seed(21)
+    convs = [nn.Conv2d(32, 32, 1), nn.Conv2d(32, 32, 1), nn.Conv2d(32, 1, 1)]
+    x = torch.randn(*shape)
+    with torch.no_grad():
+        ref = x.double()
+        for i, c in enumerate(convs):
+            ref = nn.functional.conv2d(ref, c.weight.double(), c.bias.double())
+            if i < 2:
+                ref = nn.functional.leaky_relu(ref, 0.01)
+    got = ops.pw_mlp3(x.to(DEV), *[c.to(DEV) for c in convs])
+    assert got.shape == (shape[0], 1, shape[2], shape[3])
+    if shape[0]:
+        assert rel_err(got.cpu().double(), ref) < 1e-5
+    with pytest.raises(ValueError):
+        ops.pw_mlp3(torch.zeros(1, 16, 4, 4, device=DEV), *[c.to(DEV) for c in convs])
