@@ -39,7 +39,11 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constan
   constexpr int IWP = IW + 1;  // pitch
   constexpr int KK = K * K;
   __shared__ __align__(16) float s_in[CV_CI * IH * IWP];
-  __shared__ __align__(16) float s_w[CV_CI * KK * CV_CO];
+  // weights [ci][tap][co] with a 36-float pitch: the staging loop below walks (co, ci, tap) so that a warp reads runs of
+  // CV_CI * KK contiguous floats of the torch layout (walking co fastest gathers one sector per lane), and the pitch
+  // spreads its shared-memory stores over 8 banks instead of 1
+  constexpr int WP = CV_CO + 4;
+  __shared__ __align__(16) float s_w[CV_CI * KK * WP];
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
@@ -82,11 +86,11 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constan
     }
     // stage weights [ci][tap][co]
     for (int e = tid; e < CV_CI * KK * CV_CO; e += CV_THREADS) {
-      const int co = e % CV_CO, tap = (e / CV_CO) % KK, ci = e / (CV_CO * KK);
+      const int co = e / (CV_CI * KK), r = e % (CV_CI * KK), ci = r / KK, tap = r % KK;
       float v = 0.f;
       if (co0 + co < cout_g && ci0 + ci < cin_g)
         v = p.w[((long long)(g * cout_g + co0 + co) * cin_g + (ci0 + ci)) * KK + tap];
-      s_w[e] = v;
+      s_w[(ci * KK + tap) * WP + co] = v;
     }
     __syncthreads();
     const int nci = min(CV_CI, cin_g - ci0);
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constan
         for (int k = 0; k < 4 + K - 1; ++k) a[k] = arow[k];
 #pragma unroll
         for (int dx = 0; dx < K; ++dx) {
-          const float* wp = &s_w[(ci * KK + dy * K + dx) * CV_CO + cg * 8];
+          const float* wp = &s_w[(ci * KK + dy * K + dx) * WP + cg * 8];
           const float4 w0 = *reinterpret_cast<const float4*>(wp);
           const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll
