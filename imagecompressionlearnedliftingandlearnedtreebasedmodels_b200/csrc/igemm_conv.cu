@@ -335,6 +335,12 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_
   extern __shared__ __align__(16) float s_w[];       // [NIN][region] + bias[region]
   const int cout_g = p.Cout / p.groups;
   float* s_b = s_w + NIN * p.region;
+  // per-warp input window: [Cin][ROWS][WCOLS] samples around the warp's 4 pixels.  The 32 lanes fetch it together
+  // (one bounds check + one load per sample for the whole warp) and then read it back as broadcasts; loading it per
+  // lane made ~800 of the kernel's ~1 800 instructions per work item redundant address arithmetic (ncu: issue-bound
+  // at 23 % occupancy, FMA pipe 45 % busy).
+  constexpr int WIN_CH = ROWS * WCOLS;
+  float* s_win = s_b + p.region + (threadIdx.x >> 5) * (p.Cin * WIN_CH);
   for (int i = threadIdx.x; i < (NIN + 1) * p.region; i += HD_THREADS) {
     const int k = i / p.region, d = i % p.region;
     const int gd = d / p.co_gstride, j = d % p.co_gstride, co = gd * p.co_group + j;
@@ -343,7 +349,10 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_
       if (k < NIN) v = p.w[((long long)co * CIN_G + k / LIVE) * (K * K) + k % LIVE];
       else v = p.bias ? p.bias[co] : 0.f;
     }
-    s_w[i] = v;
+    // tap rows are stored as [half][slot][4]: the first (second) 128-bit load of the 32 lanes of a warp then covers 512
+    // contiguous bytes -- with the natural [slot][8] order the lanes sit 32 bytes apart and every load is a 2-way bank
+    // conflict, which made the kernel shared-memory bound (54 conflicted LDS.128 against 432 FFMA2 per 4 pixels).
+    s_w[k < NIN ? k * p.region + ((d >> 2) & 1) * (p.region / 2) + (d >> 3) * 4 + (d & 3) : i] = v;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -359,10 +368,23 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_
     r /= qx;
     const int yy = (int)(r % p.H), b = (int)(r / p.H);
     const int slot = ch * 32 + lane;
-    const int d0 = slot * 8;
-    if (d0 >= p.region) continue;
+    const bool inreg = slot * 8 < p.region;              // lanes past the region idle but keep the warp's barriers
+    const int d0 = inreg ? slot * 8 : 0;
     const int gd = d0 / p.co_gstride, j0 = d0 % p.co_gstride, co0 = gd * p.co_group + j0;
-    const bool live = j0 < p.co_group && co0 < p.Cout;
+    const bool live = inreg && j0 < p.co_group && co0 < p.Cout;
+    // (dense head only: the grouped csc has one input channel per lane group and 12 taps -- too little arithmetic to
+    // hide the extra shared-memory hop, measured 470 -> 541 us; the dense head went 509 -> 389 us)
+    constexpr bool kSharedWindow = CIN_G > 1;
+    if (kSharedWindow) __syncwarp();                     // the previous item's window reads are done
+    for (int e = lane; kSharedWindow && e < p.Cin * WIN_CH; e += 32) {
+      const int c = e / WIN_CH, rr = (e % WIN_CH) / WCOLS, cc = e % WCOLS;
+      const int gy = yy + rr - PAD, gx = x0 + cc - PAD;
+      float v = 0.f;
+      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+        v = __ldg(p.x + ((long long)b * p.Cin + c) * Hs * Ws + (long long)(p.upsample2 ? gy >> 1 : gy) * Ws + (p.upsample2 ? gx >> 1 : gx));
+      s_win[e] = v;
+    }
+    if (kSharedWindow) __syncwarp();
     float2 acc[HD_PX][4];
     {
       const float4 b0 = *reinterpret_cast<const float4*>(&s_b[d0]), b1 = *reinterpret_cast<const float4*>(&s_b[d0 + 4]);
@@ -377,24 +399,37 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_
 #pragma unroll
       for (int ci = 0; ci < CIN_G; ++ci) {
         float win[ROWS][WCOLS];
-        const float* xc = p.x + ((long long)b * p.Cin + g * CIN_G + ci) * Hs * Ws;
+        if (kSharedWindow) {
+          const float* wc = s_win + (g * CIN_G + ci) * WIN_CH;
 #pragma unroll
-        for (int rr = 0; rr < ROWS; ++rr) {
-          const int gy = yy + rr - PAD;
-          const bool yok = gy >= 0 && gy < p.H;
-          const int sy = p.upsample2 ? gy >> 1 : gy;
+          for (int rr = 0; rr < ROWS; ++rr) {
 #pragma unroll
-          for (int cc = 0; cc < WCOLS; ++cc) {
-            const int gx = x0 + cc - PAD;
-            float v = 0.f;
-            if (yok && gx >= 0 && gx < p.W) v = __ldg(xc + (long long)sy * Ws + (p.upsample2 ? gx >> 1 : gx));
-            win[rr][cc] = v;
+            for (int cc = 0; cc < WCOLS; cc += 2) {
+              const float2 v2 = *reinterpret_cast<const float2*>(wc + rr * WCOLS + cc);
+              win[rr][cc] = v2.x;
+              win[rr][cc + 1] = v2.y;
+            }
+          }
+        } else {
+          const float* xc = p.x + ((long long)b * p.Cin + g * CIN_G + ci) * Hs * Ws;
+#pragma unroll
+          for (int rr = 0; rr < ROWS; ++rr) {
+            const int gy = yy + rr - PAD;
+            const bool yok = gy >= 0 && gy < p.H;
+            const int sy = p.upsample2 ? gy >> 1 : gy;
+#pragma unroll
+            for (int cc = 0; cc < WCOLS; ++cc) {
+              const int gx = x0 + cc - PAD;
+              float v = 0.f;
+              if (yok && gx >= 0 && gx < p.W) v = __ldg(xc + (long long)sy * Ws + (p.upsample2 ? gx >> 1 : gx));
+              win[rr][cc] = v;
+            }
           }
         }
 #pragma unroll
         for (int t = 0; t < LIVE; ++t) {
-          const float* wr = s_w + (ci * LIVE + t) * p.region + d0;
-          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+          const float* wr = s_w + (ci * LIVE + t) * p.region + slot * 4;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + p.region / 2);
           const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w);
           const float2 wc = make_float2(w1.x, w1.y), wd = make_float2(w1.z, w1.w);
 #pragma unroll
@@ -411,7 +446,7 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_
     }
 #pragma unroll
     for (int q = 0; q < HD_PX; ++q) {
-      if (x0 + q >= p.W) break;
+      if (x0 + q >= p.W || !inreg) break;
       uint32_t pk[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -565,7 +600,8 @@ int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* ou
   p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.groups = groups;
   p.upsample2 = upsample2; p.lrelu = lrelu;
   p.out_cstride = out_cstride; p.out_coff = out_coff; p.co_group = co_group; p.co_gstride = co_gstride; p.region = region;
-  const size_t smem = (size_t)(cin_g * live_taps + 1) * region * sizeof(float);
+  const int win_rows = (live_taps + K - 1) / K, win_cols = HD_PX + K - 1;   // per-warp input window, see the kernel
+  const size_t smem = ((size_t)(cin_g * live_taps + 1) * region + (size_t)(HD_THREADS / 32) * Cin * win_rows * win_cols) * sizeof(float);
   if (smem > 200 * 1024) return fail(LL_EINVAL, "ll_ctx_conv_nhwc: weights do not fit shared memory");
   const int chunks = (region / 8 + 31) / 32;
   const long long nwork = (long long)B * H * ((W + HD_PX - 1) / HD_PX) * chunks;
