@@ -302,7 +302,7 @@ def run_own(args):
     line["entropy_coder"] = coder_probe(dev)
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(budget_s=12.0)
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -694,10 +694,26 @@ def run_reference(args):
                                    "reference's torch-CPU path (the Python reference cannot travel to the GPU box)"},
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's real stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's "NCCL version ..." banner when
+    # NCCL_DEBUG is set in the environment) is sent to stderr by pointing fd 1 at fd 2 for the rest of the run
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
