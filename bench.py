@@ -295,6 +295,17 @@ def run_own(args):
             "note": "ll::lift_step_tc_kernel alone: 20 back-to-back launches between two CUDA events on the launching stream; "
                     "25.2 MB read (src, din) + 12.6 MB written per launch; frac against the TF32 dense peak (measured BF16 burst / 2)"}
         del vsrc, vdin, vout
+        # headline roofline figures = the per-launch ones (algorithmic FLOPs of one launch / its measured duration);
+        # the whole-step quotient (all levels, three overlapped streams) is kept beside them
+        rf, pl = line["roofline"], line["roofline"]["per_launch"]
+        rf["step_achieved"], rf["step_frac"] = rf["achieved"], rf["frac"]
+        rf["step_issued_tflops"], rf["step_issued_frac"] = rf["issued_tflops"], rf["issued_frac"]
+        rf["achieved"], rf["frac"] = pl["useful_tflops"], pl["useful_frac"]
+        rf["issued_tflops"], rf["issued_frac"] = pl["issued_tflops"], pl["issued_frac"]
+        rf["note"] = ("achieved = useful conv FLOPs of one ll::lift_step_tc_kernel launch (2 x 13 603 MAC per view pixel, level-0 "
+                      "row step on a (16,256,768) view) / its average duration over 20 back-to-back launches (CUDA events); "
+                      "issued = tensor-pipe FLOPs incl. the 3xTF32 split and M padding; step_* = the same quotients over the "
+                      "whole timed step (SURVEY.md 8d: 2 x 144532 FLOP per plane pixel, fwd+inv, all levels)")
     line["dwt97"] = dwt97_probe(dev, pk)
     line["context_cnn"] = context_probe(dev, pk)
     line["codec_forward"] = codec_probe(dev)
