@@ -100,18 +100,26 @@ __global__ void __launch_bounds__(RT_THREADS) cgp_tail_rate_kernel(
   __syncthreads();
   float local = 0.f;
   const long long total = (long long)B * hw;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / hw, pix = i % hw;
-    const float* hp = h2 + b * h2_sb + (long long)g * C2 * hw + pix;
-    float h[C3P];
+  // two samples per thread (i and i + half) in the halves of packed FFMA2: one broadcast weight load feeds both, so the
+  // shared-memory loads and the FMA instructions per sample halve, and twice as many global loads are in flight per batch
+  const long long half = (total + 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < half; i += (long long)gridDim.x * blockDim.x) {
+    const long long i1 = i + half;
+    const bool two = i1 < total;
+    const long long b0 = i / hw, pix0 = i % hw;
+    const long long b1 = two ? i1 / hw : b0, pix1 = two ? i1 % hw : pix0;
+    const float* hp0 = h2 + b0 * h2_sb + (long long)g * C2 * hw + pix0;
+    const float* hp1 = h2 + b1 * h2_sb + (long long)g * C2 * hw + pix1;
+    float2 h[C3P];
 #pragma unroll
-    for (int k = 0; k < C3P; ++k) h[k] = k < C3 ? s_b3[k] : 0.f;
-    // input channels in batches of 6: the six global loads of a batch are issued together (one load per iteration
+    for (int k = 0; k < C3P; ++k) h[k] = k < C3 ? make_float2(s_b3[k], s_b3[k]) : make_float2(0.f, 0.f);
+    // input channels in batches of 6: the twelve global loads of a batch are issued together (one load per iteration
     // made the loop a chain of C2 dependent DRAM round trips: 0.92 ms for 2.4 M samples, 10x over its instruction count)
     for (int c0 = 0; c0 < C2; c0 += 6) {
-      float v[6];
+      float2 v[6];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) v[j] = (c0 + j < C2) ? hp[(long long)(c0 + j) * hw] : 0.f;
+      for (int j = 0; j < 6; ++j)
+        v[j] = (c0 + j < C2) ? make_float2(hp0[(long long)(c0 + j) * hw], hp1[(long long)(c0 + j) * hw]) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         if (c0 + j < C2) {
@@ -119,32 +127,38 @@ __global__ void __launch_bounds__(RT_THREADS) cgp_tail_rate_kernel(
           for (int k = 0; k < C3P; k += 4)
             if (k < C3) {
               const float4 w = *reinterpret_cast<const float4*>(&s_w3[(c0 + j) * TL_MAXC3 + k]);
-              h[k] = fmaf(w.x, v[j], h[k]);
-              h[k + 1] = fmaf(w.y, v[j], h[k + 1]);
-              h[k + 2] = fmaf(w.z, v[j], h[k + 2]);
-              h[k + 3] = fmaf(w.w, v[j], h[k + 3]);
+              h[k] = __ffma2_rn(make_float2(w.x, w.x), v[j], h[k]);
+              h[k + 1] = __ffma2_rn(make_float2(w.y, w.y), v[j], h[k + 1]);
+              h[k + 2] = __ffma2_rn(make_float2(w.z, w.z), v[j], h[k + 2]);
+              h[k + 3] = __ffma2_rn(make_float2(w.w, w.w), v[j], h[k + 3]);
             }
         }
       }
     }
-    float sg = s_b4[0], mu = s_b4[1];
+    float2 sg = make_float2(s_b4[0], s_b4[0]), mu = make_float2(s_b4[1], s_b4[1]);
 #pragma unroll
     for (int k = 0; k < C3P; ++k)
       if (k < C3) {
-        const float a = h[k] < 0.f ? h[k] * 0.01f : h[k];
-        sg = fmaf(s_w4[k], a, sg);
-        mu = fmaf(s_w4[C3 + k], a, mu);
+        const float2 a = make_float2(h[k].x < 0.f ? h[k].x * 0.01f : h[k].x, h[k].y < 0.f ? h[k].y * 0.01f : h[k].y);
+        sg = __ffma2_rn(make_float2(s_w4[k], s_w4[k]), a, sg);
+        mu = __ffma2_rn(make_float2(s_w4[C3 + k], s_w4[C3 + k]), a, mu);
       }
-    const float xv = x[b * x_sb + (long long)g * hw + pix];
-    float y;
-    const float bt = gauss_bits(xv, sg, mu, noise ? &noise[(b * G + g) * hw + pix] : nullptr, y);
-    bits[b * bits_sb + (long long)g * hw + pix] = bt;
-    if (yout) yout[(b * G + g) * hw + pix] = y;
-    if (ms_out) {
-      ms_out[(b * 2 * G + 2 * g) * hw + pix] = sg;
-      ms_out[(b * 2 * G + 2 * g + 1) * hw + pix] = mu;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (s2 == 1 && !two) break;
+      const long long b = s2 ? b1 : b0, pix = s2 ? pix1 : pix0;
+      const float sgv = s2 ? sg.y : sg.x, muv = s2 ? mu.y : mu.x;
+      const float xv = x[b * x_sb + (long long)g * hw + pix];
+      float y;
+      const float bt = gauss_bits(xv, sgv, muv, noise ? &noise[(b * G + g) * hw + pix] : nullptr, y);
+      bits[b * bits_sb + (long long)g * hw + pix] = bt;
+      if (yout) yout[(b * G + g) * hw + pix] = y;
+      if (ms_out) {
+        ms_out[(b * 2 * G + 2 * g) * hw + pix] = sgv;
+        ms_out[(b * 2 * G + 2 * g + 1) * hw + pix] = muv;
+      }
+      local += bt;
     }
-    local += bt;
   }
   if (sum_out) {
     const float t = block_sum(local, red);
