@@ -42,15 +42,12 @@ SIGNATURES = {
     "ll_check_device": (c_int, []),
     "ll_sm_count": (c_int, []),
     "ll_pack_lift_step": (c_int, [_P] * 10 + [_P]),
-    "ll_lift_step": (c_int, [ctypes.POINTER(ll_lift_job), c_int, _P, c_float, c_float, c_int, _P]),
-    "ll_lift_set_mode": (c_int, [c_int]),
-    "ll_lift_get_mode": (c_int, []),
-    "ll_lift_set_debug_buffer": (c_int, [_P]),
+    "ll_lift_step": (c_int, [ctypes.POINTER(ll_lift_job), c_int, _P, c_float, c_float, c_int, c_int, _P]),
     "ll_lift_level_scratch_floats": (ctypes.c_size_t, [c_int, c_int, c_int]),
     "ll_lift_level_fwd": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, _P, c_int, c_int, c_int,
-                                  ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, _P]),
+                                  ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, c_int, _P]),
     "ll_lift_level_inv": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, _P, c_int, c_int, c_int,
-                                  ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, _P]),
+                                  ctypes.POINTER(c_voidp), c_float, c_int, c_int, _P, _P, c_int, _P]),
     "ll_dwt97_fwd_level": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, _P]),
     "ll_dwt97_inv_level": (c_int, [_P, c_i64, _P, c_i64, _P, c_i64, c_int, c_int, c_int, _P]),
     "ll_dwt97_scratch_floats": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
@@ -82,12 +79,45 @@ SIGNATURES = {
     "ll_gauss_rate": (c_int, [_P, c_i64, _P, c_i64, _P, _P, c_i64, _P, c_int, c_int, c_i64, _P, _P]),
     "ll_pack_eb": (c_int, [ctypes.POINTER(c_voidp), c_int, _P, _P]),
     "ll_eb_rate": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_i64, _P, _P]),
+}
+
+# libll_probe.so (include/ll_probe.h): measurement / unit probes, test and bench tooling only
+PROBE_SIGNATURES = {
     "ll_fma_peak_probe": (c_int, [_P, c_int, c_int, _P]),
     "ll_tc_tf32_probe": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "ll_tf32_peak_probe": (c_int, [_P, c_int, c_int, c_int, c_int, _P]),
+    "ll_last_error": (ctypes.c_char_p, []),
 }
 
 _lib = None
+_probe = None
 _device_ok = {}
+
+
+def load_probe():
+    """The probe library (``libll_probe.so``): not part of the product ABI."""
+    global _probe
+    if _probe is not None:
+        return _probe
+    try:
+        _build.build()
+    except Exception:
+        pass
+    path = _build.PROBE_LIB_PATH
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} is missing: run `python -m {__package__}.build`")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in PROBE_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _probe = lib
+    return lib
+
+
+def check_probe(rc):
+    if rc != LL_OK:
+        raise LLError(rc, load_probe().ll_last_error().decode(errors="replace"))
 
 
 def load(build_if_missing=True):

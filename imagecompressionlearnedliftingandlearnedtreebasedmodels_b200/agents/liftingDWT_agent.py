@@ -1,63 +1,86 @@
-"""``LiftingBasedDWTAgent``: the reference agent's data path (agents/liftingDWT_agent.py:14-190) on the B200 kernels.
+"""``LiftingBasedDWTAgent`` (reference: agents/liftingDWT_agent.py:14-390) on the B200 kernels.
 
-Scope: the agent's *computation* -- pre-processing, model forward, post-processing, the R-D scalars of
-``validate`` (:157-197) and one optimisation step of ``train_one_epoch`` (:78-125) -- behind the reference's constructor
-and method names.  The reference's loggers, Visdom, checkpoint bookkeeping of ``BaseAgent``, the image data loaders and the
-post-processing networks stay out of scope: ``data_loader`` is any iterable of RGB batches in [0, 1] handed in by the caller.
+Same constructor contract (``config``), loops and side effects as the reference: ``train_one_epoch`` (:75-111) zeroes
+and steps the optimiser on every batch, back-propagates ``rd_loss / grad_acc_iters``, switches from the distortion-only
+loss to R + lambda D when the running training MSE falls below ``loss_switch_thr`` (:103-109) and steps
+``ReduceLROnPlateau`` on the epoch's mean training loss (:110-111); ``validate`` (:154-201) has no side effect on the
+learning rate and returns the mean validation loss; ``test`` (:262-311) runs ``model.compress`` -- real bitstreams, for the
+entropy layers that have a parallel coder.  ``run / train / save_checkpoint / load_checkpoint / finalize`` come from
+``BaseAgent``.
 
 What changes on the B200 path: RGB->YCbCr / Y-0.5 is one pass (``ll_rgb_to_ycbcr_shift``); Y+0.5 /
 YCbCr->RGB / -0.5 / clamp / squared error is one pass (``ll_ycbcr_to_rgb_sse``) that leaves the per-image squared error
 in a double on the device; the bit sums are accumulated inside the rate kernels, so a validated batch costs one host
-synchronisation instead of four ``.item()`` calls and ~25 elementwise launches.
+synchronisation instead of four ``.item()`` calls and ~25 elementwise launches.  Under ``torch.distributed`` (one process
+per GPU) the gradients are averaged over ranks with bucketed all-reduces overlapped with backward
+(``parallel.GradientBuckets``); nothing else is exchanged.
+
+The image folder loaders (dataloaders/image_dl.py) are out of scope: ``data_loader`` is any object with
+``train_loader / valid_loader / test_loader`` iterables of RGB batches in [0, 1], or one iterable used for all three.
 """
 import math
 
 import torch
 from torch import optim
 
-from .. import ops
+from .. import ops, parallel
 from ..graphs.losses.rate_dist import TrainDLoss, TrainRDLoss
 from ..graphs.models.LiftingBasedDWT_net import LiftingBasedDWTNetWrapper
+from ..loggers import RDLogger
+from .base import BaseAgent
 
 
-def _cfg(config, key, default):
-    """Optional config key (EasyDict raises AttributeError, dict-backed configs KeyError)."""
-    try:
-        return getattr(config, key)
-    except (AttributeError, KeyError):
-        return default
+def configure_optimizers(net, lr):
+    """Adam over the trainable parameters in name order, one group (reference :369-389)."""
+    named = dict(net.named_parameters())
+    ordered = [named[n] for n in sorted(n for n, p in named.items() if p.requires_grad)]
+    return optim.Adam([{"params": ordered, "lr": lr}])
 
 
-def configure_optimizers(model, lr):
-    """Adam on every parameter (the reference's helper at the bottom of agents/liftingDWT_agent.py)."""
-    return optim.Adam((p for p in model.parameters() if p.requires_grad), lr=lr)
-
-
-class LiftingBasedDWTAgent:
+class LiftingBasedDWTAgent(BaseAgent):
     def __init__(self, config, data_loader=None, device=None):
-        self.config = config
+        super().__init__(config, device=device)
         self.clrch = config.clrch
-        self.device = torch.device(device if device is not None else "cuda:0")
-        # the reference sets it in its entry point; the recompute backward of train_batch runs torch
-        # convolutions and gains 35 % from the autotuned algorithms (381 vs 516 ms per config-4 step)
+        # the reference sets it at import (agents/base.py:9-10); the recompute backward of train_batch runs torch
+        # convolutions and gains 35 % from the autotuned algorithms
         torch.backends.cudnn.benchmark = True
-        self.lr = _cfg(config, "learning_rate", 1e-4)
         self.model = LiftingBasedDWTNetWrapper(config).to(self.device)
+        self.postprocessflag = self._get("postprocess", "none")
+        if self._get("mode", "train") == "train_postprocess" or self.postprocessflag not in ("none", None):
+            raise NotImplementedError("post-processing networks (postprocess != 'none') are outside the lifting hot path")
         self.optimizer = configure_optimizers(self.model, self.lr)
         self.scheduler = optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, factor=0.5, patience=5, threshold=0.0001,
                                                               threshold_mode='rel', cooldown=0, min_lr=1e-06, eps=1e-08)
-        self.grad_acc_iters = _cfg(config, "grad_acc_iters", 1)
+        self.grad_acc_iters = self._get("grad_acc_iters", 1)
+        self.loss_prnt_iters = self._get("loss_prnt_iters", 3600)
         self.lambda_ = config.lambda_
-        self.training_loss_switch = _cfg(config, "training_loss_switch", 1)
+        self.loss_switch_thr = self._get("loss_switch_thr", 0.0015)
+        self.training_loss_switch = self._get("training_loss_switch", 1)
         self.train_loss = TrainDLoss(config.lambda_) if self.training_loss_switch == 0 else TrainRDLoss(config.lambda_)
         self.valid_loss = TrainRDLoss(config.lambda_)
+        self.train_logger, self.trnit_logger = RDLogger(), RDLogger()
+        self.aux_logger, self.valid_logger, self.test_logger = RDLogger(), RDLogger(), RDLogger()
         self.data_loader = data_loader
-        self.current_epoch = 0
-        self.current_iteration = 0
+        self.imshow_validation = False
+        mode = self._get("mode", "train")
+        if mode in ("test", "validate", "validate_recu_reco"):
+            self.load_checkpoint("model_best.pth.tar")
+        elif self._get("resume_training", False):
+            self.load_checkpoint(self._get("checkpoint_file", "checkpoint.pth.tar"))
         # optional key (absent from the reference's JSON): replay the model forward of ``validate_batch`` as one CUDA graph
         # per input shape -- worth it for launch-bound inputs (tiles, small crops); weights must not change in between
-        self.cuda_graph = bool(_cfg(config, "cuda_graph", False))
+        self.cuda_graph = bool(self._get("cuda_graph", False))
         self._graphs = {}
+        self._buckets = None
+        self.last_validation = None
+        self.last_allreduce_collectives = 0
+
+    # ---- loaders ----
+    def _loader(self, which):
+        dl = self.data_loader
+        if dl is None:
+            raise RuntimeError(f"LiftingBasedDWTAgent: no data_loader was given (needed: {which})")
+        return getattr(dl, which) if hasattr(dl, which) else dl
 
     # ---- pre / post processing (:100-105, :164-181) ----
     def preprocess(self, x):
@@ -74,46 +97,97 @@ class LiftingBasedDWTAgent:
             return xhat, sse
         return ops.ycbcr_to_rgb_sse(yhat, x, want_xhat=True)
 
-    # ---- validate (:157-197) ----
-    @torch.no_grad()
-    def validate_batch(self, x):
-        """One batch of ``validate``: returns a dict of python floats (rd_loss, mse, psnr, rate1, rate2, bpp) with one
-        device->host transfer."""
-        self.model.eval()
-        x = x.to(self.device)
-        y = self.preprocess(x)
+    # ---- validate (:154-201) ----
+    def _forward_eval(self, y):
         if self.cuda_graph:
             key = (tuple(y.shape), y.dtype)
             if key not in self._graphs:
                 from ..utils.cuda_graph import GraphedForward
                 self._graphs[key] = GraphedForward(self.model, y)
-            yhat, si_xe, si_xo = self._graphs[key](y)
-        else:
-            yhat, si_xe, si_xo = self.model(y)
+            return self._graphs[key](y)
+        return self.model(y)
+
+    @torch.no_grad()
+    def validate_batch_async(self, x):
+        """Enqueue one batch of ``validate`` and return the device tensor [sse, bits_xe, bits_xo] (float64) without
+        synchronising with the host; ``x`` may be a pinned host tensor (copied with ``non_blocking``)."""
+        self.model.eval()
+        x = x.to(self.device, non_blocking=True)
+        y = self.preprocess(x)
+        yhat, si_xe, si_xo = self._forward_eval(y)
         _, sse = self.postprocess(yhat, x)
-        n = x.numel()
-        vals = torch.stack([sse.sum(), si_xe.double().sum(), sum(s.double().sum() for s in si_xo)]).cpu()
-        mse = float(vals[0]) / n
-        rate1, rate2 = float(vals[1]) / n * 3, float(vals[2]) / n * 3          # rate_dist.py:37-41
-        return {"rd_loss": rate1 + rate2 + self.lambda_ * mse, "mse": mse, "psnr": 10.0 * math.log10(1.0 / mse) if mse > 0 else float("inf"),
+        return torch.stack([sse.sum(), si_xe.double().sum(), sum(s.double().sum() for s in si_xo)])
+
+    def _rd_scalars(self, vals, numel):
+        mse = float(vals[0]) / numel
+        rate1, rate2 = float(vals[1]) / numel * 3, float(vals[2]) / numel * 3          # rate_dist.py:37-41
+        return {"rd_loss": rate1 + rate2 + self.lambda_ * mse, "mse": mse,
+                "psnr": 10.0 * math.log10(1.0 / mse) if mse > 0 else float("inf"),
                 "rate1": rate1, "rate2": rate2, "bpp": rate1 + rate2}
 
     @torch.no_grad()
-    def validate(self):
-        if self.data_loader is None:
-            raise RuntimeError("LiftingBasedDWTAgent.validate: no data_loader was given")
-        rows = [self.validate_batch(x) for x in self.data_loader]
-        if not rows:
-            raise RuntimeError("LiftingBasedDWTAgent.validate: the data_loader is empty")
-        avg = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
-        self.scheduler.step(avg["rd_loss"])
-        return avg
+    def validate_batch(self, x):
+        """One batch of ``validate``: returns a dict of python floats (rd_loss, mse, psnr, rate1, rate2, bpp) with one
+        device->host transfer."""
+        return self._rd_scalars(self.validate_batch_async(x).cpu(), x.numel())
 
-    # ---- one optimisation step of train_one_epoch (:78-125) ----
+    @torch.no_grad()
+    def validate(self):
+        rows = []
+        for x in self._loader("valid_loader"):
+            r = self.validate_batch(x)
+            self.valid_logger(r["rd_loss"], r["mse"], r["rate1"], r["rate2"])
+            rows.append(r)
+        if not rows:
+            raise RuntimeError("LiftingBasedDWTAgent.validate: the valid_loader is empty")
+        valid_rd_loss, _, _, _ = self.valid_logger.display(lr=0.0, typ="va")
+        self.last_validation = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
+        print(f" avg_psnr = {self.last_validation['psnr']:.2f}, rate_1 = {self.last_validation['rate1']}, "
+              f"rate_2 ={self.last_validation['rate2']}, total_rate = {self.last_validation['bpp']}")
+        return valid_rd_loss
+
+    @torch.no_grad()
+    def validate_recu_reco(self):
+        self.model.eval()      # the reference's body is ``pass`` (:256-259)
+
+    # ---- test (:262-311): real coding ----
+    @torch.no_grad()
+    def test(self):
+        """``model.compress`` per batch -> PSNR and the bits actually spent (bpp of the LL band and of the detail subbands).
+        Only the entropy layers with a parallel coder implement it; ``conditioned2ZTsepSubbands`` (the reference's serial
+        per-coefficient coder) raises ``NotImplementedError`` from ``compress``."""
+        self.model.eval()
+        psnr, r_hi, r_lo = [], [], []
+        for x in self._loader("test_loader"):
+            x = x.to(self.device)
+            yhat, len_xe, len_xo = self.model.compress(self.preprocess(x))
+            _, sse = self.postprocess(yhat, x)
+            mse = float(sse.sum()) / x.numel()
+            psnr.append(10.0 * math.log10(1.0 / mse) if mse > 0 else float("inf"))
+            r_hi.append(len_xo)
+            r_lo.append(len_xe)
+        if not psnr:
+            raise RuntimeError("LiftingBasedDWTAgent.test: the test_loader is empty")
+        avg = lambda v: sum(v) / len(v)
+        self.last_test = {"psnr": avg(psnr), "rate_high": avg(r_hi), "rate_low": avg(r_lo), "bpp": avg(r_hi) + avg(r_lo)}
+        print(f" avg_psnr = {self.last_test['psnr']:.2f}, rate_high = {self.last_test['rate_high']}, "
+              f"rate_low ={self.last_test['rate_low']}, total_rate = {self.last_test['bpp']}")
+        return True
+
+    # ---- one optimisation step of train_one_epoch (:78-101) ----
+    def _zero_grad(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            if self._buckets is None:
+                self._buckets = parallel.GradientBuckets(self.model.parameters())
+            self._buckets.zero()
+        else:
+            self.optimizer.zero_grad()
+
     def train_batch(self, x):
         self.model.train()
         self._graphs.clear()          # captured graphs read packed copies of the weights this step is about to change
-        x = x.to(self.device)
+        self._zero_grad()
+        x = x.to(self.device, non_blocking=True)
         y = self.preprocess(x)
         yhat, si_xe, si_xo = self.model(y)
         if self.clrch == 3:
@@ -124,15 +198,38 @@ class LiftingBasedDWTAgent:
             xs, xhat = x - 0.5, YCbCr2RGB()(yhat + shift) - 0.5
         rd_loss, mse_loss, rate1, rate2 = self.train_loss.forward3(xs, xhat, si_xe, si_xo)
         (rd_loss / self.grad_acc_iters).backward()
+        if self._buckets is not None:
+            self.last_allreduce_collectives = self._buckets.finish()
+        self.optimizer.step()
         self.current_iteration += 1
-        if self.current_iteration % self.grad_acc_iters == 0:
-            self.optimizer.step()
-            self.optimizer.zero_grad()
         return rd_loss.detach(), mse_loss.detach(), rate1.detach(), torch.as_tensor(rate2).detach()
 
     def train_one_epoch(self):
-        if self.data_loader is None:
-            raise RuntimeError("LiftingBasedDWTAgent.train_one_epoch: no data_loader was given")
-        out = [self.train_batch(x) for x in self.data_loader]
-        self.current_epoch += 1
+        out = []
+        for x in self._loader("train_loader"):
+            vals = self.train_batch(x)
+            out.append(vals)
+            scal = [float(v) for v in vals]
+            self.train_logger(*scal)
+            self.trnit_logger(*scal)
+            if (self.current_iteration + 1) % self.loss_prnt_iters == 0:
+                _, it_mse, _, _ = self.trnit_logger.display(lr=self.optimizer.param_groups[0]["lr"], typ="it")
+                if it_mse < self.loss_switch_thr and self.training_loss_switch == 0:
+                    self.train_loss = TrainRDLoss(self.lambda_)
+                    print("Switching training loss to Rate+lambda*Distortion (it was only lambda*Distortion up to here)")
+                    self.training_loss_switch = 1
+        if not out:
+            raise RuntimeError("LiftingBasedDWTAgent.train_one_epoch: the train_loader is empty")
+        train_rd_loss, _, _, _ = self.train_logger.display(lr=self.optimizer.param_groups[0]["lr"], typ="tr")
+        self.scheduler.step(train_rd_loss)
         return out
+
+    def model_size_estimation(self, print_params=False):
+        """(param MB, buffer MB) of the model (:313-366)."""
+        ps = sum(p.nelement() * p.element_size() for p in self.model.parameters())
+        bs = sum(b.nelement() * b.element_size() for b in self.model.buffers())
+        if print_params:
+            for n, p in self.model.named_parameters():
+                print(n, tuple(p.shape))
+        print(" model param+buffer=total size: {:.2f}+{:.2f}={:.2f}MB".format(ps / 1024 ** 2, bs / 1024 ** 2, (ps + bs) / 1024 ** 2))
+        return ps / 1024 ** 2, bs / 1024 ** 2

@@ -12,6 +12,8 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libll_b200.so")
+# measurement / unit probes (include/ll_probe.h): test and bench tooling, kept out of the product library
+PROBE_LIB_PATH = os.path.join(PKG_DIR, "libll_probe.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -23,33 +25,47 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale():
-    if not os.path.isfile(LIB_PATH):
+def probe_sources():
+    return sorted(glob.glob(os.path.join(CSRC, "probe", "*.cu"))) + [os.path.join(CSRC, "ll_api.cu")]
+
+
+def _headers():
+    inc = os.path.join(os.path.dirname(PKG_DIR), "include")
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+        [os.path.join(inc, "ll_api.h"), os.path.join(inc, "ll_probe.h")]
+
+
+def _stale(lib, srcs):
+    if not os.path.isfile(lib):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
-        [os.path.join(os.path.dirname(PKG_DIR), "include", "ll_api.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    t = os.path.getmtime(lib)
+    return any(os.path.getmtime(d) > t for d in srcs + _headers() if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile every ``csrc/*.cu`` for sm_100a into ``libll_b200.so``.  Returns the path."""
-    if not force and not _stale():
-        return LIB_PATH
+def _compile(lib, srcs, log_name, verbose):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: cannot build libll_b200.so")
-    tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources()
+        raise RuntimeError(f"nvcc not found: cannot build {os.path.basename(lib)}")
+    tmp = lib + ".tmp"
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + srcs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
-    with open(os.path.join(PKG_DIR, "build.log"), "w") as f:
+    with open(os.path.join(PKG_DIR, log_name), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + log[-4000:])
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, lib)
     if verbose:
         print(log)
+
+
+def build(force=False, verbose=False):
+    """Compile every ``csrc/*.cu`` for sm_100a into ``libll_b200.so`` (the product ABI, ``include/ll_api.h``) and
+    ``csrc/probe/*.cu`` into ``libll_probe.so`` (``include/ll_probe.h``).  Returns the product library's path."""
+    if force or _stale(LIB_PATH, sources()):
+        _compile(LIB_PATH, sources(), "build.log", verbose)
+    if force or _stale(PROBE_LIB_PATH, probe_sources()):
+        _compile(PROBE_LIB_PATH, probe_sources(), "build_probe.log", verbose)
     return LIB_PATH
 
 

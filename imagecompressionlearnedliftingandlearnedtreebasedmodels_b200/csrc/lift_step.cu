@@ -7,9 +7,10 @@ namespace ll {
 
 int launch_lift_step_tc(const LiftParams& p, cudaStream_t stream);                                  // lift_tc.cu
 int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream);         // lift_tc.cu
-static int g_lift_mode = LL_LIFT_TC;
+#ifdef LL_DEBUG   // timing experiments of the tensor-core kernel (scripts/gpu_lift_tc_time*.py); not in release builds
 static int g_lift_dbg = 0;
 static long long* g_lift_dbg_buf = nullptr;
+#endif
 
 __global__ void __launch_bounds__(LS_THREADS, 1) lift_step_kernel(const __grid_constant__ LiftParams p) {
   extern __shared__ __align__(16) float sm[];
@@ -48,7 +49,9 @@ __global__ void scale2_kernel(float* __restrict__ a, long long a_sb, long long a
 }
 
 static int launch_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float rw, int linear,
-                            cudaStream_t stream) {
+                            int precision, cudaStream_t stream) {
+  if (precision != LL_LIFT_FP32 && precision != LL_LIFT_TC)
+    return fail(LL_EINVAL, "ll_lift_step: unknown precision %d (LL_LIFT_FP32 = 0, LL_LIFT_TC = 1)", precision);
   if (njobs < 1 || njobs > 2) return fail(LL_EINVAL, "ll_lift_step: njobs must be 1 or 2 (got %d)", njobs);
   if (!blob) return fail(LL_EINVAL, "ll_lift_step: null blob");
   LiftParams p;
@@ -77,9 +80,11 @@ static int launch_lift_step(const ll_lift_job* jobs, int njobs, const float* blo
     p.total_units += p.units[j];
   }
   if (p.total_units == 0) return LL_OK;  // empty input: nothing to do
+#ifdef LL_DEBUG
   p.dbg = g_lift_dbg;
   p.dbg_buf = g_lift_dbg_buf;
-  if (g_lift_mode == LL_LIFT_TC) return launch_lift_step_tc(p, stream);
+#endif
+  if (precision == LL_LIFT_TC) return launch_lift_step_tc(p, stream);
   static thread_local bool attr_set[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
@@ -108,8 +113,9 @@ struct CudaBackend {
   cudaStream_t st;
   float rw;
   int linear;
+  int precision;
   int step(const ll_lift_job* jobs, int n, const float* blob, float sign) {
-    return launch_lift_step(jobs, n, blob, sign, rw, linear, st);
+    return launch_lift_step(jobs, n, blob, sign, rw, linear, precision, st);
   }
   int scale(ll_view3 v, int nb, int ny, int nx, const float* n, float base, int divide) {
     return launch_scale(v, nb, ny, nx, n, base, divide, st);
@@ -136,48 +142,44 @@ int ll_pack_lift_step(const float* pre_w, const float* w1, const float* b1, cons
   return launch_pack_lift_tc(w2, w3, blob, as_stream(stream));
 }
 
-int ll_lift_set_mode(int mode) {
-  g_lift_dbg = mode >> 8;   // undocumented: timing experiments (results are wrong when non-zero)
-  mode &= 0xff;
-  if (mode != LL_LIFT_FP32 && mode != LL_LIFT_TC) return fail(LL_EINVAL, "ll_lift_set_mode: unknown mode %d", mode);
-  g_lift_mode = mode;
+#ifdef LL_DEBUG
+int ll_dbg_lift_switches(int bits) {   // bit 0 no MMA, 1 no E-B, 2 no conv1, 3 no conv4, 4 no E-A: results are WRONG when non-zero
+  g_lift_dbg = bits;
   return LL_OK;
 }
-
-int ll_lift_get_mode(void) { return g_lift_mode; }
-
-int ll_lift_set_debug_buffer(long long* buf) {   // undocumented: per-warp phase timestamps (17 x 8 int64)
+int ll_dbg_lift_stamp_buffer(long long* buf) {   // per-warp phase timestamps (17 x 8 int64) of CTA 0
   g_lift_dbg_buf = buf;
   return LL_OK;
 }
+#endif
 
 int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float res_weight, int linear,
-                 ll_stream_t stream) {
+                 int precision, ll_stream_t stream) {
   if (!jobs) return fail(LL_EINVAL, "ll_lift_step: null jobs");
-  return launch_lift_step(jobs, njobs, blob, sign, res_weight, linear, as_stream(stream));
+  return launch_lift_step(jobs, njobs, blob, sign, res_weight, linear, precision, as_stream(stream));
 }
 
 size_t ll_lift_level_scratch_floats(int B, int h, int w) { return lift_level_scratch_floats(B, h, w); }
 
 int ll_lift_level_fwd(const float* x, int64_t x_sb, float* llp, int64_t ll_sb, float* yh, int64_t yh_sb,
                       float* scratch, int B, int h, int w, const float* const* blobs, float rw, int linear,
-                      int scale, const float* nh, const float* nl, ll_stream_t stream) {
+                      int scale, const float* nh, const float* nl, int precision, ll_stream_t stream) {
   if (B < 0 || h < 0 || w < 0 || (h & 1) || (w & 1)) return fail(LL_EINVAL, "ll_lift_level_fwd: h, w must be even (got %d x %d)", h, w);
   if ((long long)B * h * w == 0) return LL_OK;
   if (!x || !llp || !yh || !scratch || !blobs) return fail(LL_EINVAL, "ll_lift_level_fwd: null pointer");
   if (scale && (!nh || !nl)) return fail(LL_EINVAL, "ll_lift_level_fwd: scale=1 needs nh, nl");
-  CudaBackend be{as_stream(stream), rw, linear};
+  CudaBackend be{as_stream(stream), rw, linear, precision};
   return lift_level_fwd_impl(be, x, x_sb, llp, ll_sb, yh, yh_sb, scratch, B, h, w, blobs, scale, nh, nl);
 }
 
 int ll_lift_level_inv(const float* llp, int64_t ll_sb, const float* yh, int64_t yh_sb, float* x, int64_t x_sb,
                       float* scratch, int B, int h, int w, const float* const* blobs, float rw, int linear,
-                      int scale, const float* nh, const float* nl, ll_stream_t stream) {
+                      int scale, const float* nh, const float* nl, int precision, ll_stream_t stream) {
   if (B < 0 || h < 0 || w < 0 || (h & 1) || (w & 1)) return fail(LL_EINVAL, "ll_lift_level_inv: h, w must be even (got %d x %d)", h, w);
   if ((long long)B * h * w == 0) return LL_OK;
   if (!x || !llp || !yh || !scratch || !blobs) return fail(LL_EINVAL, "ll_lift_level_inv: null pointer");
   if (scale && (!nh || !nl)) return fail(LL_EINVAL, "ll_lift_level_inv: scale=1 needs nh, nl");
-  CudaBackend be{as_stream(stream), rw, linear};
+  CudaBackend be{as_stream(stream), rw, linear, precision};
   return lift_level_inv_impl(be, llp, ll_sb, yh, yh_sb, x, x_sb, scratch, B, h, w, blobs, scale, nh, nl);
 }
 

@@ -1,7 +1,8 @@
 // probe.cu -- measurement helper: FP32 FMA-pipe peak of the device (register-only FFMA2 loop).
 // Used by bench.py as the measured denominator of the learned-lifting kernels' roofline
 // (MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only).
-#include "ll_common.cuh"
+#include "../ll_common.cuh"
+#include "../../../include/ll_probe.h"
 
 namespace ll {
 

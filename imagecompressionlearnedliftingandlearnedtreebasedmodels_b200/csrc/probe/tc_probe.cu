@@ -7,8 +7,9 @@
 // this shape can be measured (ll_tc_tf32_probe returns SM cycles per chain).
 #include <stdint.h>
 
-#include "ll_common.cuh"
-#include "tc_ptx.cuh"
+#include "../ll_common.cuh"
+#include "../../../include/ll_probe.h"
+#include "../tc_ptx.cuh"
 
 namespace ll {
 

@@ -28,6 +28,7 @@ class P_block_v2(nn.Module):
         self.conv4 = nn.Conv2d(d * csize, 1 * csize, k, stride=1, padding=p)
         self.linearityFlag = linearity_flag
         self.nonLinearityFunction = nn.Tanh()
+        self.lift_precision = "tc"
 
     def params(self):
         return {k: (getattr(self, k).weight, getattr(self, k).bias) for k in ("conv1", "conv2", "conv3", "conv4")}
@@ -40,5 +41,5 @@ class P_block_v2(nn.Module):
         B, C, h, w = x.shape
         out = torch.empty_like(x)
         v = x.view(B * C, h, w)
-        ops.lift_step([(v, v, out.view(B * C, h, w))], blob, 0.0, 1.0, self.linearityFlag != 1)
+        ops.lift_step([(v, v, out.view(B * C, h, w))], blob, 0.0, 1.0, self.linearityFlag != 1, self.lift_precision)
         return out

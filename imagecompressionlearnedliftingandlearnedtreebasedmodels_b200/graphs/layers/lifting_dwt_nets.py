@@ -69,9 +69,10 @@ class SubbandAutoEncoder(nn.Module):
 
 
 class SubbandAutoEncoderBerk(nn.Module):
-    """3x3 conv + GDN / inverse-GDN scaling network (lifting_dwt_nets.py:126-165).
-    SURVEY.md 8f "next #1": runs through torch CUDA ops (cuDNN, TF32 off because it feeds
-    the quantiser) until its fused fp32 kernel lands."""
+    """3x3 conv + GDN / inverse-GDN scaling network (lifting_dwt_nets.py:126-165).  It feeds the quantiser, so it runs
+    at fp32-level accuracy: convs 2-3 and the three GDN norms as 3xTF32 tcgen05 implicit GEMMs (csrc/igemm_conv.cu),
+    the first / last conv on the exact FP32 kernels.  With autograd on (training), forward and backward run through torch
+    fp32 ops (TF32 off) -- the recompute path of ``_autograd`` -- there is no inference-time backend switch."""
 
     def __init__(self, in_ch):
         super().__init__()
@@ -86,8 +87,6 @@ class SubbandAutoEncoderBerk(nn.Module):
             nn.ConvTranspose2d(iC * H // 2, iC * H, kernel_size=K, stride=1, padding=P), GDN(iC * H, inverse=True),
             nn.ConvTranspose2d(iC * H, iC * H // 2, kernel_size=K, stride=1, padding=P), GDN(iC * H // 2, inverse=True),
             nn.ConvTranspose2d(iC * H // 2, iC * 1, kernel_size=K, stride=1, padding=P))
-        # "tc": 3xTF32 tensor-core chain (default, inference); "torch": torch fp32 convs (also used whenever autograd is on)
-        self.ae_precision = "tc"
         self._down_cache, self._up_cache = PackCache(), PackCache()
 
     @staticmethod
@@ -144,8 +143,7 @@ class SubbandAutoEncoderBerk(nn.Module):
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     def _use_tc(self, x):
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        return self.ae_precision == "tc" and not need_grad
+        return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
 
     def encode(self, x):
         if self._use_tc(x):
@@ -217,7 +215,8 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
         self.config = config
         # new optional key (default keeps reference configs valid): "tc" = conv2/conv3 of every lifting step
         # on tcgen05 with the 3xTF32 split (fp32-level accuracy), "fp32" = all layers on the FP32 FMA pipe
-        self.lift_precision = config.get("lift_precision", "tc") if hasattr(config, "get") else getattr(config, "lift_precision", "tc")
+        self._lift_precision = config.get("lift_precision", "tc") if hasattr(config, "get") else getattr(config, "lift_precision", "tc")
+        ops.lift_precision_code(self._lift_precision)
         self.depth_scale = config.depth_scale * 8
         self.preProcessingList = self.preProcessBlock(config.clrch, config.filtersize)
         if config.autoencoder == "SubbandAutoEncoder":
@@ -255,9 +254,20 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
             self.waveletInverse.append(wavelet_inverse_v2(Pi, Ui, self.res_connection_weight, n, self.preProcessingList,
                                                           self.config, self.nh, self.nl))
 
+    @property
+    def lift_precision(self):
+        return self._lift_precision
+
+    @lift_precision.setter
+    def lift_precision(self, mode):
+        """Per-module arithmetic of the lifting kernels (handed to every launch; nothing is process-wide)."""
+        ops.lift_precision_code(mode)
+        self._lift_precision = mode
+        for m in list(self.waveletForward) + list(self.waveletInverse):
+            m.lift_precision = mode
+
     def transform(self, input):
         """The lifting levels alone: x -> (LL, [Yh_l (B,3,h,w)])."""
-        ops.set_lift_mode(self.lift_precision)
         Yh = []
         ll = input
         for lvl in range(self.waveletLevel):
@@ -266,7 +276,6 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
         return ll, Yh
 
     def inverse_transform(self, Yl, Yh):
-        ops.set_lift_mode(self.lift_precision)
         ll = Yl
         for lvl in range(self.waveletLevel - 1, -1, -1):
             ll = self.waveletInverse[lvl].level(ll, Yh[lvl])

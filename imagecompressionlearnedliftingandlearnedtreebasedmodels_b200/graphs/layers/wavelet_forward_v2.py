@@ -54,6 +54,8 @@ class wavelet_forward_v2(nn.Module):
         self.nh = nh
         self.nl = nl
         self.scale = cfg.scale
+        # optional key: "tc" (conv2/conv3 on tcgen05, 3xTF32 split) | "fp32" (all layers on the FP32 FMA pipe)
+        self.lift_precision = cfg.get("lift_precision", "tc") if hasattr(cfg, "get") else getattr(cfg, "lift_precision", "tc")
         self._cache = PackCache()
 
     def _blobs(self):
@@ -74,11 +76,11 @@ class wavelet_forward_v2(nn.Module):
         if _autograd.needs_grad([x] + params):
             # training: forward on the fused kernels, backward by recomputation in torch (see _autograd.py)
             fast = lambda x, *ps: ops.lift_level_fwd(x, self._blobs(), self.resnet_weight, self._linear(), scale,
-                                                     self.nh if scale else None, self.nl if scale else None)
+                                                     self.nh if scale else None, self.nl if scale else None, precision=self.lift_precision)
             ref = lambda x, *ps: _torch_ref.lift_level_fwd(x, ps, self.resnet_weight, self._linear(), scale)
             return _autograd.run(fast, ref, [x] + params)
         return ops.lift_level_fwd(x, self._blobs(), self.resnet_weight, self._linear(), scale,
-                                  self.nh if scale else None, self.nl if scale else None, ll_out, yh_out)
+                                  self.nh if scale else None, self.nl if scale else None, ll_out, yh_out, precision=self.lift_precision)
 
     def lifting_forward_row_2_stage_lifting(self, L, H):
         """Four lifting steps along dim 2 of the (B,1,n,m) halves (wavelet_forward_v2.py:58-81)."""
@@ -87,10 +89,10 @@ class wavelet_forward_v2(nn.Module):
         Lv, Hv = L.reshape(B * C, n, m), H.reshape(B * C, n, m)
         Lo, Ho = torch.empty_like(Lv, memory_format=torch.contiguous_format), torch.empty_like(Hv, memory_format=torch.contiguous_format)
         lin = self._linear()
-        ops.lift_step([(Lv, Hv, Ho)], blobs[0], 1.0, self.resnet_weight, lin)
-        ops.lift_step([(Ho, Lv, Lo)], blobs[1], 1.0, self.resnet_weight, lin)
-        ops.lift_step([(Lo, Ho, Ho)], blobs[2], 1.0, self.resnet_weight, lin)
-        ops.lift_step([(Ho, Lo, Lo)], blobs[3], 1.0, self.resnet_weight, lin)
+        ops.lift_step([(Lv, Hv, Ho)], blobs[0], 1.0, self.resnet_weight, lin, self.lift_precision)
+        ops.lift_step([(Ho, Lv, Lo)], blobs[1], 1.0, self.resnet_weight, lin, self.lift_precision)
+        ops.lift_step([(Lo, Ho, Ho)], blobs[2], 1.0, self.resnet_weight, lin, self.lift_precision)
+        ops.lift_step([(Ho, Lo, Lo)], blobs[3], 1.0, self.resnet_weight, lin, self.lift_precision)
         Lo, Ho = Lo.view(B, C, n, m), Ho.view(B, C, n, m)
         if self.scale == 1:
             Ho = Ho * (lifting_coeff[4] + self.nh * 0.1)

@@ -23,6 +23,8 @@ class wavelet_inverse_v2(nn.Module):
         self.nh = nh
         self.nl = nl
         self.config = cfg
+        # optional key: "tc" (conv2/conv3 on tcgen05, 3xTF32 split) | "fp32" (all layers on the FP32 FMA pipe)
+        self.lift_precision = cfg.get("lift_precision", "tc") if hasattr(cfg, "get") else getattr(cfg, "lift_precision", "tc")
         self._cache = PackCache()
 
     def _blobs(self):
@@ -39,7 +41,7 @@ class wavelet_inverse_v2(nn.Module):
         scale = 1 if self.scale == 1 else 0
         params = step_params(self.P, self.U, self.convBlock, self.nh, self.nl, LL)
         fast = lambda ll, yh, *ps: ops.lift_level_inv(ll, yh, self._blobs(), self.resnet_coeff, self._linear(), scale,
-                                                      self.nh if scale else None, self.nl if scale else None)
+                                                      self.nh if scale else None, self.nl if scale else None, precision=self.lift_precision)
         ref = lambda ll, yh, *ps: _torch_ref.lift_level_inv(ll, yh, ps, self.resnet_coeff, self._linear(), scale)
         return _autograd.run(fast, ref, [LL, Yh] + params)
 
@@ -61,8 +63,8 @@ class wavelet_inverse_v2(nn.Module):
         Lv, Hv = L.reshape(B * C, n, m), H.reshape(B * C, n, m)
         Lo, Ho = torch.empty_like(Lv, memory_format=torch.contiguous_format), torch.empty_like(Hv, memory_format=torch.contiguous_format)
         lin = self._linear()
-        ops.lift_step([(Hv, Lv, Lo)], blobs[3], -1.0, self.resnet_coeff, lin)
-        ops.lift_step([(Lo, Hv, Ho)], blobs[2], -1.0, self.resnet_coeff, lin)
-        ops.lift_step([(Ho, Lo, Lo)], blobs[1], -1.0, self.resnet_coeff, lin)
-        ops.lift_step([(Lo, Ho, Ho)], blobs[0], -1.0, self.resnet_coeff, lin)
+        ops.lift_step([(Hv, Lv, Lo)], blobs[3], -1.0, self.resnet_coeff, lin, self.lift_precision)
+        ops.lift_step([(Lo, Hv, Ho)], blobs[2], -1.0, self.resnet_coeff, lin, self.lift_precision)
+        ops.lift_step([(Ho, Lo, Lo)], blobs[1], -1.0, self.resnet_coeff, lin, self.lift_precision)
+        ops.lift_step([(Lo, Ho, Ho)], blobs[0], -1.0, self.resnet_coeff, lin, self.lift_precision)
         return Lo.view(B, C, n, m), Ho.view(B, C, n, m)

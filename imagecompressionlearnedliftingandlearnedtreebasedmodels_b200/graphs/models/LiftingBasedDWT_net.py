@@ -385,6 +385,16 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
 
         return self._tc_cache[i].get(srcs, build)
 
+    def _tc_fits(self, i):
+        """The tensor-core layout holds 3 subbands x <= 128 channels (clrch = 1); other reference-valid shapes
+        (clrch = 3: 9 subbands per level) take the exact-fp32 ``_level`` path."""
+        C = self.sos[i]
+        nper = self.plc_list[i][0].out_channels // C
+        n1, n2 = self.cgp_out_xo_list[i][0].out_channels // C, self.cgp_out_xo_list[i][2].out_channels // C
+        starts = [(nper * g) // 64 * 64 for g in range(C)]
+        return C <= 3 and nper <= 128 and all(nper * g + nper <= starts[g] + 128 for g in range(C)) and \
+            C * nper <= 256 and n1 <= 192 and n2 <= 64
+
     def _level_bits_tc(self, i, x, q, con, noise, acc):
         """Self-information (B,3,h,w) of conditioned level i on the tensor cores: head -> plc igemm and
         csc land in one NHWC bf16 tensor; cgp layers 1-2 are grouped 1x1 igemms; layers 3-4 are fused
@@ -431,10 +441,13 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         B, C, h, w = x.shape
         ms = torch.empty(B, 2 * C, h, w, dtype=torch.float32, device=x.device)
         plc, cgp, csc = self.plc_list[i], self.cgp_out_xo_list[i], self.csc_list[i]
-        nper = plc[0].out_channels // C        # 81
+        # the reference chunks plc / csc 3-way whatever clrch is (:357-359); with clrch = 1 a chunk = one subband's 81 channels
+        nper = plc[2].out_channels // 3
+        if csc.out_channels != plc[2].out_channels:
+            raise ValueError("conditioned2ZT: plc and csc widths differ (parent and child levels need equal channel counts)")
         for b0 in range(0, B, CTX_BATCH_CHUNK):
             b1 = min(B, b0 + CTX_BATCH_CHUNK)
-            cat = torch.empty(b1 - b0, 2 * nper * C, h, w, dtype=torch.float32, device=x.device)
+            cat = torch.empty(b1 - b0, 2 * nper * 3, h, w, dtype=torch.float32, device=x.device)
             # (plc0, csc0, plc1, csc1, plc2, csc2) channel order of :357-359 as write patterns
             csc(q[b0:b1], out=cat, co_group=nper, co_stride=2 * nper, co_off=nper)
             t = ops.conv2d(con[b0:b1], plc[0].weight, plc[0].bias, lrelu=True, upsample2=True)
@@ -458,10 +471,14 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         con = q
         for i in range(L - 2, -1, -1):
             q = self.ent_out_xo_list[i].quantize(out_xo_list[i], mode)
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            lvl_params = list(self.plc_list[i].parameters()) + list(self.cgp_out_xo_list[i].parameters()) + \
+                list(self.csc_list[i].parameters())
+            if _autograd.needs_grad([out_xo_list[i], q, con] + lvl_params):
+                # a gradient is needed through this level: by its own parameters, or -- frozen entropy model, trainable
+                # transform -- by the subbands alone (the rate term must reach the lifting CNNs either way)
                 ms = self._level_grad(i, out_xo_list[i], q, con)
                 sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], ms, self.training, acc=acc))
-            elif self.ctx_precision == "bf16":
+            elif self.ctx_precision == "bf16" and self._tc_fits(i):
                 noise = compat.draw_noise(out_xo_list[i]) if self.training else None
                 sis.append(self._level_bits_tc(i, out_xo_list[i].contiguous(), q, con, noise, acc))
             else:
@@ -680,7 +697,7 @@ class onlyEZWT(nn.Module):
         """(sigma, mu) of level i from the dequantised parent level ``con`` (B,3,h/2,w/2) -> (B,6,h,w) (:826-831)."""
         plc = self.plc_list[i]
         B = con.shape[0]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in plc.parameters()):
+        if _autograd.needs_grad([con] + list(plc.parameters())):
             return _chain(plc[2:], _conv(plc[0], con, lrelu=True, upsample2=True))   # differentiable, whole batch
         ms = torch.empty(B, 6, 2 * con.shape[2], 2 * con.shape[3], dtype=torch.float32, device=con.device)
         # fp32-level accuracy on purpose: this layer's mu is part of the *dequantised* output (round(x - mu) + mu, :832)

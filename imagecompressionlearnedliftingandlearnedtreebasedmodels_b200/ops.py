@@ -37,17 +37,13 @@ def _f32c(t, name):
 LIFT_FP32, LIFT_TC = 0, 1
 
 
-def set_lift_mode(mode):
-    """Arithmetic of the learned-lifting kernels: ``"tc"`` (default: conv2/conv3 on tcgen05, 3xTF32 split,
-    fp32-level accuracy) or ``"fp32"`` (everything on the FP32 FMA pipe)."""
+def lift_precision_code(mode):
+    """``"tc"`` (default: conv2/conv3 on tcgen05, 3xTF32 split, fp32-level accuracy) or ``"fp32"`` (everything on the
+    FP32 FMA pipe) -> the ``precision`` argument of the lifting entry points (per call; nothing is process-wide)."""
     m = {"tc": LIFT_TC, "3xtf32": LIFT_TC, "fp32": LIFT_FP32, LIFT_TC: LIFT_TC, LIFT_FP32: LIFT_FP32}.get(mode)
     if m is None:
-        raise ValueError(f"set_lift_mode: unknown mode {mode!r}")
-    check(_lib.load().ll_lift_set_mode(m))
-
-
-def get_lift_mode():
-    return "tc" if _lib.load().ll_lift_get_mode() == LIFT_TC else "fp32"
+        raise ValueError(f"unknown lifting precision {mode!r} (\"tc\" | \"fp32\")")
+    return m
 
 
 def pack_lift_step(pre_w, conv):
@@ -77,7 +73,8 @@ def _blob_array(blobs):
     return (c_voidp * 4)(*[ptr(b) for b in blobs])
 
 
-def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, ll_out=None, yh_out=None):
+def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, ll_out=None, yh_out=None,
+                   precision="tc"):
     """x (B,1,h,w) -> (LL (B,1,h/2,w/2), Yh (B,3,h/2,w/2) = [LH,HL,HH])."""
     require_device(x)
     x = _f32c(x, "x")
@@ -94,12 +91,12 @@ def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=
     with torch.cuda.device(x.device):
         check(lib.ll_lift_level_fwd(ptr(x), x.stride(0), ptr(ll), ll.stride(0), ptr(yh), yh.stride(0), ptr(scratch),
                                     B, h, w, _blob_array(blobs), float(res_weight), int(bool(linear)), int(scale),
-                                    ptr(nh), ptr(nl), stream_ptr()))
+                                    ptr(nh), ptr(nl), lift_precision_code(precision), stream_ptr()))
     _count(8 + (6 if scale else 0))
     return ll, yh
 
 
-def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None):
+def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, precision="tc"):
     """(LL (B,1,h2,w2), Yh (B,3,h2,w2)) -> x (B,1,2*h2,2*w2)."""
     require_device(ll)
     ll = _f32c(ll, "ll")
@@ -115,7 +112,7 @@ def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None
     with torch.cuda.device(ll.device):
         check(lib.ll_lift_level_inv(ptr(ll), ll.stride(0), ptr(yh), yh.stride(0), ptr(x), x.stride(0), ptr(scratch),
                                     B, h, w, _blob_array(blobs), float(res_weight), int(bool(linear)), int(scale),
-                                    ptr(nh), ptr(nl), stream_ptr()))
+                                    ptr(nh), ptr(nl), lift_precision_code(precision), stream_ptr()))
     _count(8 + (6 if scale else 0))
     return x
 
@@ -197,7 +194,7 @@ def ae1_apply(x, blob, want_round=False):
     return (y, q) if want_round else y
 
 
-def lift_step(jobs, blob, sign, res_weight=0.1, linear=False):
+def lift_step(jobs, blob, sign, res_weight=0.1, linear=False, precision="tc"):
     """One fused lifting step on up to two (src, din, dout) triples of equally shaped
     3-D strided views (B, ny, nx); the 3-tap pre-filter runs along dim 1.  dout may alias din."""
     lib = _lib.load()
@@ -215,7 +212,8 @@ def lift_step(jobs, blob, sign, res_weight=0.1, linear=False):
             v.ptr, v.sb, v.sy, v.sx = t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
         a.nb, a.ny, a.nx = src.shape
     with torch.cuda.device(dev):
-        check(lib.ll_lift_step(arr, len(jobs), ptr(blob), float(sign), float(res_weight), int(bool(linear)), stream_ptr()))
+        check(lib.ll_lift_step(arr, len(jobs), ptr(blob), float(sign), float(res_weight), int(bool(linear)),
+                               lift_precision_code(precision), stream_ptr()))
     _count(1)
 
 
@@ -658,21 +656,41 @@ def eb_rate(x, blob, noise=None, acc=None):
     return y, bits
 
 
-# ----------------------------------------------------------------------------- measurement helper
+# ----------------------------------------------------------------------------- measurement helpers (libll_probe.so)
 def fma_peak_tflops(device=None, iters=4096):
     """Measured FP32 FMA-pipe peak (TFLOP/s) of the current device: register-only FFMA2 loop."""
     device = device or torch.device("cuda", torch.cuda.current_device())
-    lib = _lib.load()
+    lib = _lib.load_probe()
     out = torch.zeros(4, dtype=torch.float32, device=device)
-    blocks = lib.ll_sm_count() * 8
+    blocks = _lib.load().ll_sm_count() * 8
     best = 0.0
     with torch.cuda.device(device):
         for _ in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            check(lib.ll_fma_peak_probe(ptr(out), blocks, iters, stream_ptr()))
+            _lib.check_probe(lib.ll_fma_peak_probe(ptr(out), blocks, iters, stream_ptr()))
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             best = max(best, blocks * 256.0 * iters * 256.0 / (ms * 1e-3) / 1e12)
+    return best
+
+
+def tf32_peak_tflops(device=None, n=256, kblocks=16, iters=2000):
+    """Measured dense TF32 tensor-pipe peak (TFLOP/s): every SM issues ``iters`` chains of ``4 * kblocks``
+    tcgen05.mma kind::tf32 M128 x N x K8 on operands resident in shared memory (no global traffic)."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    lib = _lib.load_probe()
+    out = torch.zeros(4, dtype=torch.float32, device=device)
+    blocks = _lib.load().ll_sm_count()
+    best = 0.0
+    with torch.cuda.device(device):
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check_probe(lib.ll_tf32_peak_probe(ptr(out), blocks, iters, kblocks, n, stream_ptr()))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = max(best, blocks * float(iters) * kblocks * 4 * 2.0 * 128 * n * 8 / (ms * 1e-3) / 1e12)
     return best

@@ -87,3 +87,108 @@ def allreduce_gradients(params, bucket_bytes=32 << 20, group=None):
             flush()
     flush()
     return n_coll
+
+
+class GradientBuckets:
+    """Bucketed gradient all-reduce overlapped with backward (BASELINE config 4).
+
+    The unique trainable parameters are laid out, in reverse registration order (roughly the order backward
+    produces their gradients), in flat fp32 buckets of ``bucket_bytes``; every ``p.grad`` is a *view* into its
+    bucket, so autograd accumulates straight into the communication buffer (no gather/scatter copies).  A
+    post-accumulate hook per parameter counts its bucket down and, at zero, issues the bucket's all-reduce
+    asynchronously (NCCL runs it on its own stream while backward continues on the compute stream).
+    ``finish()`` issues the buckets that never completed (parameters without a gradient this step: ``nh``/``nl``
+    with ``scale: 0`` -- they contribute zeros, so every rank issues the same collectives), waits for all of them
+    and divides by the world size.  Call ``zero()`` instead of ``optimizer.zero_grad()`` (which would drop the views).
+    """
+
+    def __init__(self, params, bucket_bytes=16 << 20, group=None):
+        seen, uniq = set(), []
+        for p in params:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        uniq.reverse()
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.buckets = []           # [flat, [params], pending, handle]
+        cur, size = [], 0
+        for p in uniq:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(self._make(cur))
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(self._make(cur))
+        self._bucket_of = {}
+        self._hooks = []
+        for bi, b in enumerate(self.buckets):
+            for p in b["params"]:
+                self._bucket_of[id(p)] = bi
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.collectives = 0          # all-reduces issued since construction
+        self.zero()
+
+    @staticmethod
+    def _make(ps):
+        n = sum(p.numel() for p in ps)
+        flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
+        return {"flat": flat, "params": list(ps), "pending": len(ps), "handle": None}
+
+    def zero(self):
+        """Zero every bucket and (re)bind ``p.grad`` to its view."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            off = 0
+            for p in b["params"]:
+                n = p.numel()
+                p.grad = b["flat"][off:off + n].view_as(p)
+                off += n
+            b["pending"] = len(b["params"])
+            b["handle"] = None
+
+    def _launch(self, b):
+        if self.active and b["handle"] is None:
+            b["handle"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.collectives += 1
+
+    def _on_grad(self, p):
+        b = self.buckets[self._bucket_of[id(p)]]
+        if p.grad.data_ptr() != b["flat"].data_ptr() + self._offset(b, p) * 4:
+            # autograd replaced the view (first accumulation into a None grad): copy into the bucket and rebind
+            view = b["flat"][self._offset(b, p):self._offset(b, p) + p.numel()].view_as(p)
+            view.copy_(p.grad)
+            p.grad = view
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    @staticmethod
+    def _offset(b, p):
+        off = 0
+        for q in b["params"]:
+            if q is p:
+                return off
+            off += q.numel()
+        raise KeyError("parameter not in bucket")
+
+    def finish(self):
+        """After ``loss.backward()``: flush, wait, average.  Returns the number of collectives of this step."""
+        if not self.active:
+            return 0
+        for b in self.buckets:
+            self._launch(b)
+        for b in self.buckets:
+            b["handle"].wait()
+            b["flat"].div_(self.world)
+        return len(self.buckets)
+
+    def grad_bytes(self):
+        return sum(b["flat"].numel() * 4 for b in self.buckets)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -72,9 +72,15 @@ int ll_pack_lift_step(const float* pre_w, const float* w1, const float* b1, cons
  * lifting_inverse_row_2_stage_lifting (graphs/layers/wavelet_inverse_v2.py:76-90),
  * including P_block_v2.forward (graphs/layers/P_block_v2.py:40-55).
  * sign = +1 forward, -1 inverse, 0 = write the raw CNN output (stand-alone P_block_v2.forward,
- * pass pre-filter taps (0,1,0)); linear != 0 drops both tanh (linearity_flag == 0). */
+ * pass pre-filter taps (0,1,0)); linear != 0 drops both tanh (linearity_flag == 0).
+ * precision (per call, nothing process-wide):
+ *   LL_LIFT_FP32  every layer on the FP32 FMA pipe (exact, ~45 % of the FFMA2 peak);
+ *   LL_LIFT_TC    conv2 / conv3 (94 % of the MACs) on tcgen05 with the 3xTF32 hi/lo split and FP32
+ *                 accumulation in tensor memory (fp32-level accuracy, see lift_tc.cu), the rest FP32. */
+#define LL_LIFT_FP32 0
+#define LL_LIFT_TC 1
 int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float res_weight,
-                 int linear, ll_stream_t stream);
+                 int linear, int precision, ll_stream_t stream);
 
 /* One full 2-D lifting level, forward: x (B,h,w) -> ll (B,h/2,w/2), yh (B,3,h/2,w/2)
  * ordered LH,HL,HH.  Replaces wavelet_forward_v2.one_level_lifting
@@ -85,12 +91,12 @@ int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float si
 size_t ll_lift_level_scratch_floats(int B, int h, int w);
 int ll_lift_level_fwd(const float* x, int64_t x_sb, float* ll, int64_t ll_sb, float* yh, int64_t yh_sb,
                       float* scratch, int B, int h, int w, const float* const* blobs, float res_weight,
-                      int linear, int scale, const float* nh, const float* nl, ll_stream_t stream);
+                      int linear, int scale, const float* nh, const float* nl, int precision, ll_stream_t stream);
 /* Inverse level: (ll, yh) -> x.  Replaces wavelet_inverse_v2.one_level_lifting +
  * reconstruct_fun (graphs/layers/wavelet_inverse_v2.py:20-56, 68-92). */
 int ll_lift_level_inv(const float* ll, int64_t ll_sb, const float* yh, int64_t yh_sb, float* x, int64_t x_sb,
                       float* scratch, int B, int h, int w, const float* const* blobs, float res_weight,
-                      int linear, int scale, const float* nh, const float* nl, ll_stream_t stream);
+                      int linear, int scale, const float* nh, const float* nl, int precision, ll_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* CDF 9/7 fixed-filter DWT (K1)                                              */
@@ -114,18 +120,6 @@ int ll_dwt97_fwd(const float* x, float* yl, float* const* yh, float* scratch, in
                  ll_stream_t stream);
 int ll_dwt97_inv(const float* yl, const float* const* yh, float* x, float* scratch, int N, int h, int w, int J,
                  ll_stream_t stream);
-
-/* Arithmetic of the learned-lifting step kernels (process-wide, default LL_LIFT_TC):
- *   LL_LIFT_FP32  every layer on the FP32 FMA pipe (exact, ~45 % of the FFMA2 peak);
- *   LL_LIFT_TC    conv2 / conv3 (94 % of the MACs) on tcgen05 with the 3xTF32 hi/lo split and FP32
- *                 accumulation in tensor memory (fp32-level accuracy, see lift_tc.cu), the rest FP32. */
-#define LL_LIFT_FP32 0
-#define LL_LIFT_TC 1
-int ll_lift_set_mode(int mode);
-int ll_lift_get_mode(void);
-/* Profiling aid: device buffer of 17 x 8 int64 that receives per-warp clock64() stamps of one step of CTA 0
- * of the tensor-core lifting kernel (NULL = off). */
-int ll_lift_set_debug_buffer(long long* buf);
 
 /* ------------------------------------------------------------------------- */
 /* Pointwise subband auto-encoder (v1) fused with the quantiser               */
@@ -315,18 +309,6 @@ int ll_pack_eb(const float* const* params, int C, float* blob, ll_stream_t strea
  * y = round(x - median_c) + median_c (noise NULL) or x + noise; bits = -log2 max(p, 1e-9). */
 int ll_eb_rate(const float* x, const float* noise, const float* blob, float* y, float* bits, int B, int C, int64_t hw,
                double* sum_out, ll_stream_t stream);
-
-/* Unit probe of the tensor-core building block of the learned-lifting kernel (no reference
- * counterpart): D (128,64) = A (128, 8*kblocks) x B (8*kblocks, 64), fp32 in/out, computed with
- * tcgen05.mma kind::tf32 (A resident in tensor memory, B in MN-major SWIZZLE_128B shared-memory atoms);
- * split != 0 uses the 3xTF32 hi/lo split (fp32-level accuracy).  cycles (device, optional) receives
- * the SM cycles of one chain.  kblocks <= 20. */
-int ll_tc_tf32_probe(const float* A, const float* B, float* D, int kblocks, int split, int reps, long long* cycles,
-                     ll_stream_t stream);
-
-/* Measurement helper (no reference counterpart): register-only FFMA2 loop used by bench.py to
- * measure the device's FP32 FMA-pipe peak.  FLOPs = blocks * 256 * iters * 256. */
-int ll_fma_peak_probe(float* out, int blocks, int iters, ll_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,32 @@
+/*
+ * ll_probe.h -- measurement / unit-probe entry points of libll_probe.so (TEST AND BENCH TOOLING, not part of the
+ * product ABI in ll_api.h; none of them has a reference counterpart).  Built from csrc/probe/ by build.py.
+ */
+#ifndef LL_PROBE_H
+#define LL_PROBE_H
+#include "ll_api.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Unit probe of the tensor-core building block of the learned-lifting kernel (no reference
+ * counterpart): D (128,64) = A (128, 8*kblocks) x B (8*kblocks, 64), fp32 in/out, computed with
+ * tcgen05.mma kind::tf32 (A resident in tensor memory, B in MN-major SWIZZLE_128B shared-memory atoms);
+ * split != 0 uses the 3xTF32 hi/lo split (fp32-level accuracy).  cycles (device, optional) receives
+ * the SM cycles of one chain.  kblocks <= 20. */
+int ll_tc_tf32_probe(const float* A, const float* B, float* D, int kblocks, int split, int reps, long long* cycles,
+                     ll_stream_t stream);
+
+/* Measurement helper (no reference counterpart): register-only FFMA2 loop used by bench.py to
+ * measure the device's FP32 FMA-pipe peak.  FLOPs = blocks * 256 * iters * 256. */
+int ll_fma_peak_probe(float* out, int blocks, int iters, ll_stream_t stream);
+
+/* Dense tcgen05 kind::tf32 GEMM loop (A, B in shared memory, accumulator in tensor memory, no global traffic):
+ * the TF32 tensor-pipe peak of the device, measured.  Every CTA issues `iters` chains of `kblocks` MMAs of shape
+ * M128 x N x K8 (N in 16..256, multiple of 16).  FLOPs = blocks * iters * kblocks * 2 * 128 * N * 8. */
+int ll_tf32_peak_probe(float* out, int blocks, int iters, int kblocks, int n, ll_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LL_PROBE_H */

@@ -62,18 +62,18 @@ def cond2zt_forward(out_xe, out_xo, sd, pfx, L, training=False):
     """``DWTConditioned2EntropyLayerZTsepSubbands.forward`` (:322-372)."""
     mode = "noise" if training else "dequantize"
     xe_q = tp.quantize(out_xe, mode)
-    ms = causal_chain(xe_q, sd, pfx + "csc_xe.", 1)
+    ms = causal_chain(xe_q, sd, pfx + "csc_xe.", xe_q.shape[1])      # groups = ses[L-1] (:308-316)
     si_xe = _gauss_bits(out_xe, ms[:, 0::2], ms[:, 1::2], training)
     qs, sis = [], []
     i = L - 1
     q = tp.quantize(out_xo[i], mode)
-    ms = causal_chain(q, sd, f"{pfx}csc_list.{i}.", 3)
+    ms = causal_chain(q, sd, f"{pfx}csc_list.{i}.", q.shape[1])      # groups = sos[L-1] (:298-306)
     sis.append(_gauss_bits(out_xo[i], ms[:, 0::2], ms[:, 1::2], training))
     qs.append(q)
     con = upsample2(q)
     for i in range(L - 2, -1, -1):
         q = tp.quantize(out_xo[i], mode)
-        csc = masked_conv(q, sd, f"{pfx}csc_list.{i}.", "A", 3)
+        csc = masked_conv(q, sd, f"{pfx}csc_list.{i}.", "A", q.shape[1])     # groups = sos[i] (:274-277)
         plc = F.conv2d(con, sd[f"{pfx}plc_list.{i}.0.weight"], sd[f"{pfx}plc_list.{i}.0.bias"], padding=1)
         plc = F.leaky_relu(plc, LEAK)
         plc = F.conv2d(plc, sd[f"{pfx}plc_list.{i}.2.weight"], sd[f"{pfx}plc_list.{i}.2.bias"], padding=1)
@@ -81,7 +81,8 @@ def cond2zt_forward(out_xe, out_xo, sd, pfx, L, training=False):
         c0, c1, c2 = csc.chunk(3, dim=1)
         a = torch.cat((p0, c0, p1, c1, p2, c2), dim=1)
         for j, k in enumerate((0, 2, 4, 6)):
-            a = F.conv2d(a, sd[f"{pfx}cgp_out_xo_list.{i}.{k}.weight"], sd[f"{pfx}cgp_out_xo_list.{i}.{k}.bias"], groups=3)
+            # groups = inn_ch1 = sos[i+1] = channels of the parent level (:280-290); the chunking above is 3-way whatever clrch is
+            a = F.conv2d(a, sd[f"{pfx}cgp_out_xo_list.{i}.{k}.weight"], sd[f"{pfx}cgp_out_xo_list.{i}.{k}.bias"], groups=con.shape[1])
             if j < 3:
                 a = F.leaky_relu(a, LEAK)
         sis.append(_gauss_bits(out_xo[i], a[:, 0::2], a[:, 1::2], training))

@@ -40,9 +40,11 @@ def net_forward(x, sd, pfx, cfg, training=False):
 
 
 def wrapper_forward(x, sd, cfg, training=False, full=False):
-    """``LiftingBasedDWTNetWrapper.forward`` with ``clrch == 1``: three independent
-    planes, outputs concatenated plane after plane."""
-    assert cfg.clrch == 1
+    """``LiftingBasedDWTNetWrapper.forward``: ``clrch == 1`` = three independent planes, outputs
+    concatenated plane after plane; ``clrch == 3`` = one net on the whole tensor."""
+    if cfg.clrch == 3:        # one net over the three colour channels together (:40-42, 50-51)
+        o = net_forward(x, sd, "model.", cfg, training)
+        return (o[0], o[1], list(o[2]), [o]) if full else (o[0], o[1], list(o[2]))
     outs = [net_forward(x[:, c:c + 1], sd, f"model{c}.", cfg, training) for c in range(3)]
     xhat = torch.cat([o[0] for o in outs], dim=1)
     si_xe = torch.cat([o[1] for o in outs], dim=1)

@@ -19,9 +19,8 @@ for shape in [(1, 16, 64), (2, 40, 100), (1, 8, 52), (3, 70, 53), (2, 128, 384)]
     din = torch.rand(*shape, device=dev) - 0.5
     outs = {}
     for mode in ("fp32", "tc"):
-        ops.set_lift_mode(mode)
         o = torch.full(shape, 123.0, device=dev)
-        ops.lift_step([(src, din, o)], blobs[0], 1.0, 0.1, False)
+        ops.lift_step([(src, din, o)], blobs[0], 1.0, 0.1, False, mode)
         torch.cuda.synchronize()
         outs[mode] = o
     d = (outs["tc"] - outs["fp32"]).abs().max().item()
@@ -31,9 +30,8 @@ for shape in [(1, 16, 64), (2, 40, 100), (1, 8, 52), (3, 70, 53), (2, 128, 384)]
 src = torch.rand(2, 64, 128, device=dev) - 0.5
 o = {}
 for mode in ("fp32", "tc"):
-    ops.set_lift_mode(mode)
     t = torch.empty_like(src)
-    ops.lift_step([(src, src, t)], blobs[1], 0.0, 0.1, False)
+    ops.lift_step([(src, src, t)], blobs[1], 0.0, 0.1, False, mode)
     torch.cuda.synchronize(); o[mode] = t
 print("net only: max|tc-fp32| =", (o["tc"] - o["fp32"]).abs().max().item(), "scale", o["fp32"].abs().max().item())
 x = torch.rand(16, 1, 512, 768, device=dev) - 0.5

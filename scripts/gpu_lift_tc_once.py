@@ -9,7 +9,6 @@ cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="Subband
 torch.manual_seed(1337)
 net = LiftingBasedNeuralWaveletv4(cfg).to(dev).eval()
 blobs = net.waveletForward[0]._blobs()
-ops.set_lift_mode("tc")
 src = torch.rand(16, 256, 768, device=dev) - 0.5
 din = torch.rand(16, 256, 768, device=dev) - 0.5
 out = torch.empty_like(src)

@@ -20,10 +20,9 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 30):
         din = torch.rand(*shp, device=dev) - 0.5
         o1, o2 = torch.empty_like(src), torch.empty_like(src)
         for k in range(4):
-            ops.set_lift_mode("tc"); ops.lift_step([(src, din, o1)], blobs[k % len(blobs)], 1.0 if k % 2 == 0 else -1.0, 0.1, False)
-            ops.set_lift_mode("fp32"); ops.lift_step([(src, din, o2)], blobs[k % len(blobs)], 1.0 if k % 2 == 0 else -1.0, 0.1, False)
+            ops.lift_step([(src, din, o1)], blobs[k % len(blobs)], 1.0 if k % 2 == 0 else -1.0, 0.1, False, "tc")
+            ops.lift_step([(src, din, o2)], blobs[k % len(blobs)], 1.0 if k % 2 == 0 else -1.0, 0.1, False, "fp32")
             worst = max(worst, (o1 - o2).abs().max().item()); n += 1
-ops.set_lift_mode("tc")
 src = torch.rand(16, 256, 768, device=dev) - 0.5; din = torch.rand_like(src); o1 = torch.empty_like(src)
 for _ in range(2000):
     ops.lift_step([(src, din, o1)], blobs[0], 1.0, 0.1, False)

@@ -43,14 +43,21 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-def flip_audit(q_gpu, q_ref, pre_ref, eps=1e-4):
+FLIP_EPS = 1e-5          # a flip must sit within 1e-5 of a rounding boundary of the fp64 oracle
+FLIP_LOG = []            # (label, n_symbols, n_mismatch, n_unexplained) of every audit of this session
+
+
+def flip_audit(q_gpu, q_ref, pre_ref, eps=FLIP_EPS, pre_ref64=None, label=None):
     """Symbol parity.  Quantised tensors are integers (``round(x)``) or mean-shifted integers
     (``round(x - mu) + mu`` for EntropyBottleneck / onlyEZWT outputs, where mu itself is a
     context-CNN output carrying fp32 noise).  The difference is split into an integer number of
     quantisation steps k and a remainder: a sample *matches* when k == 0 and the remainder is
-    within 1e-4 relative (exactly 0 for plain rounding); a mismatch must be a single step
-    (|k| == 1) and, for plain rounding, the oracle's pre-quantiser value must sit within ``eps``
-    of the rounding boundary (frac = 0.5).  Returns (n_mismatch, n_unexplained)."""
+    within 1e-4 relative (exactly 0 for plain rounding).  A mismatch is *explained* only when it is a
+    single step (|k| == 1) and, for plain rounding, the oracle's pre-quantiser value -- the float64
+    oracle's (``pre_ref64``, the tie-break of SURVEY.md section 7) when given, else the fp32 one --
+    sits within ``eps * max(1, |x|)`` of the rounding boundary (frac = 0.5): there fp32 summation order
+    alone decides the symbol, and the reference run on another thread count flips it too.
+    Returns (n_mismatch, n_unexplained); every call is logged in ``FLIP_LOG`` and printed by the suite."""
     d = q_gpu - q_ref
     k = torch.round(d)
     integer_q = bool((q_ref == torch.round(q_ref)).all())
@@ -58,13 +65,23 @@ def flip_audit(q_gpu, q_ref, pre_ref, eps=1e-4):
     rem_ok = (d - k).abs() <= rem_tol * (1 + q_ref.abs())
     mism = (k != 0) | ~rem_ok
     n = int(mism.sum())
-    if n == 0:
-        return 0, 0
-    ok = (k[mism].abs() == 1) & rem_ok[mism]
-    if integer_q:
-        frac = (pre_ref[mism] - torch.floor(pre_ref[mism]) - 0.5).abs()
-        ok = ok & (frac <= eps)
-    return n, int((~ok).sum())
+    bad = 0
+    if n:
+        ok = (k[mism].abs() == 1) & rem_ok[mism]
+        if integer_q:
+            pre = (pre_ref64 if pre_ref64 is not None else pre_ref).double()[mism]
+            frac = (pre - torch.floor(pre) - 0.5).abs()
+            ok = ok & (frac <= eps * pre.abs().clamp(min=1.0))
+        bad = int((~ok).sum())
+    FLIP_LOG.append((label or "", int(q_ref.numel()), n, bad))
+    return n, bad
+
+
+def flip_summary():
+    tot = sum(r[1] for r in FLIP_LOG)
+    n = sum(r[2] for r in FLIP_LOG)
+    bad = sum(r[3] for r in FLIP_LOG)
+    return f"symbol audits: {len(FLIP_LOG)} tensors, {tot} symbols, {n} rounding-boundary flips, {bad} unexplained"
 
 
 def bits_check(a, b, tol_sum=1e-4, frac_outliers=1e-3):

@@ -42,6 +42,9 @@ CASES = {
     "cdf97_factorized_L2": (dict(netType="CDF97", entropy_layer="factorized", dwtlevels=2), (1, 3, 32, 32), False),
     "cdf97_cond2zt_L2_train": (dict(netType="CDF97", entropy_layer="conditioned2ZTsepSubbands", dwtlevels=2),
                                (1, 3, 32, 32), True),
+    # clrch = 3: one net over the three colour channels (9 detail subbands per level, cgp groups = 9)
+    "cdf97_cond2zt_L2_clrch3": (dict(netType="CDF97", entropy_layer="conditioned2ZTsepSubbands", dwtlevels=2, clrch=3),
+                                (1, 3, 32, 32), False),
 }
 
 
@@ -57,12 +60,18 @@ def digest_groups(sd):
     return {k: h.hexdigest() for k, h in groups.items()}
 
 
-def main():
+def main(only=None):
+    """``only``: regenerate just these cases (their npz + meta entries), keeping the rest of meta.json."""
     m = refload.load()
     torch.Tensor.cuda = lambda self, *a, **k: self   # ZTBlock hard-codes .cuda() (LiftingBasedDWT_net.py:717-718)
     torch.set_num_threads(1)
     meta = {}
+    if only:
+        with open(os.path.join(HERE, "meta.json")) as f:
+            meta = json.load(f)
     for name, (ov, shape, training) in CASES.items():
+        if only and name not in only:
+            continue
         cfg = refload.default_config(**ov)
         torch.manual_seed(1337)
         net = m.LiftingBasedDWTNetWrapper(cfg)
@@ -83,8 +92,10 @@ def main():
             for i, s in enumerate(si_xo):
                 arrays[f"si_xo_{i}"] = s.numpy()
             if not training:
-                for c, sub in enumerate((net.model0, net.model1, net.model2)):
-                    out_xe, out_xo = sub.autoencoder.encode(x[:, c:c + 1])
+                planes = [(net.model, x)] if cfg.clrch == 3 else [(sub, x[:, c:c + 1]) for c, sub in
+                                                                  enumerate((net.model0, net.model1, net.model2))]
+                for c, (sub, xin) in enumerate(planes):
+                    out_xe, out_xo = sub.autoencoder.encode(xin)
                     _, _, xe_q, xo_q = sub.entropymodel(out_xe, out_xo)
                     arrays[f"out_xe_{c}"] = out_xe.numpy()
                     arrays[f"xe_q_{c}"] = xe_q.numpy()
@@ -98,6 +109,10 @@ def main():
                       "torch": torch.__version__}
         print(name, "bpp", meta[name]["bpp"], "n keys", len(keys))
 
+    if only:
+        with open(os.path.join(HERE, "meta.json"), "w") as f:
+            json.dump(meta, f)
+        return
     # lifting-only vectors: one level forward / inverse on a ragged plane, reference modules directly
     cfg = refload.default_config(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
                                  entropy_layer="factorized", dwtlevels=1)
@@ -121,4 +136,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=sys.argv[1:] or None)

@@ -35,6 +35,21 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in ll_api.h but not exported"
     assert set(_lib.SIGNATURES) == set(syms)      # the ctypes table covers the header exactly
     assert _lib.load().ll_version() >= 100        # host-only call
+    # process-wide mode switches and debug hooks are not part of the product ABI
+    for gone in ("ll_lift_set_mode", "ll_lift_get_mode", "ll_lift_set_debug_buffer", "ll_tc_tf32_probe", "ll_fma_peak_probe"):
+        assert not hasattr(lib, gone), gone
+
+
+def test_probe_library_exports_its_header():
+    """include/ll_probe.h (measurement / unit probes) lives in its own library."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(build.PROBE_LIB_PATH)
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ll_probe.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(ll_[a-z0-9_]+)\s*\(", src)))
+    assert syms == sorted(k for k in _lib.PROBE_SIGNATURES if k != "ll_last_error")
+    for s_ in syms:
+        assert hasattr(lib, s_), s_
 
 
 def test_library_is_sm100a_native():
@@ -198,3 +213,118 @@ def test_agent_mirrors_are_importable_and_refuse_to_run_unconfigured():
     import torch
     with pytest.raises(RuntimeError):
         agent.preprocess(torch.rand(1, 3, 8, 8))          # CPU tensor: the kernels have no CPU fallback
+
+
+# ---------------------------------------------------------------------------------------------- config surface
+def test_config_surface_matches_reference_keys(tmp_path):
+    """utils/config.py + liftingDWT.json (reference: utils/config.py:50-103, liftingDWT.json:1-53)."""
+    import json
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils import config as C
+    cfg, d = C.get_config_from_json(C.DEFAULT_JSON)
+    assert isinstance(d, dict) and cfg.agent == "LiftingBasedDWTAgent" and cfg.dwtlevels == 4 and cfg["lambda_"] == 11700
+    with pytest.raises(AttributeError):
+        cfg.no_such_key
+    ref_json = "/root/reference/liftingDWT.json"
+    if os.path.isfile(ref_json):            # dev container only: same keys, same values except the machine-specific paths
+        ref = json.load(open(ref_json))
+        assert list(ref) == list(d)
+        for k, v in ref.items():
+            if not (k.startswith("train_data_") or k in ("test_data", "valid_data")):
+                assert d[k] == v, k
+    cfg.exp_name = "unit"
+    out = C.process_config(cfg, root=str(tmp_path), quiet=True)
+    for k in ("summary_dir", "checkpoint_dir", "out_dir", "log_dir"):
+        assert os.path.isdir(out[k]) and out[k].endswith(os.sep)
+    bad = tmp_path / "bad.json"
+    bad.write_text("{not json")
+    with pytest.raises(ValueError):
+        C.get_config_from_json(str(bad))
+    c3 = C.baseline_config("cfg3")
+    assert c3.netType == "LiftingBasedNeuralWaveletv4" and c3.autoencoder == "SubbandAutoEncoderBerk"
+
+
+def test_product_synthetic_weights_equal_the_oracle_recipe():
+    """utils/synthetic.keyed_weights (bench / smoke) == oracle.model.keyed_weights (what the goldens were made with)."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models.LiftingBasedDWT_net import \
+        LiftingBasedDWTNetWrapper
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils import config as C, synthetic as S
+    for name, lv in (("cfg3", 2), ("cfg1", 2)):
+        cfg = C.baseline_config(name, dwtlevels=lv)
+        torch.manual_seed(1337)
+        m = LiftingBasedDWTNetWrapper(cfg)
+        a, b = S.keyed_weights(m.state_dict()), om.keyed_weights(m.state_dict())
+        assert list(a) == list(b)
+        assert all(torch.equal(a[k], b[k]) for k in a)
+        m.load_state_dict(a, strict=True)
+    v1a, v1b = S.amplify_v1(m.state_dict()), om.amplify_v1(m.state_dict())
+    assert all(torch.equal(v1a[k], v1b[k]) for k in v1a)
+
+
+class _StubModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.ones(3))
+
+
+def test_base_agent_checkpoint_and_run_semantics(tmp_path):
+    """agents/base.py mirrors the reference's BaseAgent (agents/base.py:64-168): checkpoint dict keys, best copy,
+    resume of model + loggers but not optimizer, run() saving a checkpoint on an exception and re-raising."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.agents.base import BaseAgent
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.loggers import RDLogger
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils.config import EasyDict
+
+    class Agent(BaseAgent):
+        def __init__(self, config):
+            super().__init__(config, device="cpu")
+            self.model = _StubModel()
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.lr)
+            self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer)
+            self.train_logger, self.trnit_logger, self.valid_logger, self.test_logger = (RDLogger() for _ in range(4))
+            self.losses = [3.0, 2.0, 2.5]
+            self.boom = False
+
+        def train_one_epoch(self):
+            if self.boom:
+                raise ValueError("boom")
+            self.train_logger(1.0, 0.1, 0.5, 0.4)
+            self.current_iteration += 1
+
+        def validate(self):
+            return self.losses[self.current_epoch]
+
+    cfg = EasyDict(mode="train", max_epoch=3, validate_every=1, checkpoint_dir=str(tmp_path) + os.sep, seed=1,
+                   learning_rate=1e-3, gpu_device=0)
+    a = Agent(cfg)
+    a.run()
+    a.finalize()
+    ck = torch.load(str(tmp_path / "checkpoint.pth.tar"), weights_only=False)
+    assert set(ck) == {"epoch", "iteration", "best_valid_loss", "state_dict", "optimizer", "scheduler", "train_logger",
+                       "trnit_logger", "valid_logger", "test_logger"}
+    assert a.best_valid_loss == 2.0 and os.path.isfile(str(tmp_path / "model_best.pth.tar"))
+    assert torch.load(str(tmp_path / "model_best.pth.tar"), weights_only=False)["best_valid_loss"] == 2.0
+    b = Agent(cfg)
+    with torch.no_grad():
+        a.model.w.mul_(2)
+    a.save_checkpoint()
+    assert b.load_checkpoint("checkpoint.pth.tar") and torch.equal(b.model.w, a.model.w)
+    assert b.current_iteration == a.current_iteration and b.train_logger.state_dict() == a.train_logger.state_dict()
+    assert b.load_checkpoint("missing.pth.tar") is False          # skipped silently, like the reference
+    os.remove(str(tmp_path / "checkpoint.pth.tar"))
+    b.boom = True
+    b.current_epoch = 0
+    with pytest.raises(ValueError):
+        b.run()
+    assert os.path.isfile(str(tmp_path / "checkpoint.pth.tar"))   # exception -> checkpoint -> re-raise
+    cfg2 = EasyDict(cfg, mode="nonsense")
+    with pytest.raises(NameError):
+        Agent(cfg2).run()
+
+
+def test_rdlogger_state_dict_layout():
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.loggers import RDLogger
+    lg = RDLogger()
+    lg(2.0, 0.01, 0.5, 0.25)
+    lg(4.0, 0.03, 1.5, 0.0)
+    assert set(lg.state_dict()) == {"loss", "mse", "rate", "rate2", "it", "ep"} and lg.state_dict()["it"] == 2
+    loss, mse, rate, rate2 = lg.display(lr=1e-4, typ="tr")
+    assert (loss, rate, rate2) == (3.0, 1.0, 0.25) and abs(mse - 0.02) < 1e-12 and lg.current_epoch == 1

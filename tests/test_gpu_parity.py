@@ -21,7 +21,7 @@ DEV = "cuda:0"
 
 
 def _planes(model):
-    return [model.model0, model.model1, model.model2]
+    return model.planes()
 
 
 TC_LAYERS = ("conditioned2ZTsepSubbands",)   # entropy layers with a tensor-core (bf16) context path
@@ -50,15 +50,15 @@ def test_model_forward_matches_reference_golden(name, prec):
         xhat, si_xe, si_xo = model(x)
         # symbols and coefficients, plane by plane
         for c, sub in enumerate(_planes(model)):
-            out_xe, out_xo = sub.autoencoder.encode(x[:, c:c + 1])
+            out_xe, out_xo = sub.autoencoder.encode(x if cfg.clrch == 3 else x[:, c:c + 1])
             _, _, xe_q, xo_q = sub.entropymodel(out_xe, out_xo)
             assert rel_err(out_xe.cpu(), g[f"out_xe_{c}"]) < 1e-4
-            n, bad = flip_audit(xe_q.cpu(), g[f"xe_q_{c}"], g[f"out_xe_{c}"])
-            assert bad == 0 and n <= 1, (n, bad)
+            n, bad = flip_audit(xe_q.cpu(), g[f"xe_q_{c}"], g[f"out_xe_{c}"], label=f"{name}/{prec}/xe{c}")
+            assert bad == 0 and n == 0, (n, bad)
             for i in range(cfg.dwtlevels):
                 assert rel_err(out_xo[i].cpu(), g[f"out_xo_{c}_{i}"]) < 1e-4
-                n, bad = flip_audit(xo_q[i].cpu(), g[f"xo_q_{c}_{i}"], g[f"out_xo_{c}_{i}"])
-                assert bad == 0 and n <= 2, (c, i, n, bad)
+                n, bad = flip_audit(xo_q[i].cpu(), g[f"xo_q_{c}_{i}"], g[f"out_xo_{c}_{i}"], label=f"{name}/{prec}/xo{c}_{i}")
+                assert bad == 0 and n == 0, (c, i, n, bad)
     assert rel_err(xhat.cpu(), g["xhat"]) < 1e-4
     assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=1e-3)[2]
     for i, s in enumerate(si_xo):
@@ -105,8 +105,6 @@ def test_training_mode_noise_parity(prec):
 
 @pytest.mark.parametrize("mode", ["tc", "fp32"])
 def test_lifting_level_golden(mode):
-    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
-    ops.set_lift_mode(mode)
     m = META["lifting_one_level"]
     model, cfg = product_model(dict(m["config"], lift_precision=mode))
     keyed_state(model)
@@ -129,7 +127,6 @@ def test_learned_lifting_vs_oracle(shape, levels, mode):
     with the 3xTF32 split (default), "fp32" = every layer on the FP32 FMA pipe.  Same 1e-5 bar for both."""
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers import lifting_dwt_nets as ldn
-    ops.set_lift_mode(mode)
     cfg = om.default_cfg(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder", dwtlevels=levels,
                          lift_precision=mode)
     torch.manual_seed(1337)
@@ -153,9 +150,9 @@ def test_learned_lifting_vs_oracle(shape, levels, mode):
         L, H = f0.lifting_forward_row_2_stage_lifting(x[:, :, 0::2].to(DEV), x[:, :, 1::2].to(DEV))
         oL, oH = olift.lift_rows_forward(x[:, :, 0::2], x[:, :, 1::2], sd, "m.autoencoder.waveletForward.0.", cfg)
         assert rel_err(L.cpu(), oL) < 1e-5 and rel_err(H.cpu(), oH) < 1e-5
+        net.P_blocks[0].lift_precision = mode
         pb = net.P_blocks[0](x.to(DEV))
         assert rel_err(pb.cpu(), olift.p_block(x, sd, "m.autoencoder.P_blocks.0.")) < 1e-5
-    ops.set_lift_mode("tc")
 
 
 @pytest.mark.parametrize("shape,J", [((2, 3, 64, 96), 3), ((1, 1, 16, 24), 3), ((1, 2, 8, 8), 2), ((1, 1, 256, 256), 4),

@@ -13,11 +13,11 @@ DEV = "cuda:0"
 
 def _probe(A, B, split, reps=1):
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_probe()
     kb = A.shape[1] // 8
     D = torch.empty(128, 64, device=DEV)
     cyc = torch.zeros(1, dtype=torch.int64, device=DEV)
-    _lib.check(lib.ll_tc_tf32_probe(A.data_ptr(), B.data_ptr(), D.data_ptr(), kb, split, reps, cyc.data_ptr(),
+    _lib.check_probe(lib.ll_tc_tf32_probe(A.data_ptr(), B.data_ptr(), D.data_ptr(), kb, split, reps, cyc.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return D, int(cyc.item())
@@ -47,3 +47,13 @@ def test_tf32_mma_issue_rate():
     _, c3 = _probe(A, B, 5, reps=50)
     print(f"20 k-blocks x 50 chains: {c1 / 20:.1f} (1 MMA/block) / {c3 / 60:.1f} (3xTF32) cycles per M128xN64xK8 MMA")
     assert c1 > 0 and c3 > 0
+
+
+def test_measured_peaks_are_plausible():
+    """The FFMA2 and dense TF32 probes (libll_probe.so) that bench.py uses as roofline denominators."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    fma = ops.fma_peak_tflops()
+    tf32 = ops.tf32_peak_tflops()
+    print(f"measured peaks: FFMA2 {fma:.1f} TFLOP/s, dense TF32 (tcgen05 SS, M128xN256xK8) {tf32:.1f} TFLOP/s")
+    assert 40 < fma < 100
+    assert 400 < tf32 < 1300

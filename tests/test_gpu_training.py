@@ -76,3 +76,29 @@ def test_gradients_match_oracle_autograd(overrides, shape):
         assert err <= 2e-3, (names[0], err)
         checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("layer", ["conditioned2ZTsepSubbands", "onlyEZWT"])
+def test_frozen_entropy_model_still_sends_rate_gradient_to_the_transform(layer):
+    """with the entropy model frozen (fine-tuning only the transform) the rate term must still
+    back-propagate through the context CNNs into the subbands; the inference kernels have no grad_fn."""
+    model, cfg = product_model(dict(netType="LiftingBasedNeuralWaveletv4", autoencoder="SubbandAutoEncoder",
+                                    entropy_layer=layer, dwtlevels=2))
+    keyed_state(model)
+    model = model.to(DEV).train()
+    for sub in model.planes():
+        for p in sub.entropymodel.parameters():
+            p.requires_grad_(False)
+    torch.manual_seed(3)
+    x = om.preprocess(torch.rand(1, 3, 32, 32)).to(DEV)
+    sub = model.model0
+    out_xe, out_xo = sub.autoencoder.encode(x[:, 0:1])
+    out_xo = [t.detach().requires_grad_(True) for t in out_xo]
+    si_xe, si_xo, _, _ = sub.entropymodel(out_xe.detach().requires_grad_(True), out_xo)
+    assert all(s.grad_fn is not None for s in si_xo)
+    sum(s.sum() for s in si_xo).backward()
+    for i, t in enumerate(out_xo):
+        assert t.grad is not None and float(t.grad.abs().max()) > 0, i
+    # parent -> child conditioning: the coarser level's gradient includes the finer level's rate
+    rate_only_fine = torch.autograd.grad(sub.entropymodel(out_xe.detach(), out_xo)[1][0].sum(), out_xo[1], allow_unused=True)[0]
+    assert rate_only_fine is not None and float(rate_only_fine.abs().max()) > 0
