@@ -17,7 +17,7 @@ LEAK = 0.01  # nn.LeakyReLU() default slope
 
 def conv_mask(kh, kw, mask_type, like):
     """``MaskedConv2d`` mask geometry (graphs/layers/masked_conv2d.py:9-17)."""
-    m = torch.ones(kh, kw, dtype=like.dtype)
+    m = torch.ones(kh, kw, dtype=like.dtype, device=like.device)
     b = 1 if mask_type == "B" else 0
     if kw > 1:
         m[kh // 2, kw // 2 + b:] = 0
@@ -155,8 +155,8 @@ def ztblock_forward(out_xe, out_xo, sd, pfx, L, training=False):
         for j in range(3):
             xin = out_xo[lvl][:, j:j + 1]
             B, _, H, W = xin.shape
-            mu = torch.empty(B, 1, H, W)
-            sg = torch.empty(B, 1, H, W)
+            mu = torch.empty(B, 1, H, W, dtype=xin.dtype, device=xin.device)
+            sg = torch.empty(B, 1, H, W, dtype=xin.dtype, device=xin.device)
             qq = tp.quantize(xin, mode)
             ee, eo, oe = qq[:, :, 0::2, 0::2], qq[:, :, 0::2, 1::2], qq[:, :, 1::2, 0::2]
             d1 = con[:, j:j + 1]

@@ -95,3 +95,72 @@ def test_world2_gradient_allreduce():
     assert torch.allclose(torch.tensor(gs), torch.arange(5.0) * 1.5)
     assert torch.allclose(torch.tensor(g3), torch.full((7,), 0.5))
     assert g4 is None
+
+
+class _TinyNet(torch.nn.Module):
+    """Shared parameter (registered twice, like the lifting blocks) + a parameter that gets no gradient (nh / nl)."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(6, 5)
+        self.b = torch.nn.Linear(5, 4)
+        self.again = self.a                      # alias
+        self.unused = torch.nn.Parameter(torch.ones(3))
+
+    def forward(self, x):
+        return self.b(torch.tanh(self.again(x))).pow(2).sum()
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = _TinyNet()
+        bk = parallel.GradientBuckets(net.parameters(), bucket_bytes=64)     # tiny buckets: several collectives
+        res = []
+        for step in range(2):                    # two steps: zero() must rebind the views and clear the sums
+            bk.zero()
+            torch.manual_seed(10 * step + rank)
+            net(torch.randn(3, 6)).backward()
+            n = bk.finish()
+            res.append((n, [p.grad.clone().tolist() for p in net.parameters()]))
+        if rank == 0:
+            out.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_overlapped_gradient_buckets():
+    """``GradientBuckets`` (hooks + async bucketed all-reduce) == the mean of the two ranks' plain autograd gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = q.get()
+    for step, (n, grads) in enumerate(res):
+        assert n >= 2
+        want = None
+        for rank in range(2):
+            torch.manual_seed(0)
+            net = _TinyNet()
+            torch.manual_seed(10 * step + rank)
+            net(torch.randn(3, 6)).backward()
+            g = [(p.grad if p.grad is not None else torch.zeros_like(p)) for p in net.parameters()]
+            want = g if want is None else [a + b for a, b in zip(want, g)]
+        for got, w in zip(grads, want):
+            assert torch.allclose(torch.tensor(got), w / 2, atol=1e-6)
+
+
+def test_gradient_buckets_single_process_is_a_no_op():
+    net = _TinyNet()
+    bk = parallel.GradientBuckets(net.parameters())
+    bk.zero()
+    net(torch.ones(2, 6)).backward()
+    assert bk.finish() == 0 and net.a.weight.grad.abs().sum() > 0 and float(net.unused.grad.abs().sum()) == 0.0
