@@ -64,7 +64,7 @@ SIGNATURES = {
     "ll_igemm_conv": (c_int, [_P, _P, _P] + [c_int] * 9 + [ctypes.POINTER(c_int), c_int, _P, c_i64, c_int, c_int, c_int, _P,
                               c_int, c_int, c_int, _P]),
     "ll_pack_tf32_weight": (c_int, [_P, _P] + [c_int] * 6 + [_P]),
-    "ll_igemm_tf32": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P, _P, _P]),
+    "ll_igemm_tf32": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P, _P, c_int, _P]),
     "ll_nchw_to_nhwc_split": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P]),
     "ll_nhwc_split_to_nchw": (c_int, [_P, _P] + [c_int] * 4 + [_P]),
     "ll_nhwc_split_conv3": (c_int, [_P, _P, _P, _P] + [c_int] * 5 + [_P]),

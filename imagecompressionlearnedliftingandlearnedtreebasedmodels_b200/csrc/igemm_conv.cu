@@ -304,6 +304,219 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3xTF32 implicit GEMM on CTA PAIRS (cta_group::2) -- the conv / GDN kernels of SubbandAutoEncoderBerk.
+//
+// ncu on the single-CTA instance (profiles/r02_ncu_berk_igemm_first.csv): tensor pipe 28-34 % active with L2 and DRAM
+// far from their limits -- the MMA waits for operand bytes: every 32-channel k-block was fetched three times
+// (A_lo|B_hi, A_hi|B_lo, A_hi|B_hi = 3 x 40 KB per 12 MMAs at N = 192).  Here
+//   * a k-block is fetched ONCE: stage = {A_hi, A_lo, B_hi, B_lo}, 12 MMAs per stage;
+//   * two CTAs of a cluster run one M = 256 MMA: each holds its own 128 pixels of A and HALF of the weight rows, the
+//     tensor cores of the pair read both halves -- the weight tile crosses L2 -> SM once per pair.
+// 56 KB per CTA per 12 MMAs instead of 120 KB (N = 192).  Accumulators (main + small-term, see ll_igemm_tf32) and the
+// epilogues are those of igemm_conv_kernel<true>; every CTA drains its own 128 TMEM lanes.
+// Protocol: full[s] lives in the leader (even) CTA and counts the bytes of both CTAs' TMA loads; empty[s] / tfull[a]
+// are arrived in both CTAs by multicast tcgen05.commit; tempty[a] lives in the leader, 16 arrivals (8 epilogue warps x 2).
+// ------------------------------------------------------------------------------------------------
+constexpr int PR_MAXST = 6;
+constexpr int PR_A_BYTES = IG_BM * 128;              // 128 pixels x 32 tf32
+constexpr int PR_SMEM_LIMIT = 232448;                // 227 KB
+constexpr int PR_TAIL_BYTES = 256 + IG_MAXN * 4;     // barriers + tmem slot, bias
+
+struct PairParams {
+  const float* bias;
+  float* y;
+  float* sz;
+  int B, H, W, C, Cout, Npad, taps, epi, inverse;
+  int tiles_x, tiles_y;
+  long long ntiles, npairs;
+  int kb;                                  // 32-channel k-blocks
+  int stages, stage_bytes, bhalf_bytes;    // per CTA
+  int nacc_stages, stage_cols, acc_cols;   // TMEM plan (as IgemmParams)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
+igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
+  const uint32_t bars = base + ring_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (PR_MAXST + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * PR_MAXST + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * PR_MAXST + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 4));
+  float* s_bias = reinterpret_cast<float*>(gen + ring_bytes + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  for (int i = threadIdx.x; i < IG_MAXN; i += IG_THREADS) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), IG_TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int iters = p.taps * p.kb;
+  const long long per_img = (long long)p.tiles_x * p.tiles_y;
+  const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nhalf = p.Npad / 2;
+      for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+        const long long t = 2 * pt + rank;             // an odd tile count leaves the last pair's second CTA on an
+        const int b = (int)(t / per_img);              // out-of-range image index: TMA zero-fills, nothing is stored
+        const int r = (int)(t % per_img);
+        const int y0 = (r / p.tiles_x) * IG_TH, x0 = (r % p.tiles_x) * IG_TW;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int kb = 0; kb < p.kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
+            const uint32_t sa = base + stage * p.stage_bytes;
+            tma_load_4d_2sm(sa, &tmA, full_bar(stage), 32 * kb, x0 + dx, y0 + dy, b);
+            tma_load_4d_2sm(sa + PR_A_BYTES, &tmA, full_bar(stage), p.C + 32 * kb, x0 + dx, y0 + dy, b);
+            tma_load_3d_2sm(sa + 2 * PR_A_BYTES, &tmB, full_bar(stage), 32 * kb, (int)rank * nhalf, tap);
+            tma_load_3d_2sm(sa + 2 * PR_A_BYTES + p.bhalf_bytes, &tmB, full_bar(stage), p.C + 32 * kb, (int)rank * nhalf, tap);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // D fp32, A/B tf32 K-major, N = Npad, M = 256 across the pair
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * p.stage_cols);
+        const uint32_t d_small = d_main + (uint32_t)p.acc_cols;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * p.stage_bytes;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
+          const uint32_t cont = (uint32_t)(it != 0);
+          // the two small terms first (own accumulator: its ulp is 2^-11 of the main one's), then A_hi * B_hi
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+          tc_commit_2sm(empty_bar(stage), 3);          // both CTAs' copies of the stage are reusable
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(tfull_bar(acc), 3);              // accumulators complete, in both CTAs
+        if (++acc == p.nacc_stages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int ty = row / IG_TW, tx = row % IG_TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int nchunks = (p.Npad + 31) / 32;
+    for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+      const long long t = 2 * pt + rank;
+      const int b = (int)(t / per_img);
+      const int r = (int)(t % per_img);
+      const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
+      const bool valid = t < p.ntiles && y < p.H && x < p.W;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.stage_cols);
+      const long long px = ((long long)b * p.H + y) * p.W + x;
+      for (int c = chunk0; c < nchunks; c += 2) {
+        float o[32];
+        const bool chunk_on = valid && c * 32 < p.Cout;
+        if (p.epi == 2 && chunk_on) {
+          const float* yq = p.y + px * p.Cout + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(yq + j);
+            o[j] = t4.x; o[j + 1] = t4.y; o[j + 2] = t4.z; o[j + 3] = t4.w;
+          }
+        }
+        uint32_t v[32], w[32];
+        tc_ld32(taddr + c * 32, v);
+        tc_ld32(taddr + p.acc_cols + c * 32, w);
+        tc_wait_ld();
+        if (chunk_on) {
+          float* yp = p.y + px * p.Cout + c * 32;
+          float* zp = p.sz + px * (2 * p.Cout) + c * 32;
+          float hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = (__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 32 + j];
+            float rr;
+            if (p.epi == 2) rr = o[j] * (p.inverse ? sqrtf(a) : rsqrtf(a));
+            else { o[j] = a; rr = a * a; }
+            hi[j] = tf32_rna(rr);
+            lo[j] = tf32_rna(rr - hi[j]);
+          }
+          if (p.epi != 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          }
+          if (p.epi != 3) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              *reinterpret_cast<float4*>(zp + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+              *reinterpret_cast<float4*>(zp + p.Cout + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == p.nacc_stages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // neither CTA frees tensor memory / exits while the pair is still working
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, IG_TMEM_COLS);
+  }
+}
+
 // Small-Cin convs of the context models written channels-last in bf16 for the igemm layers:
 //   plc head  Conv2d(3, 243, 3, padding=1) + LeakyReLU on the nearest-2x-upsampled parent (:271,355)
 //   csc       MaskedConv2d('A', 3, 243, 5, padding=2, groups=3) on the quantised child (:274-277,353);
@@ -736,8 +949,66 @@ int ll_pack_tf32_weight(const float* w, float* wp, int Co, int Ci, int taps, int
   return LL_OK;
 }
 
+static int launch_igemm_tf32_pair(const float* a_nhwc, const float* wp, const float* bias, int B, int H, int W, int C, int Npad,
+                                  int Cout, int taps, int epi, int inverse, float* y, float* sz, cudaStream_t stream) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmA, tmB;
+  const int Ca = 2 * C;   // [hi | lo]
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Ca, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Ca * 4, (cuuint64_t)W * Ca * 4, (cuuint64_t)H * W * Ca * 4};
+    cuuint32_t box[4] = {32, IG_TW, IG_TH, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_nhwc), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Ca, (cuuint64_t)Npad, (cuuint64_t)taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)Ca * 4, (cuuint64_t)Npad * Ca * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)(Npad / 2), 1};     // each CTA of a pair fetches half of the weight rows
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wp), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  PairParams p = {};
+  p.bias = bias; p.y = y; p.sz = sz;
+  p.B = B; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.Npad = Npad; p.taps = taps; p.epi = epi; p.inverse = inverse;
+  p.tiles_x = (W + IG_TW - 1) / IG_TW;
+  p.tiles_y = (H + IG_TH - 1) / IG_TH;
+  p.ntiles = (long long)B * p.tiles_x * p.tiles_y;
+  p.npairs = (p.ntiles + 1) / 2;
+  p.kb = C / 32;
+  p.bhalf_bytes = (Npad / 2) * 128;
+  p.stage_bytes = 2 * PR_A_BYTES + 2 * p.bhalf_bytes;
+  p.stages = (PR_SMEM_LIMIT - 1024 - PR_TAIL_BYTES) / p.stage_bytes;
+  if (p.stages > PR_MAXST) p.stages = PR_MAXST;
+  if (p.stages < 2) return fail(LL_EINVAL, "ll_igemm_tf32: stage of %d bytes leaves fewer than 2 pipeline stages", p.stage_bytes);
+  p.acc_cols = (Npad + 31) / 32 * 32;
+  if (2 * p.acc_cols <= IG_MAXN) { p.nacc_stages = 2; p.stage_cols = IG_MAXN; }
+  else { p.nacc_stages = 1; p.stage_cols = IG_TMEM_COLS; }
+  const int smem = 1024 + p.stages * p.stage_bytes + PR_TAIL_BYTES;
+  static thread_local bool attr[64] = {false};
+  int dev = 0;
+  LL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr[dev]) {
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_LIMIT));
+    attr[dev] = true;
+  }
+  long long pairs = sm_count_cached() / 2;
+  if (pairs > p.npairs) pairs = p.npairs;
+  if (pairs < 1) pairs = 1;
+  igemm_tf32_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, stream>>>(tmA, tmB, p);
+  LL_LAUNCH_OK("igemm_tf32_pair_kernel");
+  return LL_OK;
+}
+
 int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B, int H, int W, int C, int Npad, int Cout,
-                  int taps, int epi, int inverse, float* y, float* sz, ll_stream_t stream) {
+                  int taps, int epi, int inverse, float* y, float* sz, int pair, ll_stream_t stream) {
   if (B < 0 || H < 0 || W < 0 || C < 32 || C % 32 || Npad < 16 || Npad % 16 || Npad > IG_MAXN || Cout < 32 || Cout % 32 ||
       Cout > Npad || (taps != 1 && taps != 9) || epi < 1 || epi > 3)
     return fail(LL_EINVAL, "ll_igemm_tf32: bad extents (C, Cout multiples of 32, Npad %%16 <= 256, taps 1|9, epi 1..3)");
@@ -746,6 +1017,7 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
   if (!a_nhwc || !wp || !y || (epi != 3 && !sz)) return fail(LL_EINVAL, "ll_igemm_tf32: null pointer");
   if (((uintptr_t)a_nhwc & 15) || ((uintptr_t)wp & 15) || ((uintptr_t)y & 15) || ((uintptr_t)sz & 15))
     return fail(LL_EINVAL, "ll_igemm_tf32: buffers must be 16-byte aligned");
+  if (pair) return launch_igemm_tf32_pair(a_nhwc, wp, bias, B, H, W, C, Npad, Cout, taps, epi, inverse, y, sz, as_stream(stream));
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LL_ECUDA, "ll_igemm_tf32: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tmA, tmB;

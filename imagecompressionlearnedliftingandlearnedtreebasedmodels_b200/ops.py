@@ -394,7 +394,7 @@ def pack_tf32_weight(weight, transposed=False):
     return wp
 
 
-def igemm_tf32(a_split, wp, bias, cout, epi, inverse=False, y=None):
+def igemm_tf32(a_split, wp, bias, cout, epi, inverse=False, y=None, pair=True):
     """3xTF32 implicit-GEMM conv of a channels-last fp32 split tensor (B,H,W,2C).  epi 1: returns (y, split(y^2));
     epi 2 (GDN): returns (y, split(y * rsqrt(acc + bias))) with ``y`` given; epi 3: returns (y, None)."""
     require_device(a_split)
@@ -414,7 +414,7 @@ def igemm_tf32(a_split, wp, bias, cout, epi, inverse=False, y=None):
     sz = torch.empty(B, H, W, 2 * cout, dtype=torch.float32, device=a_split.device) if epi != 3 else None
     with torch.cuda.device(a_split.device):
         check(_lib.load().ll_igemm_tf32(ptr(a_split), ptr(wp), ptr(b), B, H, W, C, npad, cout, taps, epi, int(bool(inverse)),
-                                        ptr(y), ptr(sz), stream_ptr()))
+                                        ptr(y), ptr(sz), int(bool(pair)), stream_ptr()))
     _count(1)
     return y, sz
 

@@ -218,9 +218,11 @@ int ll_pack_tf32_weight(const float* w, float* wp, int Co, int Ci, int taps, int
                         ll_stream_t stream);
 /* a_nhwc (B,H,W,2C) [hi | lo]; wp from ll_pack_tf32_weight with Kpad == C; bias[Cout].  epi 1: conv -> y (B,H,W,Cout)
  * raw output and sz (B,H,W,2*Cout) = split of y^2 (the GDN norm input); epi 2: GDN -> sz = split of
- * y * rsqrt(acc + bias) (inverse != 0: * sqrt), y is READ; epi 3: conv -> y only.  C, Cout multiples of 32. */
+ * y * rsqrt(acc + bias) (inverse != 0: * sqrt), y is READ; epi 3: conv -> y only.  C, Cout multiples of 32.
+ * pair != 0 (the product's choice): CTA pairs (clusters of 2, tcgen05 cta_group::2, M = 256) that fetch every k-block once
+ * and share the weight tile; pair == 0: the single-CTA kernel (kept for A/B measurements).  Same results bit for bit. */
 int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B, int H, int W, int C, int Npad, int Cout,
-                  int taps, int epi, int inverse, float* y, float* sz, ll_stream_t stream);
+                  int taps, int epi, int inverse, float* y, float* sz, int pair, ll_stream_t stream);
 /* fp32 NCHW (B,C,H,W) -> y NHWC raw (optional) and sz NHWC (B,H,W,2C) = split of x^2 (mode 0) or of x (mode 1). */
 int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int H, int W, int mode, ll_stream_t stream);
 /* z NHWC (B,H,W,2C) [hi | lo] -> fp32 NCHW (B,C,H,W) = hi + lo. */

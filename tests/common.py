@@ -47,31 +47,38 @@ FLIP_EPS = 1e-5          # a flip must sit within 1e-5 of a
 FLIP_LOG = []            # (label, n_symbols, n_mismatch, n_unexplained) of every audit of this session
 
 
-def flip_audit(q_gpu, q_ref, pre_ref, eps=FLIP_EPS, pre_ref64=None, label=None):
+def flip_audit(q_gpu, q_ref, pre_ref, eps=FLIP_EPS, pre_ref64=None, label=None, q_ref64=None):
     """Symbol parity.  Quantised tensors are integers (``round(x)``) or mean-shifted integers
     (``round(x - mu) + mu`` for EntropyBottleneck / onlyEZWT outputs, where mu itself is a
     context-CNN output carrying fp32 noise).  The difference is split into an integer number of
-    quantisation steps k and a remainder: a sample *matches* when k == 0 and the remainder is
-    within 1e-4 relative (exactly 0 for plain rounding).  A mismatch is *explained* only when it is a
-    single step (|k| == 1) and, for plain rounding, the oracle's pre-quantiser value -- the float64
-    oracle's (``pre_ref64``, the tie-break of SURVEY.md section 7) when given, else the fp32 one --
-    sits within ``eps * max(1, |x|)`` of the rounding boundary (frac = 0.5): there fp32 summation order
-    alone decides the symbol, and the reference run on another thread count flips it too.
+    quantisation steps k and a remainder: a sample *matches* when k == 0 and the remainder (the
+    difference of the two mu) is within 1e-4 of the tensor's scale (exactly 0 for plain rounding).
+    A mismatch is *explained* only when it is a single step (|k| == 1) and the oracle's pre-rounding
+    value -- the float64 oracle's (``pre_ref64`` / ``q_ref64``, the tie-break of SURVEY.md section 7)
+    when given, else the fp32 one -- sits within ``eps * max(1, |x|)`` of the rounding boundary: there
+    fp32 summation order alone decides the symbol, and the reference run on another thread count flips
+    it too.  For mean-shifted rounding the rounded quantity is x - mu and its distance to the boundary
+    is 0.5 - |x - q| (q - mu is an integer).
     Returns (n_mismatch, n_unexplained); every call is logged in ``FLIP_LOG`` and printed by the suite."""
     d = q_gpu - q_ref
     k = torch.round(d)
     integer_q = bool((q_ref == torch.round(q_ref)).all())
-    rem_tol = 0.0 if integer_q else 1e-4
-    rem_ok = (d - k).abs() <= rem_tol * (1 + q_ref.abs())
+    rem_tol = 0.0 if integer_q else 1e-4 * max(1.0, float(q_ref.abs().max()))
+    rem_ok = (d - k).abs() <= rem_tol
     mism = (k != 0) | ~rem_ok
     n = int(mism.sum())
     bad = 0
     if n:
         ok = (k[mism].abs() == 1) & rem_ok[mism]
+        pre = (pre_ref64 if pre_ref64 is not None else pre_ref).double()[mism]
         if integer_q:
-            pre = (pre_ref64 if pre_ref64 is not None else pre_ref).double()[mism]
-            frac = (pre - torch.floor(pre) - 0.5).abs()
-            ok = ok & (frac <= eps * pre.abs().clamp(min=1.0))
+            dist = (pre - torch.floor(pre) - 0.5).abs()
+            scale = pre.abs().clamp(min=1.0)
+        else:
+            qr = (q_ref64 if (q_ref64 is not None and pre_ref64 is not None) else q_ref).double()[mism]
+            dist = 0.5 - (pre - qr).abs()
+            scale = torch.maximum(pre.abs(), qr.abs()).clamp(min=1.0)
+        ok = ok & (dist <= eps * scale)
         bad = int((~ok).sum())
     FLIP_LOG.append((label or "", int(q_ref.numel()), n, bad))
     return n, bad

@@ -198,10 +198,8 @@ def test_berk_autoencoder_tc_matches_torch_fp32(in_ch, shape):
     with torch.no_grad():
         for name in ("encode", "decode"):
             ref = getattr(ae64, "ae_down" if name == "encode" else "ae_up")(x.double())     # float64 ground truth
-            ae.ae_precision = "tc"
-            got = getattr(ae, name)(x)
-            ae.ae_precision = "torch"
-            t32 = getattr(ae, name)(x)
+            got = getattr(ae, name)(x)                                        # the product path (3xTF32 chain)
+            t32 = ae._exact(ae.ae_down if name == "encode" else ae.ae_up, x)  # the module's torch layers, TF32 off
             scale = ref.abs().max().item()
             err_tc = (got.double() - ref).abs().max().item() / scale
             err_t32 = (t32.double() - ref).abs().max().item() / scale
@@ -234,3 +232,36 @@ def test_nhwc_split_tail_conv_matches_torch(C, Cout, shape):
     assert (nob.double() - (ref - b.double().view(1, -1, 1, 1))).abs().max().item() <= 2e-6 * ref.abs().max().item()
     with pytest.raises(Exception):
         ops.nhwc_split_conv3(z[..., :2 * C - 2].contiguous(), w, b)
+
+
+@pytest.mark.parametrize("C,N,taps,epi,shape", [(96, 192, 9, 1, (2, 37, 50)), (192, 96, 9, 1, (1, 24, 40)), (96, 96, 1, 2, (3, 16, 16)),
+                                                (256, 256, 9, 3, (1, 9, 33)), (32, 64, 9, 1, (1, 8, 16)), (64, 32, 1, 2, (1, 5, 7))])
+def test_igemm_tf32_cta_pairs_match_single_cta_kernel(C, N, taps, epi, shape):
+    """``ll_igemm_tf32`` on CTA pairs (clusters of 2, tcgen05 cta_group::2, every k-block fetched once, weight tile shared)
+    against the single-CTA kernel: same MMA order per accumulator, so the outputs must be identical bit for bit -- on even
+    and odd tile counts, ragged planes, 3x3 and 1x1 (GDN) instances, both accumulator plans (N <= 128 and N > 128)."""
+    ops = _ops()
+    torch.manual_seed(C * 7 + N + taps)
+    B, H, W = shape
+    v = torch.randn(B, H, W, C, device=DEV)
+    hi = (v.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    a = torch.cat([hi, v - hi], dim=3).contiguous()
+    k = 3 if taps == 9 else 1
+    wt = torch.randn(N, C, k, k, device=DEV) * (1.0 / (C * taps) ** 0.5)
+    wp = ops.pack_tf32_weight(wt)
+    bias = torch.rand(N, device=DEV) + (1.0 if epi == 2 else 0.0)
+    if epi == 2:
+        with torch.no_grad():
+            wp.abs_()                                   # a GDN norm: non-negative weights on squares, positive beta
+            a.abs_()
+    y_in = torch.randn(B, H, W, N, device=DEV) if epi == 2 else None
+    y1, z1 = ops.igemm_tf32(a, wp, bias, N, epi=epi, y=y_in, pair=False)
+    y2, z2 = ops.igemm_tf32(a, wp, bias, N, epi=epi, y=y_in.clone() if epi == 2 else None, pair=True)
+    torch.cuda.synchronize()
+    if epi != 2:
+        assert torch.equal(y1, y2)
+        ref = F.conv2d(v.double().permute(0, 3, 1, 2), wt.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
+        assert (y2.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()      # fp32-level
+    if epi != 3:
+        assert torch.equal(z1, z2)
+        assert torch.isfinite(z2).all()
