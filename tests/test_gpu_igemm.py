@@ -261,7 +261,7 @@ def test_igemm_tf32_cta_pairs_match_single_cta_kernel(C, N, taps, epi, shape):
     if epi != 2:
         assert torch.equal(y1, y2)
         ref = F.conv2d(v.double().permute(0, 3, 1, 2), wt.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
-        assert (y2.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()      # fp32-level
+        assert (y2.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()      # fp32-level (K up to 2304 terms)
     if epi != 3:
         assert torch.equal(z1, z2)
         assert torch.isfinite(z2).all()
