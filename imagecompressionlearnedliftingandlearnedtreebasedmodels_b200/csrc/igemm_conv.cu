@@ -517,6 +517,288 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused 3x3 conv + GDN / inverse GDN on CTA pairs (SubbandAutoEncoderBerk, lifting_dwt_nets.py:140-148 and
+// graphs/layers/gdn.py:54-92):   z = y * rsqrt(beta + gamma . y^2)   (inverse: * sqrt),   y = conv(a) + bias.
+// The un-fused chain wrote y (4 B) and the [hi|lo] split of y^2 (8 B) per value and ran the norm as a second GEMM that
+// read them back (12 B) and wrote the split of z (8 B): 32 B of HBM traffic per value and two kernels that ncu showed
+// bound by their epilogues' global loads / stores.  Here the conv's accumulator tile never leaves the SM:
+//   E1   epilogue warps: y = main + small + bias, written back IN PLACE into tensor memory;
+//   S    staging rounds: [hi | lo] split of y^2 for KS channels -> tensor memory as the A operand (tcgen05.st);
+//   G    tcgen05.mma (A from tensor memory, B = gamma rows streamed through the TMA ring) accumulates the norm of NP output
+//        channels, small terms and main term in separate accumulators as in the conv;
+//   E2   z = y * rsqrt(norm + beta) -> [hi | lo] split -> the only global stores of the kernel (8 B per value).
+// Tensor-memory plan per CTA (columns): y [0, N) | norm main [N, N + NP) | norm small [N + NP, N + 2 NP) | staging
+// hi [N + 2 NP, +KS) lo [.., +KS).  N = 192: NP = 96 (two passes), KS = 64 -> 512 columns; N <= 96: NP = KS = N.
+// Every warp of parity e (two epilogue warps per TMEM lane quarter) only touches 32-column chunks of y with global
+// index = e (mod 2), so no y column is read by a warp other than the one that wrote it.
+// ------------------------------------------------------------------------------------------------
+struct GdnPairParams {
+  const float* bias;
+  const float* beta;
+  float* sz;
+  int B, H, W, C, N, taps, inverse;
+  int tiles_x, tiles_y;
+  long long ntiles, npairs;
+  int kb;
+  int stages, stage_bytes, bhalf_bytes;
+  int NP, KS, passes, rpp;                 // outputs per pass, channels per staging round, passes, rounds per pass
+  int ghalf_bytes;                         // (NP / 2) rows x 128 B
+  int col_nm, col_ns, col_st;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
+igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmG, const __grid_constant__ GdnPairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
+  const uint32_t bars = base + ring_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (PR_MAXST + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * PR_MAXST), tempty_bar = bars + 8u * (2 * PR_MAXST + 1);
+  const uint32_t aready_bar = bars + 8u * (2 * PR_MAXST + 2), gdone_bar = bars + 8u * (2 * PR_MAXST + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 4));
+  float* s_bias = reinterpret_cast<float*>(gen + ring_bytes + 256);
+  float* s_beta = s_bias + IG_MAXN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  for (int i = threadIdx.x; i < IG_MAXN; i += IG_THREADS) {
+    s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+    s_beta[i] = i < p.N ? p.beta[i] : 1.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 16);
+    mbar_init(aready_bar, 16);
+    mbar_init(gdone_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), IG_TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int iters = p.taps * p.kb;
+  const int gkb = p.N / 32;                              // k-blocks of one GDN pass
+  const long long per_img = (long long)p.tiles_x * p.tiles_y;
+  const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nhalf = p.N / 2, ghalf = p.NP / 2;
+      for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+        const long long t = 2 * pt + rank;
+        const int b = (int)(t / per_img);
+        const int r = (int)(t % per_img);
+        const int y0 = (r / p.tiles_x) * IG_TH, x0 = (r % p.tiles_x) * IG_TW;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int kb = 0; kb < p.kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
+            const uint32_t sa = base + stage * p.stage_bytes;
+            tma_load_4d_2sm(sa, &tmA, full_bar(stage), 32 * kb, x0 + dx, y0 + dy, b);
+            tma_load_4d_2sm(sa + PR_A_BYTES, &tmA, full_bar(stage), p.C + 32 * kb, x0 + dx, y0 + dy, b);
+            tma_load_3d_2sm(sa + 2 * PR_A_BYTES, &tmB, full_bar(stage), 32 * kb, (int)rank * nhalf, tap);
+            tma_load_3d_2sm(sa + 2 * PR_A_BYTES + p.bhalf_bytes, &tmB, full_bar(stage), p.C + 32 * kb, (int)rank * nhalf, tap);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        // gamma rows of every pass, k-block by k-block, in the order the norm MMAs consume them
+        for (int ps = 0; ps < p.passes; ++ps) {
+          for (int kb = 0; kb < gkb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (leader) mbar_expect_tx(full_bar(stage), 4u * (uint32_t)p.ghalf_bytes);
+            const uint32_t sa = base + stage * p.stage_bytes;
+            tma_load_3d_2sm(sa, &tmG, full_bar(stage), 32 * kb, ps * p.NP + (int)rank * ghalf, 0);
+            tma_load_3d_2sm(sa + p.ghalf_bytes, &tmG, full_bar(stage), p.N + 32 * kb, ps * p.NP + (int)rank * ghalf, 0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, te_phase = 0, ar_phase = 0;
+      const uint32_t d_main = tmem_base, d_small = tmem_base + (uint32_t)p.N;
+      const uint32_t d_nm = tmem_base + (uint32_t)p.col_nm, d_ns = tmem_base + (uint32_t)p.col_ns;
+      const uint32_t a_st = tmem_base + (uint32_t)p.col_st;
+      for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+        mbar_wait(tempty_bar, te_phase ^ 1);
+        te_phase ^= 1;
+        tc_fence_after();
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * p.stage_bytes;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
+          const uint32_t cont = (uint32_t)(it != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+          tc_commit_2sm(empty_bar(stage), 3);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(tfull_bar, 3);
+        // norm GEMMs: A = staged split of y^2 in tensor memory, B = gamma rows from the ring
+        for (int ps = 0; ps < p.passes; ++ps) {
+          for (int rd = 0; rd < p.rpp; ++rd) {
+            mbar_wait(aready_bar, ar_phase);
+            ar_phase ^= 1;
+            tc_fence_after();
+            for (int kbr = 0; kbr < p.KS / 32; ++kbr) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = base + stage * p.stage_bytes;
+              const uint64_t g_hi = umma_desc_sw128(sa), g_lo = umma_desc_sw128(sa + p.ghalf_bytes);
+              const uint32_t cont = (uint32_t)((rd | kbr) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ah = a_st + (uint32_t)(kbr * 32 + 8 * k), al = ah + (uint32_t)p.KS;
+                tc_mma_tf32_ts_2sm(d_ns, al, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
+                tc_mma_tf32_ts_2sm(d_ns, ah, g_lo + 2 * k, idesc_g, 1u);
+                tc_mma_tf32_ts_2sm(d_nm, ah, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
+              }
+              tc_commit_2sm(empty_bar(stage), 3);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit_2sm(gdone_bar, 3);                // this round's MMAs done: staging reusable / norm complete
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int par = (warp - 2) >> 2;                    // chunk parity of this warp
+    const int row = q * 32 + lane;
+    const int ty = row / IG_TW, tx = row % IG_TW;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tf_phase = 0;
+    unsigned gcount = 0;                                // completions of gdone consumed so far (parity = gcount & 1)
+    const int nchunks = p.N / 32;
+    for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+      const long long t = 2 * pt + rank;
+      const int b = (int)(t / per_img);
+      const int r = (int)(t % per_img);
+      const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
+      const bool valid = t < p.ntiles && y < p.H && x < p.W;
+      const long long px = ((long long)b * p.H + y) * p.W + x;
+      mbar_wait(tfull_bar, tf_phase);
+      tf_phase ^= 1;
+      tc_fence_after();
+      // E1: y = main + small + bias, in place
+      for (int c = par; c < nchunks; c += 2) {
+        uint32_t v[32], w[32];
+        tc_ld32(tlane + c * 32, v);
+        tc_ld32(tlane + p.N + c * 32, w);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 32 + j]);
+        tmem_st32(tlane + c * 32, v);
+      }
+      tmem_wait_st();
+      const unsigned g0 = gcount;
+      for (int ps = 0; ps < p.passes; ++ps) {
+        for (int rd = 0; rd < p.rpp; ++rd) {
+          const unsigned need = (unsigned)(ps * p.rpp + rd);     // rounds that must have completed before the staging is rewritten
+          while (gcount - g0 < need) { mbar_wait(gdone_bar, gcount & 1u); ++gcount; }
+          tc_fence_after();
+          for (int cc = 0; cc < p.KS / 32; ++cc) {
+            const int gc = rd * (p.KS / 32) + cc;                // global chunk index of these y columns
+            if ((gc & 1) != par) continue;
+            uint32_t v[32], lo[32];
+            tc_ld32(tlane + gc * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float yy = __uint_as_float(v[j]);
+              const float sq = yy * yy;
+              const float h = tf32_rna(sq);
+              v[j] = __float_as_uint(h);
+              lo[j] = __float_as_uint(tf32_rna(sq - h));
+            }
+            tmem_st32(tlane + p.col_st + cc * 32, v);
+            tmem_st32(tlane + p.col_st + p.KS + cc * 32, lo);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(aready_bar);
+        }
+        // the pass's last round done -> norm of channels [ps NP, ps NP + NP) complete
+        const unsigned need = (unsigned)((ps + 1) * p.rpp);
+        while (gcount - g0 < need) { mbar_wait(gdone_bar, gcount & 1u); ++gcount; }
+        tc_fence_after();
+        for (int cc = 0; cc < p.NP / 32; ++cc) {
+          const int gc = ps * (p.NP / 32) + cc;
+          if ((gc & 1) != par) continue;
+          uint32_t yv[32], nm[32], ns[32];
+          tc_ld32(tlane + gc * 32, yv);
+          tc_ld32(tlane + p.col_nm + cc * 32, nm);
+          tc_ld32(tlane + p.col_ns + cc * 32, ns);
+          tc_wait_ld();
+          if (valid) {
+            float* zp = p.sz + px * (2 * p.N) + gc * 32;
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+              float hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = (__uint_as_float(nm[j0 + j]) + __uint_as_float(ns[j0 + j])) + s_beta[gc * 32 + j0 + j];
+                const float rr = __uint_as_float(yv[j0 + j]) * (p.inverse ? sqrtf(a) : rsqrtf(a));
+                hi[j] = tf32_rna(rr);
+                lo[j] = tf32_rna(rr - hi[j]);
+              }
+              st_global_v8(zp + j0, hi);
+              st_global_v8(zp + p.N + j0, lo);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, IG_TMEM_COLS);
+  }
+}
+
 // Small-Cin convs of the context models written channels-last in bf16 for the igemm layers:
 //   plc head  Conv2d(3, 243, 3, padding=1) + LeakyReLU on the nearest-2x-upsampled parent (:271,355)
 //   csc       MaskedConv2d('A', 3, 243, 5, padding=2, groups=3) on the quantised child (:274-277,353);
@@ -1078,6 +1360,89 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
   const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
   igemm_conv_kernel<true><<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
   LL_LAUNCH_OK("igemm_conv_kernel<tf32>");
+  return LL_OK;
+}
+
+// Fused conv (taps 1 | 9) + GDN / inverse GDN: a_nhwc (B,H,W,2C) [hi|lo] -> sz (B,H,W,2N) [hi|lo] of
+// y * rsqrt(beta + gamma . y^2) (inverse: * sqrt), y = conv(a) + bias.  wp: conv weights from ll_pack_tf32_weight
+// (Npad == N, Kpad == C); gp: gamma (N,N,1,1) packed the same way (Npad == Kpad == N); beta: N reparametrised values.
+int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
+                      int W, int C, int N, int taps, int inverse, float* sz, ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || C < 32 || C % 32 || C > 256 || (taps != 1 && taps != 9))
+    return fail(LL_EINVAL, "ll_igemm_tf32_gdn: bad extents (C a multiple of 32 up to 256, taps 1|9)");
+  if (N != 32 && N != 64 && N != 96 && N != 192)
+    return fail(LL_EINVAL, "ll_igemm_tf32_gdn: N must be 32, 64, 96 or 192 (tensor-memory plan), got %d", N);
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!a_nhwc || !wp || !gp || !beta || !sz) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: null pointer");
+  if (((uintptr_t)a_nhwc & 15) || ((uintptr_t)wp & 15) || ((uintptr_t)gp & 15) || ((uintptr_t)sz & 31))
+    return fail(LL_EINVAL, "ll_igemm_tf32_gdn: operands must be 16-byte aligned, the output 32-byte aligned");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled not available from the driver");
+  GdnPairParams p = {};
+  p.NP = N == 192 ? 96 : N;
+  p.KS = N == 192 ? 64 : N;
+  p.passes = N / p.NP;
+  p.rpp = N / p.KS;
+  p.col_nm = N; p.col_ns = N + p.NP; p.col_st = N + 2 * p.NP;
+  if (p.col_st + 2 * p.KS > IG_TMEM_COLS) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: tensor-memory plan does not fit");
+  CUtensorMap tmA, tmB, tmG;
+  const int Ca = 2 * C;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Ca, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)Ca * 4, (cuuint64_t)W * Ca * 4, (cuuint64_t)H * W * Ca * 4};
+    cuuint32_t box[4] = {32, IG_TW, IG_TH, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_nhwc), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Ca, (cuuint64_t)N, (cuuint64_t)taps};
+    cuuint64_t gstr[2] = {(cuuint64_t)Ca * 4, (cuuint64_t)N * Ca * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)(N / 2), 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wp), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)(2 * N), (cuuint64_t)N, 1};
+    cuuint64_t gstr[2] = {(cuuint64_t)(2 * N) * 4, (cuuint64_t)N * (2 * N) * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)(p.NP / 2), 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(gp), gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled(G) failed with %d", (int)r);
+  }
+  p.bias = bias; p.beta = beta; p.sz = sz;
+  p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.inverse = inverse;
+  p.tiles_x = (W + IG_TW - 1) / IG_TW;
+  p.tiles_y = (H + IG_TH - 1) / IG_TH;
+  p.ntiles = (long long)B * p.tiles_x * p.tiles_y;
+  p.npairs = (p.ntiles + 1) / 2;
+  p.kb = C / 32;
+  p.bhalf_bytes = (N / 2) * 128;
+  p.ghalf_bytes = (p.NP / 2) * 128;
+  p.stage_bytes = 2 * PR_A_BYTES + 2 * p.bhalf_bytes;
+  p.stages = (PR_SMEM_LIMIT - 1024 - PR_TAIL_BYTES - IG_MAXN * 4) / p.stage_bytes;
+  if (p.stages > PR_MAXST) p.stages = PR_MAXST;
+  if (p.stages < 2) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: stage of %d bytes leaves fewer than 2 pipeline stages", p.stage_bytes);
+  const int smem = 1024 + p.stages * p.stage_bytes + PR_TAIL_BYTES + IG_MAXN * 4;
+  static thread_local bool attr[64] = {false};
+  int dev = 0;
+  LL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 64 && !attr[dev]) {
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_tf32_gdn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_LIMIT));
+    attr[dev] = true;
+  }
+  long long pairs = sm_count_cached() / 2;
+  if (pairs > p.npairs) pairs = p.npairs;
+  if (pairs < 1) pairs = 1;
+  igemm_tf32_gdn_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, as_stream(stream)>>>(tmA, tmB, tmG, p);
+  LL_LAUNCH_OK("igemm_tf32_gdn_pair_kernel");
   return LL_OK;
 }
 

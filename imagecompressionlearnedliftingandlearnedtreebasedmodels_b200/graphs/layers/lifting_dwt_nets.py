@@ -103,6 +103,7 @@ class SubbandAutoEncoderBerk(nn.Module):
 
     # ---- tensor-core path: convs 2-3 and the three GDN norms as 3xTF32 implicit GEMMs (fp32-level accuracy) ----
     AE_BATCH_CHUNK = 8     # images per launch group: bounds the channels-last fp32 intermediates
+    fuse_gdn = True        # convs 2-3 run fused with their GDN (ll_igemm_tf32_gdn); False = the two-kernel chain (A/B checks)
 
     def _pack(self, seq, transposed, cache):
         convs = [seq[0], seq[2], seq[4], seq[6]]
@@ -134,10 +135,16 @@ class SubbandAutoEncoderBerk(nn.Module):
             y, s = ops.nchw_to_nhwc_split(c1, squares=True)
             del c1
             _, z = ops.igemm_tf32(s, pk["gdn"][0][0], pk["gdn"][0][1], y.shape[3], epi=2, inverse=inv, y=y)
-            for k in (0, 1):
-                y, s = ops.igemm_tf32(z, pk["wp"][k], convs[1 + k].bias, convs[1 + k].weight.shape[1 if transposed else 0], epi=1)
-                _, z = ops.igemm_tf32(s, pk["gdn"][1 + k][0], pk["gdn"][1 + k][1], y.shape[3], epi=2, inverse=inv, y=y)
             del y, s
+            for k in (0, 1):
+                cout = convs[1 + k].weight.shape[1 if transposed else 0]
+                if self.fuse_gdn and cout in ops.GDN_FUSED_WIDTHS:
+                    # conv + GDN in one kernel: the conv output, its square and the norm stay in tensor memory
+                    z = ops.igemm_tf32_gdn(z, pk["wp"][k], convs[1 + k].bias, pk["gdn"][1 + k][0], pk["gdn"][1 + k][1], cout, inverse=inv)
+                else:
+                    y, s = ops.igemm_tf32(z, pk["wp"][k], convs[1 + k].bias, cout, epi=1)
+                    _, z = ops.igemm_tf32(s, pk["gdn"][1 + k][0], pk["gdn"][1 + k][1], cout, epi=2, inverse=inv, y=y)
+                    del y, s
             outs.append(ops.nhwc_split_conv3(z, pk["w3"], convs[3].bias))     # exact fp32, straight from the chain's layout
             del z
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

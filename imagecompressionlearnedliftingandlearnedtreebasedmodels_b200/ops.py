@@ -419,6 +419,30 @@ def igemm_tf32(a_split, wp, bias, cout, epi, inverse=False, y=None, pair=True):
     return y, sz
 
 
+def igemm_tf32_gdn(a_split, wp, bias, gp, beta, cout, inverse=False):
+    """Fused 3xTF32 conv + GDN / inverse GDN on CTA pairs (ll_igemm_tf32_gdn): channels-last split tensor (B,H,W,2C) ->
+    split (B,H,W,2*cout) of y * rsqrt(beta + gamma . y^2); the conv output and the norm never leave the SM."""
+    require_device(a_split)
+    if a_split.dtype != torch.float32 or not a_split.is_contiguous() or a_split.dim() != 4:
+        raise TypeError("igemm_tf32_gdn: a_split must be a contiguous fp32 (B,H,W,2C) tensor")
+    B, H, W, c2 = a_split.shape
+    C = c2 // 2
+    taps, npad, k2 = wp.shape
+    if k2 != 2 * C or npad != cout or tuple(gp.shape) != (1, cout, 2 * cout):
+        raise ValueError(f"igemm_tf32_gdn: packed weights {tuple(wp.shape)} / {tuple(gp.shape)} do not fit C={C}, N={cout}")
+    b = _f32c(bias.detach(), "bias")
+    bt = _f32c(beta.detach(), "beta")
+    sz = torch.empty(B, H, W, 2 * cout, dtype=torch.float32, device=a_split.device)
+    with torch.cuda.device(a_split.device):
+        check(_lib.load().ll_igemm_tf32_gdn(ptr(a_split), ptr(wp), ptr(b), ptr(gp), ptr(bt), B, H, W, C, cout, taps,
+                                            int(bool(inverse)), ptr(sz), stream_ptr()))
+    _count(1)
+    return sz
+
+
+GDN_FUSED_WIDTHS = (32, 64, 96, 192)
+
+
 def nchw_to_nhwc_split(x, squares=True, want_y=True):
     """fp32 NCHW -> (y NHWC raw | None, split NHWC (B,H,W,2C) of x^2 (``squares``) or x)."""
     require_device(x)

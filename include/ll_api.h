@@ -223,6 +223,13 @@ int ll_pack_tf32_weight(const float* w, float* wp, int Co, int Ci, int taps, int
  * and share the weight tile; pair == 0: the single-CTA kernel (kept for A/B measurements).  Same results bit for bit. */
 int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B, int H, int W, int C, int Npad, int Cout,
                   int taps, int epi, int inverse, float* y, float* sz, int pair, ll_stream_t stream);
+/* Fused conv (taps 1 | 9) + GDN / inverse GDN of SubbandAutoEncoderBerk (lifting_dwt_nets.py:140-148, graphs/layers/gdn.py:54-92)
+ * on CTA pairs: sz (B,H,W,2N) = [hi | lo] split of y * rsqrt(beta + gamma . y^2) (inverse != 0: * sqrt), y = conv(a) + bias.
+ * The conv output, its square and the norm stay in tensor memory.  wp: ll_pack_tf32_weight of the conv (Npad == N,
+ * Kpad == C); gp: ll_pack_tf32_weight of the reparametrised gamma (N,N,1,1); beta: N reparametrised values.
+ * N in {32, 64, 96, 192}; C a multiple of 32 up to 256. */
+int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
+                      int W, int C, int N, int taps, int inverse, float* sz, ll_stream_t stream);
 /* fp32 NCHW (B,C,H,W) -> y NHWC raw (optional) and sz NHWC (B,H,W,2C) = split of x^2 (mode 0) or of x (mode 1). */
 int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int H, int W, int mode, ll_stream_t stream);
 /* z NHWC (B,H,W,2C) [hi | lo] -> fp32 NCHW (B,C,H,W) = hi + lo. */

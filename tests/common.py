@@ -76,7 +76,9 @@ def flip_audit(q_gpu, q_ref, pre_ref, eps=FLIP_EPS, pre_ref64=None, label=None, 
             scale = pre.abs().clamp(min=1.0)
         else:
             qr = (q_ref64 if (q_ref64 is not None and pre_ref64 is not None) else q_ref).double()[mism]
-            dist = 0.5 - (pre - qr).abs()
+            # the rounded quantity is x - mu: the two sides' mu differ by exactly d - k at this sample (a context-CNN
+            # output, itself held to 1e-4 of the tensor scale by rem_ok), which moves the boundary by that much
+            dist = 0.5 - (pre - qr).abs() - (d - k).abs().double()[mism]
             scale = torch.maximum(pre.abs(), qr.abs()).clamp(min=1.0)
         ok = ok & (dist <= eps * scale)
         bad = int((~ok).sum())

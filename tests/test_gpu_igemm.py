@@ -265,3 +265,38 @@ def test_igemm_tf32_cta_pairs_match_single_cta_kernel(C, N, taps, epi, shape):
     if epi != 3:
         assert torch.equal(z1, z2)
         assert torch.isfinite(z2).all()
+
+
+@pytest.mark.parametrize("C,N,taps,inverse,shape", [(96, 192, 9, False, (2, 37, 50)), (192, 96, 9, False, (1, 24, 40)), (96, 192, 9, True, (1, 16, 32)),
+                                                    (32, 64, 9, False, (3, 16, 16)), (64, 32, 9, True, (1, 9, 33)), (96, 96, 1, False, (1, 8, 16))])
+def test_fused_conv_gdn_matches_two_kernel_chain_and_float64(C, N, taps, inverse, shape):
+    """``ll_igemm_tf32_gdn`` (conv + GDN in one kernel, the conv output / its square / the norm resident in tensor memory)
+    against (1) the two-kernel chain ``ll_igemm_tf32`` epi 1 -> epi 2 and (2) a float64 evaluation of
+    y * rsqrt(beta + gamma . y^2): fp32-level accuracy, both GDN directions, every tensor-memory plan (N = 32, 64, 96, 192)."""
+    ops = _ops()
+    torch.manual_seed(C + 3 * N + taps)
+    B, H, W = shape
+    v = torch.randn(B, H, W, C, device=DEV)
+    hi = (v.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    a = torch.cat([hi, v - hi], dim=3).contiguous()
+    k = 3 if taps == 9 else 1
+    wt = torch.randn(N, C, k, k, device=DEV) * (1.0 / (C * taps) ** 0.5)
+    bias = torch.randn(N, device=DEV) * 0.1
+    gamma = (torch.rand(N, N, device=DEV) * 0.02 + 0.1 * torch.eye(N, device=DEV)).reshape(N, N, 1, 1).contiguous()
+    beta = torch.rand(N, device=DEV) + 0.5
+    wp, gp = ops.pack_tf32_weight(wt), ops.pack_tf32_weight(gamma)
+    z = ops.igemm_tf32_gdn(a, wp, bias, gp, beta, N, inverse=inverse)
+    y, s = ops.igemm_tf32(a, wp, bias, N, epi=1)
+    _, z2 = ops.igemm_tf32(s, gp, beta, N, epi=2, inverse=inverse, y=y)
+    torch.cuda.synchronize()
+    got, two = z[..., :N] + z[..., N:], z2[..., :N] + z2[..., N:]
+    y64 = F.conv2d(v.double().permute(0, 3, 1, 2), wt.double(), bias.double(), padding=k // 2)
+    norm = F.conv2d(y64 ** 2, gamma.double(), beta.double())
+    ref = (y64 * (norm.sqrt() if inverse else norm.rsqrt())).permute(0, 2, 3, 1)
+    scale = ref.abs().max().item()
+    e_f, e_2 = (got.double() - ref).abs().max().item() / scale, (two.double() - ref).abs().max().item() / scale
+    print(f"C={C} N={N} taps={taps} inverse={inverse}: fused {e_f:.2e}, two-kernel chain {e_2:.2e} of the output scale vs float64")
+    assert e_f <= max(2 * e_2, 4e-6), (e_f, e_2)
+    assert torch.isfinite(z).all()
+    # [hi | lo] layout: hi is TF32-representable, lo the TF32 rounding of the rest
+    assert torch.equal((z[..., :N].view(torch.int32) & 0x1FFF), torch.zeros_like(z[..., :N], dtype=torch.int32))
