@@ -66,6 +66,7 @@ SIGNATURES = {
     "ll_pack_tf32_weight": (c_int, [_P, _P] + [c_int] * 6 + [_P]),
     "ll_igemm_tf32": (c_int, [_P, _P, _P] + [c_int] * 9 + [_P, _P, c_int, _P]),
     "ll_igemm_tf32_gdn": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 7 + [_P, _P]),
+    "ll_conv3_gdn_head": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 6 + [_P, _P]),
     "ll_nchw_to_nhwc_split": (c_int, [_P, _P, _P] + [c_int] * 5 + [_P]),
     "ll_nhwc_split_to_nchw": (c_int, [_P, _P] + [c_int] * 4 + [_P]),
     "ll_nhwc_split_conv3": (c_int, [_P, _P, _P, _P] + [c_int] * 5 + [_P]),

@@ -545,6 +545,11 @@ struct GdnPairParams {
   int NP, KS, passes, rpp;                 // outputs per pass, channels per staging round, passes, rounds per pass
   int ghalf_bytes;                         // (NP / 2) rows x 128 B
   int col_nm, col_ns, col_st;
+  // head mode (first layer of the scaling network: Conv2d(iC, N, 3, padding=1), iC <= 3, K = 9 iC <= 27): y is computed by
+  // the epilogue warps in exact FP32 FMA from the fp32 NCHW input instead of by the tensor cores; everything after E1 is shared
+  int head, iC;
+  const float* x;                          // (B, iC, H, W)
+  const float* w0;                         // (N, iC, 3, 3) torch layout
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
@@ -563,6 +568,7 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 4));
   float* s_bias = reinterpret_cast<float*>(gen + ring_bytes + 256);
   float* s_beta = s_bias + IG_MAXN;
+  float* s_w0 = s_beta + IG_MAXN;                        // head mode: [k = ci*9 + tap][N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -571,6 +577,10 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   for (int i = threadIdx.x; i < IG_MAXN; i += IG_THREADS) {
     s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
     s_beta[i] = i < p.N ? p.beta[i] : 1.f;
+  }
+  if (p.head) {
+    const int K0 = 9 * p.iC;
+    for (int i = threadIdx.x; i < K0 * p.N; i += IG_THREADS) s_w0[i] = p.w0[(i % p.N) * K0 + i / p.N];
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -648,26 +658,28 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const uint32_t d_nm = tmem_base + (uint32_t)p.col_nm, d_ns = tmem_base + (uint32_t)p.col_ns;
       const uint32_t a_st = tmem_base + (uint32_t)p.col_st;
       for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
-        mbar_wait(tempty_bar, te_phase ^ 1);
-        te_phase ^= 1;
-        tc_fence_after();
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(full_bar(stage), phase);
+        if (!p.head) {
+          mbar_wait(tempty_bar, te_phase ^ 1);
+          te_phase ^= 1;
           tc_fence_after();
-          const uint32_t sa = base + stage * p.stage_bytes;
-          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
-          const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
-          const uint32_t cont = (uint32_t)(it != 0);
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = base + stage * p.stage_bytes;
+            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
+            const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
+            const uint32_t cont = (uint32_t)(it != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
-          tc_commit_2sm(empty_bar(stage), 3);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+            tc_commit_2sm(empty_bar(stage), 3);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit_2sm(tfull_bar, 3);
         }
-        tc_commit_2sm(tfull_bar, 3);
         // norm GEMMs: A = staged split of y^2 in tensor memory, B = gamma rows from the ring
         for (int ps = 0; ps < p.passes; ++ps) {
           for (int rd = 0; rd < p.rpp; ++rd) {
@@ -712,18 +724,55 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
       const bool valid = t < p.ntiles && y < p.H && x < p.W;
       const long long px = ((long long)b * p.H + y) * p.W + x;
-      mbar_wait(tfull_bar, tf_phase);
-      tf_phase ^= 1;
-      tc_fence_after();
-      // E1: y = main + small + bias, in place
-      for (int c = par; c < nchunks; c += 2) {
-        uint32_t v[32], w[32];
-        tc_ld32(tlane + c * 32, v);
-        tc_ld32(tlane + p.N + c * 32, w);
-        tc_wait_ld();
+      if (p.head) {
+        // E1 (head): y = Conv2d(iC, N, 3, padding=1)(x) + bias in exact FP32 FMA, one pixel per thread, -> tensor memory
+        float win[27];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 32 + j]);
-        tmem_st32(tlane + c * 32, v);
+        for (int k = 0; k < 27; ++k) {
+          const int ci = k / 9, dy = (k % 9) / 3 - 1, dx = k % 3 - 1;
+          const int gy = y + dy, gx = x + dx;
+          float v = 0.f;
+          if (valid && ci < p.iC && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+            v = __ldg(p.x + (((long long)b * p.iC + ci) * p.H + gy) * p.W + gx);
+          win[k] = v;
+        }
+        for (int c = par; c < nchunks; c += 2) {
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = s_bias[c * 32 + j];
+#pragma unroll
+          for (int k = 0; k < 27; ++k) {
+            if (k < 9 * p.iC) {
+              const float4* wr = reinterpret_cast<const float4*>(s_w0 + k * p.N + c * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 w4 = wr[j4];
+                acc[4 * j4 + 0] = fmaf(win[k], w4.x, acc[4 * j4 + 0]);
+                acc[4 * j4 + 1] = fmaf(win[k], w4.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(win[k], w4.z, acc[4 * j4 + 2]);
+                acc[4 * j4 + 3] = fmaf(win[k], w4.w, acc[4 * j4 + 3]);
+              }
+            }
+          }
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
+          tmem_st32(tlane + c * 32, v);
+        }
+      } else {
+        mbar_wait(tfull_bar, tf_phase);
+        tf_phase ^= 1;
+        tc_fence_after();
+        // E1: y = main + small + bias, in place
+        for (int c = par; c < nchunks; c += 2) {
+          uint32_t v[32], w[32];
+          tc_ld32(tlane + c * 32, v);
+          tc_ld32(tlane + p.N + c * 32, w);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 32 + j]);
+          tmem_st32(tlane + c * 32, v);
+        }
       }
       tmem_wait_st();
       const unsigned g0 = gcount;
@@ -1366,16 +1415,21 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
 // Fused conv (taps 1 | 9) + GDN / inverse GDN: a_nhwc (B,H,W,2C) [hi|lo] -> sz (B,H,W,2N) [hi|lo] of
 // y * rsqrt(beta + gamma . y^2) (inverse: * sqrt), y = conv(a) + bias.  wp: conv weights from ll_pack_tf32_weight
 // (Npad == N, Kpad == C); gp: gamma (N,N,1,1) packed the same way (Npad == Kpad == N); beta: N reparametrised values.
-int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
-                      int W, int C, int N, int taps, int inverse, float* sz, ll_stream_t stream) {
-  if (B < 0 || H < 0 || W < 0 || C < 32 || C % 32 || C > 256 || (taps != 1 && taps != 9))
+static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
+                           int W, int C, int N, int taps, int inverse, float* sz, const float* x_head, const float* w0_head, int iC,
+                           cudaStream_t stream) {
+  const bool head = x_head != nullptr;
+  if (B < 0 || H < 0 || W < 0) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: negative extent");
+  if (!head && (C < 32 || C % 32 || C > 256 || (taps != 1 && taps != 9)))
     return fail(LL_EINVAL, "ll_igemm_tf32_gdn: bad extents (C a multiple of 32 up to 256, taps 1|9)");
+  if (head && (iC < 1 || iC > 3)) return fail(LL_EINVAL, "ll_conv3_gdn_head: 1..3 input channels, got %d", iC);
   if (N != 32 && N != 64 && N != 96 && N != 192)
     return fail(LL_EINVAL, "ll_igemm_tf32_gdn: N must be 32, 64, 96 or 192 (tensor-memory plan), got %d", N);
   if ((long long)B * H * W == 0) return LL_OK;
-  if (!a_nhwc || !wp || !gp || !beta || !sz) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: null pointer");
+  if ((!head && (!a_nhwc || !wp)) || (head && !w0_head) || !gp || !beta || !sz) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: null pointer");
   if (((uintptr_t)a_nhwc & 15) || ((uintptr_t)wp & 15) || ((uintptr_t)gp & 15) || ((uintptr_t)sz & 31))
     return fail(LL_EINVAL, "ll_igemm_tf32_gdn: operands must be 16-byte aligned, the output 32-byte aligned");
+  if (head) { C = 32; taps = 0; }
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled not available from the driver");
   GdnPairParams p = {};
@@ -1387,7 +1441,7 @@ int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, c
   if (p.col_st + 2 * p.KS > IG_TMEM_COLS) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: tensor-memory plan does not fit");
   CUtensorMap tmA, tmB, tmG;
   const int Ca = 2 * C;
-  {
+  if (!head) {
     cuuint64_t gdim[4] = {(cuuint64_t)Ca, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)Ca * 4, (cuuint64_t)W * Ca * 4, (cuuint64_t)H * W * Ca * 4};
     cuuint32_t box[4] = {32, IG_TW, IG_TH, 1};
@@ -1397,7 +1451,7 @@ int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, c
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
-  {
+  if (!head) {
     cuuint64_t gdim[3] = {(cuuint64_t)Ca, (cuuint64_t)N, (cuuint64_t)taps};
     cuuint64_t gstr[2] = {(cuuint64_t)Ca * 4, (cuuint64_t)N * Ca * 4};
     cuuint32_t box[3] = {32, (cuuint32_t)(N / 2), 1};
@@ -1417,20 +1471,23 @@ int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, c
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(LL_ECUDA, "ll_igemm_tf32_gdn: cuTensorMapEncodeTiled(G) failed with %d", (int)r);
   }
+  if (head) { tmA = tmG; tmB = tmG; }      // never dereferenced in head mode
+  p.head = head ? 1 : 0; p.iC = iC; p.x = x_head; p.w0 = w0_head;
   p.bias = bias; p.beta = beta; p.sz = sz;
   p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.inverse = inverse;
   p.tiles_x = (W + IG_TW - 1) / IG_TW;
   p.tiles_y = (H + IG_TH - 1) / IG_TH;
   p.ntiles = (long long)B * p.tiles_x * p.tiles_y;
   p.npairs = (p.ntiles + 1) / 2;
-  p.kb = C / 32;
+  p.kb = head ? 0 : C / 32;
   p.bhalf_bytes = (N / 2) * 128;
   p.ghalf_bytes = (p.NP / 2) * 128;
-  p.stage_bytes = 2 * PR_A_BYTES + 2 * p.bhalf_bytes;
-  p.stages = (PR_SMEM_LIMIT - 1024 - PR_TAIL_BYTES - IG_MAXN * 4) / p.stage_bytes;
+  p.stage_bytes = head ? 2 * p.ghalf_bytes : 2 * PR_A_BYTES + 2 * p.bhalf_bytes;
+  const int tail = PR_TAIL_BYTES + IG_MAXN * 4 + (head ? 27 * IG_MAXN * 4 : 0);
+  p.stages = (PR_SMEM_LIMIT - 1024 - tail) / p.stage_bytes;
   if (p.stages > PR_MAXST) p.stages = PR_MAXST;
   if (p.stages < 2) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: stage of %d bytes leaves fewer than 2 pipeline stages", p.stage_bytes);
-  const int smem = 1024 + p.stages * p.stage_bytes + PR_TAIL_BYTES + IG_MAXN * 4;
+  const int smem = 1024 + p.stages * p.stage_bytes + tail;
   static thread_local bool attr[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
@@ -1441,9 +1498,22 @@ int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, c
   long long pairs = sm_count_cached() / 2;
   if (pairs > p.npairs) pairs = p.npairs;
   if (pairs < 1) pairs = 1;
-  igemm_tf32_gdn_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, as_stream(stream)>>>(tmA, tmB, tmG, p);
+  igemm_tf32_gdn_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, stream>>>(tmA, tmB, tmG, p);
   LL_LAUNCH_OK("igemm_tf32_gdn_pair_kernel");
   return LL_OK;
+}
+
+int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
+                      int W, int C, int N, int taps, int inverse, float* sz, ll_stream_t stream) {
+  return launch_gdn_pair(a_nhwc, wp, bias, gp, beta, B, H, W, C, N, taps, inverse, sz, nullptr, nullptr, 0, as_stream(stream));
+}
+
+// First layer of SubbandAutoEncoderBerk fused with its GDN: x (B,iC,H,W) fp32 NCHW, w0 (N,iC,3,3) (for the decoder: the
+// equivalent conv of the ConvTranspose2d), exact FP32 FMA conv -> GDN / inverse GDN on the tensor cores -> sz (B,H,W,2N).
+int ll_conv3_gdn_head(const float* x, const float* w0, const float* bias, const float* gp, const float* beta, int B, int iC, int H,
+                      int W, int N, int inverse, float* sz, ll_stream_t stream) {
+  if (!x) return fail(LL_EINVAL, "ll_conv3_gdn_head: null input");
+  return launch_gdn_pair(nullptr, nullptr, bias, gp, beta, B, H, W, 32, N, 0, inverse, sz, x, w0, iC, as_stream(stream));
 }
 
 // fp32 NCHW (B,C,H,W) -> Y NHWC (B,H,W,C) raw and S NHWC (B,H,W,2C) = [hi | lo] of x^2 (mode 0) or of x (mode 1)

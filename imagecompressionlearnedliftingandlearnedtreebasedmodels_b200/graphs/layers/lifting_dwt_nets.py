@@ -131,11 +131,16 @@ class SubbandAutoEncoderBerk(nn.Module):
         outs = []
         for b0 in range(0, x.shape[0], self.AE_BATCH_CHUNK):
             xb = x[b0:b0 + self.AE_BATCH_CHUNK].contiguous()
-            c1 = ops.conv2d(xb, pk["w0"], convs[0].bias)                                   # exact fp32 SIMT (K = 9 * iC)
-            y, s = ops.nchw_to_nhwc_split(c1, squares=True)
-            del c1
-            _, z = ops.igemm_tf32(s, pk["gdn"][0][0], pk["gdn"][0][1], y.shape[3], epi=2, inverse=inv, y=y)
-            del y, s
+            c0 = pk["w0"].shape[0]
+            if self.fuse_gdn and c0 in ops.GDN_FUSED_WIDTHS and xb.shape[1] <= 3:
+                # first conv (K = 9 iC, exact FP32 FMA) + its GDN in one kernel
+                z = ops.conv3_gdn_head(xb, pk["w0"], convs[0].bias, pk["gdn"][0][0], pk["gdn"][0][1], inverse=inv)
+            else:
+                c1 = ops.conv2d(xb, pk["w0"], convs[0].bias)                               # exact fp32 SIMT (K = 9 * iC)
+                y, s = ops.nchw_to_nhwc_split(c1, squares=True)
+                del c1
+                _, z = ops.igemm_tf32(s, pk["gdn"][0][0], pk["gdn"][0][1], y.shape[3], epi=2, inverse=inv, y=y)
+                del y, s
             for k in (0, 1):
                 cout = convs[1 + k].weight.shape[1 if transposed else 0]
                 if self.fuse_gdn and cout in ops.GDN_FUSED_WIDTHS:

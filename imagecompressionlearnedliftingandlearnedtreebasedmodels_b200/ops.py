@@ -443,6 +443,26 @@ def igemm_tf32_gdn(a_split, wp, bias, gp, beta, cout, inverse=False):
 GDN_FUSED_WIDTHS = (32, 64, 96, 192)
 
 
+def conv3_gdn_head(x, w0, bias, gp, beta, inverse=False):
+    """First layer of SubbandAutoEncoderBerk fused with its GDN (ll_conv3_gdn_head): x (B,iC,H,W) fp32 NCHW, w0 (N,iC,3,3)
+    -> channels-last split (B,H,W,2N) of y * rsqrt(beta + gamma . y^2), y = conv3x3(x) + bias in exact FP32 FMA."""
+    require_device(x)
+    x = _f32c(x, "x")
+    w = _f32c(w0.detach(), "w0")
+    B, iC, H, W = x.shape
+    N = w.shape[0]
+    if tuple(w.shape) != (N, iC, 3, 3) or tuple(gp.shape) != (1, N, 2 * N):
+        raise ValueError(f"conv3_gdn_head: weights {tuple(w.shape)} / {tuple(gp.shape)} do not fit the input {tuple(x.shape)}")
+    b = _f32c(bias.detach(), "bias")
+    bt = _f32c(beta.detach(), "beta")
+    sz = torch.empty(B, H, W, 2 * N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_conv3_gdn_head(ptr(x), ptr(w), ptr(b), ptr(gp), ptr(bt), B, iC, H, W, N, int(bool(inverse)), ptr(sz),
+                                            stream_ptr()))
+    _count(1)
+    return sz
+
+
 def nchw_to_nhwc_split(x, squares=True, want_y=True):
     """fp32 NCHW -> (y NHWC raw | None, split NHWC (B,H,W,2C) of x^2 (``squares``) or x)."""
     require_device(x)

@@ -230,6 +230,11 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
  * N in {32, 64, 96, 192}; C a multiple of 32 up to 256. */
 int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
                       int W, int C, int N, int taps, int inverse, float* sz, ll_stream_t stream);
+/* First layer of SubbandAutoEncoderBerk (Conv2d(iC, N, 3, padding=1), iC <= 3; for ae_up the equivalent conv of the
+ * ConvTranspose2d) fused with its GDN / inverse GDN: x (B,iC,H,W) fp32 NCHW, w0 (N,iC,3,3); the conv runs in exact FP32 FMA
+ * inside the same CTA-pair kernel, the norm on the tensor cores; sz as ll_igemm_tf32_gdn. */
+int ll_conv3_gdn_head(const float* x, const float* w0, const float* bias, const float* gp, const float* beta, int B, int iC, int H,
+                      int W, int N, int inverse, float* sz, ll_stream_t stream);
 /* fp32 NCHW (B,C,H,W) -> y NHWC raw (optional) and sz NHWC (B,H,W,2C) = split of x^2 (mode 0) or of x (mode 1). */
 int ll_nchw_to_nhwc_split(const float* x, float* y, float* sz, int B, int C, int H, int W, int mode, ll_stream_t stream);
 /* z NHWC (B,H,W,2C) [hi | lo] -> fp32 NCHW (B,C,H,W) = hi + lo. */

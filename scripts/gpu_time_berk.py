@@ -35,3 +35,12 @@ with torch.no_grad():
             ms = t(lambda: ops.igemm_tf32(a, wp, b, N, epi=1, pair=pair), 10)
             fl = 2.0 * C * N * 9 * 8 * 256 * 384
             print(f"conv {C}->{N} pair={pair}: {ms:.3f} ms, useful {fl / ms / 1e9:.0f} TFLOP/s, issued {3 * fl / ms / 1e9:.0f} TFLOP/s")
+    # fused conv + GDN kernels alone
+    for C, N in ((96, 192), (192, 96)):
+        a = torch.randn(8, 256, 384, 2 * C, device="cuda:0")
+        wp = ops.pack_tf32_weight(torch.randn(N, C, 3, 3, device="cuda:0") * 0.05)
+        gp = ops.pack_tf32_weight((torch.rand(N, N, device="cuda:0") * 0.01 + 0.1 * torch.eye(N, device="cuda:0")).reshape(N, N, 1, 1).contiguous())
+        b = torch.zeros(N, device="cuda:0"); beta = torch.ones(N, device="cuda:0")
+        ms = t(lambda: ops.igemm_tf32_gdn(a, wp, b, gp, beta, N), 10)
+        fl = 2.0 * (C * 9 + N) * N * 8 * 256 * 384
+        print(f"fused conv {C}->{N} + GDN: {ms:.3f} ms, useful {fl / ms / 1e9:.0f} TFLOP/s, issued {3 * fl / ms / 1e9:.0f} TFLOP/s")

@@ -300,3 +300,26 @@ def test_fused_conv_gdn_matches_two_kernel_chain_and_float64(C, N, taps, inverse
     assert torch.isfinite(z).all()
     # [hi | lo] layout: hi is TF32-representable, lo the TF32 rounding of the rest
     assert torch.equal((z[..., :N].view(torch.int32) & 0x1FFF), torch.zeros_like(z[..., :N], dtype=torch.int32))
+
+
+@pytest.mark.parametrize("iC,N,inverse,shape", [(3, 96, False, (2, 37, 50)), (1, 32, False, (3, 16, 16)), (3, 96, True, (1, 9, 33)), (1, 32, True, (1, 8, 16))])
+def test_fused_head_conv_gdn_matches_float64(iC, N, inverse, shape):
+    """``ll_conv3_gdn_head``: first layer of SubbandAutoEncoderBerk (3x3 conv of the 1- or 3-channel subband tensor, exact FP32
+    FMA in the epilogue warps) + its GDN on the tensor cores, against float64."""
+    ops = _ops()
+    torch.manual_seed(iC + N)
+    B, H, W = shape
+    x = torch.randn(B, iC, H, W, device=DEV) * 2
+    w0 = torch.randn(N, iC, 3, 3, device=DEV) * (1.0 / (9 * iC) ** 0.5)
+    bias = torch.randn(N, device=DEV) * 0.1
+    gamma = (torch.rand(N, N, device=DEV) * 0.02 + 0.1 * torch.eye(N, device=DEV)).reshape(N, N, 1, 1).contiguous()
+    beta = torch.rand(N, device=DEV) + 0.5
+    z = ops.conv3_gdn_head(x, w0, bias, ops.pack_tf32_weight(gamma), beta, inverse=inverse)
+    torch.cuda.synchronize()
+    y64 = F.conv2d(x.double(), w0.double(), bias.double(), padding=1)
+    norm = F.conv2d(y64 ** 2, gamma.double(), beta.double())
+    ref = (y64 * (norm.sqrt() if inverse else norm.rsqrt())).permute(0, 2, 3, 1)
+    got = z[..., :N].double() + z[..., N:].double()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    print(f"head iC={iC} N={N} inverse={inverse}: {err:.2e} of the output scale vs float64")
+    assert err <= 3e-6, err
