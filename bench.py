@@ -261,6 +261,7 @@ def run_own(args):
                                "scaling network 2 x 260 822, conditioned2ZT 430 482) / step time"},
     }
     line["roofline"] = roofline_block(dev, pk, pk_kind, agent, ms_step)
+    line["roofline_lifting"] = roofline_lifting_block(dev)
     if "component_ms" in blocks:
         line["component_ms"] = component_block(dev, agent)
     line.update(multi)
@@ -298,34 +299,63 @@ def parse_blocks(spec):
 
 # ------------------------------------------------------------------------------------------------ roofline of the dominant kernel
 def roofline_block(dev, pk, pk_kind, agent, ms_step):
-    """Dominant kernel of the headline step = ``ll::igemm_conv_kernel<TF32>`` (the two 3x3 convs of every
-    SubbandAutoEncoderBerk encode / decode, 3xTF32 on tcgen05): one launch of its largest instance -- conv 96 -> 192 on the
-    level-0 subbands of 8 images (8 x 256 x 384 pixels) -- timed alone with CUDA events on the launching stream.
-    achieved = useful conv FLOPs of the launch (2 x 96 x 192 x 9 per pixel; the 3x split and the N / K padding are NOT
-    counted) / its duration; peak = the dense TF32 tensor-pipe rate measured in this run by ``ll_tf32_peak_probe``."""
+    """Dominant kernel family of the headline step = the 3xTF32 conv + GDN kernels of SubbandAutoEncoderBerk (~45 % of the step;
+    the tensor-core lifting kernel, ~37 %, is reported beside it as ``roofline_lifting``).  One launch of its largest instance
+    -- ``ll::igemm_tf32_gdn_pair_kernel``: 3x3 conv 96 -> 192 fused with its GDN on the level-0 subbands of 8 images
+    (8 x 256 x 384 pixels) -- timed alone with CUDA events on the launching stream.
+    achieved = useful FLOPs of the launch (2 x (96 x 9 + 192) x 192 per pixel: conv + GDN norm; the 3x split and padding are
+    NOT counted) / its duration; peak = the dense TF32 tensor-pipe rate measured in this run by ``ll_tf32_peak_probe``."""
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
     nb, h, w = 8, H // 2, W // 2
-    a = torch.randn(nb, h, w, 2 * 96, device=dev)
-    wt = torch.randn(192, 96, 3, 3, device=dev) * 0.05
-    wp = ops.pack_tf32_weight(wt)
-    bias = torch.zeros(192, device=dev)
-    ms = ev_time(lambda: ops.igemm_tf32(a, wp, bias, 192, epi=1), 10)
-    flop = 2.0 * 96 * 192 * 9 * nb * h * w
+    C, N = 96, 192
+    a = torch.randn(nb, h, w, 2 * C, device=dev)
+    wp = ops.pack_tf32_weight(torch.randn(N, C, 3, 3, device=dev) * 0.05)
+    gp = ops.pack_tf32_weight((torch.rand(N, N, device=dev) * 0.01 + 0.1 * torch.eye(N, device=dev)).reshape(N, N, 1, 1).contiguous())
+    bias, beta = torch.zeros(N, device=dev), torch.ones(N, device=dev)
+    ms = ev_time(lambda: ops.igemm_tf32_gdn(a, wp, bias, gp, beta, N), 10)
+    flop = 2.0 * (C * 9 + N) * N * nb * h * w
     tf32_peak = ops.tf32_peak_tflops()
     achieved = flop / (ms * 1e-3) / 1e12
-    traffic, src = ncu_traffic("igemm_conv_kernel<tf32> conv 96->192 8x256x384")
+    traffic, src = ncu_traffic("igemm_tf32_gdn_pair_kernel conv 96->192 + GDN 8x256x384")
     rf = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
           "traffic": traffic, "traffic_source": src,
-          "kernel": "ll::igemm_conv_kernel<true> (3xTF32 implicit-GEMM 3x3 conv 96->192, 8x256x384 px)",
+          "kernel": "ll::igemm_tf32_gdn_pair_kernel (CTA pairs, 3xTF32 implicit-GEMM 3x3 conv 96->192 + GDN, 8x256x384 px)",
           "ms_per_launch": ms, "issued_tflops": 3 * achieved, "issued_frac": 3 * achieved / tf32_peak,
           "peak_kind": "measured in this run: dense tcgen05 kind::tf32 M128xN256xK8 from shared memory on all SMs (ll_tf32_peak_probe); "
                        f"for context the {pk_kind} cuBLAS bf16 burst peak is {pk['bf16_tflops']} TFLOP/s",
-          "algorithmic_bytes": (2 * 96 + 3 * 192) * 4.0 * nb * h * w,
+          "algorithmic_bytes": (2 * C + 2 * N) * 4.0 * nb * h * w,
           "note": "achieved = algorithmic FLOPs of ONE launch / its average duration over 10 back-to-back launches (CUDA events on "
-                  "the launching stream); issued = x3 for the 3xTF32 split that gives fp32-level accuracy; algorithmic_bytes = "
-                  "[hi|lo] input read once + raw output + [hi|lo] squared output written once"}
+                  "the launching stream); issued = x3 for the 3xTF32 split that gives fp32-level accuracy (the path feeds the "
+                  "quantiser); algorithmic_bytes = [hi|lo] input read once + [hi|lo] output written once"}
     del a
     return rf
+
+
+def roofline_lifting_block(dev):
+    """Second kernel family of the headline step: ``ll::lift_step_tc_kernel`` timed alone (level-0 row step on a (16,256,768)
+    view: 2 x 13 603 MAC per view pixel, 94 % of them as 3xTF32 on tcgen05) against the measured TF32 peak."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers.lifting_dwt_nets import \
+        LiftingBasedNeuralWaveletv4
+    cfg = cfg_of("cfg2")
+    torch.manual_seed(1337)
+    net = LiftingBasedNeuralWaveletv4(cfg).to(dev).eval()
+    blobs = net.waveletForward[0]._blobs()
+    nb = 16
+    vsrc = torch.rand(nb, H // 2, W, device=dev) - 0.5
+    vdin = torch.rand(nb, H // 2, W, device=dev) - 0.5
+    vout = torch.empty_like(vsrc)
+    k_ms = ev_time(lambda: ops.lift_step([(vsrc, vdin, vout)], blobs[0], 1.0, 0.1, False), 20)
+    tf32_peak = ops.tf32_peak_tflops()
+    k_flop = 2.0 * 13603 * vsrc.numel()
+    traffic, src = ncu_traffic("lift_step_tc_kernel level-0 row step (16,256,768)")
+    ach = k_flop / (k_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+            "traffic": traffic, "traffic_source": src, "kernel": "ll::lift_step_tc_kernel (level-0 row step, (16,256,768) view)",
+            "ms_per_launch": k_ms, "issued_frac": ach * 0.94 * 3 * 128 / 80 / tf32_peak,
+            "algorithmic_bytes": 12.0 * vsrc.numel(),
+            "note": "useful conv FLOPs of one launch / its duration; issued = tensor-pipe FLOPs incl. the 3xTF32 split and the "
+                    "M = 80-of-128 padding of the weights-as-M mapping (lift_tc.cu)"}
 
 
 def component_block(dev, agent):

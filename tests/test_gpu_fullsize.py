@@ -93,8 +93,9 @@ def test_full_size_forward_vs_oracle(name):
             rec_forced.append(sub.autoencoder.decode(ref[3].to(DEV), [t.to(DEV) for t in ref[4]]))
     print(f"{name}: {nsym} symbols, {flips} rounding-boundary flips, {bad} unexplained")
     assert bad == 0, (name, flips, bad)
-    # every accepted flip sits within 1e-5 of a rounding boundary of the float64 oracle; about 2e-5 of all symbols do
-    assert flips <= max(2, nsym // 50000), (name, flips)
+    # every accepted flip sits within 1e-5 of a rounding boundary of the float64 oracle (about 2e-5 of all symbols do); for
+    # onlyEZWT the rounded quantity is x - mu and mu is a context-CNN output held to 1e-4, so its boundary band is wider
+    assert flips <= max(2, nsym // (10000 if ezwt else 50000)), (name, flips)
     rel_forced = rel_err(torch.cat(rec_forced, dim=1).cpu(), oxhat)
     print(f"{name}: reconstruction rel err on identical symbols {rel_forced:.2e}")
     assert rel_forced < 1e-4, rel_forced
