@@ -510,11 +510,16 @@ def nhwc_lrelu_conv1(y, w, bias, cin, out=None, lrelu=True):
 RANS_GAUSS, RANS_EB, RANS_GAUSS_GRID = 0, 1, 2
 
 
-def rans_streams_per_image(n_per_image, target=8192):
+def rans_streams_per_image(n_per_image, target=8192, batch=1, min_target=2048, fill_warps=148 * 8):
     """Streams per image: ~``target`` samples per stream.  A stream costs 8 bytes on top of its payload (32-bit flush +
     32-bit length entry), i.e. 0.008 bit per sample at the default -- small against the ~0.02 bit a near-certain symbol
-    costs at low rates; more streams = more parallelism (one GPU thread each) at a proportionally higher overhead."""
-    return int(max(1, min(4096, (int(n_per_image) + target - 1) // target)))
+    costs at low rates.  One warp codes one stream, so when ``batch`` images at ``target`` would leave SMs idle (fewer than
+    ``fill_warps`` streams in the launch) the streams are shortened, down to ``min_target`` samples (0.03 bit per sample)."""
+    n = int(n_per_image)
+    s = (n + target - 1) // target
+    if batch * s < fill_warps:
+        s = max(s, min((n + min_target - 1) // min_target, (fill_warps + batch - 1) // max(int(batch), 1)))
+    return int(max(1, min(4096, s)))
 
 
 def rans_encode(mode, y, par, streams=None):
@@ -526,7 +531,7 @@ def rans_encode(mode, y, par, streams=None):
     par = _f32c(par, "par")
     B, C, H, W = y.shape
     hw = H * W
-    S = int(streams) if streams else rans_streams_per_image(C * hw)
+    S = int(streams) if streams else rans_streams_per_image(C * hw, batch=B)
     lib = _lib.load()
     cap = int(lib.ll_rans_stream_cap(C * hw, S))
     scratch = torch.empty(B * S * cap, dtype=torch.int16, device=y.device)
