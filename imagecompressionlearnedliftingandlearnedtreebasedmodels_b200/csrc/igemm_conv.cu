@@ -717,6 +717,27 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint32_t tf_phase = 0;
     unsigned gcount = 0;                                // completions of gdone consumed so far (parity = gcount & 1)
     const int nchunks = p.N / 32;
+    // head mode: the 3x3 x iC input window of this thread's pixel; the NEXT tile's window is requested as soon as the
+    // current one has been consumed, so its global-load latency hides behind the GDN phases (ncu: 22 % of the kernel's
+    // stall samples sat on the first use of these loads when they were issued at the top of the tile)
+    float win[27];
+    auto load_window = [&](long long pt_) {
+      const long long t_ = 2 * pt_ + rank;
+      const int b_ = (int)(t_ / per_img);
+      const int r_ = (int)(t_ % per_img);
+      const int y_ = (r_ / p.tiles_x) * IG_TH + ty, x_ = (r_ % p.tiles_x) * IG_TW + tx;
+      const bool ok_ = pt_ < p.npairs && t_ < p.ntiles && y_ < p.H && x_ < p.W;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const int ci = k / 9, dy = (k % 9) / 3 - 1, dx = k % 3 - 1;
+        const int gy = y_ + dy, gx = x_ + dx;
+        float v = 0.f;
+        if (ok_ && ci < p.iC && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+          v = __ldg(p.x + (((long long)b_ * p.iC + ci) * p.H + gy) * p.W + gx);
+        win[k] = v;
+      }
+    };
+    if (p.head) load_window(pair0);
     for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
       const long long t = 2 * pt + rank;
       const int b = (int)(t / per_img);
@@ -726,16 +747,6 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const long long px = ((long long)b * p.H + y) * p.W + x;
       if (p.head) {
         // E1 (head): y = Conv2d(iC, N, 3, padding=1)(x) + bias in exact FP32 FMA, one pixel per thread, -> tensor memory
-        float win[27];
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
-          const int ci = k / 9, dy = (k % 9) / 3 - 1, dx = k % 3 - 1;
-          const int gy = y + dy, gx = x + dx;
-          float v = 0.f;
-          if (valid && ci < p.iC && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-            v = __ldg(p.x + (((long long)b * p.iC + ci) * p.H + gy) * p.W + gx);
-          win[k] = v;
-        }
         for (int c = par; c < nchunks; c += 2) {
           float acc[32];
 #pragma unroll
@@ -759,6 +770,7 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
           tmem_st32(tlane + c * 32, v);
         }
+        load_window(pt + pair_step);
       } else {
         mbar_wait(tfull_bar, tf_phase);
         tf_phase ^= 1;

@@ -102,7 +102,7 @@ class SubbandAutoEncoderBerk(nn.Module):
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_c, old_m
 
     # ---- tensor-core path: convs 2-3 and the three GDN norms as 3xTF32 implicit GEMMs (fp32-level accuracy) ----
-    AE_BATCH_CHUNK = 8     # images per launch group: bounds the channels-last fp32 intermediates
+    AE_BATCH_CHUNK = 32    # images per launch group: bounds the channels-last fp32 intermediates (4.8 GB per layer output at 256x384)
     fuse_gdn = True        # convs 2-3 run fused with their GDN (ll_igemm_tf32_gdn); False = the two-kernel chain (A/B checks)
 
     def _pack(self, seq, transposed, cache):

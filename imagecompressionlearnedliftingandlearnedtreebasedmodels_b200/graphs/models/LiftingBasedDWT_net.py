@@ -26,7 +26,7 @@ SCALES_MAX = 256
 SCALES_LEVELS = 64
 # images per launch group inside the context models: bounds the 243/486-channel intermediates
 # (level 0 of a 512x768 plane needs ~0.6 GB per image in fp32)
-CTX_BATCH_CHUNK = 8
+CTX_BATCH_CHUNK = 16
 
 
 def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
