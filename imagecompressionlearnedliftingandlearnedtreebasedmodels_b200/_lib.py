@@ -88,6 +88,8 @@ PROBE_SIGNATURES = {
     "ll_fma_peak_probe": (c_int, [_P, c_int, c_int, _P]),
     "ll_tc_tf32_probe": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "ll_tf32_peak_probe": (c_int, [_P, c_int, c_int, c_int, c_int, _P]),
+    "ll_halo_probe": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "ll_probe_set_timeline": (c_int, [_P]),
     "ll_last_error": (ctypes.c_char_p, []),
 }
 

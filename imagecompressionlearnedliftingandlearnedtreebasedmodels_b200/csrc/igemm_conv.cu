@@ -123,7 +123,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int G = p.groups;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -136,10 +136,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), stage_tx);
-            const uint32_t sa = base + stage * IG_STAGE_BYTES;
-            tma_load_4d(sa, &tmA, full_bar(stage), p.a_koff[g][kb], x0 + dx, y0 + dy, b);
-            tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), p.b_koff[kb], 0, g * p.taps + tap);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), stage_tx);
+              const uint32_t sa = base + stage * IG_STAGE_BYTES;
+              tma_load_4d(sa, &tmA, full_bar(stage), p.a_koff[g][kb], x0 + dx, y0 + dy, b);
+              tma_load_3d(sa + IG_A_BYTES, &tmB, full_bar(stage), p.b_koff[kb], 0, g * p.taps + tap);
+            }
+            __syncwarp();
             if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -147,7 +150,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform loops, one elected lane issues (see igemm_tf32_gdn_pair_kernel: `if (lane == 0)` wraps every MMA in an
+    // ELECT / R2UR loop of ~95 cycles)
+    {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = Npad, M = 128
       const uint32_t fmt = TF32 ? 2u : 1u;   // operand format: TF32 (fp32 containers) or BF16
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(IG_BM >> 4) << 24);
@@ -161,21 +166,25 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const int sel = p.acc_sel[it % p.kblocks];
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.stage_cols + sel * p.acc_cols);
-          const uint32_t first = ((started >> sel) & 1u) ^ 1u;
-          const uint32_t sa = base + stage * IG_STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + IG_A_BYTES);
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.stage_cols + sel * p.acc_cols);
+            const uint32_t first = ((started >> sel) & 1u) ^ 1u;
+            const uint32_t sa = base + stage * IG_STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + IG_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < IG_BK / 16; ++k) {  // 32 bytes (16 bf16 / 8 tf32) per MMA along K: +2 in 16-byte units
-            const uint32_t accum = (uint32_t)(k != 0) | (first ^ 1u);
-            if (TF32) tc_mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-            else tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            for (int k = 0; k < IG_BK / 16; ++k) {  // 32 bytes (16 bf16 / 8 tf32) per MMA along K: +2 in 16-byte units
+              const uint32_t accum = (uint32_t)(k != 0) | (first ^ 1u);
+              if (TF32) tc_mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+              else tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            }
+            tc_commit(empty_bar(stage));           // smem stage reusable once these MMAs have read it
           }
+          __syncwarp();
           started |= 1u << sel;
-          tc_commit(empty_bar(stage));           // smem stage reusable once these MMAs have read it
           if (++stage == IG_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(acc));               // accumulator complete
+        if (elect_one()) tc_commit(tfull_bar(acc));   // accumulator complete
+        __syncwarp();
         if (++acc == p.nstages) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -384,7 +393,7 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int nhalf = p.Npad / 2;
@@ -397,12 +406,15 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
           for (int kb = 0; kb < p.kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
-            const uint32_t sa = base + stage * p.stage_bytes;
-            tma_load_4d_2sm(sa, &tmA, full_bar(stage), 32 * kb, x0 + dx, y0 + dy, b);
-            tma_load_4d_2sm(sa + PR_A_BYTES, &tmA, full_bar(stage), p.C + 32 * kb, x0 + dx, y0 + dy, b);
-            tma_load_3d_2sm(sa + 2 * PR_A_BYTES, &tmB, full_bar(stage), 32 * kb, (int)rank * nhalf, tap);
-            tma_load_3d_2sm(sa + 2 * PR_A_BYTES + p.bhalf_bytes, &tmB, full_bar(stage), p.C + 32 * kb, (int)rank * nhalf, tap);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
+              const uint32_t sa = base + stage * p.stage_bytes;
+              tma_load_4d_2sm(sa, &tmA, full_bar(stage), 32 * kb, x0 + dx, y0 + dy, b);
+              tma_load_4d_2sm(sa + PR_A_BYTES, &tmA, full_bar(stage), p.C + 32 * kb, x0 + dx, y0 + dy, b);
+              tma_load_3d_2sm(sa + 2 * PR_A_BYTES, &tmB, full_bar(stage), 32 * kb, (int)rank * nhalf, tap);
+              tma_load_3d_2sm(sa + 2 * PR_A_BYTES + p.bhalf_bytes, &tmB, full_bar(stage), p.C + 32 * kb, (int)rank * nhalf, tap);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -410,7 +422,7 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {                                  // warp-uniform loops, one elected lane issues
       // D fp32, A/B tf32 K-major, N = Npad, M = 256 across the pair
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int stage = 0, acc = 0;
@@ -423,21 +435,25 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int it = 0; it < iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * p.stage_bytes;
-          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
-          const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
-          const uint32_t cont = (uint32_t)(it != 0);
-          // the two small terms first (own accumulator: its ulp is 2^-11 of the main one's), then A_hi * B_hi
+          if (elect_one()) {
+            const uint32_t sa = base + stage * p.stage_bytes;
+            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
+            const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
+            const uint32_t cont = (uint32_t)(it != 0);
+            // the two small terms first (own accumulator: its ulp is 2^-11 of the main one's), then A_hi * B_hi
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
-          tc_commit_2sm(empty_bar(stage), 3);          // both CTAs' copies of the stage are reusable
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+            tc_commit_2sm(empty_bar(stage), 3);          // both CTAs' copies of the stage are reusable
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit_2sm(tfull_bar(acc), 3);              // accumulators complete, in both CTAs
+        if (elect_one()) tc_commit_2sm(tfull_bar(acc), 3);   // accumulators complete, in both CTAs
+        __syncwarp();
         if (++acc == p.nacc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -548,9 +564,20 @@ struct GdnPairParams {
   // head mode (first layer of the scaling network: Conv2d(iC, N, 3, padding=1), iC <= 3, K = 9 iC <= 27): y is computed by
   // the epilogue warps in exact FP32 FMA from the fp32 NCHW input instead of by the tensor cores; everything after E1 is shared
   int head, iC;
+  int stagger;                             // SM cycles by which pair i delays its start, times (i mod 8); 0 = off
   const float* x;                          // (B, iC, H, W)
   const float* w0;                         // (N, iC, 3, 3) torch layout
+#ifdef LL_TIMELINE
+  long long* tl;                           // probe build only (csrc/probe/igemm_timeline.cu): clock64 stamps of CTA 0
+#endif
 };
+static int g_stagger = 0;   // measured: lockstep pairs are faster (1.44 ms vs 1.65 ms at 8192 cycles, conv 96->192 + GDN)
+#ifdef LL_TIMELINE
+static long long* g_timeline = nullptr;
+#define LL_TL(tile, slot) do { if (p.tl && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < 16) p.tl[(tile) * 64 + (slot)] = clock64(); } while (0)
+#else
+#define LL_TL(tile, slot) do { } while (0)
+#endif
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
 igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -564,8 +591,17 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PR_MAXST + s); };
   const uint32_t tfull_bar = bars + 8u * (2 * PR_MAXST), tempty_bar = bars + 8u * (2 * PR_MAXST + 1);
-  const uint32_t aready_bar = bars + 8u * (2 * PR_MAXST + 2), gdone_bar = bars + 8u * (2 * PR_MAXST + 3);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 4));
+  // GDN hand-offs, one pair of barriers per 32-channel staging slot (at most 3 slots): aready[c] = the split of y^2 of slot
+  // c is in tensor memory (8 arrivals: the 4 warps that own the slot x 2 CTAs), gdone[c] = the MMAs that read it are
+  // complete; e2done = every warp is done with E1 / with the previous pass's norm (16 arrivals, once per pass)
+  auto aready_bar = [&](int c) { return bars + 8u * (2 * PR_MAXST + 2 + c); };
+  auto gdone_bar = [&](int c) { return bars + 8u * (2 * PR_MAXST + 5 + c); };
+  const uint32_t e2done_bar = bars + 8u * (2 * PR_MAXST + 8);
+  // pdone = all norm MMAs of a pass are complete.  Its own barrier, waited once per pass by every warp: a warp may only wait
+  // on a barrier whose every phase it observes (a parity wait cannot tell phase k from phase k - 2), and a slot's gdone is
+  // observed round by round by its owners only.
+  const uint32_t pdone_bar = bars + 8u * (2 * PR_MAXST + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 10));
   float* s_bias = reinterpret_cast<float*>(gen + ring_bytes + 256);
   float* s_beta = s_bias + IG_MAXN;
   float* s_w0 = s_beta + IG_MAXN;                        // head mode: [k = ci*9 + tap][N]
@@ -592,8 +628,12 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 16);
-    mbar_init(aready_bar, 16);
-    mbar_init(gdone_bar, 1);
+    for (int c = 0; c < 3; ++c) {
+      mbar_init(aready_bar(c), 8);
+      mbar_init(gdone_bar(c), 1);
+    }
+    mbar_init(e2done_bar, 16);
+    mbar_init(pdone_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -606,13 +646,19 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Every tile costs the same, so all pairs of a launch would run their phases in lockstep: the E2 stores of the whole chip
+  // (N x 1 KB per CTA) land in one burst while HBM idles during the mainloops.  A one-off start offset per pair spreads them.
+  if (p.stagger) {
+    const long long until = clock64() + (long long)p.stagger * ((blockIdx.x >> 1) & 7);
+    while (clock64() < until) { }
+  }
   const int iters = p.taps * p.kb;
   const int gkb = p.N / 32;                              // k-blocks of one GDN pass
   const long long per_img = (long long)p.tiles_x * p.tiles_y;
   const long long pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int nhalf = p.N / 2, ghalf = p.NP / 2;
@@ -625,12 +671,15 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
           for (int kb = 0; kb < p.kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
-            const uint32_t sa = base + stage * p.stage_bytes;
-            tma_load_4d_2sm(sa, &tmA, full_bar(stage), 32 * kb, x0 + dx, y0 + dy, b);
-            tma_load_4d_2sm(sa + PR_A_BYTES, &tmA, full_bar(stage), p.C + 32 * kb, x0 + dx, y0 + dy, b);
-            tma_load_3d_2sm(sa + 2 * PR_A_BYTES, &tmB, full_bar(stage), 32 * kb, (int)rank * nhalf, tap);
-            tma_load_3d_2sm(sa + 2 * PR_A_BYTES + p.bhalf_bytes, &tmB, full_bar(stage), p.C + 32 * kb, (int)rank * nhalf, tap);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)p.stage_bytes);
+              const uint32_t sa = base + stage * p.stage_bytes;
+              tma_load_4d_2sm(sa, &tmA, full_bar(stage), 32 * kb, x0 + dx, y0 + dy, b);
+              tma_load_4d_2sm(sa + PR_A_BYTES, &tmA, full_bar(stage), p.C + 32 * kb, x0 + dx, y0 + dy, b);
+              tma_load_3d_2sm(sa + 2 * PR_A_BYTES, &tmB, full_bar(stage), 32 * kb, (int)rank * nhalf, tap);
+              tma_load_3d_2sm(sa + 2 * PR_A_BYTES + p.bhalf_bytes, &tmB, full_bar(stage), p.C + 32 * kb, (int)rank * nhalf, tap);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -638,10 +687,13 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         for (int ps = 0; ps < p.passes; ++ps) {
           for (int kb = 0; kb < gkb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            if (leader) mbar_expect_tx(full_bar(stage), 4u * (uint32_t)p.ghalf_bytes);
-            const uint32_t sa = base + stage * p.stage_bytes;
-            tma_load_3d_2sm(sa, &tmG, full_bar(stage), 32 * kb, ps * p.NP + (int)rank * ghalf, 0);
-            tma_load_3d_2sm(sa + p.ghalf_bytes, &tmG, full_bar(stage), p.N + 32 * kb, ps * p.NP + (int)rank * ghalf, 0);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(full_bar(stage), 4u * (uint32_t)p.ghalf_bytes);
+              const uint32_t sa = base + stage * p.stage_bytes;
+              tma_load_3d_2sm(sa, &tmG, full_bar(stage), 32 * kb, ps * p.NP + (int)rank * ghalf, 0);
+              tma_load_3d_2sm(sa + p.ghalf_bytes, &tmG, full_bar(stage), p.N + 32 * kb, ps * p.NP + (int)rank * ghalf, 0);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -649,61 +701,85 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    // The whole warp walks the loops (warp-uniform control flow) and one elected lane issues: descriptors and tensor-memory
+    // addresses then live in uniform registers.  Issued from `if (lane == 0)` every tcgen05.mma was wrapped in an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~95 cycles per MMA: the timeline probe showed the N = 96 mainloop and the
+    // norm GEMMs running at half the tensor rate, issue-bound).
+    if (leader) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t idesc_g = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NP >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int stage = 0;
-      uint32_t phase = 0, te_phase = 0, ar_phase = 0;
+      uint32_t phase = 0, te_phase = 0, ar_phase = 0, e2_phase = 0;
       const uint32_t d_main = tmem_base, d_small = tmem_base + (uint32_t)p.N;
       const uint32_t d_nm = tmem_base + (uint32_t)p.col_nm, d_ns = tmem_base + (uint32_t)p.col_ns;
       const uint32_t a_st = tmem_base + (uint32_t)p.col_st;
-      for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+      int tli = 0;
+      for (long long pt = pair0; pt < p.npairs; pt += pair_step, ++tli) {
         if (!p.head) {
-          mbar_wait(tempty_bar, te_phase ^ 1);
+          LL_TL(tli, 0);
+          mbar_wait_spin(tempty_bar, te_phase ^ 1);
           te_phase ^= 1;
           tc_fence_after();
+          LL_TL(tli, 1);
           for (int it = 0; it < iters; ++it) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t sa = base + stage * p.stage_bytes;
-            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
-            const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
-            const uint32_t cont = (uint32_t)(it != 0);
+            if (elect_one()) {
+              const uint32_t sa = base + stage * p.stage_bytes;
+              const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + PR_A_BYTES);
+              const uint64_t b_hi = umma_desc_sw128(sa + 2 * PR_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * PR_A_BYTES + p.bhalf_bytes);
+              const uint32_t cont = (uint32_t)(it != 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+              for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_lo + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_small, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
-            tc_commit_2sm(empty_bar(stage), 3);
+              for (int k = 0; k < 4; ++k) tc_mma_tf32_ss_2sm(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, cont | (uint32_t)(k != 0));
+              tc_commit_2sm(empty_bar(stage), 3);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          tc_commit_2sm(tfull_bar, 3);
+          if (elect_one()) tc_commit_2sm(tfull_bar, 3);
+          __syncwarp();
+          LL_TL(tli, 2);
         }
-        // norm GEMMs: A = staged split of y^2 in tensor memory, B = gamma rows from the ring
+        // norm GEMMs: A = staged split of y^2 in tensor memory, B = gamma rows from the ring.  Slot by slot: the MMAs of
+        // slot c start as soon as its owners have staged it, while the other parity's warps stage the next slot.
         for (int ps = 0; ps < p.passes; ++ps) {
+          // every warp of the pair has finished E1 (pass 0: the small-term accumulator shares its columns with the norm) /
+          // has read the previous pass's norm: the MMAs may overwrite the norm accumulators
+          mbar_wait_spin(e2done_bar, e2_phase);
+          e2_phase ^= 1;
           for (int rd = 0; rd < p.rpp; ++rd) {
-            mbar_wait(aready_bar, ar_phase);
-            ar_phase ^= 1;
-            tc_fence_after();
             for (int kbr = 0; kbr < p.KS / 32; ++kbr) {
+              mbar_wait_spin(aready_bar(kbr), ar_phase);
+              tc_fence_after();
+              if (kbr == 0) LL_TL(tli, 4 + 2 * (ps * p.rpp + rd));
               mbar_wait(full_bar(stage), phase);
               tc_fence_after();
-              const uint32_t sa = base + stage * p.stage_bytes;
-              const uint64_t g_hi = umma_desc_sw128(sa), g_lo = umma_desc_sw128(sa + p.ghalf_bytes);
-              const uint32_t cont = (uint32_t)((rd | kbr) != 0);
+              if (elect_one()) {
+                const uint32_t sa = base + stage * p.stage_bytes;
+                const uint64_t g_hi = umma_desc_sw128(sa), g_lo = umma_desc_sw128(sa + p.ghalf_bytes);
+                const uint32_t cont = (uint32_t)((rd | kbr) != 0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t ah = a_st + (uint32_t)(kbr * 32 + 8 * k), al = ah + (uint32_t)p.KS;
-                tc_mma_tf32_ts_2sm(d_ns, al, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
-                tc_mma_tf32_ts_2sm(d_ns, ah, g_lo + 2 * k, idesc_g, 1u);
-                tc_mma_tf32_ts_2sm(d_nm, ah, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t ah = a_st + (uint32_t)(kbr * 32 + 8 * k), al = ah + (uint32_t)p.KS;
+                  tc_mma_tf32_ts_2sm(d_ns, al, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
+                  tc_mma_tf32_ts_2sm(d_ns, ah, g_lo + 2 * k, idesc_g, 1u);
+                  tc_mma_tf32_ts_2sm(d_nm, ah, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
+                }
+                tc_commit_2sm(empty_bar(stage), 3);
+                tc_commit_2sm(gdone_bar(kbr), 3);       // this slot's MMAs done: staging reusable / (last slot) norm complete
               }
-              tc_commit_2sm(empty_bar(stage), 3);
+              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            tc_commit_2sm(gdone_bar, 3);                // this round's MMAs done: staging reusable / norm complete
+            ar_phase ^= 1;
+            LL_TL(tli, 5 + 2 * (ps * p.rpp + rd));
           }
+          if (elect_one()) tc_commit_2sm(pdone_bar, 3);   // the pass's norm is complete
+          __syncwarp();
         }
       }
     }
@@ -714,8 +790,8 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const int row = q * 32 + lane;
     const int ty = row / IG_TW, tx = row % IG_TW;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t tf_phase = 0;
-    unsigned gcount = 0;                                // completions of gdone consumed so far (parity = gcount & 1)
+    uint32_t tf_phase = 0, pd_phase = 0;
+    unsigned ground = 0;                                // staging rounds so far, over all tiles: every slot's gdone completes once per round
     const int nchunks = p.N / 32;
     // head mode: the 3x3 x iC input window of this thread's pixel; the NEXT tile's window is requested as soon as the
     // current one has been consumed, so its global-load latency hides behind the GDN phases (ncu: 22 % of the kernel's
@@ -738,7 +814,14 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       }
     };
     if (p.head) load_window(pair0);
-    for (long long pt = pair0; pt < p.npairs; pt += pair_step) {
+    int tli = 0;
+#ifdef LL_TIMELINE
+    const bool tlw = warp == 2 && lane == 0;
+#define LL_TLE(slot) do { if (tlw) LL_TL(tli, slot); } while (0)
+#else
+#define LL_TLE(slot) do { } while (0)
+#endif
+    for (long long pt = pair0; pt < p.npairs; pt += pair_step, ++tli) {
       const long long t = 2 * pt + rank;
       const int b = (int)(t / per_img);
       const int r = (int)(t % per_img);
@@ -772,9 +855,11 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
         load_window(pt + pair_step);
       } else {
-        mbar_wait(tfull_bar, tf_phase);
+        LL_TLE(32);
+        mbar_wait_spin(tfull_bar, tf_phase);
         tf_phase ^= 1;
         tc_fence_after();
+        LL_TLE(33);
         // E1: y = main + small + bias, in place
         for (int c = par; c < nchunks; c += 2) {
           uint32_t v[32], w[32];
@@ -787,15 +872,21 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
       }
       tmem_wait_st();
-      const unsigned g0 = gcount;
+      LL_TLE(34);
+      const int slots = p.KS / 32;
       for (int ps = 0; ps < p.passes; ++ps) {
-        for (int rd = 0; rd < p.rpp; ++rd) {
-          const unsigned need = (unsigned)(ps * p.rpp + rd);     // rounds that must have completed before the staging is rewritten
-          while (gcount - g0 < need) { mbar_wait(gdone_bar, gcount & 1u); ++gcount; }
-          tc_fence_after();
-          for (int cc = 0; cc < p.KS / 32; ++cc) {
-            const int gc = rd * (p.KS / 32) + cc;                // global chunk index of these y columns
-            if ((gc & 1) != par) continue;
+        // pass 0: this warp's E1 is done (and, in head mode, its E2 of the previous tile); later passes: it has read the
+        // previous pass's norm
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(e2done_bar);
+        for (int rd = 0; rd < p.rpp; ++rd, ++ground) {
+          LL_TLE(36 + 2 * (ps * p.rpp + rd));
+          for (int cc = par; cc < slots; cc += 2) {              // the slots this warp owns (slot parity = chunk parity)
+            const int gc = rd * slots + cc;                      // global chunk index of these y columns
+            // the MMAs that read this slot in the previous round (of this or of the previous tile) are complete
+            if (ground) mbar_wait_spin(gdone_bar(cc), (ground - 1) & 1u);
+            tc_fence_after();
             uint32_t v[32], lo[32];
             tc_ld32(tlane + gc * 32, v);
             tc_wait_ld();
@@ -809,16 +900,18 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             }
             tmem_st32(tlane + p.col_st + cc * 32, v);
             tmem_st32(tlane + p.col_st + p.KS + cc * 32, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(aready_bar(cc));
           }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(aready_bar);
+          LL_TLE(37 + 2 * (ps * p.rpp + rd));
         }
-        // the pass's last round done -> norm of channels [ps NP, ps NP + NP) complete
-        const unsigned need = (unsigned)((ps + 1) * p.rpp);
-        while (gcount - g0 < need) { mbar_wait(gdone_bar, gcount & 1u); ++gcount; }
+        // norm of channels [ps NP, ps NP + NP) complete
+        mbar_wait_spin(pdone_bar, pd_phase);
+        pd_phase ^= 1;
         tc_fence_after();
+        LL_TLE(50 + 2 * ps);
         for (int cc = 0; cc < p.NP / 32; ++cc) {
           const int gc = ps * (p.NP / 32) + cc;
           if ((gc & 1) != par) continue;
@@ -844,6 +937,7 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             }
           }
         }
+        LL_TLE(51 + 2 * ps);
       }
       tc_fence_before();
       __syncwarp();
@@ -1485,6 +1579,9 @@ static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bi
   }
   if (head) { tmA = tmG; tmB = tmG; }      // never dereferenced in head mode
   p.head = head ? 1 : 0; p.iC = iC; p.x = x_head; p.w0 = w0_head;
+#ifdef LL_TIMELINE
+  p.tl = g_timeline;
+#endif
   p.bias = bias; p.beta = beta; p.sz = sz;
   p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.inverse = inverse;
   p.tiles_x = (W + IG_TW - 1) / IG_TW;
@@ -1510,6 +1607,7 @@ static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bi
   long long pairs = sm_count_cached() / 2;
   if (pairs > p.npairs) pairs = p.npairs;
   if (pairs < 1) pairs = 1;
+  p.stagger = (p.npairs >= 8 * pairs) ? g_stagger : 0;       // only where the offset (<= 7 x stagger cycles) is a small share of the launch
   igemm_tf32_gdn_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, stream>>>(tmA, tmB, tmG, p);
   LL_LAUNCH_OK("igemm_tf32_gdn_pair_kernel");
   return LL_OK;

@@ -26,6 +26,17 @@ int ll_fma_peak_probe(float* out, int blocks, int iters, ll_stream_t stream);
  * M128 x N x K8 (N in 16..256, multiple of 16).  FLOPs = blocks * iters * kblocks * 2 * 128 * N * 8. */
 int ll_tf32_peak_probe(float* out, int blocks, int iters, int kblocks, int n, ll_stream_t stream);
 
+/* Shifted-window operand addressing for a 3x3 implicit GEMM (csrc/probe/halo_probe.cu): one TMA load of an 18 x pitch
+ * pixel halo tile of a (18,16,32) fp32 channels-last tensor `a`, A operand of tap (dy,dx) addressed inside it by a
+ * K-major SWIZZLE_128B descriptor with start address moved by whole rows and stride byte offset = pitch * 128.
+ * d (128,32) = A_tap (128 = 16 rows x 8 pixels, 32) x b (32,32)^T.  bo_mode 1: descriptor base_offset = start bits 7..9. */
+int ll_halo_probe(const float* a, const float* b, float* d, int pitch, int dy, int dx, int bo_mode, ll_stream_t stream);
+
+/* libll_probe.so carries a copy of csrc/igemm_conv.cu compiled with LL_TIMELINE (csrc/probe/igemm_timeline.cu): when a
+ * device buffer of 16 x 64 int64 is registered here, CTA 0 of igemm_tf32_gdn_pair_kernel launched THROUGH THE PROBE
+ * LIBRARY's ll_igemm_tf32_gdn / ll_conv3_gdn_head stamps clock64() at every hand-off of its first 16 tiles. */
+int ll_probe_set_timeline(long long* buf);
+
 #ifdef __cplusplus
 }
 #endif
