@@ -90,6 +90,9 @@ PROBE_SIGNATURES = {
     "ll_tf32_peak_probe": (c_int, [_P, c_int, c_int, c_int, c_int, _P]),
     "ll_halo_probe": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "ll_probe_set_timeline": (c_int, [_P]),
+    "ll_probe_set_nostore": (c_int, [c_int]),
+    "ll_dbg_lift_switches": (c_int, [c_int]),
+    "ll_dbg_lift_stamp_buffer": (c_int, [_P]),
     "ll_last_error": (ctypes.c_char_p, []),
 }
 

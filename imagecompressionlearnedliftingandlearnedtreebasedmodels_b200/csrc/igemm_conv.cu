@@ -564,14 +564,12 @@ struct GdnPairParams {
   // head mode (first layer of the scaling network: Conv2d(iC, N, 3, padding=1), iC <= 3, K = 9 iC <= 27): y is computed by
   // the epilogue warps in exact FP32 FMA from the fp32 NCHW input instead of by the tensor cores; everything after E1 is shared
   int head, iC;
-  int stagger;                             // SM cycles by which pair i delays its start, times (i mod 8); 0 = off
   const float* x;                          // (B, iC, H, W)
   const float* w0;                         // (N, iC, 3, 3) torch layout
 #ifdef LL_TIMELINE
   long long* tl;                           // probe build only (csrc/probe/igemm_timeline.cu): clock64 stamps of CTA 0
 #endif
 };
-static int g_stagger = 0;   // measured: lockstep pairs are faster (1.44 ms vs 1.65 ms at 8192 cycles, conv 96->192 + GDN)
 #ifdef LL_TIMELINE
 __device__ int g_nostore_dev = 0;
 static long long* g_timeline = nullptr;
@@ -647,12 +645,9 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Every tile costs the same, so all pairs of a launch would run their phases in lockstep: the E2 stores of the whole chip
-  // (N x 1 KB per CTA) land in one burst while HBM idles during the mainloops.  A one-off start offset per pair spreads them.
-  if (p.stagger) {
-    const long long until = clock64() + (long long)p.stagger * ((blockIdx.x >> 1) & 7);
-    while (clock64() < until) { }
-  }
+  // (All pairs of a launch run their phases in lockstep -- every tile costs the same.  Spreading them with a one-off start
+  // offset per pair was measured and is SLOWER: conv 96->192 + GDN 1.44 ms in lockstep, 1.53 / 1.65 ms at 4096 / 8192 cycles
+  // x (pair mod 8): neighbouring tiles that run together share their halo rows and the weight tiles in L2.)
   const int iters = p.taps * p.kb;
   const int gkb = p.N / 32;                              // k-blocks of one GDN pass
   const long long per_img = (long long)p.tiles_x * p.tiles_y;
@@ -1611,7 +1606,6 @@ static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bi
   long long pairs = sm_count_cached() / 2;
   if (pairs > p.npairs) pairs = p.npairs;
   if (pairs < 1) pairs = 1;
-  p.stagger = (p.npairs >= 8 * pairs) ? g_stagger : 0;       // only where the offset (<= 7 x stagger cycles) is a small share of the launch
   igemm_tf32_gdn_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, stream>>>(tmA, tmB, tmG, p);
   LL_LAUNCH_OK("igemm_tf32_gdn_pair_kernel");
   return LL_OK;

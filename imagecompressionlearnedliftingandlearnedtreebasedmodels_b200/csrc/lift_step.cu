@@ -50,8 +50,8 @@ __global__ void scale2_kernel(float* __restrict__ a, long long a_sb, long long a
 
 static int launch_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float rw, int linear,
                             int precision, cudaStream_t stream) {
-  if (precision != LL_LIFT_FP32 && precision != LL_LIFT_TC)
-    return fail(LL_EINVAL, "ll_lift_step: unknown precision %d (LL_LIFT_FP32 = 0, LL_LIFT_TC = 1)", precision);
+  if (precision != LL_LIFT_FP32 && precision != LL_LIFT_TC && precision != LL_LIFT_TC16)
+    return fail(LL_EINVAL, "ll_lift_step: unknown precision %d (LL_LIFT_FP32 = 0, LL_LIFT_TC = 1, LL_LIFT_TC16 = 2)", precision);
   if (njobs < 1 || njobs > 2) return fail(LL_EINVAL, "ll_lift_step: njobs must be 1 or 2 (got %d)", njobs);
   if (!blob) return fail(LL_EINVAL, "ll_lift_step: null blob");
   LiftParams p;
@@ -84,7 +84,8 @@ static int launch_lift_step(const ll_lift_job* jobs, int njobs, const float* blo
   p.dbg = g_lift_dbg;
   p.dbg_buf = g_lift_dbg_buf;
 #endif
-  if (precision == LL_LIFT_TC) return launch_lift_step_tc(p, stream);
+  p.f16 = precision == LL_LIFT_TC16;
+  if (precision != LL_LIFT_FP32) return launch_lift_step_tc(p, stream);
   static thread_local bool attr_set[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));

@@ -59,7 +59,8 @@ constexpr int BL_B4 = BL_W4 + 400;   // 1 (+3 pad)
 constexpr int BL_TOTAL = BL_B4 + 4;   // end of the part the SIMT kernel stages in shared memory
 // tensor-core weight block (lift_tc.cu): [layer 2][term hi|lo][row dx*16+co (80)][col dy*16+ci (80)]
 constexpr int BL_TC = BL_TOTAL;
-constexpr int BL_ALL = BL_TC + 4 * 80 * 80;
+constexpr int BL_TC16 = BL_TC + 4 * 80 * 80;   // fp16 weight block of the 3xFP16 kernel: 4 x 80 x 40 32-bit words (lift_tc.cu)
+constexpr int BL_ALL = BL_TC16 + 4 * 80 * 40;
 static_assert(BL_ALL == LL_LIFT_BLOB_FLOATS, "blob layout");
 
 // shared memory layout (floats)
@@ -84,6 +85,7 @@ struct LiftParams {
   int nstrips[2], nchunks[2];
   long long units[2];  // nb * nstrips * nchunks per job
   long long total_units;
+  int f16;             // tensor-core kernel: 3xFP16 operands (LL_LIFT_TC16) instead of 3xTF32
   int dbg;             // timing experiments only (lift_tc.cu): bit 0 no MMA, 1 no E-B, 2 no conv1, 3 no conv4, 4 no E-A
   long long* dbg_buf;  // optional [17 warps][8] clock64 stamps of CTA 0 at global step 40 (lift_tc.cu)
 };

@@ -38,6 +38,7 @@
 // Tap rows outside the plane read a block of zeros (branch-free); tanh runs two values at a time on the packed FP32
 // pipe.  A row produced in step s is consumed in steps > s, ring depths follow.  Every intermediate is forced to 0
 // outside the plane (each conv zero-pads its own input).  Timing hooks live in the DBG instantiation only.
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -117,6 +118,49 @@ __device__ __forceinline__ float2 tanh2(float2 x) {
   return make_float2(ax < 0.625f ? q.x : copysignf(b.x, x.x), ay < 0.625f ? q.y : copysignf(b.y, x.y));
 }
 
+// ---- 3xFP16 variant (LL_LIFT_TC16) -------------------------------------------------------------------------------------
+// kind::f16 runs at twice the kind::tf32 rate and an fp16 significand is as wide as a tf32 one (11 bits), so
+//   a b  ~=  a_hi b_hi + a_lo b_hi + a_hi b_lo,   hi = fp16(v), lo = fp16(v - hi)
+// carries the same 22 bits per operand as the 3xTF32 split at half the tensor time and half the operand bytes.  What fp16
+// lacks is exponent range: the lo parts (2^-12 of the value) would be subnormal.  Both operands are therefore pre-scaled by
+// a power of two -- activations (tanh outputs, |a| < 1) and weights by 2^8 -- which keeps hi below 65504 and lo normal for
+// every |a| >= 1e-3 (smaller values lose bits only below 3e-8 / 2^8 absolute); all three products then land in ONE fp32
+// accumulator that holds 2^16 times the sum, and the epilogue multiplies by 2^-16 (exact).  Only used with the tanh
+// nonlinearity (linear = 0): without it the activations are unbounded and the launcher keeps the TF32 kernel.
+constexpr float TC16_SA = 256.f, TC16_SW = 256.f, TC16_UNSCALE = 1.f / (256.f * 256.f);
+
+// byte offset of 4 consecutive columns i..i+3 (i % 4 == 0) of channel ci inside an fp16 ring row (hi half): MN-major
+// SWIZZLE_128B, atom = 8 channels x 64 columns (128 B rows, 16-byte chunks XOR channel), two atoms along K
+__device__ __forceinline__ int ring_off16(int ci, int i) {
+  const int r = ci & 7;
+  return (ci >> 3) * 1024 + r * 128 + ((((i >> 3) ^ r)) << 4) + ((i & 7) << 1);
+}
+
+__device__ __forceinline__ void split_store16(uint8_t* row, int ci, int i, const float (&v)[4]) {
+  __half hi[4], lo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float s = v[k] * TC16_SA;
+    hi[k] = __float2half_rn(s);
+    lo[k] = __float2half_rn(s - __half2float(hi[k]));
+  }
+  uint8_t* q = row + ring_off16(ci, i);
+  const __half2 h01 = __halves2half2(hi[0], hi[1]), h23 = __halves2half2(hi[2], hi[3]);
+  const __half2 l01 = __halves2half2(lo[0], lo[1]), l23 = __halves2half2(lo[2], lo[3]);
+  *reinterpret_cast<uint2*>(q) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  *reinterpret_cast<uint2*>(q + 2048) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
+// D[tmem] (+)= A[tmem, fp16 pairs per column] * B[smem desc]; FP16 inputs, FP32 accumulation.
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void split_store(uint8_t* row, int ci, int i, const float (&v)[4]) {
   float hi[4], lo[4];
 #pragma unroll
@@ -141,7 +185,7 @@ struct TcSeg {
   int j, b, x0, ya, yb, ny, nx;
 };
 
-template <bool DBG>
+template <bool DBG, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __grid_constant__ LiftParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -182,7 +226,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (warp < 4) {   // weights -> tensor memory: row m = dx*16 + co (rows 80..127 zero), 4 regions of 80 columns
+  if (F16 && warp < 4) {   // fp16 weights: row m = dx*16 + co, 4 regions [layer][term] of 40 columns = [dy 5][ci pair 8]
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(p.blob + BL_TC16);
+    for (int reg = 0; reg < 4; ++reg) {
+      const uint32_t* src = words + ((long long)reg * 80 + tid) * 40;
+      for (int c = 0; c < 40; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tid < 80 ? src[c + k] : 0u;
+        tmem_st8(trow + TM_W + reg * 40 + c, v);
+      }
+    }
+    tmem_wait_st();
+  }
+  if (!F16 && warp < 4) {   // weights -> tensor memory: row m = dx*16 + co (rows 80..127 zero), 4 regions of 80 columns
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     for (int reg = 0; reg < 4; ++reg) {
       const float* src = p.blob + BL_TC + ((long long)reg * 80 + tid) * 80;
@@ -200,9 +258,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   tc_fence_after();
 
   // instruction descriptor: D fp32, A/B tf32, A K-major (TMEM), B MN-major, N = 64, M = 128
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint64_t desc_ra1 = umma_desc_mn_sw128_32b(base + TS_RA1, 1024, 512);
-  const uint64_t desc_ra2 = umma_desc_mn_sw128_32b(base + TS_RA2, 1024, 512);
+  // (F16: D fp32, A/B fp16 = format 0, B MN-major plain SWIZZLE_128B, 8-channel atoms 1024 B apart along K)
+  const uint32_t idesc = F16 ? (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)
+                             : (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t desc_ra1 = F16 ? umma_desc_mn_sw128(base + TS_RA1, 1024, 1024) : umma_desc_mn_sw128_32b(base + TS_RA1, 1024, 512);
+  const uint64_t desc_ra2 = F16 ? umma_desc_mn_sw128(base + TS_RA2, 1024, 1024) : umma_desc_mn_sw128_32b(base + TS_RA2, 1024, 512);
 
   const int ncta = gridDim.x;
   const long long lo_u = p.total_units * (long long)blockIdx.x / ncta;
@@ -346,6 +406,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                 const int rr = r2m + dy - 2;
                 if (rr >= 0 && rr < s.ny) {
                   const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                  if (F16) {                                                        // K = 16 channels per MMA
+                    const uint32_t ah = tmem + TM_W + 0 * 80 + dy * 8, al = ah + 40;
+                    tc_mma_f16_ts(acc2, ah, bd, idesc, acc);                        // hi * hi
+                    tc_mma_f16_ts(acc2, al, bd, idesc, 1u);                         // lo * hi
+                    tc_mma_f16_ts(acc2, ah, bd + (2048 >> 4), idesc, 1u);           // hi * lo
+                  } else {
                   const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
                   tc_mma_tf32_ts(acc2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
                   tc_mma_tf32_ts(acc2, al, bd, idesc, 1u);                        // lo * hi
@@ -353,6 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                   tc_mma_tf32_ts(acc2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
                   tc_mma_tf32_ts(acc2, al + 8, bd + (2048 >> 4), idesc, 1u);
                   tc_mma_tf32_ts(acc2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                  }
                   acc = 1;
                 }
               }
@@ -369,6 +436,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                 const int rr = r3m + dy - 2;
                 if (rr >= 0 && rr < s.ny) {
                   const uint64_t bd = desc_ra2 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                  if (F16) {
+                    const uint32_t ah = tmem + TM_W + 1 * 80 + dy * 8, al = ah + 40;
+                    tc_mma_f16_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
+                    tc_mma_f16_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
+                    tc_mma_f16_ts(tmem + TM_ACC3, ah, bd + (2048 >> 4), idesc, 1u);
+                  } else {
                   const uint32_t ah = tmem + TM_W + 1 * 160 + dy * 16, al = ah + 80;
                   tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
                   tc_mma_tf32_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
@@ -376,6 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                   tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + (2048 >> 4), idesc, 1u);
                   tc_mma_tf32_ts(tmem + TM_ACC3, al + 8, bd + (2048 >> 4), idesc, 1u);
                   tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                  }
                   acc = 1;
                 }
               }
@@ -458,8 +532,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             if (e2 && !TC_OFF(2)) {
               const float* pr = P2 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
               const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
-              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x), __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y),
-                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z), __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w)};
+              const float us = F16 ? TC16_UNSCALE : 1.f;   // the fp16 accumulators hold 2^16 x the sum (exact to undo)
+              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x) * us, __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y) * us,
+                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z) * us, __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w) * us};
               const float bias = SW[SW_B2 + co];
               float v[4];
               {
@@ -476,13 +551,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                   v[k] = (c >= 0 && c < s.nx && i0 + k < 60) ? x[k] : 0.f;
                 }
               }
-              split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
+              if (F16) split_store16(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
+              else split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
             }
             if (e3 && !TC_OFF(2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
               const float* pr = P3 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
               const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
-              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x), __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y),
-                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z), __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w)};
+              const float us = F16 ? TC16_UNSCALE : 1.f;
+              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x) * us, __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y) * us,
+                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z) * us, __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w) * us};
               const float bias = SW[SW_B3 + co];
               const float4 o1 = *reinterpret_cast<const float4*>(O1 + ((r3e % TC_RO) * 16 + co) * TC_P3 + i0);
               const float o1v[4] = {o1.x, o1.y, o1.z, o1.w};
@@ -556,7 +633,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               av[k] = in ? (h ? th[k].y : th[k].x) : 0.f;
             }
             const int co = 2 * cp + h;
-            split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
+            if (F16) split_store16(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
+            else split_store(gen + TS_RA1 + (t % TC_RA) * TC_SLOT, co, i1, av);
             if (i1 >= 4 && i1 < 60)
               *reinterpret_cast<float4*>(O1 + ((t % TC_RO) * 16 + co) * TC_P3 + i1 - 4) = make_float4(ov[0], ov[1], ov[2], ov[3]);
           }
@@ -607,6 +685,25 @@ __global__ void pack_lift_tc_kernel(const float* __restrict__ w2, const float* _
   }
 }
 
+// fp16 weight block (LL_LIFT_TC16): [region = layer*2 + term][row m = dx*16 + co][word = dy*8 + ci/2], each word the fp16
+// pair (ci even, ci odd) of hi = fp16(256 w) or lo = fp16(256 w - hi)
+__global__ void pack_lift_tc16_kernel(const float* __restrict__ w2, const float* __restrict__ w3, float* __restrict__ blob) {
+  uint32_t* words = reinterpret_cast<uint32_t*>(blob + BL_TC16);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * 80 * 40; i += gridDim.x * blockDim.x) {
+    const int word = i % 40, m = (i / 40) % 80, reg = i / 3200;
+    const int dy = word / 8, cp = word % 8, dx = m / 16, co = m % 16;
+    __half h[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float w = ((reg >> 1) ? w3 : w2)[(co * 16 + 2 * cp + e) * 25 + dy * 5 + dx] * TC16_SW;
+      const __half hi = __float2half_rn(w);
+      h[e] = (reg & 1) ? __float2half_rn(w - __half2float(hi)) : hi;
+    }
+    const __half2 pr = __halves2half2(h[0], h[1]);
+    words[i] = *reinterpret_cast<const uint32_t*>(&pr);
+  }
+}
+
 int launch_lift_step_tc(const LiftParams& p0, cudaStream_t stream) {
   LiftParams p = p0;
   p.total_units = 0;
@@ -626,14 +723,21 @@ int launch_lift_step_tc(const LiftParams& p0, cudaStream_t stream) {
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LL_CUDA_OK(cudaFuncSetAttribute(lift_step_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set[dev] = true;
   }
   long long grid = sm_count_cached();
   if (grid > p.total_units) grid = p.total_units;
-  if (p.dbg || p.dbg_buf) lift_step_tc_kernel<true><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
-  else lift_step_tc_kernel<false><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+  const bool f16 = p.f16 && !p.linear;       // without tanh the activations are unbounded: fp16 operands are not safe
+  const bool dbg = p.dbg || p.dbg_buf;
+  if (f16) {
+    if (dbg) lift_step_tc_kernel<true, true><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+    else lift_step_tc_kernel<false, true><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+  } else if (dbg) lift_step_tc_kernel<true, false><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+  else lift_step_tc_kernel<false, false><<<(unsigned)grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
   LL_LAUNCH_OK("lift_step_tc_kernel");
   return LL_OK;
 }
@@ -641,6 +745,8 @@ int launch_lift_step_tc(const LiftParams& p0, cudaStream_t stream) {
 int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream) {
   pack_lift_tc_kernel<<<100, 256, 0, stream>>>(w2, w3, blob);
   LL_LAUNCH_OK("pack_lift_tc_kernel");
+  pack_lift_tc16_kernel<<<50, 256, 0, stream>>>(w2, w3, blob);
+  LL_LAUNCH_OK("pack_lift_tc16_kernel");
   return LL_OK;
 }
 

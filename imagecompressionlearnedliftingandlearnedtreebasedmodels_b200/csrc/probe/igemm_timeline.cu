@@ -10,11 +10,6 @@ extern "C" int ll_probe_set_timeline(long long* buf) {
   return LL_OK;
 }
 
-extern "C" int ll_probe_set_stagger(int cycles) {
-  ll::g_stagger = cycles;
-  return LL_OK;
-}
-
 extern "C" int ll_probe_set_nostore(int on) {   // timeline experiments: E2 without its global stores (results are then garbage)
   return cudaMemcpyToSymbol(ll::g_nostore_dev, &on, sizeof(int)) == cudaSuccess ? LL_OK : LL_ECUDA;
 }

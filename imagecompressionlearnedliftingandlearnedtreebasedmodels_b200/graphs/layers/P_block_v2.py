@@ -28,7 +28,7 @@ class P_block_v2(nn.Module):
         self.conv4 = nn.Conv2d(d * csize, 1 * csize, k, stride=1, padding=p)
         self.linearityFlag = linearity_flag
         self.nonLinearityFunction = nn.Tanh()
-        self.lift_precision = "tc"
+        self.lift_precision = ops.DEFAULT_LIFT_PRECISION
 
     def params(self):
         return {k: (getattr(self, k).weight, getattr(self, k).bias) for k in ("conv1", "conv2", "conv3", "conv4")}

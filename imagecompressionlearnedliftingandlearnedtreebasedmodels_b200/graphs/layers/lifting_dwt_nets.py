@@ -227,7 +227,7 @@ class LiftingBasedNeuralWaveletv4(nn.Module):
         self.config = config
         # new optional key (default keeps reference configs valid): "tc" = conv2/conv3 of every lifting step
         # on tcgen05 with the 3xTF32 split (fp32-level accuracy), "fp32" = all layers on the FP32 FMA pipe
-        self._lift_precision = config.get("lift_precision", "tc") if hasattr(config, "get") else getattr(config, "lift_precision", "tc")
+        self._lift_precision = config.get("lift_precision", ops.DEFAULT_LIFT_PRECISION) if hasattr(config, "get") else getattr(config, "lift_precision", ops.DEFAULT_LIFT_PRECISION)
         ops.lift_precision_code(self._lift_precision)
         self.depth_scale = config.depth_scale * 8
         self.preProcessingList = self.preProcessBlock(config.clrch, config.filtersize)

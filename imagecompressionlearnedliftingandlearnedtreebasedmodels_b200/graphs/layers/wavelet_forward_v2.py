@@ -55,7 +55,7 @@ class wavelet_forward_v2(nn.Module):
         self.nl = nl
         self.scale = cfg.scale
         # optional key: "tc" (conv2/conv3 on tcgen05, 3xTF32 split) | "fp32" (all layers on the FP32 FMA pipe)
-        self.lift_precision = cfg.get("lift_precision", "tc") if hasattr(cfg, "get") else getattr(cfg, "lift_precision", "tc")
+        self.lift_precision = cfg.get("lift_precision", ops.DEFAULT_LIFT_PRECISION) if hasattr(cfg, "get") else getattr(cfg, "lift_precision", ops.DEFAULT_LIFT_PRECISION)
         self._cache = PackCache()
 
     def _blobs(self):

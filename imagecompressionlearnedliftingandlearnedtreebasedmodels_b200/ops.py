@@ -23,7 +23,7 @@ def _count(n):
     _LAUNCHES += n
 
 
-LIFT_BLOB_FLOATS = 39256
+LIFT_BLOB_FLOATS = 52056
 AE1_BLOB_FLOATS = 2212
 
 
@@ -34,15 +34,19 @@ def _f32c(t, name):
 
 
 # ----------------------------------------------------------------------------- learned lifting
-LIFT_FP32, LIFT_TC = 0, 1
+LIFT_FP32, LIFT_TC, LIFT_TC16 = 0, 1, 2
+# conv2 / conv3 of the lifting CNNs as a 3xFP16 split on tcgen05 (same 22 significand bits per operand as 3xTF32 at half
+# the tensor time; falls back to the 3xTF32 kernel inside the library when the tanh nonlinearity is switched off)
+DEFAULT_LIFT_PRECISION = "tc16"
 
 
 def lift_precision_code(mode):
-    """``"tc"`` (default: conv2/conv3 on tcgen05, 3xTF32 split, fp32-level accuracy) or ``"fp32"`` (everything on the
-    FP32 FMA pipe) -> the ``precision`` argument of the lifting entry points (per call; nothing is process-wide)."""
-    m = {"tc": LIFT_TC, "3xtf32": LIFT_TC, "fp32": LIFT_FP32, LIFT_TC: LIFT_TC, LIFT_FP32: LIFT_FP32}.get(mode)
+    """``"tc16"`` (default: conv2/conv3 on tcgen05, 3xFP16 split of pre-scaled operands), ``"tc"`` (3xTF32 split; both
+    have fp32-level accuracy) or ``"fp32"`` (everything on the FP32 FMA pipe) -> the ``precision`` argument of the lifting entry points (per call; nothing is process-wide)."""
+    m = {"tc": LIFT_TC, "3xtf32": LIFT_TC, "tc16": LIFT_TC16, "3xfp16": LIFT_TC16, "fp32": LIFT_FP32,
+         LIFT_TC: LIFT_TC, LIFT_FP32: LIFT_FP32, LIFT_TC16: LIFT_TC16}.get(mode)
     if m is None:
-        raise ValueError(f"unknown lifting precision {mode!r} (\"tc\" | \"fp32\")")
+        raise ValueError(f"unknown lifting precision {mode!r} (\"tc\" | \"tc16\" | \"fp32\")")
     return m
 
 
@@ -74,7 +78,7 @@ def _blob_array(blobs):
 
 
 def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, ll_out=None, yh_out=None,
-                   precision="tc"):
+                   precision=DEFAULT_LIFT_PRECISION):
     """x (B,1,h,w) -> (LL (B,1,h/2,w/2), Yh (B,3,h/2,w/2) = [LH,HL,HH])."""
     require_device(x)
     x = _f32c(x, "x")
@@ -96,7 +100,7 @@ def lift_level_fwd(x, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=
     return ll, yh
 
 
-def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, precision="tc"):
+def lift_level_inv(ll, yh, blobs, res_weight=0.1, linear=False, scale=0, nh=None, nl=None, precision=DEFAULT_LIFT_PRECISION):
     """(LL (B,1,h2,w2), Yh (B,3,h2,w2)) -> x (B,1,2*h2,2*w2)."""
     require_device(ll)
     ll = _f32c(ll, "ll")
@@ -194,7 +198,7 @@ def ae1_apply(x, blob, want_round=False):
     return (y, q) if want_round else y
 
 
-def lift_step(jobs, blob, sign, res_weight=0.1, linear=False, precision="tc"):
+def lift_step(jobs, blob, sign, res_weight=0.1, linear=False, precision=DEFAULT_LIFT_PRECISION):
     """One fused lifting step on up to two (src, din, dout) triples of equally shaped
     3-D strided views (B, ny, nx); the 3-tap pre-filter runs along dim 1.  dout may alias din."""
     lib = _lib.load()

@@ -5,7 +5,7 @@ names, return values and side effects (experiment directories under ``experiment
 console + two rotating-file log handlers); ``EasyDict`` is a local stand-in for the ``easydict`` package the
 reference imports (attribute access on a dict, applied recursively, ``AttributeError`` on a missing key).
 
-New optional keys (absent keys keep the reference's behaviour): ``lift_precision`` ("tc" | "fp32"),
+New optional keys (absent keys keep the reference's behaviour): ``lift_precision`` ("tc16" | "tc" | "fp32"),
 ``ctx_precision`` ("bf16" | "fp32"), ``cuda_graph`` (bool).  ``default_config()`` returns the keys of
 ``liftingDWT.json`` as shipped in this package (same keys and values as the reference's file).
 """

@@ -56,7 +56,7 @@ typedef struct ll_lift_job {
   int32_t nb, ny, nx;
 } ll_lift_job;
 
-#define LL_LIFT_BLOB_FLOATS 39256
+#define LL_LIFT_BLOB_FLOATS 52056
 
 /* Packs one lifting step's parameters into the kernel's blob layout (device to
  * device, on `stream`).  pre_w: (3,) taps of convBlock[k] (lifting_dwt_nets.py:784-827);
@@ -76,9 +76,14 @@ int ll_pack_lift_step(const float* pre_w, const float* w1, const float* b1, cons
  * precision (per call, nothing process-wide):
  *   LL_LIFT_FP32  every layer on the FP32 FMA pipe (exact, ~45 % of the FFMA2 peak);
  *   LL_LIFT_TC    conv2 / conv3 (94 % of the MACs) on tcgen05 with the 3xTF32 hi/lo split and FP32
- *                 accumulation in tensor memory (fp32-level accuracy, see lift_tc.cu), the rest FP32. */
+ *                 accumulation in tensor memory (fp32-level accuracy, see lift_tc.cu), the rest FP32;
+ *   LL_LIFT_TC16  the same kernel with conv2 / conv3 as a 3xFP16 split (kind::f16 at twice the TF32 rate; hi = fp16(v),
+ *                 lo = fp16(v - hi) of operands pre-scaled by 2^8 so that the lo parts stay normal: 22 significand bits
+ *                 per operand like 3xTF32, one FP32 accumulator, exact 2^-16 in the epilogue).  Needs bounded
+ *                 activations: with linear != 0 (no tanh) the call runs the 3xTF32 kernel instead. */
 #define LL_LIFT_FP32 0
 #define LL_LIFT_TC 1
+#define LL_LIFT_TC16 2
 int ll_lift_step(const ll_lift_job* jobs, int njobs, const float* blob, float sign, float res_weight,
                  int linear, int precision, ll_stream_t stream);
 

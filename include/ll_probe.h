@@ -36,6 +36,15 @@ int ll_halo_probe(const float* a, const float* b, float* d, int pitch, int dy, i
  * device buffer of 16 x 64 int64 is registered here, CTA 0 of igemm_tf32_gdn_pair_kernel launched THROUGH THE PROBE
  * LIBRARY's ll_igemm_tf32_gdn / ll_conv3_gdn_head stamps clock64() at every hand-off of its first 16 tiles. */
 int ll_probe_set_timeline(long long* buf);
+/* Timeline experiments only: E2 of the probe library's fused kernel skips its global stores (results are then garbage). */
+int ll_probe_set_nostore(int on);
+
+/* libll_probe.so also carries csrc/lift_step.cu + csrc/lift_tc.cu compiled with LL_DEBUG (csrc/probe/lift_dbg.cu), reached
+ * through the probe library's own ll_lift_step: role ablation of lift_step_tc_kernel (bit 0 no MMA, 1 no E-B, 2 no conv1,
+ * 3 no conv4, 4 no E-A: results are WRONG when non-zero) and the clock64 stamps of CTA 0's 17 warps at global step 40
+ * (device buffer of 17 x 8 int64, NULL = off).  scripts/gpu_lift_tc_timeline.py. */
+int ll_dbg_lift_switches(int bits);
+int ll_dbg_lift_stamp_buffer(long long* buf);
 
 #ifdef __cplusplus
 }

@@ -9,10 +9,6 @@ lib = _lib.load_probe()
 P = ctypes.c_void_p
 lib.ll_igemm_tf32_gdn.restype = ctypes.c_int
 lib.ll_igemm_tf32_gdn.argtypes = [P] * 5 + [ctypes.c_int] * 7 + [P, P]
-lib.ll_probe_set_stagger.restype = ctypes.c_int
-lib.ll_probe_set_stagger.argtypes = [ctypes.c_int]
-lib.ll_probe_set_nostore.restype = ctypes.c_int
-lib.ll_probe_set_nostore.argtypes = [ctypes.c_int]
 def timed(fn, n=10):
     for _ in range(2): fn()
     torch.cuda.synchronize()
@@ -29,7 +25,6 @@ for C, N in ((96, 192), (192, 96)):
     b = torch.zeros(N, device="cuda:0"); beta = torch.ones(N, device="cuda:0")
     sz = torch.empty(8, 256, 384, 2 * N, device="cuda:0")
     run = lambda: _lib.check_probe(lib.ll_igemm_tf32_gdn(ptr(a), ptr(wp), ptr(b), ptr(gp), ptr(beta), 8, 256, 384, C, N, 9, 0, ptr(sz), stream_ptr()))
-    lib.ll_probe_set_stagger(0)
     for ns in (1, 0):
         lib.ll_probe_set_nostore(ns)
         print(f"conv {C}->{N} + GDN, E2 global stores {'off' if ns else 'on'}: {timed(run):.3f} ms", flush=True)

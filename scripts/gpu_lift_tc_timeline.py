@@ -19,14 +19,13 @@ out = torch.empty_like(src)
 # route ops.lift_step's library call through the probe build
 probe.ll_lift_step.restype = ctypes.c_int
 probe.ll_lift_step.argtypes = real.ll_lift_step.argtypes
-probe.ll_dbg_lift_switches.argtypes = [ctypes.c_int]
-probe.ll_dbg_lift_stamp_buffer.argtypes = [P]
 class Shim:
     def __getattr__(self, k):
         return getattr(probe if k == "ll_lift_step" else real, k)
 _lib._lib = Shim()
+MODE = sys.argv[1] if len(sys.argv) > 1 else "tc"
 def run():
-    ops.lift_step([(src, din, out)], blobs[0], 1.0, 0.1, False)
+    ops.lift_step([(src, din, out)], blobs[0], 1.0, 0.1, False, MODE)
 def timed(n=10):
     for _ in range(2): run()
     torch.cuda.synchronize()

@@ -55,7 +55,8 @@ def flip_audit(q_gpu, q_ref, pre_ref, eps=FLIP_EPS, pre_ref64=None, label=None, 
     difference of the two mu) is within 1e-4 of the tensor's scale (exactly 0 for plain rounding).
     A mismatch is *explained* only when it is a single step (|k| == 1) and the oracle's pre-rounding
     value -- the float64 oracle's (``pre_ref64`` / ``q_ref64``, the tie-break of SURVEY.md section 7)
-    when given, else the fp32 one -- sits within ``eps * max(1, |x|)`` of the rounding boundary: there
+    when given, else the fp32 one -- sits within ``eps * max(1, |x|)`` (plus, with the float64 tie-break, the fp32
+    reference's own distance from the float64 value at that sample) of the rounding boundary: there
     fp32 summation order alone decides the symbol, and the reference run on another thread count flips
     it too.  For mean-shifted rounding the rounded quantity is x - mu and its distance to the boundary
     is 0.5 - |x - q| (q - mu is an integer).
@@ -80,8 +81,15 @@ def flip_audit(q_gpu, q_ref, pre_ref, eps=FLIP_EPS, pre_ref64=None, label=None, 
             # output, itself held to 1e-4 of the tensor scale by rem_ok), which moves the boundary by that much
             dist = 0.5 - (pre - qr).abs() - (d - k).abs().double()[mism]
             scale = torch.maximum(pre.abs(), qr.abs()).clamp(min=1.0)
-        ok = ok & (dist <= eps * scale)
+        # the fp32 reference's own deviation from the float64 oracle AT THIS SAMPLE widens the band: a symbol the reference
+        # itself only decides within that margin cannot be held against the GPU more tightly
+        slack = (pre_ref.double()[mism] - pre).abs() if pre_ref64 is not None else torch.zeros_like(dist)
+        ok = ok & (dist <= eps * scale + slack)
         bad = int((~ok).sum())
+        if bad:
+            print(f"  unexplained flips in {label}: |k| {k[mism][~ok].abs().tolist()[:4]}, distance to the boundary / (eps * scale) "
+                  f"{(dist / (eps * scale))[~ok].tolist()[:4]}, reference fp32-vs-fp64 slack / (eps * scale) "
+                  f"{(slack / (eps * scale))[~ok].tolist()[:4]}, remainder ok {rem_ok[mism][~ok].tolist()[:4]}")
     FLIP_LOG.append((label or "", int(q_ref.numel()), n, bad))
     return n, bad
 

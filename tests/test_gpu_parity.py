@@ -103,7 +103,7 @@ def test_training_mode_noise_parity(prec):
     assert abs(tot - ref) <= 1e-3 * ref                    # bpp within 0.1 % in either precision
 
 
-@pytest.mark.parametrize("mode", ["tc", "fp32"])
+@pytest.mark.parametrize("mode", ["tc16", "tc", "fp32"])
 def test_lifting_level_golden(mode):
     m = META["lifting_one_level"]
     model, cfg = product_model(dict(m["config"], lift_precision=mode))
@@ -119,7 +119,7 @@ def test_lifting_level_golden(mode):
     assert (rec.cpu() - g["x"]).abs().max().item() < 1e-5      # perfect reconstruction
 
 
-@pytest.mark.parametrize("mode", ["tc", "fp32"])
+@pytest.mark.parametrize("mode", ["tc16", "tc", "fp32"])
 @pytest.mark.parametrize("shape,levels", [((2, 1, 48, 80), 3), ((1, 1, 128, 256), 4), ((3, 1, 16, 16), 2),
                                           ((1, 1, 64, 1024), 1), ((2, 1, 104, 106), 1)])
 def test_learned_lifting_vs_oracle(shape, levels, mode):
@@ -275,16 +275,25 @@ def test_full_size_codec_properties():
             sub = model.model0
             oxe, oxo = sub.autoencoder.encode(x[:, 0:1])
             _, _, xe_q, xo_q = sub.entropymodel(oxe, oxo)
+            dec0 = sub.autoencoder.decode(xe_q, list(xo_q))
+            if tag == "fp32_lift":          # the fp32-lifting symbols decoded by the default (tensor-core) inverse transform
+                forced = outs["tc_bf16"][4].autoencoder.decode(xe_q, list(xo_q))
         bits = float(si_xe.double().sum() + sum(s.double().sum() for s in si_xo))
-        outs[tag] = (xhat, bits, [xe_q] + list(xo_q), [oxe] + list(oxo))
+        outs[tag] = (xhat, bits, [xe_q] + list(xo_q), [oxe] + list(oxo), sub, dec0)
         del model
     a, b, c = outs["tc_bf16"], outs["tc_fp32ctx"], outs["fp32_lift"]
     assert abs(a[1] - b[1]) <= 1e-3 * b[1]                                   # bpp within 0.1 %
     assert torch.equal(a[0], b[0]) and all(torch.equal(p, q) for p, q in zip(a[2], b[2]))
-    assert rel_err(a[0], c[0]) < 1e-4
+    flips = 0
     for qa, qc, pre in zip(a[2], c[2], c[3]):
         n, bad = flip_audit(qa.cpu(), qc.cpu(), pre.cpu())
         assert bad == 0 and n <= max(2, qa.numel() // 20000), (n, bad)     # rounding-boundary flips only
+        flips += n
+    # reconstruction: on IDENTICAL symbols the two lifting arithmetics agree to 1e-4 (a flipped symbol moves the samples
+    # under its synthesis footprint by a quantisation step, so whole reconstructions are only compared when nothing flipped)
+    assert rel_err(forced, c[5]) < 1e-4, rel_err(forced, c[5])
+    if flips == 0:
+        assert rel_err(a[0], c[0]) < 1e-4
 
 
 def test_config5_tile_five_levels_vs_oracle():
