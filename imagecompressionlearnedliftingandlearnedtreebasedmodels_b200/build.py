@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
     ``csrc/probe/*.cu`` into ``libll_probe.so`` (``include/ll_probe.h``).  Returns the product library's path."""
     if force or _stale(LIB_PATH, sources()):
         _compile(LIB_PATH, sources(), "build.log", verbose)
-    if force or _stale(PROBE_LIB_PATH, probe_sources()):
+    if force or _stale(PROBE_LIB_PATH, probe_sources() + sources()):      # the probe builds #include product sources
         _compile(PROBE_LIB_PATH, probe_sources(), "build_probe.log", verbose)
     return LIB_PATH
 

@@ -546,9 +546,16 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 //   E2   z = y * rsqrt(norm + beta) -> [hi | lo] split -> the only global stores of the kernel (8 B per value).
 // Tensor-memory plan per CTA (columns): y [0, N) | norm main [N, N + NP) | norm small [N + NP, N + 2 NP) | staging
 // hi [N + 2 NP, +KS) lo [.., +KS).  N = 192: NP = 96 (two passes), KS = 64 -> 512 columns; N <= 96: NP = KS = N.
-// Every warp of parity e (two epilogue warps per TMEM lane quarter) only touches 32-column chunks of y with global
-// index = e (mod 2), so no y column is read by a warp other than the one that wrote it.
+// 16 epilogue warps = 4 groups x 4 TMEM lane quarters.  Group g only touches the 16-column chunks of y whose global index
+// is g (mod 4), so no y column is read by a warp other than the one that wrote it; a staging round's slots (16 channels
+// each) are staged by different groups at the same time and their MMAs start slot by slot.  In E2 a warp first pulls y and
+// the norm of its chunks into registers and finishes the arithmetic, THEN releases tensor memory (the next pass's norm
+// MMAs / the next tile's mainloop start) and only then splits and stores: the global stores of a tile overlap the tensor
+// work that follows.  (Timeline of the 8-warp version, conv 96->192: mainloop 30 k cycles, then 30 k cycles of E1 /
+// staging / E2 with the tensor pipe idle.)
 // ------------------------------------------------------------------------------------------------
+constexpr int GD_THREADS = 576;   // TMA warp, MMA warp, 16 epilogue warps
+constexpr int GD_EPI_WARPS = 16;
 struct GdnPairParams {
   const float* bias;
   const float* beta;
@@ -578,7 +585,8 @@ static long long* g_timeline = nullptr;
 #define LL_TL(tile, slot) do { } while (0)
 #endif
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(IG_THREADS, 1)
+template <bool HEAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GD_THREADS, 1)
 igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmG, const __grid_constant__ GdnPairParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -590,17 +598,17 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PR_MAXST + s); };
   const uint32_t tfull_bar = bars + 8u * (2 * PR_MAXST), tempty_bar = bars + 8u * (2 * PR_MAXST + 1);
-  // GDN hand-offs, one pair of barriers per 32-channel staging slot (at most 3 slots): aready[c] = the split of y^2 of slot
+  // GDN hand-offs, one pair of barriers per 16-channel staging slot (at most 6 slots): aready[c] = the split of y^2 of slot
   // c is in tensor memory (8 arrivals: the 4 warps that own the slot x 2 CTAs), gdone[c] = the MMAs that read it are
-  // complete; e2done = every warp is done with E1 / with the previous pass's norm (16 arrivals, once per pass)
+  // complete; e2done = every warp is done with E1 / has read the previous pass's norm (32 arrivals, once per pass)
   auto aready_bar = [&](int c) { return bars + 8u * (2 * PR_MAXST + 2 + c); };
-  auto gdone_bar = [&](int c) { return bars + 8u * (2 * PR_MAXST + 5 + c); };
-  const uint32_t e2done_bar = bars + 8u * (2 * PR_MAXST + 8);
+  auto gdone_bar = [&](int c) { return bars + 8u * (2 * PR_MAXST + 8 + c); };
+  const uint32_t e2done_bar = bars + 8u * (2 * PR_MAXST + 14);
   // pdone = all norm MMAs of a pass are complete.  Its own barrier, waited once per pass by every warp: a warp may only wait
   // on a barrier whose every phase it observes (a parity wait cannot tell phase k from phase k - 2), and a slot's gdone is
   // observed round by round by its owners only.
-  const uint32_t pdone_bar = bars + 8u * (2 * PR_MAXST + 9);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 10));
+  const uint32_t pdone_bar = bars + 8u * (2 * PR_MAXST + 15);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 16));
   float* s_bias = reinterpret_cast<float*>(gen + ring_bytes + 256);
   float* s_beta = s_bias + IG_MAXN;
   float* s_w0 = s_beta + IG_MAXN;                        // head mode: [k = ci*9 + tap][N]
@@ -609,13 +617,13 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
-  for (int i = threadIdx.x; i < IG_MAXN; i += IG_THREADS) {
+  for (int i = threadIdx.x; i < IG_MAXN; i += GD_THREADS) {
     s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
     s_beta[i] = i < p.N ? p.beta[i] : 1.f;
   }
-  if (p.head) {
+  if (HEAD) {
     const int K0 = 9 * p.iC;
-    for (int i = threadIdx.x; i < K0 * p.N; i += IG_THREADS) s_w0[i] = p.w0[(i % p.N) * K0 + i / p.N];
+    for (int i = threadIdx.x; i < K0 * p.N; i += GD_THREADS) s_w0[i] = p.w0[(i % p.N) * K0 + i / p.N];
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -626,12 +634,12 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 16);
-    for (int c = 0; c < 3; ++c) {
+    mbar_init(tempty_bar, 2 * GD_EPI_WARPS);
+    for (int c = 0; c < 6; ++c) {
       mbar_init(aready_bar(c), 8);
       mbar_init(gdone_bar(c), 1);
     }
-    mbar_init(e2done_bar, 16);
+    mbar_init(e2done_bar, 2 * GD_EPI_WARPS);
     mbar_init(pdone_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -711,12 +719,19 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const uint32_t a_st = tmem_base + (uint32_t)p.col_st;
       int tli = 0;
       for (long long pt = pair0; pt < p.npairs; pt += pair_step, ++tli) {
-        if (!p.head) {
+        if (!HEAD) {
           LL_TL(tli, 0);
           mbar_wait_spin(tempty_bar, te_phase ^ 1);
           te_phase ^= 1;
           tc_fence_after();
           LL_TL(tli, 1);
+#ifdef LL_TIMELINE
+          if (p.tl && blockIdx.x == 0 && lane == 0 && tli < 16) {   // wall clock beside the cycle stamp: the SM clock under load
+            long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            p.tl[tli * 64 + 60] = gt;
+          }
+#endif
           for (int it = 0; it < iters; ++it) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -749,26 +764,31 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           e2_phase ^= 1;
           for (int rd = 0; rd < p.rpp; ++rd) {
             for (int kbr = 0; kbr < p.KS / 32; ++kbr) {
-              mbar_wait_spin(aready_bar(kbr), ar_phase);
-              tc_fence_after();
-              if (kbr == 0) LL_TL(tli, 4 + 2 * (ps * p.rpp + rd));
               mbar_wait(full_bar(stage), phase);
               tc_fence_after();
-              if (elect_one()) {
-                const uint32_t sa = base + stage * p.stage_bytes;
-                const uint64_t g_hi = umma_desc_sw128(sa), g_lo = umma_desc_sw128(sa + p.ghalf_bytes);
-                const uint32_t cont = (uint32_t)((rd | kbr) != 0);
+              const uint32_t sa = base + stage * p.stage_bytes;
+              const uint64_t g_hi = umma_desc_sw128(sa), g_lo = umma_desc_sw128(sa + p.ghalf_bytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t ah = a_st + (uint32_t)(kbr * 32 + 8 * k), al = ah + (uint32_t)p.KS;
-                  tc_mma_tf32_ts_2sm(d_ns, al, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
-                  tc_mma_tf32_ts_2sm(d_ns, ah, g_lo + 2 * k, idesc_g, 1u);
-                  tc_mma_tf32_ts_2sm(d_nm, ah, g_hi + 2 * k, idesc_g, cont | (uint32_t)(k != 0));
+              for (int h = 0; h < 2; ++h) {             // the two 16-channel slots of this 32-channel gamma k-block
+                const int slot = 2 * kbr + h;
+                mbar_wait_spin(aready_bar(slot), ar_phase);
+                tc_fence_after();
+                if (slot == 0) LL_TL(tli, 4 + 2 * (ps * p.rpp + rd));
+                if (elect_one()) {
+                  const uint32_t cont = (uint32_t)((rd | slot) != 0);
+#pragma unroll
+                  for (int kk = 0; kk < 2; ++kk) {
+                    const int k = 2 * h + kk;
+                    const uint32_t ah = a_st + (uint32_t)(kbr * 32 + 8 * k), al = ah + (uint32_t)p.KS;
+                    tc_mma_tf32_ts_2sm(d_ns, al, g_hi + 2 * k, idesc_g, cont | (uint32_t)(kk != 0));
+                    tc_mma_tf32_ts_2sm(d_ns, ah, g_lo + 2 * k, idesc_g, 1u);
+                    tc_mma_tf32_ts_2sm(d_nm, ah, g_hi + 2 * k, idesc_g, cont | (uint32_t)(kk != 0));
+                  }
+                  if (h == 1) tc_commit_2sm(empty_bar(stage), 3);
+                  tc_commit_2sm(gdone_bar(slot), 3);    // this slot's MMAs done: staging reusable / (last slot) norm complete
                 }
-                tc_commit_2sm(empty_bar(stage), 3);
-                tc_commit_2sm(gdone_bar(kbr), 3);       // this slot's MMAs done: staging reusable / (last slot) norm complete
+                __syncwarp();
               }
-              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             ar_phase ^= 1;
@@ -782,13 +802,14 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int par = (warp - 2) >> 2;                    // chunk parity of this warp
+    const int grp = (warp - 2) >> 2;                    // this warp owns the 16-column chunks of y with index = grp (mod 4)
     const int row = q * 32 + lane;
     const int ty = row / IG_TW, tx = row % IG_TW;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tf_phase = 0, pd_phase = 0;
     unsigned ground = 0;                                // staging rounds so far, over all tiles: every slot's gdone completes once per round
-    const int nchunks = p.N / 32;
+    const int nch = p.N / 16;                           // 16-column chunks of y
+    const int slots = p.KS / 16, npc = p.NP / 16;
     // head mode: the 3x3 x iC input window of this thread's pixel; the NEXT tile's window is requested as soon as the
     // current one has been consumed, so its global-load latency hides behind the GDN phases (ncu: 22 % of the kernel's
     // stall samples sat on the first use of these loads when they were issued at the top of the tile)
@@ -809,7 +830,7 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         win[k] = v;
       }
     };
-    if (p.head) load_window(pair0);
+    if (HEAD) load_window(pair0);
     int tli = 0;
 #ifdef LL_TIMELINE
     const bool tlw = warp == 2 && lane == 0;
@@ -824,18 +845,18 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
       const bool valid = t < p.ntiles && y < p.H && x < p.W;
       const long long px = ((long long)b * p.H + y) * p.W + x;
-      if (p.head) {
+      if (HEAD) {
         // E1 (head): y = Conv2d(iC, N, 3, padding=1)(x) + bias in exact FP32 FMA, one pixel per thread, -> tensor memory
-        for (int c = par; c < nchunks; c += 2) {
-          float acc[32];
+        for (int c = grp; c < nch; c += 4) {
+          float acc[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = s_bias[c * 32 + j];
+          for (int j = 0; j < 16; ++j) acc[j] = s_bias[c * 16 + j];
 #pragma unroll
           for (int k = 0; k < 27; ++k) {
             if (k < 9 * p.iC) {
-              const float4* wr = reinterpret_cast<const float4*>(s_w0 + k * p.N + c * 32);
+              const float4* wr = reinterpret_cast<const float4*>(s_w0 + k * p.N + c * 16);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
+              for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 w4 = wr[j4];
                 acc[4 * j4 + 0] = fmaf(win[k], w4.x, acc[4 * j4 + 0]);
                 acc[4 * j4 + 1] = fmaf(win[k], w4.y, acc[4 * j4 + 1]);
@@ -844,10 +865,10 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
               }
             }
           }
-          uint32_t v[32];
+          uint32_t v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
-          tmem_st32(tlane + c * 32, v);
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(acc[j]);
+          tmem_st16(tlane + c * 16, v);
         }
         load_window(pt + pair_step);
       } else {
@@ -857,45 +878,43 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         tc_fence_after();
         LL_TLE(33);
         // E1: y = main + small + bias, in place
-        for (int c = par; c < nchunks; c += 2) {
-          uint32_t v[32], w[32];
-          tc_ld32(tlane + c * 32, v);
-          tc_ld32(tlane + p.N + c * 32, w);
+        for (int c = grp; c < nch; c += 4) {
+          uint32_t v[16], w[16];
+          tc_ld16(tlane + c * 16, v);
+          tc_ld16(tlane + p.N + c * 16, w);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 32 + j]);
-          tmem_st32(tlane + c * 32, v);
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint((__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 16 + j]);
+          tmem_st16(tlane + c * 16, v);
         }
       }
       tmem_wait_st();
       LL_TLE(34);
-      const int slots = p.KS / 32;
+      // this warp's E1 is done (its reads of the previous tile's norm were released at the end of that tile's E2)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(e2done_bar);
       for (int ps = 0; ps < p.passes; ++ps) {
-        // pass 0: this warp's E1 is done (and, in head mode, its E2 of the previous tile); later passes: it has read the
-        // previous pass's norm
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(e2done_bar);
         for (int rd = 0; rd < p.rpp; ++rd, ++ground) {
           LL_TLE(36 + 2 * (ps * p.rpp + rd));
-          for (int cc = par; cc < slots; cc += 2) {              // the slots this warp owns (slot parity = chunk parity)
+          for (int cc = grp; cc < slots; cc += 4) {              // the slots this warp owns (slot index = chunk index mod 4)
             const int gc = rd * slots + cc;                      // global chunk index of these y columns
             // the MMAs that read this slot in the previous round (of this or of the previous tile) are complete
             if (ground) mbar_wait_spin(gdone_bar(cc), (ground - 1) & 1u);
             tc_fence_after();
-            uint32_t v[32], lo[32];
-            tc_ld32(tlane + gc * 32, v);
+            uint32_t v[16], lo[16];
+            tc_ld16(tlane + gc * 16, v);
             tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const float yy = __uint_as_float(v[j]);
               const float sq = yy * yy;
               const float h = tf32_rna(sq);
               v[j] = __float_as_uint(h);
               lo[j] = __float_as_uint(tf32_rna(sq - h));
             }
-            tmem_st32(tlane + p.col_st + cc * 32, v);
-            tmem_st32(tlane + p.col_st + p.KS + cc * 32, lo);
+            tmem_st16(tlane + p.col_st + cc * 16, v);
+            tmem_st16(tlane + p.col_st + p.KS + cc * 16, lo);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -908,39 +927,57 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         pd_phase ^= 1;
         tc_fence_after();
         LL_TLE(50 + 2 * ps);
-        for (int cc = 0; cc < p.NP / 32; ++cc) {
-          const int gc = ps * (p.NP / 32) + cc;
-          if ((gc & 1) != par) continue;
-          uint32_t yv[32], nm[32], ns[32];
-          tc_ld32(tlane + gc * 32, yv);
-          tc_ld32(tlane + p.col_nm + cc * 32, nm);
-          tc_ld32(tlane + p.col_ns + cc * 32, ns);
-          tc_wait_ld();
-          if (valid) {
-            float* zp = p.sz + px * (2 * p.N) + gc * 32;
+        // E2, first half: y and the norm of this warp's (at most two) chunks of the pass -> registers -> z
+        const int cbase = ps * npc;
+        const int first = cbase + ((grp - cbase) & 3);
+        float rr[2][16];
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 8) {
-              float hi[8], lo[8];
+        for (int i = 0; i < 2; ++i) {
+          const int gc = first + 4 * i;
+          if (gc < cbase + npc) {
+            const int cc = gc - cbase;
+            uint32_t yv[16], nm[16], ns[16];
+            tc_ld16(tlane + gc * 16, yv);
+            tc_ld16(tlane + p.col_nm + cc * 16, nm);
+            tc_ld16(tlane + p.col_ns + cc * 16, ns);
+            tc_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float a = (__uint_as_float(nm[j0 + j]) + __uint_as_float(ns[j0 + j])) + s_beta[gc * 32 + j0 + j];
-                const float rr = __uint_as_float(yv[j0 + j]) * (p.inverse ? sqrtf(a) : rsqrtf(a));
-                hi[j] = tf32_rna(rr);
-                lo[j] = tf32_rna(rr - hi[j]);
-              }
+            for (int j = 0; j < 16; ++j) {
+              const float a = (__uint_as_float(nm[j]) + __uint_as_float(ns[j])) + s_beta[gc * 16 + j];
+              rr[i][j] = __uint_as_float(yv[j]) * (p.inverse ? sqrtf(a) : rsqrtf(a));
+            }
+          }
+        }
+        // tensor memory released: the next pass's norm MMAs / the next tile's mainloop may overwrite the accumulators
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(ps + 1 < p.passes ? e2done_bar : tempty_bar);
+        // E2, second half: [hi | lo] split and the kernel's only global stores, overlapping the tensor work that follows
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int gc = first + 4 * i;
+            if (gc < cbase + npc) {
+              float* zp = p.sz + px * (2 * p.N) + gc * 16;
+#pragma unroll
+              for (int j0 = 0; j0 < 16; j0 += 8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  hi[j] = tf32_rna(rr[i][j0 + j]);
+                  lo[j] = tf32_rna(rr[i][j0 + j] - hi[j]);
+                }
 #ifdef LL_TIMELINE
-              if (g_nostore_dev && hi[0] != 12345.678f) continue;
+                if (g_nostore_dev && hi[0] != 12345.678f) continue;
 #endif
-              st_global_v8(zp + j0, hi);
-              st_global_v8(zp + p.N + j0, lo);
+                st_global_v8(zp + j0, hi);
+                st_global_v8(zp + p.N + j0, lo);
+              }
             }
           }
         }
         LL_TLE(51 + 2 * ps);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(tempty_bar);
     }
   }
 
@@ -1544,6 +1581,9 @@ static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bi
   p.rpp = N / p.KS;
   p.col_nm = N; p.col_ns = N + p.NP; p.col_st = N + 2 * p.NP;
   if (p.col_st + 2 * p.KS > IG_TMEM_COLS) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: tensor-memory plan does not fit");
+  // chunk ownership (16 columns, owner = index mod 4) must not move between staging rounds; <= 6 slots, <= 2 chunks per group and pass
+  if ((p.rpp > 1 && (p.KS / 16) % 4) || p.KS / 16 > 6 || p.NP / 16 > 8)
+    return fail(LL_EINVAL, "ll_igemm_tf32_gdn: staging plan (KS %d, NP %d) does not fit the epilogue's chunk ownership", p.KS, p.NP);
   CUtensorMap tmA, tmB, tmG;
   const int Ca = 2 * C;
   if (!head) {
@@ -1600,13 +1640,15 @@ static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bi
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 64 && !attr[dev]) {
-    LL_CUDA_OK(cudaFuncSetAttribute(igemm_tf32_gdn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_LIMIT));
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_tf32_gdn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_LIMIT));
+    LL_CUDA_OK(cudaFuncSetAttribute(igemm_tf32_gdn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_LIMIT));
     attr[dev] = true;
   }
   long long pairs = sm_count_cached() / 2;
   if (pairs > p.npairs) pairs = p.npairs;
   if (pairs < 1) pairs = 1;
-  igemm_tf32_gdn_pair_kernel<<<(unsigned)(2 * pairs), IG_THREADS, smem, stream>>>(tmA, tmB, tmG, p);
+  if (head) igemm_tf32_gdn_pair_kernel<true><<<(unsigned)(2 * pairs), GD_THREADS, smem, stream>>>(tmA, tmB, tmG, p);
+  else igemm_tf32_gdn_pair_kernel<false><<<(unsigned)(2 * pairs), GD_THREADS, smem, stream>>>(tmA, tmB, tmG, p);
   LL_LAUNCH_OK("igemm_tf32_gdn_pair_kernel");
   return LL_OK;
 }

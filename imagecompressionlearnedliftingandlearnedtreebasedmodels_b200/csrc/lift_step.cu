@@ -6,7 +6,7 @@
 namespace ll {
 
 int launch_lift_step_tc(const LiftParams& p, cudaStream_t stream);                                  // lift_tc.cu
-int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream);         // lift_tc.cu
+int launch_pack_lift_tc(const float* w2, const float* w3, const float* w4, float* blob, cudaStream_t stream);         // lift_tc.cu
 #ifdef LL_DEBUG   // timing experiments of the tensor-core kernel (scripts/gpu_lift_tc_time*.py); not in release builds
 static int g_lift_dbg = 0;
 static long long* g_lift_dbg_buf = nullptr;
@@ -140,7 +140,7 @@ int ll_pack_lift_step(const float* pre_w, const float* w1, const float* b1, cons
     return fail(LL_EINVAL, "ll_pack_lift_step: null pointer");
   pack_lift_step_kernel<<<(BL_TOTAL + 255) / 256, 256, 0, as_stream(stream)>>>(pre_w, w1, b1, w2, b2, w3, b3, w4, b4, blob);
   LL_LAUNCH_OK("pack_lift_step_kernel");
-  return launch_pack_lift_tc(w2, w3, blob, as_stream(stream));
+  return launch_pack_lift_tc(w2, w3, w4, blob, as_stream(stream));
 }
 
 #ifdef LL_DEBUG

@@ -48,8 +48,14 @@
 
 namespace ll {
 
-constexpr int TC_THREADS = 544;  // 8 epilogue warps + 8 SIMT warps + 1 MMA warp
-constexpr int TC_MMA_WARP = 16;
+// 8 epilogue warps + 8 SIMT warps + 1 MMA warp.  Warp w issues on SM sub-partition w % 4; the epilogue's accumulator drains
+// run on warps 0-2 / 4-6 (TMEM lane quarter = warp % 4), so sub-partition 3 carries ~300 instructions per step less than
+// the others.  The MMA warp (~265 per step) is therefore warp 19 -- warps 16-18 exist only to put it there and exit after
+// the set-up -- instead of warp 16, which made sub-partition 0 the step's critical path (1800 vs 1535 issue slots).
+constexpr int TC_THREADS = 640;
+constexpr int TC_MMA_WARP = 19;
+constexpr int TC_LIVE = 544;     // threads that take part in the step barriers
+#define TC_BAR0() asm volatile("bar.sync 0, 544;" ::: "memory")
 constexpr int TC_WO = 52;        // output columns per strip
 constexpr int TC_RA = 6;         // a1 / a2 ring rows
 constexpr int TC_R3 = 6;         // a3 ring rows
@@ -64,11 +70,19 @@ constexpr int TC_PS = 72;        // skip pitch
 constexpr int TM_W = 192;        // [layer 2][term 2][dy 5][ci 16] (320 columns, behind the accumulators: the dx-shifted drains
                                  // read up to 4 columns past an accumulator, which must stay inside the allocation)
 constexpr int TM_ACC2 = 0, TM_ACC3 = 64, TM_ACC2B = 128;   // conv2 accumulator double-buffered (steps alternate)
+// 3xFP16 kernel only: conv4 (16 -> 1) is a third tensor-core layer, two MMAs per vertical tap: the three terms of the split sit
+// in different ROWS of the accumulator -- region 0 (times the hi half of a3): rows dx = w_hi, rows 8 + dx = w_lo; region 1 (times
+// the lo half of a3): rows 16 + dx = w_hi -- and the drain adds the three row groups.  2 x 40 columns behind the 160 of
+// conv2 / conv3; accumulator D4[row 24][column 64].
+constexpr int TM_W4 = TM_W + 160, TM_ACC4 = TM_W4 + 80;
+static_assert(TM_ACC4 + 64 <= 512, "tensor-memory budget");
 // shared memory (bytes from the 1024-aligned base)
 constexpr int TS_RA1 = 0;
 constexpr int TS_RA2 = TS_RA1 + TC_RA * TC_SLOT;
 constexpr int TS_A3 = TS_RA2 + TC_RA * TC_SLOT;
-constexpr int TS_O1 = TS_A3 + TC_R3 * 8 * TC_PA3 * 4;
+constexpr int TS_A3_BYTES = TC_R3 * 4096;   // fp32 pair-interleaved ring (TC_R3 * 8 * TC_PA3 * 4 = 23 808 B) or the fp16 operand ring (4 KB rows)
+static_assert(TC_R3 * 8 * TC_PA3 * 4 <= TS_A3_BYTES && TS_A3 % 1024 == 0, "a3 ring");
+constexpr int TS_O1 = TS_A3 + TS_A3_BYTES;
 constexpr int TS_P2 = TS_O1 + TC_RO * 16 * TC_P3 * 4;
 constexpr int TS_P3 = TS_P2 + 48 * TC_PP * 4;   // partial planes: [dx pair 3][co 16][TC_PP]
 constexpr int TS_SK = TS_P3 + 48 * TC_PP * 4;
@@ -77,10 +91,11 @@ constexpr int TS_W = TS_SK + TC_RS * TC_PS * 4;
 // (channel-pair float2 loads feed packed FFMA2 with a broadcast activation)
 constexpr int SW_PRE = 0, SW_W1 = 4, SW_B1 = SW_W1 + 400, SW_B2 = SW_B1 + 16, SW_B3 = SW_B2 + 16, SW_W4 = SW_B3 + 16,
               SW_B4 = SW_W4 + 400, SW_ZERO = SW_B4 + 4, SW_TOTAL = SW_ZERO + 16;   // SW_ZERO: 64 B of zeros = "row outside the plane"
-constexpr int TS_BAR = TS_W + SW_TOTAL * 4;
-constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;
+constexpr int TS_P4 = TS_W + SW_TOTAL * 4;          // conv4 partial rows D4[row 24][TC_PP] (3xFP16 kernel)
+constexpr int TS_BAR = TS_P4 + 24 * TC_PP * 4;
+constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;   // barriers at +0, +16, +32; tensor-memory slot at +24
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(TS_RA2 % 1024 == 0 && TS_A3 % 16 == 0 && TS_O1 % 16 == 0 && TS_P2 % 16 == 0 && TS_SK % 16 == 0 && TS_W % 16 == 0 && TS_BAR % 8 == 0, "align");
+static_assert(TS_RA2 % 1024 == 0 && TS_A3 % 16 == 0 && TS_O1 % 16 == 0 && TS_P2 % 16 == 0 && TS_SK % 16 == 0 && TS_W % 16 == 0 && TS_P4 % 16 == 0 && TS_BAR % 8 == 0, "align");
 
 // byte offset of 4 consecutive columns i..i+3 (i % 4 == 0) of channel ci inside a ring row (hi half)
 __device__ __forceinline__ int ring_off(int ci, int i) {
@@ -136,11 +151,14 @@ __device__ __forceinline__ int ring_off16(int ci, int i) {
   return (ci >> 3) * 1024 + r * 128 + ((((i >> 3) ^ r)) << 4) + ((i & 7) << 1);
 }
 
+// (SCALE = 1 for the a3 ring: the input of conv4 is not bounded by a tanh, so it keeps the whole fp16 range -- |a3| up to
+// 65504 -- and its lo part goes subnormal below |a3| = 0.125, an absolute error of at most 3e-8 per element)
+template <int SCALE = 256>
 __device__ __forceinline__ void split_store16(uint8_t* row, int ci, int i, const float (&v)[4]) {
   __half hi[4], lo[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float s = v[k] * TC16_SA;
+    const float s = SCALE == 1 ? v[k] : v[k] * (float)SCALE;
     hi[k] = __float2half_rn(s);
     lo[k] = __float2half_rn(s - __half2float(hi[k]));
   }
@@ -197,14 +215,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   float* P3 = reinterpret_cast<float*>(gen + TS_P3);
   float* SK = reinterpret_cast<float*>(gen + TS_SK);
   float* SW = reinterpret_cast<float*>(gen + TS_W);
-  const uint32_t bar_mma = base + TS_BAR, bar_free3 = base + TS_BAR + 16;
+  const uint32_t bar_mma = base + TS_BAR, bar_free3 = base + TS_BAR + 16, bar_free4 = base + TS_BAR + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + TS_BAR + 24);
+  float* P4 = reinterpret_cast<float*>(gen + TS_P4);
+  constexpr int TEND = F16 ? 12 : 11;   // steps past the last output row (the 3xFP16 kernel drains conv4 one step after its MMAs)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (tid == 0) {
     mbar_init(bar_mma, 1);
     mbar_init(bar_free3, 4);
+    mbar_init(bar_free4, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -238,6 +259,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         tmem_st8(trow + TM_W + reg * 40 + c, v);
       }
     }
+    // conv4: two regions of 40 columns = [dy 5][ci pair 8] x 24 rows (see pack_lift_tc16_conv4_kernel); rows 24..127 zero
+    const uint32_t* words4 = reinterpret_cast<const uint32_t*>(p.blob + BL_TC16_4);
+    for (int reg = 0; reg < 2; ++reg) {
+      for (int c = 0; c < 40; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tid < 24 ? words4[(reg * 24 + tid) * 40 + c + k] : 0u;
+        tmem_st8(trow + TM_W4 + reg * 40 + c, v);
+      }
+    }
     tmem_wait_st();
   }
   if (!F16 && warp < 4) {   // weights -> tensor memory: row m = dx*16 + co (rows 80..127 zero), 4 regions of 80 columns
@@ -256,6 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (warp >= 16 && warp != TC_MMA_WARP) return;   // placeholder warps (see TC_MMA_WARP)
 
   // instruction descriptor: D fp32, A/B tf32, A K-major (TMEM), B MN-major, N = 64, M = 128
   // (F16: D fp32, A/B fp16 = format 0, B MN-major plain SWIZZLE_128B, 8-channel atoms 1024 B apart along K)
@@ -263,6 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                              : (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t desc_ra1 = F16 ? umma_desc_mn_sw128(base + TS_RA1, 1024, 1024) : umma_desc_mn_sw128_32b(base + TS_RA1, 1024, 512);
   const uint64_t desc_ra2 = F16 ? umma_desc_mn_sw128(base + TS_RA2, 1024, 1024) : umma_desc_mn_sw128_32b(base + TS_RA2, 1024, 512);
+  const uint64_t desc_a3 = umma_desc_mn_sw128(base + TS_A3, 1024, 1024);   // 3xFP16 kernel: a3 ring rows of 4 KB
 
   const int ncta = gridDim.x;
   const long long lo_u = p.total_units * (long long)blockIdx.x / ncta;
@@ -382,12 +415,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         if (rr >= sk_lo && rr < sk_hi) skip_row(rr, e % 68);
       }
     }
-    __syncthreads();
+    TC_BAR0();
 
     // One step loop per warp role (instead of one loop with a role switch inside): each role keeps only its own
     // loop invariants in registers.  All three loops run the same steps and meet at barrier 0 once per step.
     if (warp == TC_MMA_WARP) {
-      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+      for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
         const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
         const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
         const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
@@ -395,6 +428,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           // conv2 alternates between two accumulators: the one of step n was drained in step n-1 (behind the
           // end-of-step barrier), so its MMAs start at once; only conv3 waits for this step's drain.
           TC_STAMP(0);
+          if (DBG && p.dbg_buf && blockIdx.x == 0 && lane == 0 && (n == 40 || n == 240)) {   // wall clock beside the cycle counter: SM clock under load
+            long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            p.dbg_buf[warp * 8 + (n == 40 ? 3 : 4)] = gt;
+            if (n == 240) p.dbg_buf[warp * 8 + 5] = clock64();
+          }
           tc_fence_after();
           const uint32_t acc2 = tmem + TM_ACC2 + (n & 1) * (TM_ACC2B - TM_ACC2);
           const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
@@ -426,6 +465,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             }
           }
           TC_STAMP(1);
+          if (F16) {
+            // conv4 row t-11 (its a3 rows were completed in step t-1) as soon as the previous step's D4 has been drained: that
+            // happens early in the step, while the conv3 accumulator is only free after E-A -- so conv4 goes first
+            const int r4m = t - 11;
+            const bool m4 = r4m >= s.ya && r4m < s.yb;
+            mbar_wait(bar_free4, n & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              if (m4 && !TC_OFF(1)) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int dy = 0; dy < 5; ++dy) {
+                  const int rr = r4m + dy - 2;
+                  if (rr >= 0 && rr < s.ny) {
+                    const uint64_t bd = desc_a3 + (uint32_t)((rr % TC_R3) * (4096 >> 4));
+                    const uint32_t a0 = tmem + TM_W4 + dy * 8, a1 = a0 + 40;
+                    tc_mma_f16_ts(tmem + TM_ACC4, a0, bd, idesc, acc);                  // rows dx: hi * hi, rows 8 + dx: lo * hi
+                    tc_mma_f16_ts(tmem + TM_ACC4, a1, bd + (2048 >> 4), idesc, 1u);     // rows 16 + dx: hi * lo
+                    acc = 1;
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
           mbar_wait(bar_free3, n & 1);
           tc_fence_after();
           if (elect_one()) {
@@ -459,11 +523,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           __syncwarp();
           TC_STAMP(2);
         TC_STAMP(6);
-        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_BAR0();   // end of step: every role loop issues exactly one per step
         TC_STAMP(7);
       }
     } else if (warp < 8) {
-      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+      for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
         const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
         const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
         const bool e2 = r2e >= a2_lo && r2e < a2_hi, e3 = r3e >= a3_lo && r3e < a3_hi;
@@ -570,6 +634,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                 const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
                 v[k] = (c >= 0 && c < s.nx) ? x : 0.f;
               }
+              if (F16) {   // conv4 runs on the tensor cores: a3 goes to its operand ring as an UNSCALED fp16 hi/lo pair
+                if (xq >= 14) v[0] = v[1] = v[2] = v[3] = 0.f;   // columns 56..63 only feed accumulator columns nobody reads
+                split_store16<1>(gen + TS_A3 + (r3e % TC_R3) * 4096, co, i0, v);
+              } else {
               // the partner lane (xor 16) holds the other channel of the pair for the same 4 columns
               float o[4];
 #pragma unroll
@@ -578,6 +646,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               if (xq < 14) {
                 if (co & 1) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[2], v[2], o[3], v[3]);   // columns i0+2, i0+3
                 else *reinterpret_cast<float4*>(dst) = make_float4(v[0], o[0], v[1], o[1]);               // columns i0, i0+1
+              }
               }
             }
           }
@@ -588,9 +657,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             SK[(rs & (TC_RS - 1)) * TC_PS + (tid - 128)] = v;
           }
           TC_STAMP(5);
-          fence_proxy_async();   // a2 ring writes -> visible to the tensor core's operand reads
+          fence_proxy_async();   // a2 (and a3) ring writes -> visible to the tensor core's operand reads
         TC_STAMP(6);
-        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_BAR0();   // end of step: every role loop issues exactly one per step
         TC_STAMP(7);
       }
     } else if (warp < 12) {
@@ -603,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
 #pragma unroll
       for (int k = 0; k < 25; ++k) wr[k] = *reinterpret_cast<const float2*>(SW + SW_W1 + k * 16 + 2 * cp);
       const float2 b1 = *reinterpret_cast<const float2*>(SW + SW_B1 + 2 * cp);
-      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+      for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
         TC_STAMP(0);
         if (t >= a1_lo && t < a1_hi && !TC_OFF(4)) {
           float2 acc[4] = {b1, b1, b1, b1};
@@ -642,14 +711,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         TC_STAMP(1);
         fence_proxy_async();   // a1 ring writes -> visible to the tensor core's operand reads
         TC_STAMP(6);
-        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_BAR0();   // end of step: every role loop issues exactly one per step
         TC_STAMP(7);
       }
     } else {
       // ======================= conv4 + output warps 12-15 (104 active threads) =======================
       const int c4 = tid - 384;
       const bool act4 = c4 < 104;
-      for (int t = s.ya - 6; t < s.yb + 11; ++t, ++n) {
+      if (F16) {
+        // 3xFP16 kernel: conv4 ran on the tensor cores in the previous step.  Warp 12 (TMEM lane quarter 0) moves the five
+        // rows D4[dx][0..63] to shared memory; thread c4 < 52 then owns output column c4: net = sum_dx D4[dx][c4 + dx].
+        const bool col4 = c4 < TC_WO && s.x0 + c4 < s.nx;
+        for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
+          const int r4 = t - 12;
+          const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8);
+          const float dv = *((do4 && col4) ? din_b + (long long)r4 * J.din.sy + (long long)(s.x0 + c4) * J.din.sx : din_b);
+          TC_STAMP(0);
+          if (warp == 12) {
+            if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
+            tc_fence_after();
+            if (do4) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                uint32_t v[16];
+                tc_ld16(tmem + TM_ACC4 + 16 * r, v);
+                tc_wait_ld();
+                if (lane < 24 && (lane & 7) < 5) {
+                  float* o = P4 + lane * TC_PP + 16 * r;
+#pragma unroll
+                  for (int k = 0; k < 16; k += 4)
+                    *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free4);
+          }
+          TC_STAMP(1);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (do4 && col4) {
+            float a4 = 0.f;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx)      // small terms first, then the hi * hi row
+              a4 = __fadd_rn(a4, __fadd_rn(__fadd_rn(P4[(8 + dx) * TC_PP + c4 + dx], P4[(16 + dx) * TC_PP + c4 + dx]), P4[dx * TC_PP + c4 + dx]));
+            const float net = __fadd_rn(a4 * (1.f / TC16_SW), SW[SW_B4]);
+            const float sk = SK[(r4 & (TC_RS - 1)) * TC_PS + c4 + 8];
+            const float tn = __fmul_rn(net, p.rw);
+            const float o = p.sign > 0.f ? __fadd_rn(__fadd_rn(dv, sk), tn)
+                                         : p.sign < 0.f ? __fadd_rn(__fadd_rn(dv, -sk), -tn) : net;
+            J.dout.ptr[(long long)s.b * J.dout.sb + (long long)r4 * J.dout.sy + (long long)(s.x0 + c4) * J.dout.sx] = o;
+          }
+          TC_STAMP(2);
+          TC_STAMP(6);
+          TC_BAR0();
+          TC_STAMP(7);
+        }
+      } else
+      for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
         const int r4 = t - 11;
         const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8);
         float dv[4];
@@ -658,7 +777,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
         if (do4) conv4_out(r4, c4, act4, dv);
         TC_STAMP(2);
         TC_STAMP(6);
-        asm volatile("bar.sync 0;" ::: "memory");   // end of step: every role loop issues exactly one per step
+        TC_BAR0();   // end of step: every role loop issues exactly one per step
         TC_STAMP(7);
       }
     }
@@ -667,7 +786,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   // drain: the last step's commit must have landed before tensor memory is released
   if (warp < 8 && n > 0) mbar_wait(bar_mma, (n - 1) & 1);
   tc_fence_before();
-  __syncthreads();
+  TC_BAR0();
   if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -698,6 +817,27 @@ __global__ void pack_lift_tc16_kernel(const float* __restrict__ w2, const float*
       const float w = ((reg >> 1) ? w3 : w2)[(co * 16 + 2 * cp + e) * 25 + dy * 5 + dx] * TC16_SW;
       const __half hi = __float2half_rn(w);
       h[e] = (reg & 1) ? __float2half_rn(w - __half2float(hi)) : hi;
+    }
+    const __half2 pr = __halves2half2(h[0], h[1]);
+    words[i] = *reinterpret_cast<const uint32_t*>(&pr);
+  }
+}
+
+// conv4 block of the 3xFP16 kernel: [region 2][row 24][word = dy*8 + ci/2], fp16 pairs (ci even, ci odd).  Region 0 multiplies
+// the hi half of a3: rows dx = hi = fp16(256 w), rows 8 + dx = lo = fp16(256 w - hi); region 1 multiplies the lo half: rows
+// 16 + dx = hi; every other row is zero.  w4 is the torch (1,16,5,5) tensor.
+__global__ void pack_lift_tc16_conv4_kernel(const float* __restrict__ w4, float* __restrict__ blob) {
+  uint32_t* words = reinterpret_cast<uint32_t*>(blob + BL_TC16_4);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * 24 * 40; i += gridDim.x * blockDim.x) {
+    const int word = i % 40, row = (i / 40) % 24, reg = i / 960;
+    const int dy = word / 8, cp = word % 8, dx = row & 7, grp = row >> 3;
+    const bool live = dx < 5 && (reg == 0 ? grp < 2 : grp == 2);
+    __half h[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float w = live ? w4[(2 * cp + e) * 25 + dy * 5 + dx] * TC16_SW : 0.f;
+      const __half hi = __float2half_rn(w);
+      h[e] = grp == 1 ? __float2half_rn(w - __half2float(hi)) : hi;
     }
     const __half2 pr = __halves2half2(h[0], h[1]);
     words[i] = *reinterpret_cast<const uint32_t*>(&pr);
@@ -742,7 +882,9 @@ int launch_lift_step_tc(const LiftParams& p0, cudaStream_t stream) {
   return LL_OK;
 }
 
-int launch_pack_lift_tc(const float* w2, const float* w3, float* blob, cudaStream_t stream) {
+int launch_pack_lift_tc(const float* w2, const float* w3, const float* w4, float* blob, cudaStream_t stream) {
+  pack_lift_tc16_conv4_kernel<<<8, 256, 0, stream>>>(w4, blob);
+  LL_LAUNCH_OK("pack_lift_tc16_conv4_kernel");
   pack_lift_tc_kernel<<<100, 256, 0, stream>>>(w2, w3, blob);
   LL_LAUNCH_OK("pack_lift_tc_kernel");
   pack_lift_tc16_kernel<<<50, 256, 0, stream>>>(w2, w3, blob);

@@ -36,6 +36,8 @@ for C, N in ((96, 192), (192, 96)):
     _lib.check_probe(lib.ll_probe_set_timeline(None))
     t = tl.cpu()
     print(f"== conv {C}->{N} + GDN: cycles relative to the tile's mainloop start (slot 1)")
+    if int(t[9][60]) and int(t[2][60]):
+        print(f"SM clock under load: {(int(t[9][1]) - int(t[2][1])) / (int(t[9][60]) - int(t[2][60])):.3f} GHz (tiles 2..9 of CTA 0)")
     rounds = 6 if N == 192 else 1
     passes = 2 if N == 192 else 1
     for i in range(2, 8):

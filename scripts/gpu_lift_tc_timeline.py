@@ -34,17 +34,24 @@ def timed(n=10):
     for _ in range(n): run()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+ONLY = [int(b) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else None   # a subset of the switch sets (own process per set)
 for name, bits in (("full", 0), ("no MMA", 1), ("no E-B", 2), ("no conv1", 4), ("no conv4", 8), ("no E-A", 16),
                    ("no workers' math", 2 | 4 | 8 | 16), ("nothing", 31)):
+    if ONLY is not None and bits not in ONLY:
+        continue
     probe.ll_dbg_lift_switches(bits)
     print(f"{name:20s} {timed():.3f} ms", flush=True)
 probe.ll_dbg_lift_switches(0)
-buf = torch.zeros(17, 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(20, 8, dtype=torch.int64, device=dev)
 probe.ll_dbg_lift_stamp_buffer(ops.ptr(buf))
 run(); torch.cuda.synchronize()
 probe.ll_dbg_lift_stamp_buffer(None)
 t = buf.cpu()
+if int(t[19][4]) and int(t[19][3]):
+    print(f"SM clock under load: {(int(t[19][5]) - int(t[19][0])) / (int(t[19][4]) - int(t[19][3])):.3f} GHz; "
+          f"{(int(t[19][5]) - int(t[19][0])) / 200:.0f} cycles per step (steps 40..240 of CTA 0)")
+    t[19][3:6] = 0
 t0 = int(t[t > 0].min())
-names = {0: "epi0", 1: "epi1", 4: "epi4(conv3 drain)", 6: "epi6", 8: "conv1", 12: "conv4", 16: "MMA"}
+names = {0: "epi0", 1: "epi1", 4: "epi4(conv3 drain)", 6: "epi6", 8: "conv1", 12: "conv4", 19: "MMA"}
 for w, nm in names.items():
     print(f"warp {w:2d} {nm:18s}", [int(v) - t0 if v else None for v in t[w]])
