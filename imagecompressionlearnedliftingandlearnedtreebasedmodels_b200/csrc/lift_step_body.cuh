@@ -60,8 +60,8 @@ constexpr int BL_TOTAL = BL_B4 + 4;   // end of the part the SIMT kernel stages 
 // tensor-core weight block (lift_tc.cu): [layer 2][term hi|lo][row dx*16+co (80)][col dy*16+ci (80)]
 constexpr int BL_TC = BL_TOTAL;
 constexpr int BL_TC16 = BL_TC + 4 * 80 * 80;   // fp16 weight block of the 3xFP16 kernel: 4 x 80 x 40 32-bit words (lift_tc.cu)
-constexpr int BL_TC16_4 = BL_TC16 + 4 * 80 * 40;   // conv4 block of the 3xFP16 kernel: 2 x 24 x 40 words
-constexpr int BL_ALL = BL_TC16_4 + 2 * 24 * 40;
+constexpr int BL_TC16_4 = BL_TC16 + 4 * 80 * 40;   // conv4 block of the 3xFP16 kernel: 2 x 16 x 40 words
+constexpr int BL_ALL = BL_TC16_4 + 2 * 16 * 40;
 static_assert(BL_ALL == LL_LIFT_BLOB_FLOATS, "blob layout");
 
 // shared memory layout (floats)

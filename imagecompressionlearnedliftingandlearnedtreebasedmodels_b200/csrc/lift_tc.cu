@@ -50,12 +50,13 @@ namespace ll {
 
 // 8 epilogue warps + 8 SIMT warps + 1 MMA warp.  Warp w issues on SM sub-partition w % 4; the epilogue's accumulator drains
 // run on warps 0-2 / 4-6 (TMEM lane quarter = warp % 4), so sub-partition 3 carries ~300 instructions per step less than
-// the others.  The MMA warp (~265 per step) is therefore warp 19 -- warps 16-18 exist only to put it there and exit after
+// the others.  The MMA warp (~265 per step) is therefore warp 19 -- warps 16-18 exist only to put it there and idle at
 // the set-up -- instead of warp 16, which made sub-partition 0 the step's critical path (1800 vs 1535 issue slots).
+// The placeholder warps stay resident and take part in every block barrier: letting them exit and counting 544 threads at
+// barrier 0 faulted intermittently ("unspecified launch failure", timing dependent).
 constexpr int TC_THREADS = 640;
 constexpr int TC_MMA_WARP = 19;
-constexpr int TC_LIVE = 544;     // threads that take part in the step barriers
-#define TC_BAR0() asm volatile("bar.sync 0, 544;" ::: "memory")
+#define TC_BAR0() asm volatile("bar.sync 0;" ::: "memory")
 constexpr int TC_WO = 52;        // output columns per strip
 constexpr int TC_RA = 6;         // a1 / a2 ring rows
 constexpr int TC_R3 = 6;         // a3 ring rows
@@ -70,12 +71,15 @@ constexpr int TC_PS = 72;        // skip pitch
 constexpr int TM_W = 192;        // [layer 2][term 2][dy 5][ci 16] (320 columns, behind the accumulators: the dx-shifted drains
                                  // read up to 4 columns past an accumulator, which must stay inside the allocation)
 constexpr int TM_ACC2 = 0, TM_ACC3 = 64, TM_ACC2B = 128;   // conv2 accumulator double-buffered (steps alternate)
-// 3xFP16 kernel only: conv4 (16 -> 1) is a third tensor-core layer, two MMAs per vertical tap: the three terms of the split sit
-// in different ROWS of the accumulator -- region 0 (times the hi half of a3): rows dx = w_hi, rows 8 + dx = w_lo; region 1 (times
-// the lo half of a3): rows 16 + dx = w_hi -- and the drain adds the three row groups.  2 x 40 columns behind the 160 of
-// conv2 / conv3; accumulator D4[row 24][column 64].
-constexpr int TM_W4 = TM_W + 160, TM_ACC4 = TM_W4 + 80;
-static_assert(TM_ACC4 + 64 <= 512, "tensor-memory budget");
+// 3xFP16 kernel: weights need 160 columns instead of 320, so the conv3 accumulator is double-buffered as well (no MMA of a
+// step waits for a drain) and conv4 (16 -> 1) is a third tensor-core layer, two MMAs per vertical tap.  Its weights live in
+// the rows the conv2 regions leave unused -- region 0 (conv2 hi; B = the hi half of a3): rows 96 + dx = w4_hi, rows 101 + dx =
+// w4_lo; region 1 (conv2 lo; B = the lo half of a3): rows 106 + dx = w4_hi -- so the three terms of the split land in
+// different ROWS of D4 (rows 0..79 of D4 are conv2-weights x a3 garbage nobody reads; conv2's own rows 96.. likewise), all
+// fifteen inside the first 16 lanes of TMEM lane quarter 3: ONE 16-lane load drains them (tensor-memory reads run at
+// 64 B/clk per SM and the E-A drains already need 40 KB of them per step).
+constexpr int TM16_ACC3B = 192, TM16_W = 256, TM16_ACC4 = TM16_W + 160;
+static_assert(TM16_ACC4 + 64 <= 512, "tensor-memory budget");
 // shared memory (bytes from the 1024-aligned base)
 constexpr int TS_RA1 = 0;
 constexpr int TS_RA2 = TS_RA1 + TC_RA * TC_SLOT;
@@ -91,9 +95,9 @@ constexpr int TS_W = TS_SK + TC_RS * TC_PS * 4;
 // (channel-pair float2 loads feed packed FFMA2 with a broadcast activation)
 constexpr int SW_PRE = 0, SW_W1 = 4, SW_B1 = SW_W1 + 400, SW_B2 = SW_B1 + 16, SW_B3 = SW_B2 + 16, SW_W4 = SW_B3 + 16,
               SW_B4 = SW_W4 + 400, SW_ZERO = SW_B4 + 4, SW_TOTAL = SW_ZERO + 16;   // SW_ZERO: 64 B of zeros = "row outside the plane"
-constexpr int TS_P4 = TS_W + SW_TOTAL * 4;          // conv4 partial rows D4[row 24][TC_PP] (3xFP16 kernel)
-constexpr int TS_BAR = TS_P4 + 24 * TC_PP * 4;
-constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;   // barriers at +0, +16, +32; tensor-memory slot at +24
+constexpr int TS_P4 = TS_W + SW_TOTAL * 4;          // conv4 partial rows D4[row 15][TC_PP] (3xFP16 kernel)
+constexpr int TS_BAR = TS_P4 + 16 * TC_PP * 4;
+constexpr int TC_SMEM_BYTES = 1024 + TS_BAR + 64;   // barriers at +0, +16, +32, +40; tensor-memory slot at +24
 static_assert(TC_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(TS_RA2 % 1024 == 0 && TS_A3 % 16 == 0 && TS_O1 % 16 == 0 && TS_P2 % 16 == 0 && TS_SK % 16 == 0 && TS_W % 16 == 0 && TS_P4 % 16 == 0 && TS_BAR % 8 == 0, "align");
 
@@ -216,6 +220,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   float* SK = reinterpret_cast<float*>(gen + TS_SK);
   float* SW = reinterpret_cast<float*>(gen + TS_W);
   const uint32_t bar_mma = base + TS_BAR, bar_free3 = base + TS_BAR + 16, bar_free4 = base + TS_BAR + 32;
+  // bar_seen: every warp that waits for the commit of step n-1 (parity wait) arrives here once it has seen it, and the MMA warp
+  // waits for all of them before it commits step n.  Without it a commit that completes early -- nothing but the accumulator
+  // drains holds the MMA warp back -- flips the barrier's phase a second time before a slow waiter has looked, the waiter then
+  // takes the NEXT phase for the one it is waiting for and the CTA deadlocks (seen as the bounded wait's trap).
+  const uint32_t bar_seen = base + TS_BAR + 40;
+  constexpr int NSEEN = F16 ? 9 : 8;       // epilogue warps 0-7 (+ the conv4 drain warp 15)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + TS_BAR + 24);
   float* P4 = reinterpret_cast<float*>(gen + TS_P4);
   constexpr int TEND = F16 ? 12 : 11;   // steps past the last output row (the 3xFP16 kernel drains conv4 one step after its MMAs)
@@ -226,6 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
     mbar_init(bar_mma, 1);
     mbar_init(bar_free3, 4);
     mbar_init(bar_free4, 1);
+    mbar_init(bar_seen, NSEEN);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -250,23 +261,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   if (F16 && warp < 4) {   // fp16 weights: row m = dx*16 + co, 4 regions [layer][term] of 40 columns = [dy 5][ci pair 8]
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(p.blob + BL_TC16);
+    const uint32_t* words4 = reinterpret_cast<const uint32_t*>(p.blob + BL_TC16_4);   // conv4: [region 2][row 16][40] -> rows 96..111
     for (int reg = 0; reg < 4; ++reg) {
-      const uint32_t* src = words + ((long long)reg * 80 + tid) * 40;
+      const uint32_t* src = tid < 80 ? words + ((long long)reg * 80 + tid) * 40
+                                     : (tid >= 96 && tid < 112 && reg < 2) ? words4 + (reg * 16 + (tid - 96)) * 40 : nullptr;
       for (int c = 0; c < 40; c += 8) {
         uint32_t v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = tid < 80 ? src[c + k] : 0u;
-        tmem_st8(trow + TM_W + reg * 40 + c, v);
-      }
-    }
-    // conv4: two regions of 40 columns = [dy 5][ci pair 8] x 24 rows (see pack_lift_tc16_conv4_kernel); rows 24..127 zero
-    const uint32_t* words4 = reinterpret_cast<const uint32_t*>(p.blob + BL_TC16_4);
-    for (int reg = 0; reg < 2; ++reg) {
-      for (int c = 0; c < 40; c += 8) {
-        uint32_t v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = tid < 24 ? words4[(reg * 24 + tid) * 40 + c + k] : 0u;
-        tmem_st8(trow + TM_W4 + reg * 40 + c, v);
+        for (int k = 0; k < 8; ++k) v[k] = src ? src[c + k] : 0u;
+        tmem_st8(trow + TM16_W + reg * 40 + c, v);
       }
     }
     tmem_wait_st();
@@ -287,7 +290,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp >= 16 && warp != TC_MMA_WARP) return;   // placeholder warps (see TC_MMA_WARP)
 
   // instruction descriptor: D fp32, A/B tf32, A K-major (TMEM), B MN-major, N = 64, M = 128
   // (F16: D fp32, A/B fp16 = format 0, B MN-major plain SWIZZLE_128B, 8-channel atoms 1024 B apart along K)
@@ -419,7 +421,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
 
     // One step loop per warp role (instead of one loop with a role switch inside): each role keeps only its own
     // loop invariants in registers.  All three loops run the same steps and meet at barrier 0 once per step.
-    if (warp == TC_MMA_WARP) {
+    if (warp >= 16 && warp != TC_MMA_WARP) {          // placeholder warps (see TC_MMA_WARP): only the step barriers
+      for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) TC_BAR0();
+    } else if (warp == TC_MMA_WARP) {
       for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
         const int r2m = t - 3, r3m = t - 7;      // rows whose MMAs are issued in this step
         const int r2e = t - 4, r3e = t - 8;      // rows whose accumulators are drained in this step
@@ -437,37 +441,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           tc_fence_after();
           const uint32_t acc2 = tmem + TM_ACC2 + (n & 1) * (TM_ACC2B - TM_ACC2);
           const bool m2 = r2m >= a2_lo && r2m < a2_hi, m3 = r3m >= a3_lo && r3m < a3_hi;
-          if (elect_one()) {
-            if (m2 && !TC_OFF(1)) {
-              uint32_t acc = 0;
+          if (F16) {
+            // Both accumulators of step n were drained in step n-1: all 30 MMAs of conv2 / conv3 go out at the barrier, the
+            // two layers' (independent) accumulation chains interleaved tap by tap.
+            const uint32_t acc3 = tmem + ((n & 1) ? TM16_ACC3B : TM_ACC3);
+            if (elect_one()) {
+              if (!TC_OFF(1)) {
+                uint32_t c2 = 0, c3 = 0;
 #pragma unroll
-              for (int dy = 0; dy < 5; ++dy) {
-                const int rr = r2m + dy - 2;
-                if (rr >= 0 && rr < s.ny) {
-                  const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
-                  if (F16) {                                                        // K = 16 channels per MMA
-                    const uint32_t ah = tmem + TM_W + 0 * 80 + dy * 8, al = ah + 40;
-                    tc_mma_f16_ts(acc2, ah, bd, idesc, acc);                        // hi * hi
-                    tc_mma_f16_ts(acc2, al, bd, idesc, 1u);                         // lo * hi
-                    tc_mma_f16_ts(acc2, ah, bd + (2048 >> 4), idesc, 1u);           // hi * lo
-                  } else {
-                  const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
-                  tc_mma_tf32_ts(acc2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
-                  tc_mma_tf32_ts(acc2, al, bd, idesc, 1u);                        // lo * hi
-                  tc_mma_tf32_ts(acc2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
-                  tc_mma_tf32_ts(acc2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
-                  tc_mma_tf32_ts(acc2, al + 8, bd + (2048 >> 4), idesc, 1u);
-                  tc_mma_tf32_ts(acc2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
-                  }
-                  acc = 1;
+                for (int dy = 0; dy < 5; ++dy) {
+                  const int rr2 = r2m + dy - 2, rr3 = r3m + dy - 2;
+                  const bool ok2 = m2 && rr2 >= 0 && rr2 < s.ny, ok3 = m3 && rr3 >= 0 && rr3 < s.ny;
+                  const uint64_t bd2 = desc_ra1 + (uint32_t)(((rr2 + TC_RA) % TC_RA) * (TC_SLOT >> 4));
+                  const uint64_t bd3 = desc_ra2 + (uint32_t)(((rr3 + TC_RA) % TC_RA) * (TC_SLOT >> 4));
+                  const uint32_t ah2 = tmem + TM16_W + 0 * 80 + dy * 8, al2 = ah2 + 40;
+                  const uint32_t ah3 = tmem + TM16_W + 1 * 80 + dy * 8, al3 = ah3 + 40;
+                  if (ok2) tc_mma_f16_ts(acc2, ah2, bd2, idesc, c2);                   // hi * hi
+                  if (ok3) tc_mma_f16_ts(acc3, ah3, bd3, idesc, c3);
+                  if (ok2) tc_mma_f16_ts(acc2, al2, bd2, idesc, 1u);                   // lo * hi
+                  if (ok3) tc_mma_f16_ts(acc3, al3, bd3, idesc, 1u);
+                  if (ok2) tc_mma_f16_ts(acc2, ah2, bd2 + (2048 >> 4), idesc, 1u);     // hi * lo
+                  if (ok3) tc_mma_f16_ts(acc3, ah3, bd3 + (2048 >> 4), idesc, 1u);
+                  if (ok2) c2 = 1;
+                  if (ok3) c3 = 1;
                 }
               }
             }
-          }
-          TC_STAMP(1);
-          if (F16) {
-            // conv4 row t-11 (its a3 rows were completed in step t-1) as soon as the previous step's D4 has been drained: that
-            // happens early in the step, while the conv3 accumulator is only free after E-A -- so conv4 goes first
+            __syncwarp();
+            TC_STAMP(1);
+            // conv4 row t-11 (its a3 rows were completed in step t-1) once the previous step's D4 has been drained
             const int r4m = t - 11;
             const bool m4 = r4m >= s.ya && r4m < s.yb;
             mbar_wait(bar_free4, n & 1);
@@ -480,17 +482,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                   const int rr = r4m + dy - 2;
                   if (rr >= 0 && rr < s.ny) {
                     const uint64_t bd = desc_a3 + (uint32_t)((rr % TC_R3) * (4096 >> 4));
-                    const uint32_t a0 = tmem + TM_W4 + dy * 8, a1 = a0 + 40;
-                    tc_mma_f16_ts(tmem + TM_ACC4, a0, bd, idesc, acc);                  // rows dx: hi * hi, rows 8 + dx: lo * hi
-                    tc_mma_f16_ts(tmem + TM_ACC4, a1, bd + (2048 >> 4), idesc, 1u);     // rows 16 + dx: hi * lo
+                    const uint32_t a0 = tmem + TM16_W + dy * 8, a1 = a0 + 40;
+                    tc_mma_f16_ts(tmem + TM16_ACC4, a0, bd, idesc, acc);                  // rows 96 + dx: hi * hi, rows 101 + dx: lo * hi
+                    tc_mma_f16_ts(tmem + TM16_ACC4, a1, bd + (2048 >> 4), idesc, 1u);     // rows 106 + dx: hi * lo
                     acc = 1;
                   }
                 }
               }
             }
             __syncwarp();
+            mbar_wait(bar_seen, n & 1);
+            if (elect_one()) tc_commit(bar_mma);
+          } else {
+          if (elect_one()) {
+            if (m2 && !TC_OFF(1)) {
+              uint32_t acc = 0;
+#pragma unroll
+              for (int dy = 0; dy < 5; ++dy) {
+                const int rr = r2m + dy - 2;
+                if (rr >= 0 && rr < s.ny) {
+                  const uint64_t bd = desc_ra1 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
+                  const uint32_t ah = tmem + TM_W + 0 * 160 + dy * 16, al = ah + 80;
+                  tc_mma_tf32_ts(acc2, ah, bd, idesc, acc);                       // hi * hi, ci 0-7
+                  tc_mma_tf32_ts(acc2, al, bd, idesc, 1u);                        // lo * hi
+                  tc_mma_tf32_ts(acc2, ah, bd + (4096 >> 4), idesc, 1u);          // hi * lo
+                  tc_mma_tf32_ts(acc2, ah + 8, bd + (2048 >> 4), idesc, 1u);      // ci 8-15
+                  tc_mma_tf32_ts(acc2, al + 8, bd + (2048 >> 4), idesc, 1u);
+                  tc_mma_tf32_ts(acc2, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
+                  acc = 1;
+                }
+              }
+            }
           }
-          mbar_wait(bar_free3, n & 1);
+          TC_STAMP(1);
+          mbar_wait(bar_free3, n & 1);       // only conv3 waits for this step's drain (one conv3 accumulator)
           tc_fence_after();
           if (elect_one()) {
             if (m3 && !TC_OFF(1)) {
@@ -500,12 +525,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                 const int rr = r3m + dy - 2;
                 if (rr >= 0 && rr < s.ny) {
                   const uint64_t bd = desc_ra2 + (uint32_t)((rr % TC_RA) * (TC_SLOT >> 4));
-                  if (F16) {
-                    const uint32_t ah = tmem + TM_W + 1 * 80 + dy * 8, al = ah + 40;
-                    tc_mma_f16_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
-                    tc_mma_f16_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
-                    tc_mma_f16_ts(tmem + TM_ACC3, ah, bd + (2048 >> 4), idesc, 1u);
-                  } else {
                   const uint32_t ah = tmem + TM_W + 1 * 160 + dy * 16, al = ah + 80;
                   tc_mma_tf32_ts(tmem + TM_ACC3, ah, bd, idesc, acc);
                   tc_mma_tf32_ts(tmem + TM_ACC3, al, bd, idesc, 1u);
@@ -513,12 +532,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                   tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + (2048 >> 4), idesc, 1u);
                   tc_mma_tf32_ts(tmem + TM_ACC3, al + 8, bd + (2048 >> 4), idesc, 1u);
                   tc_mma_tf32_ts(tmem + TM_ACC3, ah + 8, bd + ((4096 + 2048) >> 4), idesc, 1u);
-                  }
                   acc = 1;
                 }
               }
             }
-            tc_commit(bar_mma);
+          }
+          __syncwarp();
+          mbar_wait(bar_seen, n & 1);
+          if (elect_one()) tc_commit(bar_mma);
           }
           __syncwarp();
           TC_STAMP(2);
@@ -550,6 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
           TC_STAMP(0);
           // ---- E-A: accumulators of the previous step -> partial planes ----
           if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
+          if (lane == 0) mbar_arrive(bar_seen);
           tc_fence_after();
           TC_STAMP(1);
           // Warps 0-3 drain the conv2 accumulator, warps 4-7 the conv3 one; warp quarter q owns accumulator lanes
@@ -561,7 +583,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             const int q = warp & 3, l3 = warp >> 2;
             const bool on = (l3 ? e3 : e2) && q < 3 && !TC_OFF(16);
             if (on) {
-              const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (l3 ? TM_ACC3 : ((n & 1) ? TM_ACC2 : TM_ACC2B)) + 2 * q;   // conv2: buffer of step n-1
+              const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (l3 ? (F16 ? ((n & 1) ? TM_ACC3 : TM16_ACC3B) : TM_ACC3) : ((n & 1) ? TM_ACC2 : TM_ACC2B)) + 2 * q;   // buffers of step n-1
               float* o = (l3 ? P3 : P2) + (q * 16 + (lane & 15)) * TC_PP + 32 * (lane >> 4);
 #pragma unroll
               for (int r = 0; r < 4; ++r) {            // four rounds of 8 columns per half keep 16 registers live
@@ -585,6 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (l3 && lane == 0) mbar_arrive(bar_free3);   // this warp's share of the conv3 accumulator is drained
+            if (F16 && l3) asm volatile("bar.arrive 3, 256;" ::: "memory");   // conv3 pair planes complete: warps 12-15 take them from here
           }
           TC_STAMP(2);
           asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -618,7 +641,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
               if (F16) split_store16(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
               else split_store(gen + TS_RA2 + (r2e % TC_RA) * TC_SLOT, co, i0, v);
             }
-            if (e3 && !TC_OFF(2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
+            if (!F16 && e3 && !TC_OFF(2)) {       // (xq = 14, 15 compute on stale columns and store nothing)
               const float* pr = P3 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
               const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
               const float us = F16 ? TC16_UNSCALE : 1.f;
@@ -634,10 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
                 const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
                 v[k] = (c >= 0 && c < s.nx) ? x : 0.f;
               }
-              if (F16) {   // conv4 runs on the tensor cores: a3 goes to its operand ring as an UNSCALED fp16 hi/lo pair
-                if (xq >= 14) v[0] = v[1] = v[2] = v[3] = 0.f;   // columns 56..63 only feed accumulator columns nobody reads
-                split_store16<1>(gen + TS_A3 + (r3e % TC_R3) * 4096, co, i0, v);
-              } else {
+              {
               // the partner lane (xor 16) holds the other channel of the pair for the same 4 columns
               float o[4];
 #pragma unroll
@@ -719,29 +739,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
       const int c4 = tid - 384;
       const bool act4 = c4 < 104;
       if (F16) {
-        // 3xFP16 kernel: conv4 ran on the tensor cores in the previous step.  Warp 12 (TMEM lane quarter 0) moves the five
-        // rows D4[dx][0..63] to shared memory; thread c4 < 52 then owns output column c4: net = sum_dx D4[dx][c4 + dx].
+        // 3xFP16 kernel.  (1) conv4 ran on the tensor cores in the previous step: warp 15 (TMEM lane quarter 3) moves the
+        // fifteen rows of D4 that carry the three terms to shared memory, thread c4 < 52 then owns output column c4:
+        // net = sum_dx (lo*hi + hi*lo + hi*hi)[dx][c4 + dx].  (2) The conv3 half of E-B: pair planes -> + bias + o1 -> a3 operand
+        // ring (UNSCALED fp16 hi/lo: the input of conv4 is not bounded by a tanh), two (channel, column quad) items per thread.
         const bool col4 = c4 < TC_WO && s.x0 + c4 < s.nx;
         for (int t = s.ya - 6; t < s.yb + TEND; ++t, ++n) {
-          const int r4 = t - 12;
+          const int r4 = t - 12, r3e = t - 8;
           const bool do4 = r4 >= s.ya && r4 < s.yb && !TC_OFF(8);
+          const bool e3 = r3e >= a3_lo && r3e < a3_hi;
           const float dv = *((do4 && col4) ? din_b + (long long)r4 * J.din.sy + (long long)(s.x0 + c4) * J.din.sx : din_b);
           TC_STAMP(0);
-          if (warp == 12) {
+          if (warp == 15) {
             if (n > 0) mbar_wait(bar_mma, (n - 1) & 1);
+            if (lane == 0) mbar_arrive(bar_seen);
             tc_fence_after();
             if (do4) {
+              // threads 0-15 <- D4 row 96 + t, columns 0..31; threads 16-31 <- row 96 + (t - 16), columns 32..63
+              uint32_t v[32];
+              tc_ld16x32bx2_x32(tmem + ((uint32_t)96 << 16) + TM16_ACC4, v);
+              tc_wait_ld();
+              if ((lane & 15) < 15) {
+                float* o = P4 + (lane & 15) * TC_PP + 32 * (lane >> 4);
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                uint32_t v[16];
-                tc_ld16(tmem + TM_ACC4 + 16 * r, v);
-                tc_wait_ld();
-                if (lane < 24 && (lane & 7) < 5) {
-                  float* o = P4 + lane * TC_PP + 16 * r;
-#pragma unroll
-                  for (int k = 0; k < 16; k += 4)
-                    *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-                }
+                for (int k = 0; k < 32; k += 4)
+                  *reinterpret_cast<float4*>(o + k) = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
               }
             }
             tc_fence_before();
@@ -754,7 +776,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             float a4 = 0.f;
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx)      // small terms first, then the hi * hi row
-              a4 = __fadd_rn(a4, __fadd_rn(__fadd_rn(P4[(8 + dx) * TC_PP + c4 + dx], P4[(16 + dx) * TC_PP + c4 + dx]), P4[dx * TC_PP + c4 + dx]));
+              a4 = __fadd_rn(a4, __fadd_rn(__fadd_rn(P4[(5 + dx) * TC_PP + c4 + dx], P4[(10 + dx) * TC_PP + c4 + dx]), P4[dx * TC_PP + c4 + dx]));
             const float net = __fadd_rn(a4 * (1.f / TC16_SW), SW[SW_B4]);
             const float sk = SK[(r4 & (TC_RS - 1)) * TC_PS + c4 + 8];
             const float tn = __fmul_rn(net, p.rw);
@@ -763,6 +785,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lift_step_tc_kernel(const __gri
             J.dout.ptr[(long long)s.b * J.dout.sb + (long long)r4 * J.dout.sy + (long long)(s.x0 + c4) * J.dout.sx] = o;
           }
           TC_STAMP(2);
+          asm volatile("bar.sync 3, 256;" ::: "memory");     // conv3 pair planes of this step (E-A of warps 4-6)
+          if (e3 && !TC_OFF(2)) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int item = c4 + 128 * it, co = item >> 4, xq = item & 15, i0 = 4 * xq;
+              const float* pr = P3 + co * TC_PP + i0;     // pair-sum planes already hold the dx-shifted samples
+              const float4 s01 = lds128(pr), s23 = lds128(pr + 16 * TC_PP), s4 = lds128(pr + 32 * TC_PP);
+              const float sacc[4] = {__fadd_rn(__fadd_rn(s01.x, s23.x), s4.x) * TC16_UNSCALE, __fadd_rn(__fadd_rn(s01.y, s23.y), s4.y) * TC16_UNSCALE,
+                                     __fadd_rn(__fadd_rn(s01.z, s23.z), s4.z) * TC16_UNSCALE, __fadd_rn(__fadd_rn(s01.w, s23.w), s4.w) * TC16_UNSCALE};
+              const float bias = SW[SW_B3 + co];
+              const float4 o1 = *reinterpret_cast<const float4*>(O1 + ((r3e % TC_RO) * 16 + co) * TC_P3 + i0);
+              const float o1v[4] = {o1.x, o1.y, o1.z, o1.w};
+              float v[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = s.x0 - 2 + i0 + k;
+                const float x = __fadd_rn(__fadd_rn(sacc[k], bias), o1v[k]);
+                v[k] = (c >= 0 && c < s.nx && xq < 14) ? x : 0.f;   // columns 56..63 only feed accumulator columns nobody reads
+              }
+              split_store16<1>(gen + TS_A3 + (r3e % TC_R3) * 4096, co, i0, v);
+            }
+          }
+          TC_STAMP(3);
+          fence_proxy_async();   // a3 ring writes -> visible to the tensor core's operand reads
           TC_STAMP(6);
           TC_BAR0();
           TC_STAMP(7);
@@ -823,15 +869,15 @@ __global__ void pack_lift_tc16_kernel(const float* __restrict__ w2, const float*
   }
 }
 
-// conv4 block of the 3xFP16 kernel: [region 2][row 24][word = dy*8 + ci/2], fp16 pairs (ci even, ci odd).  Region 0 multiplies
-// the hi half of a3: rows dx = hi = fp16(256 w), rows 8 + dx = lo = fp16(256 w - hi); region 1 multiplies the lo half: rows
-// 16 + dx = hi; every other row is zero.  w4 is the torch (1,16,5,5) tensor.
+// conv4 block of the 3xFP16 kernel: [region 2][row 16][word = dy*8 + ci/2], fp16 pairs (ci even, ci odd).  Region 0 multiplies
+// the hi half of a3: rows dx = hi = fp16(256 w), rows 5 + dx = lo = fp16(256 w - hi); region 1 multiplies the lo half: rows
+// 10 + dx = hi; every other row is zero.  (The kernel puts them at tensor-memory rows 96..111.)  w4 is the torch (1,16,5,5) tensor.
 __global__ void pack_lift_tc16_conv4_kernel(const float* __restrict__ w4, float* __restrict__ blob) {
   uint32_t* words = reinterpret_cast<uint32_t*>(blob + BL_TC16_4);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * 24 * 40; i += gridDim.x * blockDim.x) {
-    const int word = i % 40, row = (i / 40) % 24, reg = i / 960;
-    const int dy = word / 8, cp = word % 8, dx = row & 7, grp = row >> 3;
-    const bool live = dx < 5 && (reg == 0 ? grp < 2 : grp == 2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * 16 * 40; i += gridDim.x * blockDim.x) {
+    const int word = i % 40, row = (i / 40) % 16, reg = i / 640;
+    const int dy = word / 8, cp = word % 8, grp = row / 5, dx = row % 5;
+    const bool live = row < 15 && (reg == 0 ? grp < 2 : grp == 2);
     __half h[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {

@@ -23,7 +23,7 @@ def _count(n):
     _LAUNCHES += n
 
 
-LIFT_BLOB_FLOATS = 53976
+LIFT_BLOB_FLOATS = 53336
 AE1_BLOB_FLOATS = 2212
 
 

@@ -56,7 +56,7 @@ typedef struct ll_lift_job {
   int32_t nb, ny, nx;
 } ll_lift_job;
 
-#define LL_LIFT_BLOB_FLOATS 53976
+#define LL_LIFT_BLOB_FLOATS 53336
 
 /* Packs one lifting step's parameters into the kernel's blob layout (device to
  * device, on `stream`).  pre_w: (3,) taps of convBlock[k] (lifting_dwt_nets.py:784-827);
