@@ -1148,6 +1148,85 @@ __global__ void __launch_bounds__(HD_THREADS) ctx_conv_nhwc_kernel(const __grid_
 }
 
 // (Co, Ci, R, S) fp32 -> [R*S][Npad][Kpad] bf16, zero padded.
+// ------------------------------------------------------------------------------------------------
+// Operand builder for the two small-Cin context convs as tensor-core GEMMs (LiftingBasedDWT_net.py:271,274-277):
+//   plc head  Conv2d(3, 243, 3, padding=1) on the nearest-2x-upsampled parent   K = 3 x 9 = 27
+//   csc       MaskedConv2d('A', 3, 243, 5, padding=2, groups=3) on the child     K = 12 live taps per group
+// As SIMT convs they produced 243 channels from 3 at ~21 TFLOP/s and cost 29 % of the layer.  Here one pass writes, per
+// pixel, the im2col row of both convs as a bf16 SPLIT  v = hi + lo  (hi = bf16(v), lo = bf16(v - hi): the inputs are
+// quantised coefficients, integers well beyond bf16's 8 bits), and the convs become 1-tap igemm layers whose packed
+// weights repeat the split on their side:   [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]   (16 bits per operand; the
+// fp32 SIMT kernel rounded its OUTPUT to bf16, which stays the dominant error).
+// Channels of the output pixel (320 bf16):  [0, 81) head: part p = c / 27 (hi, lo, hi), k = c % 27 = ci * 9 + tap;
+// [81, 128) zero;  128 + 64 g + [0, 36): csc group g: part p = r / 12, tap = r % 12 (row-major 5x5);  rest zero.
+// One thread = one pixel x 8 channels (a 16-byte store), 40 slots per pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int IM_CH = 320, IM_SLOTS = IM_CH / 8;
+constexpr int IM_SPAN = 128;                       // pixels of one image row per block
+constexpr int IM_THREADS = IM_SLOTS * 8;           // 40 slots x 8 pixel lanes
+constexpr int IM_UPW = IM_SPAN + 2, IM_CHW = IM_SPAN + 4;
+constexpr int IM_UP = 0, IM_CHD = IM_UP + 3 * 3 * IM_UPW, IM_ZERO = IM_CHD + 3 * 3 * IM_CHW, IM_TILE = IM_ZERO + IM_SPAN + 8;
+// Block = one image row x IM_SPAN pixels.  The 3 x 3 rows of the upsampled parent window and the 3 x 3 child rows the live
+// taps touch (dy = -2, -1, 0) are staged in shared memory with the zero padding already in place, so a channel is one
+// LDS at a per-thread constant offset: thread = (slot of 8 channels, pixel lane); the channel decode (divisions) runs once.
+__global__ void __launch_bounds__(IM_THREADS) ctx_im2col_kernel(const float* __restrict__ con, const float* __restrict__ q,
+                                                                __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  __shared__ float tile[IM_TILE];
+  const int spans = (W + IM_SPAN - 1) / IM_SPAN;
+  const int hs = H >> 1, ws = W >> 1;
+  const int slot = threadIdx.x % IM_SLOTS, plane = threadIdx.x / IM_SLOTS;
+  int off[8];
+  unsigned lo_mask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = slot * 8 + j;
+    int o = IM_ZERO;                                 // a run of zeros
+    if (c < 81) {
+      const int pt = c / 27, k = c % 27, ci = k / 9, tap = k % 9;
+      o = IM_UP + (ci * 3 + tap / 3) * IM_UPW + tap % 3;            // + local x
+      if (pt == 1) lo_mask |= 1u << j;
+    } else if (c >= 128) {
+      const int g = (c - 128) >> 6, r = (c - 128) & 63;
+      if (r < 36) {
+        const int pt = r / 12, tap = r % 12;
+        o = IM_CHD + (g * 3 + tap / 5) * IM_CHW + tap % 5;
+        if (pt == 1) lo_mask |= 1u << j;
+      }
+    }
+    off[j] = o;
+  }
+  for (long long blk = blockIdx.x; blk < (long long)B * H * spans; blk += gridDim.x) {
+    const int sp = (int)(blk % spans), y = (int)((blk / spans) % H), b = (int)(blk / ((long long)spans * H));
+    const int x0 = sp * IM_SPAN;
+    __syncthreads();
+    for (int i = threadIdx.x; i < IM_TILE; i += IM_THREADS) {
+      float v = 0.f;
+      if (i < IM_CHD) {
+        const int ci = i / (3 * IM_UPW), r = (i / IM_UPW) % 3, cx = i % IM_UPW;
+        const int yy = y + r - 1, xx = x0 + cx - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(con + (((long long)b * 3 + ci) * hs + (yy >> 1)) * ws + (xx >> 1));
+      } else if (i < IM_ZERO) {
+        const int k = i - IM_CHD, g = k / (3 * IM_CHW), r = (k / IM_CHW) % 3, cx = k % IM_CHW;
+        const int yy = y + r - 2, xx = x0 + cx - 2;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(q + (((long long)b * 3 + g) * H + yy) * W + xx);
+      }
+      tile[i] = v;
+    }
+    __syncthreads();
+    __nv_bfloat16* orow = out + (((long long)b * H + y) * W + x0) * IM_CH + slot * 8;
+    for (int xl = plane; xl < IM_SPAN && x0 + xl < W; xl += 8) {
+      __nv_bfloat16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = tile[off[j] + xl];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        o[j] = ((lo_mask >> j) & 1u) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+      }
+      *reinterpret_cast<uint4*>(orow + (long long)xl * IM_CH) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
 __global__ void pack_igemm_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Co, int Ci,
                                          int taps, int Npad, int Kpad) {
   const long long total = (long long)taps * Npad * Kpad;
@@ -1262,6 +1341,20 @@ static EncodeTiledFn encode_fn() {
 using namespace ll;
 
 extern "C" {
+
+// con (B,3,H/2,W/2) fp32 quantised parent, q (B,3,H,W) fp32 quantised child -> out (B,H,W,320) bf16: the split im2col rows of
+// the plc head (on the nearest-2x-upsampled parent) and of the masked csc (see ctx_im2col_kernel)
+int ll_ctx_im2col(const float* con, const float* q, void* out, int B, int H, int W, ll_stream_t stream) {
+  if (B < 0 || H < 0 || W < 0 || (H & 1) || (W & 1)) return fail(LL_EINVAL, "ll_ctx_im2col: bad extents (even H, W)");
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!con || !q || !out || ((uintptr_t)out & 15)) return fail(LL_EINVAL, "ll_ctx_im2col: null / misaligned pointer");
+  long long blocks = (long long)B * H * ((W + IM_SPAN - 1) / IM_SPAN);
+  const long long cap = (long long)sm_count_cached() * 12;
+  if (blocks > cap) blocks = cap;
+  ctx_im2col_kernel<<<(unsigned)blocks, IM_THREADS, 0, as_stream(stream)>>>(con, q, reinterpret_cast<__nv_bfloat16*>(out), B, H, W);
+  LL_LAUNCH_OK("ctx_im2col_kernel");
+  return LL_OK;
+}
 
 int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W, int Cout,
                      int K, int groups, int live_taps, int upsample2, int lrelu, int out_cstride, int out_coff,

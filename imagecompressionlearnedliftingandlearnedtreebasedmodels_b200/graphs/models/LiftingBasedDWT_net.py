@@ -356,7 +356,7 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         """Packed BF16 weights of level i: plc conv2 (9 taps, 256x256), cgp layer 1 (per group
         K = [128-channel window of plc | 128-channel csc slot], N = 192) and layer 2 (K = 192, N = 64)."""
         plc, cgp = self.plc_list[i], self.cgp_out_xo_list[i]
-        srcs = [plc[2].weight, cgp[0].weight, cgp[2].weight]
+        srcs = [plc[2].weight, cgp[0].weight, cgp[2].weight, plc[0].weight, self.csc_list[i].weight]
 
         def build():
             C = self.sos[i]
@@ -380,8 +380,24 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
                 l2.append(ops.pack_igemm_weight(w2[n2 * g:n2 * (g + 1)].reshape(n2, n1, 1, 1).contiguous(), npad=64, kpad=192))
                 k1.append([starts[g], starts[g] + 64, 256 + 128 * g, 256 + 128 * g + 64])
             k2 = [[192 * g, 192 * g + 64, 192 * g + 128] for g in range(C)]
-            return dict(plc=wp_plc, l1=torch.stack(l1).contiguous(), l2=torch.stack(l2).contiguous(), k1=k1, k2=k2,
-                        nper=nper, n1=n1, n2=n2)
+            pk = dict(plc=wp_plc, l1=torch.stack(l1).contiguous(), l2=torch.stack(l2).contiguous(), k1=k1, k2=k2,
+                      nper=nper, n1=n1, n2=n2)
+            # plc head (3x3 on the upsampled parent) and masked csc as 1-tap GEMMs over the split im2col rows of
+            # ops.ctx_im2col: weights [W_hi | W_hi | W_lo] against [x_hi | x_lo | x_hi]
+            csc = self.csc_list[i]
+            if C == 3 and plc[0].in_channels == 3 and tuple(plc[0].kernel_size) == (3, 3) and csc.groups == 3 and \
+                    tuple(csc.kernel_size) == (5, 5) and csc.in_channels == 3:
+                csc.apply_mask()
+                wh = torch.zeros(plc[0].out_channels, 128, 1, 1, device=dev)
+                wh[:, :81, 0, 0] = ops.split_bf16_weight(plc[0].weight.detach().reshape(plc[0].out_channels, 27))
+                pk["head"] = ops.pack_igemm_weight(wh, npad=256, kpad=128)
+                wc = []
+                for g in range(3):
+                    wg = torch.zeros(nper, 64, 1, 1, device=dev)
+                    wg[:, :36, 0, 0] = ops.split_bf16_weight(csc.weight.detach()[nper * g:nper * (g + 1), 0].reshape(nper, 25)[:, :12])
+                    wc.append(ops.pack_igemm_weight(wg, npad=128, kpad=64))
+                pk["csc"] = torch.stack(wc).contiguous()
+            return pk
 
         return self._tc_cache[i].get(srcs, build)
 
@@ -408,11 +424,20 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
             b1 = min(B, b0 + CTX_BATCH_CHUNK)
             n = b1 - b0
             g_in = torch.empty(n, h, w, 256 + 128 * C, dtype=torch.bfloat16, device=x.device)
-            t = ops.ctx_conv_nhwc(con[b0:b1], plc[0].weight, plc[0].bias, upsample2=True, lrelu=True, region=256)
+            if "head" in pk:
+                # both small-Cin convs on the tensor cores: one im2col pass, then 1-tap igemm layers
+                a = ops.ctx_im2col(con[b0:b1], q[b0:b1])
+                t = torch.empty(n, h, w, 256, dtype=torch.bfloat16, device=x.device)
+                ops.igemm_conv(a, pk["head"], plc[0].bias, plc[0].out_channels, lrelu=True, out_nhwc=t, koff=[[0, 64]])
+                ops.igemm_conv(a, pk["csc"], csc.bias, pk["nper"], out_nhwc=g_in, nhwc_coff=256, nhwc_gstride=128,
+                               koff=[[128], [192], [256]])
+                del a
+            else:
+                t = ops.ctx_conv_nhwc(con[b0:b1], plc[0].weight, plc[0].bias, upsample2=True, lrelu=True, region=256)
+                ops.ctx_conv_nhwc(q[b0:b1], csc.weight, csc.bias, groups=csc.groups, live_taps=12, out=g_in, coff=256,
+                                  co_group=pk["nper"], co_gstride=128, region=128 * C)
             ops.igemm_conv(t, pk["plc"], plc[2].bias, plc[2].out_channels, out_nhwc=g_in, nhwc_coff=0)
             del t
-            ops.ctx_conv_nhwc(q[b0:b1], csc.weight, csc.bias, groups=csc.groups, live_taps=12, out=g_in, coff=256,
-                              co_group=pk["nper"], co_gstride=128, region=128 * C)
             h1 = torch.empty(n, h, w, 192 * C, dtype=torch.bfloat16, device=x.device)
             ops.igemm_conv(g_in, pk["l1"], cgp[0].bias, pk["n1"], lrelu=True, out_nhwc=h1, nhwc_gstride=192, koff=pk["k1"])
             del g_in

@@ -306,6 +306,32 @@ def ctx_conv_nhwc(x, weight, bias, groups=1, live_taps=None, upsample2=False, lr
     return out
 
 
+IM2COL_CH = 320   # ll_ctx_im2col: [0,128) plc head (27 x [hi|lo|hi]), 128 + 64 g: csc group g (12 x [hi|lo|hi])
+
+
+def ctx_im2col(con, q):
+    """Quantised parent ``con`` (B,3,H/2,W/2) and child ``q`` (B,3,H,W) -> bf16 (B,H,W,320): the split im2col rows of the
+    plc head and the masked csc for their 1-tap igemm layers (ll_ctx_im2col)."""
+    require_device(q)
+    con, q = _f32c(con, "con"), _f32c(q, "q")
+    B, C, H, W = q.shape
+    if C != 3 or tuple(con.shape) != (B, 3, H // 2, W // 2) or H % 2 or W % 2:
+        raise ValueError(f"ctx_im2col: child {tuple(q.shape)} / parent {tuple(con.shape)} (3 subbands, parent at half size)")
+    out = torch.empty(B, H, W, IM2COL_CH, dtype=torch.bfloat16, device=q.device)
+    with torch.cuda.device(q.device):
+        check(_lib.load().ll_ctx_im2col(ptr(con), ptr(q), ptr(out), B, H, W, stream_ptr()))
+    _count(1)
+    return out
+
+
+def split_bf16_weight(w2d):
+    """(N, K) fp32 -> (N, 3K) fp32 holding [W_hi | W_hi | W_lo] (W_hi = bf16(W), W_lo = bf16(W - W_hi), exact in bf16):
+    the weight side of the [x_hi | x_lo | x_hi] operands ``ctx_im2col`` writes."""
+    hi = w2d.to(torch.bfloat16).to(torch.float32)
+    lo = (w2d - hi).to(torch.bfloat16).to(torch.float32)
+    return torch.cat((hi, hi, lo), dim=1)
+
+
 def pack_igemm_weight(weight, npad=None, kpad=None):
     """(Co,Ci,R,S) fp32 -> bf16 [R*S][Npad][Kpad] device blob for ``igemm_conv``."""
     require_device(weight)

@@ -186,6 +186,13 @@ int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* ou
                      int Cout, int K, int groups, int live_taps, int upsample2, int lrelu, int out_cstride,
                      int out_coff, int co_group, int co_gstride, int region, ll_stream_t stream);
 
+/* The two small-Cin context convs as tensor-core GEMMs (reference: graphs/models/LiftingBasedDWT_net.py:271,274-277,353-355):
+ * con (B,3,H/2,W/2) quantised parent, q (B,3,H,W) quantised child -> out (B,H,W,320) bf16 = per pixel the im2col row of
+ * the plc head (3x3 on the nearest-2x-upsampled parent, K = 27) and of the masked csc (12 live taps per group), each
+ * value split hi + lo in bf16: channels [0,81) head as [hi | lo | hi], [81,128) zero, 128 + 64 g + [0,36) csc group g as
+ * [hi | lo | hi], rest zero.  Consumed by ll_igemm_conv with 1-tap weights packed as [W_hi | W_hi | W_lo]. */
+int ll_ctx_im2col(const float* con, const float* q, void* out, int B, int H, int W, ll_stream_t stream);
+
 /* Weight packing for ll_igemm_conv: torch layout (Co,Ci,R,S) fp32 (taps = R*S in {1,9}) ->
  * bf16 [taps][Npad][Kpad], zero padded; Npad % 16 == 0 (<= 256), Kpad % 64 == 0. */
 int ll_pack_igemm_weight(const float* w, void* wp, int Co, int Ci, int taps, int Npad, int Kpad, ll_stream_t stream);

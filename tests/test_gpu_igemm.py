@@ -123,6 +123,58 @@ def test_ctx_conv_nhwc_masked_grouped_csc():
     assert (out[..., :256] == 7.0).all()
 
 
+def test_ctx_im2col_split_gemm_matches_fp32_convs():
+    """The plc head and the masked csc as 1-tap tensor-core GEMMs over ll_ctx_im2col's split rows: values far beyond bf16's
+    8 bits (quantised coefficients) must come out as accurately as from the fp32 SIMT convs (both round the OUTPUT to bf16)."""
+    ops = _ops()
+    torch.manual_seed(14)
+    B, H, W = 2, 12, 20
+    con = (torch.round(torch.randn(B, 3, H // 2, W // 2) * 300) + torch.rand(B, 3, H // 2, W // 2) * 0.37).to(DEV)   # round(x - mu) + mu
+    q = (torch.round(torch.randn(B, 3, H, W) * 200) + 0.123).to(DEV)
+    wh = ((torch.rand(243, 3, 3, 3) * 2 - 1) * 0.3).to(DEV)
+    bh = (torch.rand(243) - 0.5).to(DEV)
+    wc = ((torch.rand(243, 1, 5, 5) * 2 - 1) * 0.2)
+    mask = torch.ones(5, 5)
+    mask[2, 2:] = 0
+    mask[3:] = 0
+    wc = (wc * mask).to(DEV)
+    bc = (torch.rand(243) - 0.5).to(DEV)
+    a = ops.ctx_im2col(con, q)
+    assert tuple(a.shape) == (B, H, W, 320) and a.dtype == torch.bfloat16
+    # the rows themselves: hi + lo reproduces the fp32 window to 16 bits, unused channels are zero
+    up = con.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    cols = F.unfold(up, 3, padding=1).reshape(B, 27, H, W).permute(0, 2, 3, 1)
+    af = a.float()
+    assert torch.equal(af[..., 0:27], af[..., 54:81])
+    assert ((af[..., 0:27] + af[..., 27:54]) - cols).abs().max().item() <= 2.0 ** -15 * cols.abs().max().item()
+    assert (a[..., 81:128] == 0).all() and (a[..., 128 + 36:192] == 0).all()
+    whp = torch.zeros(243, 128, 1, 1, device=DEV)
+    whp[:, :81, 0, 0] = ops.split_bf16_weight(wh.reshape(243, 27))
+    t = torch.full((B, H, W, 256), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.igemm_conv(a, ops.pack_igemm_weight(whp, npad=256, kpad=128), bh, 243, lrelu=True, out_nhwc=t, koff=[[0, 64]])
+    ref = F.leaky_relu(F.conv2d(up, wh, bh, padding=1), 0.01).permute(0, 2, 3, 1)
+    old = ops.ctx_conv_nhwc(con, wh, bh, upsample2=True, lrelu=True, region=256)
+    scale = ref.abs().max().item()
+    assert (t[..., :243].float() - ref).abs().max().item() <= 2.0 ** -8 * scale
+    assert (t[..., :243].float() - old[..., :243].float()).abs().max().item() <= 2.0 ** -7 * scale   # one bf16 ulp apart at most
+    assert (t[..., 243:] == 0).all()
+    wcp = []
+    for g in range(3):
+        wg = torch.zeros(81, 64, 1, 1, device=DEV)
+        wg[:, :36, 0, 0] = ops.split_bf16_weight(wc[81 * g:81 * (g + 1), 0].reshape(81, 25)[:, :12])
+        wcp.append(ops.pack_igemm_weight(wg, npad=128, kpad=64))
+    g_in = torch.full((B, H, W, 640), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.igemm_conv(a, torch.stack(wcp).contiguous(), bc, 81, out_nhwc=g_in, nhwc_coff=256, nhwc_gstride=128,
+                   koff=[[128], [192], [256]])
+    refc = F.conv2d(q, wc, bc, padding=2, groups=3).permute(0, 2, 3, 1)
+    sc = refc.abs().max().item()
+    for g in range(3):
+        got = g_in[..., 256 + 128 * g:256 + 128 * g + 81].float()
+        assert (got - refc[..., 81 * g:81 * g + 81]).abs().max().item() <= 2.0 ** -8 * sc
+        assert (g_in[..., 256 + 128 * g + 81:256 + 128 * (g + 1)] == 0).all()
+    assert (g_in[..., :256] == 7.0).all()
+
+
 def test_igemm_grouped_1x1_with_koff():
     """cgp layer shape: 3 groups, each reading 4 k-blocks at per-group channel offsets of one NHWC tensor."""
     ops = _ops()
