@@ -59,6 +59,7 @@ SIGNATURES = {
     "ll_pw_mlp3": (c_int, [_P, c_i64, _P, _P, _P, _P, _P, _P, _P, c_i64, c_int, c_int, c_i64, _P]),
     "ll_ctx_conv_nhwc": (c_int, [_P, _P, _P, _P] + [c_int] * 15 + [_P]),
     "ll_ctx_im2col": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "ll_igemm_cgp_tail": (c_int, [_P, _P, _P] + [c_int] * 7 + [ctypes.POINTER(c_int), _P, _P, _P, _P, c_int, _P, c_i64, _P, _P, c_i64, _P, _P]),
     "ll_cgp_tail_rate": (c_int, [_P, c_i64, _P, _P, _P, _P, _P, c_i64, _P, _P, c_i64, _P, _P, c_int, c_int, c_int, c_int, c_i64, _P, _P]),
     "ll_pack_igemm_weight": (c_int, [_P, _P] + [c_int] * 5 + [_P]),
     "ll_nchw_to_nhwc_bf16": (c_int, [_P, c_i64, _P] + [c_int] * 6 + [_P]),

@@ -44,7 +44,8 @@ constexpr int IG_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two p
 constexpr int IG_TMEM_COLS = 512;
 constexpr int IG_MAXG = 3;       // channel groups per launch (the cgp MLP has groups = 3)
 constexpr int IG_MAXSLOTS = 24;  // k-blocks per (group, tap); the 3xTF32 chain of a 192-channel layer needs 18
-constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXG * IG_MAXN * 4;
+constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXG * IG_MAXN * 4 +
+                              IG_MAXG * (64 * 20 + 20 + 40 + 4) * 4 /*cgp tail weights (epi 4)*/;
 
 struct IgemmParams {
   const float* bias;
@@ -68,7 +69,15 @@ struct IgemmParams {
   int acc_sel[IG_MAXSLOTS];
   float* y;                               // NHWC fp32 (B,H,W,Cout)
   float* sz;                              // NHWC fp32 (B,H,W,2*Cout)
+  // epi 4 (BF16 kernel): cgp layer 2 + layers 3-4 + Gaussian rate in the epilogue (ll_igemm_cgp_tail)
+  const float *t_w3, *t_b3, *t_w4, *t_b4, *t_x, *t_noise;
+  float* t_bits;
+  double* t_sum;
+  long long t_xsb, t_bsb;
+  int t_c3;
 };
+constexpr int TL_K = 20;                                   // layer-3 outputs per group, padded (float4 rows)
+constexpr int TL_GROUP = IG_BK * TL_K + TL_K + 2 * TL_K + 4;   // per group: w3t[c 64][20] | b3[20] | w4 sigma[20] | w4 mu[20] | b4[2]
 
 // ---------------------------------------------------------------------------------------- kernel
 template <bool TF32>
@@ -87,8 +96,29 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + IG_STAGES * IG_STAGE_BYTES + 8 * (2 * IG_STAGES + 4));
   float* s_bias = reinterpret_cast<float*>(gen + IG_STAGES * IG_STAGE_BYTES + 1024);
   int* s_cmap = reinterpret_cast<int*>(s_bias + IG_MAXG * IG_MAXN);
+  float* s_tail = reinterpret_cast<float*>(s_cmap + IG_MAXG * IG_MAXN);
+  const bool tail = !TF32 && p.epi == 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (tail) {
+    for (int i = threadIdx.x; i < p.groups * TL_GROUP; i += IG_THREADS) {
+      const int g = i / TL_GROUP, r = i % TL_GROUP;
+      float v = 0.f;
+      if (r < IG_BK * TL_K) {
+        const int c = r / TL_K, k = r % TL_K;
+        if (c < p.Cout && k < p.t_c3) v = p.t_w3[((long long)g * p.t_c3 + k) * p.Cout + c];
+      } else if (r < IG_BK * TL_K + TL_K) {
+        const int k = r - IG_BK * TL_K;
+        if (k < p.t_c3) v = p.t_b3[g * p.t_c3 + k];
+      } else if (r < IG_BK * TL_K + 3 * TL_K) {
+        const int k = (r - IG_BK * TL_K - TL_K) % TL_K, which = (r - IG_BK * TL_K - TL_K) / TL_K;   // 0 sigma, 1 mu
+        if (k < p.t_c3) v = p.t_w4[((long long)g * 2 + which) * p.t_c3 + k];
+      } else if (r < IG_BK * TL_K + 3 * TL_K + 2) {
+        v = p.t_b4[g * 2 + (r - IG_BK * TL_K - 3 * TL_K)];
+      }
+      s_tail[i] = v;
+    }
+  }
 
   for (int i = threadIdx.x; i < p.groups * IG_MAXN; i += IG_THREADS) {
     const int g = i / IG_MAXN, c = i % IG_MAXN, co = g * p.Cout + c;   // channel index across groups
@@ -104,7 +134,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), tail ? 4 : 8);   // one arrival per epilogue warp (epi 4: a stage belongs to one warp parity)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -200,7 +230,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     const int nchunks = p.Npad / 32 + ((p.Npad % 32) ? 1 : 0);
-    for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    float tail_sum = 0.f;
+    unsigned unit = 0;
+    for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++unit) {
+      if (tail && (int)(unit & 1u) != chunk0) {       // epi 4: the even units (accumulator stage 0) belong to the warps of
+        if (++acc == p.nstages) { acc = 0; acc_phase ^= 1; }   // parity 0, the odd ones to parity 1 -- no hand-off inside a unit
+        continue;
+      }
       const int g = (int)(t % G);
       const long long tt = t / G;
       const int b = (int)(tt / per_img);
@@ -215,6 +251,55 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float* of = p.out_f32 ? p.out_f32 + (long long)b * p.out_sb + (long long)y * p.W + x : nullptr;
       __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (((long long)b * p.H + y) * p.W + x) * p.out_cstride + p.out_coff + g * p.out_gstride : nullptr;
       const long long plane = (long long)p.H * p.W;
+      if (tail) {
+        // cgp layer 2 -> (LeakyReLU) -> layer 3 (C2 -> C3, LeakyReLU) -> layer 4 (sigma, mu) -> Gaussian rate, one pixel per
+        // thread, in the operation order of cgp_tail_rate_kernel (rate.cu): the 54-channel map never leaves the SM.
+        uint32_t v0[32], v1[32];
+        tc_ld32(taddr, v0);
+        tc_ld32(taddr + 32, v1);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));        // accumulator stage free: the arithmetic below overlaps the next MMAs
+        const float* tw = s_tail + g * TL_GROUP;
+        float h[TL_K];
+#pragma unroll
+        for (int k = 0; k < TL_K; ++k) h[k] = tw[IG_BK * TL_K + k];
+#pragma unroll
+        for (int c = 0; c < IG_BK; ++c) {
+          if (c < p.Cout) {
+            float a = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]) + gb[c];
+            a = a < 0.f ? a * 0.01f : a;
+#pragma unroll
+            for (int k4 = 0; k4 < TL_K / 4; ++k4) {
+              const float4 w = *reinterpret_cast<const float4*>(tw + c * TL_K + 4 * k4);
+              h[4 * k4 + 0] = fmaf(w.x, a, h[4 * k4 + 0]);
+              h[4 * k4 + 1] = fmaf(w.y, a, h[4 * k4 + 1]);
+              h[4 * k4 + 2] = fmaf(w.z, a, h[4 * k4 + 2]);
+              h[4 * k4 + 3] = fmaf(w.w, a, h[4 * k4 + 3]);
+            }
+          }
+        }
+        float sg = tw[IG_BK * TL_K + 3 * TL_K], mu = tw[IG_BK * TL_K + 3 * TL_K + 1];
+#pragma unroll
+        for (int k = 0; k < TL_K; ++k) {
+          if (k < p.t_c3) {
+            const float a = h[k] < 0.f ? h[k] * 0.01f : h[k];
+            sg = fmaf(tw[IG_BK * TL_K + TL_K + k], a, sg);
+            mu = fmaf(tw[IG_BK * TL_K + 2 * TL_K + k], a, mu);
+          }
+        }
+        if (valid) {
+          const long long pix = (long long)y * p.W + x;
+          const float xv = p.t_x[(long long)b * p.t_xsb + (long long)g * plane + pix];
+          float yq;
+          const float bt = gauss_bits(xv, sg, mu, p.t_noise ? &p.t_noise[((long long)b * G + g) * plane + pix] : nullptr, yq);
+          p.t_bits[(long long)b * p.t_bsb + (long long)g * plane + pix] = bt;
+          tail_sum += bt;
+        }
+        if (++acc == p.nstages) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int c = chunk0; c < nchunks; c += 2) {
         // GDN epilogue: the raw conv output y of this chunk is fetched first, so its global latency overlaps the
         // tensor-memory loads below (it used to be issued behind them, one dependent round trip per chunk)
@@ -302,6 +387,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == p.nstages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (tail && p.t_sum) {       // sum of the self-information (TrainRDLoss.forward3's reduction), one atomic per warp
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tail_sum += __shfl_xor_sync(0xffffffffu, tail_sum, o);
+      if (lane == 0) atomicAdd(p.t_sum, (double)tail_sum);
     }
   }
 
@@ -1425,10 +1515,18 @@ int ll_nchw_to_nhwc_bf16(const float* x, int64_t x_sb, void* out, int B, int C, 
   return LL_OK;
 }
 
-int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Cin_total, int Kpad,
+struct TailArgs {
+  const float *w3, *b3, *w4, *b4, *x, *noise;
+  float* bits;
+  double* sum;
+  long long x_sb, bits_sb;
+  int c3;
+};
+
+static int launch_igemm_bf16(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Cin_total, int Kpad,
                   int Npad, int Cout, int taps, int groups, const int* koff, int lrelu, float* out_f32, int64_t out_sb,
                   int co_group, int co_stride, int co_off, void* out_bf16, int out_cstride, int out_coff, int out_gstride,
-                  ll_stream_t stream) {
+                  const TailArgs* tail, ll_stream_t stream) {
   if (B < 0 || H < 0 || W < 0 || Kpad < IG_BK || Kpad % IG_BK || Npad < 16 || Npad % 16 || Npad > IG_MAXN || Cout < 1 ||
       Cout > Npad || (taps != 1 && taps != 9))
     return fail(LL_EINVAL, "ll_igemm_conv: bad extents (Kpad %%64, Npad %%16 in 16..256, Cout <= Npad, taps 1|9)");
@@ -1438,7 +1536,7 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
   if (!koff && (groups != 1 || Cin_total != Kpad)) return fail(LL_EINVAL, "ll_igemm_conv: koff is required when groups > 1 or Cin_total != Kpad");
   if (B > 65535 * 4 || H > (1 << 20) || W > (1 << 20)) return fail(LL_EINVAL, "ll_igemm_conv: extents too large");
   if ((long long)B * H * W == 0) return LL_OK;
-  if (!x_nhwc || !wp || (!out_f32 && !out_bf16)) return fail(LL_EINVAL, "ll_igemm_conv: null pointer");
+  if (!x_nhwc || !wp || (!out_f32 && !out_bf16 && !tail)) return fail(LL_EINVAL, "ll_igemm_conv: null pointer");
   if (((uintptr_t)x_nhwc & 15) || ((uintptr_t)wp & 15)) return fail(LL_EINVAL, "ll_igemm_conv: operands must be 16-byte aligned");
   if (out_bf16 && (out_coff < 0 || out_gstride < 0 || out_cstride < out_coff + (groups - 1) * out_gstride + Npad))
     return fail(LL_EINVAL, "ll_igemm_conv: bad NHWC output slice (all Npad channels of every group are written)");
@@ -1494,11 +1592,40 @@ int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, 
   }
   for (int k = 0; k < p.kblocks; ++k) p.b_koff[k] = k * IG_BK;
   p.nstages = 2; p.stage_cols = IG_MAXN; p.nacc = 1; p.acc_cols = 0;
+  if (tail) {
+    p.epi = 4;
+    p.t_w3 = tail->w3; p.t_b3 = tail->b3; p.t_w4 = tail->w4; p.t_b4 = tail->b4; p.t_x = tail->x; p.t_noise = tail->noise;
+    p.t_bits = tail->bits; p.t_sum = tail->sum; p.t_xsb = tail->x_sb; p.t_bsb = tail->bits_sb; p.t_c3 = tail->c3;
+  }
   const long long sms = sm_count_cached();
   const unsigned grid = (unsigned)(p.ntiles < sms ? p.ntiles : sms);
   igemm_conv_kernel<false><<<grid, IG_THREADS, IG_SMEM_BYTES, as_stream(stream)>>>(tmA, tmB, p);
   LL_LAUNCH_OK("igemm_conv_kernel");
   return LL_OK;
+}
+
+int ll_igemm_conv(const void* x_nhwc, const void* wp, const float* bias, int B, int H, int W, int Cin_total, int Kpad,
+                  int Npad, int Cout, int taps, int groups, const int* koff, int lrelu, float* out_f32, int64_t out_sb,
+                  int co_group, int co_stride, int co_off, void* out_bf16, int out_cstride, int out_coff, int out_gstride,
+                  ll_stream_t stream) {
+  return launch_igemm_bf16(x_nhwc, wp, bias, B, H, W, Cin_total, Kpad, Npad, Cout, taps, groups, koff, lrelu, out_f32, out_sb,
+                           co_group, co_stride, co_off, out_bf16, out_cstride, out_coff, out_gstride, nullptr, stream);
+}
+
+// cgp layers 2-4 + Gaussian rate in one launch (LiftingBasedDWT_net.py:362-365): h1 (B,H,W,Cin_total) bf16 -> layer 2 as a
+// grouped 1x1 tcgen05 GEMM (weights wp [groups][1][Npad = 64][Kpad], bias2 (groups*C2), LeakyReLU) whose accumulator is
+// consumed in place by layers 3 (w3 (groups*C3, C2), b3, LeakyReLU) and 4 (w4 (2*groups, C3): row 2g = sigma, 2g+1 = mu; b4)
+// and the rate of x (B,groups,H,W; batch stride x_sb) -> bits (batch stride bits_sb), sum of bits added to *sum_out.
+int ll_igemm_cgp_tail(const void* h1, const void* wp, const float* bias2, int B, int H, int W, int Cin_total, int Kpad, int C2,
+                      int groups, const int* koff, const float* w3, const float* b3, const float* w4, const float* b4, int C3,
+                      const float* x, int64_t x_sb, const float* noise, float* bits, int64_t bits_sb, double* sum_out,
+                      ll_stream_t stream) {
+  if (C2 < 1 || C2 > IG_BK || C3 < 1 || C3 > TL_K) return fail(LL_EINVAL, "ll_igemm_cgp_tail: C2 <= %d and C3 <= %d", IG_BK, TL_K);
+  if ((long long)B * H * W == 0) return LL_OK;
+  if (!w3 || !b3 || !w4 || !b4 || !x || !bits || !bias2) return fail(LL_EINVAL, "ll_igemm_cgp_tail: null pointer");
+  TailArgs t = {w3, b3, w4, b4, x, noise, bits, sum_out, (long long)x_sb, (long long)bits_sb, C3};
+  return launch_igemm_bf16(h1, wp, bias2, B, H, W, Cin_total, Kpad, IG_BK, C2, 1, groups, koff, 1, nullptr, 0, 0, 0, 0, nullptr, 0, 0, 0,
+                           &t, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,4 +36,18 @@ int sm_count_cached();
 
 inline cudaStream_t as_stream(ll_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// GaussianConditional.forward + -log2 for one coefficient, in the reference's operation order (compressai 1.2.1; call
+// sites LiftingBasedDWT_net.py:334-335,345-346,364-365).  Shared by rate.cu and the fused cgp tail of igemm_conv.cu.
+__device__ __forceinline__ float gauss_bits(float xv, float sg, float mu, const float* noise, float& y) {
+  if (noise) y = __fadd_rn(xv, *noise);
+  else y = __fadd_rn(rintf(__fsub_rn(xv, mu)), mu);
+  const float v = fabsf(__fsub_rn(y, mu));
+  const float s = fmaxf(sg, 0.11f);
+  const float kc = -0.70710678118654752440f;  // float(-(2 ** -0.5))
+  const float up = 0.5f * erfcf(kc * __fdiv_rn(0.5f - v, s));
+  const float lo = 0.5f * erfcf(kc * __fdiv_rn(-0.5f - v, s));
+  const float pr = fmaxf(up - lo, 1e-9f);
+  return -log2f(pr);
+}
+
 }  // namespace ll

@@ -36,19 +36,6 @@ __global__ void quantize_kernel(const float* __restrict__ x, const float* __rest
     q[i] = noise ? __fadd_rn(x[i], noise[i]) : rintf(x[i]);
 }
 
-// GaussianConditional.forward + -log2 for one coefficient, in the reference's operation order.
-__device__ __forceinline__ float gauss_bits(float xv, float sg, float mu, const float* noise, float& y) {
-  if (noise) y = __fadd_rn(xv, *noise);
-  else y = __fadd_rn(rintf(__fsub_rn(xv, mu)), mu);
-  const float v = fabsf(__fsub_rn(y, mu));
-  const float s = fmaxf(sg, 0.11f);
-  const float kc = -0.70710678118654752440f;  // float(-(2 ** -0.5))
-  const float up = 0.5f * erfcf(kc * __fdiv_rn(0.5f - v, s));
-  const float lo = 0.5f * erfcf(kc * __fdiv_rn(-0.5f - v, s));
-  const float pr = fmaxf(up - lo, 1e-9f);
-  return -log2f(pr);
-}
-
 // x: (B, C, hw) with batch stride x_sb and channel offset folded into the pointer;
 // ms: (B, 2C, hw): channel 2c = sigma, 2c+1 = mu.
 __global__ void __launch_bounds__(RT_THREADS) gauss_rate_kernel(

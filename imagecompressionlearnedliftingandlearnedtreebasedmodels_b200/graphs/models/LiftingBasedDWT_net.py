@@ -441,11 +441,17 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
             h1 = torch.empty(n, h, w, 192 * C, dtype=torch.bfloat16, device=x.device)
             ops.igemm_conv(g_in, pk["l1"], cgp[0].bias, pk["n1"], lrelu=True, out_nhwc=h1, nhwc_gstride=192, koff=pk["k1"])
             del g_in
-            h2 = ops.igemm_conv(h1, pk["l2"], cgp[2].bias, pk["n2"], lrelu=True, koff=pk["k2"])
-            del h1
-            bits[b0:b1] = ops.cgp_tail_rate(h2, cgp[4].weight, cgp[4].bias, cgp[6].weight, cgp[6].bias, x[b0:b1],
-                                            noise[b0:b1] if noise is not None else None, acc=acc)
-            del h2
+            nz = noise[b0:b1] if noise is not None else None
+            if pk["n2"] <= 64 and cgp[6].weight.shape[1] <= 20:
+                # layers 2-4 + rate in one launch: the 54-channel map stays in tensor memory / registers
+                bits[b0:b1] = ops.igemm_cgp_tail(h1, pk["l2"], cgp[2].bias, pk["n2"], pk["k2"], cgp[4].weight, cgp[4].bias,
+                                                 cgp[6].weight, cgp[6].bias, x[b0:b1], nz, acc=acc)
+                del h1
+            else:
+                h2 = ops.igemm_conv(h1, pk["l2"], cgp[2].bias, pk["n2"], lrelu=True, koff=pk["k2"])
+                del h1
+                bits[b0:b1] = ops.cgp_tail_rate(h2, cgp[4].weight, cgp[4].bias, cgp[6].weight, cgp[6].bias, x[b0:b1], nz, acc=acc)
+                del h2
         return bits
 
     def _level_grad(self, i, x, q, con):

@@ -667,6 +667,39 @@ def cgp_tail_rate(h2, w3, b3, w4, b4, x, noise=None, want_y=False, want_ms=False
     return res[0] if len(res) == 1 else res
 
 
+def igemm_cgp_tail(h1, wp2, bias2, c2, koff, w3, b3, w4, b4, x, noise=None, acc=None):
+    """cgp layers 2-4 + Gaussian rate in one launch (ll_igemm_cgp_tail): ``h1`` bf16 (B,H,W,C) -> grouped 1x1 tcgen05 GEMM
+    (``wp2`` (G,1,64,Kpad)) whose accumulator feeds layers 3-4 and the rate of ``x`` (B,G,H,W).  Returns bits (B,G,H,W);
+    same arithmetic as ``igemm_conv`` + ``cgp_tail_rate`` without the fp32 map in between."""
+    require_device(x)
+    x = _f32c(x, "x")
+    B, G, H, W = x.shape
+    if h1.dtype != torch.bfloat16 or not h1.is_contiguous() or tuple(h1.shape[:3]) != (B, H, W):
+        raise TypeError("igemm_cgp_tail: h1 must be a contiguous bf16 (B,H,W,C) tensor")
+    if wp2.dtype != torch.bfloat16 or not wp2.is_contiguous() or wp2.dim() != 4 or wp2.shape[0] != G or wp2.shape[1] != 1 or wp2.shape[2] != 64:
+        raise TypeError("igemm_cgp_tail: wp2 must be a (G,1,64,Kpad) stack from pack_igemm_weight")
+    kpad = wp2.shape[3]
+    kb = kpad // IG_BK
+    flat = [int(v) for row in koff for v in row]
+    if len(flat) != G * kb:
+        raise ValueError(f"igemm_cgp_tail: koff has {len(flat)} entries, expected {G}x{kb}")
+    karr = (ctypes.c_int * len(flat))(*flat)
+    c3 = w4.shape[1]
+    if w3.shape[0] != G * c3 or w3.shape[1] != c2 or w4.shape[0] != 2 * G:
+        raise ValueError("igemm_cgp_tail: shape mismatch")
+    if noise is not None:
+        noise = _f32c(noise, "noise")
+    b2c, w3c, b3c, w4c, b4c = (_f32c(t.detach(), "w") for t in (bias2, w3, b3, w4, b4))
+    bits = torch.empty_like(x)
+    hw = H * W
+    with torch.cuda.device(x.device):
+        check(_lib.load().ll_igemm_cgp_tail(ptr(h1), ptr(wp2), ptr(b2c), B, H, W, h1.shape[3], kpad, c2, G, karr, ptr(w3c), ptr(b3c),
+                                            ptr(w4c), ptr(b4c), c3, ptr(x), G * hw, ptr(noise), ptr(bits), G * hw, ptr(acc),
+                                            stream_ptr()))
+    _count(1)
+    return bits
+
+
 def quantize(x, noise=None):
     """round-half-even(x), or x + noise in training (ll_quantize)."""
     require_device(x)

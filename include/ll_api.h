@@ -186,6 +186,19 @@ int ll_ctx_conv_nhwc(const float* x, const float* w, const float* bias, void* ou
                      int Cout, int K, int groups, int live_taps, int upsample2, int lrelu, int out_cstride,
                      int out_coff, int co_group, int co_gstride, int region, ll_stream_t stream);
 
+/* cgp layers 2-4 + Gaussian rate in one launch (reference: graphs/models/LiftingBasedDWT_net.py:362-365, the last three
+ * grouped 1x1 convs of cgp_out_xo_list[i] and GaussianConditional + -log2): h1 (B,H,W,Cin_total) bf16 NHWC -> layer 2 as a
+ * grouped 1x1 tcgen05 GEMM (wp bf16 [groups][1][64][Kpad] from ll_pack_igemm_weight, koff as in ll_igemm_conv, bias2
+ * (groups*C2), LeakyReLU) whose accumulator feeds layers 3 (w3 (groups*C3, C2), b3 (groups*C3), LeakyReLU) and 4 (w4
+ * (2*groups, C3): row 2g = sigma, 2g+1 = mu; b4 (2*groups)) and the rate of x (B,groups,H,W fp32, batch stride x_sb;
+ * noise: training-mode additive noise or NULL) in the epilogue -> bits (B,groups,H,W; batch stride bits_sb); the sum of
+ * the bits is added to *sum_out when non-NULL.  C2 <= 64, C3 <= 20.  Same arithmetic and operation order as
+ * ll_igemm_conv followed by ll_cgp_tail_rate, without the fp32 map in between. */
+int ll_igemm_cgp_tail(const void* h1, const void* wp, const float* bias2, int B, int H, int W, int Cin_total, int Kpad, int C2,
+                      int groups, const int* koff, const float* w3, const float* b3, const float* w4, const float* b4, int C3,
+                      const float* x, int64_t x_sb, const float* noise, float* bits, int64_t bits_sb, double* sum_out,
+                      ll_stream_t stream);
+
 /* The two small-Cin context convs as tensor-core GEMMs (reference: graphs/models/LiftingBasedDWT_net.py:271,274-277,353-355):
  * con (B,3,H/2,W/2) quantised parent, q (B,3,H,W) quantised child -> out (B,H,W,320) bf16 = per pixel the im2col row of
  * the plc head (3x3 on the nearest-2x-upsampled parent, K = 27) and of the masked csc (12 live taps per group), each

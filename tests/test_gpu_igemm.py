@@ -220,6 +220,37 @@ def test_cgp_tail_rate_matches_torch():
     assert abs(float(acc.item()) - float(bits.double().sum().item())) <= 1e-3 * float(acc.item())
 
 
+@pytest.mark.parametrize("B,H,W,train", [(2, 12, 20, False), (1, 37, 50, False), (3, 16, 24, True)])
+def test_fused_cgp_layer2_tail_rate_equals_the_two_kernel_chain(B, H, W, train):
+    """ll_igemm_cgp_tail (cgp layer 2 as a grouped 1x1 tcgen05 GEMM, layers 3-4 and the Gaussian rate in its epilogue) against
+    ll_igemm_conv + ll_cgp_tail_rate on the same operands: the same products in the same order -> identical bits."""
+    ops = _ops()
+    torch.manual_seed(21)
+    G = 3
+    h1 = (torch.rand(B, H, W, 576) * 2 - 1).to(torch.bfloat16).to(DEV)
+    k2 = [[192 * g, 192 * g + 64, 192 * g + 128] for g in range(G)]
+    w2 = [((torch.rand(54, 162, 1, 1) * 2 - 1) * 0.15) for _ in range(G)]
+    for g in range(G):
+        w2[g] = torch.nn.functional.pad(w2[g], (0, 0, 0, 0, 0, 30)).to(DEV)      # K 162 -> 192
+    wp2 = torch.stack([ops.pack_igemm_weight(w, npad=64, kpad=192) for w in w2]).contiguous()
+    b2 = (torch.rand(G * 54) - 0.5).to(DEV)
+    w3, b3 = (torch.randn(G * 18, 54, 1, 1) * 0.2).to(DEV), (torch.randn(G * 18) * 0.1).to(DEV)
+    w4, b4 = (torch.randn(G * 2, 18, 1, 1) * 0.3).to(DEV), torch.randn(G * 2) * 0.1
+    b4[0::2] += 3.0
+    b4 = b4.to(DEV)
+    x = (torch.randn(B, G, H, W) * 5).to(DEV)
+    noise = (torch.rand(B, G, H, W) - 0.5).to(DEV) if train else None
+    acc_a = torch.zeros(1, dtype=torch.float64, device=DEV)
+    acc_b = torch.zeros(1, dtype=torch.float64, device=DEV)
+    h2 = ops.igemm_conv(h1, wp2, b2, 54, lrelu=True, koff=k2)
+    ref = ops.cgp_tail_rate(h2, w3, b3, w4, b4, x, noise, acc=acc_a)
+    got = ops.igemm_cgp_tail(h1, wp2, b2, 54, k2, w3, b3, w4, b4, x, noise, acc=acc_b)
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, ref)
+    assert abs(acc_a.item() - acc_b.item()) <= 1e-5 * abs(acc_a.item())
+    assert abs(acc_b.item() - got.double().sum().item()) <= 1e-5 * abs(acc_b.item())
+
+
 def test_nchw_to_nhwc_bf16_slice():
     ops = _ops()
     torch.manual_seed(5)
