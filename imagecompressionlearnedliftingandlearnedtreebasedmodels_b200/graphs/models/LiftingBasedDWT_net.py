@@ -27,6 +27,9 @@ SCALES_LEVELS = 64
 # images per launch group inside the context models: bounds the 243/486-channel intermediates
 # (level 0 of a 512x768 plane needs ~0.6 GB per image in fp32)
 CTX_BATCH_CHUNK = 16
+# A/B switches of the tensor-core context path (measurement scripts only; both on in the product):
+CTX_GEMM_HEAD = True     # plc head / masked csc as 1-tap igemm layers over ops.ctx_im2col (else the fp32 SIMT ctx_conv_nhwc)
+CTX_FUSED_TAIL = True    # cgp layers 2-4 + rate in one launch (else igemm_conv + cgp_tail_rate)
 
 
 def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
@@ -424,7 +427,7 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
             b1 = min(B, b0 + CTX_BATCH_CHUNK)
             n = b1 - b0
             g_in = torch.empty(n, h, w, 256 + 128 * C, dtype=torch.bfloat16, device=x.device)
-            if "head" in pk:
+            if "head" in pk and CTX_GEMM_HEAD:
                 # both small-Cin convs on the tensor cores: one im2col pass, then 1-tap igemm layers
                 a = ops.ctx_im2col(con[b0:b1], q[b0:b1])
                 t = torch.empty(n, h, w, 256, dtype=torch.bfloat16, device=x.device)
@@ -442,7 +445,7 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
             ops.igemm_conv(g_in, pk["l1"], cgp[0].bias, pk["n1"], lrelu=True, out_nhwc=h1, nhwc_gstride=192, koff=pk["k1"])
             del g_in
             nz = noise[b0:b1] if noise is not None else None
-            if pk["n2"] <= 64 and cgp[6].weight.shape[1] <= 20:
+            if CTX_FUSED_TAIL and pk["n2"] <= 64 and cgp[6].weight.shape[1] <= 20:
                 # layers 2-4 + rate in one launch: the 54-channel map stays in tensor memory / registers
                 bits[b0:b1] = ops.igemm_cgp_tail(h1, pk["l2"], cgp[2].bias, pk["n2"], pk["k2"], cgp[4].weight, cgp[4].bias,
                                                  cgp[6].weight, cgp[6].bias, x[b0:b1], nz, acc=acc)

@@ -15,6 +15,12 @@ def run(tag):
     print(f"{tag:50s} {ms:8.1f} ms  {64 * 512 * 768 / 1e6 / (ms * 1e-3):6.2f} MP/s  bpp {v['bpp']:.6f}  peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
     torch.cuda.reset_peak_memory_stats()
 run("default")
+M.CTX_GEMM_HEAD = False
+run("context head / csc on the fp32 SIMT kernels")
+M.CTX_FUSED_TAIL = False
+run("... and cgp tail unfused (the path before)")
+M.CTX_GEMM_HEAD = M.CTX_FUSED_TAIL = True
+run("default again")
 for ae in (16, 32, 64):
     L.SubbandAutoEncoderBerk.AE_BATCH_CHUNK = ae
     run(f"AE_BATCH_CHUNK={ae}")
