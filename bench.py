@@ -261,7 +261,7 @@ def run_own(args):
                                "scaling network 2 x 260 822, conditioned2ZT 430 482) / step time"},
     }
     line["roofline"] = roofline_block(dev, pk, pk_kind, agent, ms_step)
-    line["roofline_lifting"] = roofline_lifting_block(dev)
+    line["roofline_lifting"] = roofline_lifting_block(dev, pk, pk_kind)
     if "component_ms" in blocks:
         line["component_ms"] = component_block(dev, agent)
     line.update(multi)
@@ -331,9 +331,16 @@ def roofline_block(dev, pk, pk_kind, agent, ms_step):
     return rf
 
 
-def roofline_lifting_block(dev):
-    """Second kernel family of the headline step: ``ll::lift_step_tc_kernel`` timed alone (level-0 row step on a (16,256,768)
-    view: 2 x 13 603 MAC per view pixel, 94 % of them as 3xTF32 on tcgen05) against the measured TF32 peak."""
+# per 52-column row step the 3xFP16 lifting kernel issues 40 tcgen05.mma (M128 x N64 x K16, kind::f16): 15 each for conv2 / conv3
+# (5 vertical taps x 3 terms of the split) and 10 for conv4 (5 taps x 2: the three terms sit in different accumulator rows)
+LIFT_ISSUED_FLOP_PER_PX = 40 * 2.0 * 128 * 64 * 16 / 52
+LIFT_MAC_PER_PX = 13603          # conv1 400 (SIMT) + conv2 6400 + conv3 6400 + conv4 400 + 3-tap pre-filter
+
+
+def roofline_lifting_block(dev, pk, pk_kind):
+    """Second kernel family of the headline step: ``ll::lift_step_tc_kernel`` (3xFP16 variant, the default) timed alone --
+    level-0 row step on a (16,256,768) view: 2 x 13 603 MAC per view pixel, 97 % of them (conv2, conv3, conv4) as a 3xFP16
+    split on tcgen05 ``kind::f16`` -- against the measured dense 16-bit tensor peak (cuBLAS bf16, MEASURED_PEAKS.json)."""
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200 import ops
     from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.layers.lifting_dwt_nets import \
         LiftingBasedNeuralWaveletv4
@@ -346,16 +353,21 @@ def roofline_lifting_block(dev):
     vdin = torch.rand(nb, H // 2, W, device=dev) - 0.5
     vout = torch.empty_like(vsrc)
     k_ms = ev_time(lambda: ops.lift_step([(vsrc, vdin, vout)], blobs[0], 1.0, 0.1, False), 20)
-    tf32_peak = ops.tf32_peak_tflops()
-    k_flop = 2.0 * 13603 * vsrc.numel()
+    peak = float(pk["bf16_tflops"])
+    k_flop = 2.0 * LIFT_MAC_PER_PX * vsrc.numel()
     traffic, src = ncu_traffic("lift_step_tc_kernel level-0 row step (16,256,768)")
     ach = k_flop / (k_ms * 1e-3) / 1e12
-    return {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-            "traffic": traffic, "traffic_source": src, "kernel": "ll::lift_step_tc_kernel (level-0 row step, (16,256,768) view)",
-            "ms_per_launch": k_ms, "issued_frac": ach * 0.94 * 3 * 128 / 80 / tf32_peak,
+    issued = LIFT_ISSUED_FLOP_PER_PX * vsrc.numel() / (k_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": traffic, "traffic_source": src,
+            "kernel": "ll::lift_step_tc_kernel<3xFP16> (level-0 row step, (16,256,768) view)",
+            "ms_per_launch": k_ms, "issued_tflops": issued, "issued_frac": issued / peak,
+            "peak_kind": f"{pk_kind} dense 16-bit tensor peak (cuBLAS bf16 burst) -- the kernel's MMAs are kind::f16",
             "algorithmic_bytes": 12.0 * vsrc.numel(),
-            "note": "useful conv FLOPs of one launch / its duration; issued = tensor-pipe FLOPs incl. the 3xTF32 split and the "
-                    "M = 80-of-128 padding of the weights-as-M mapping (lift_tc.cu)"}
+            "note": "useful conv FLOPs of one launch / its duration; issued = the 40 M128xN64xK16 MMAs per 52-column row step "
+                    "(3-term split, weights-as-M: 80 of 128 rows used by conv2 / conv3, 15 by conv4, 52 of 64 columns kept). "
+                    "The kernel is bound by the MMA rate at this shape (62 cycles per N = 64 kind::f16 MMA with an MN-major B "
+                    "operand, measured) and by the SIMT roles that share the SM, not by the tensor pipe's peak"}
 
 
 def component_block(dev, agent):
@@ -416,25 +428,27 @@ def lifting_block(dev, pk):
             net.lift_precision = "fp32"
         ms32 = ev_time(step, 2, 1)
         for net in nets:
-            net.lift_precision = "tc"
+            net.lift_precision = "tc16"
         blobs = nets[0].waveletForward[0]._blobs()
         vsrc = torch.rand(nb, H // 2, W, device=dev) - 0.5
         vdin = torch.rand(nb, H // 2, W, device=dev) - 0.5
         vout = torch.empty_like(vsrc)
         k_ms = ev_time(lambda: ops.lift_step([(vsrc, vdin, vout)], blobs[0], 1.0, 0.1, False), 20)
-    tf32_peak = ops.tf32_peak_tflops()
     fma_peak = ops.fma_peak_tflops()
-    k_flop = 2.0 * 13603 * vsrc.numel()
+    peak16 = float(pk["bf16_tflops"])
+    k_flop = 2.0 * LIFT_MAC_PER_PX * vsrc.numel()
+    k_issued = LIFT_ISSUED_FLOP_PER_PX * vsrc.numel()
     flops = 2 * 144532.0 * 3 * nb * H * W
     return {"workload": "configs[1]: learned lifting DWT 4-level forward+inverse, batch 16 of 512x768, 3 colour planes",
             "mp_per_s": nb * H * W / 1e6 / (ms * 1e-3), "ms_per_step": ms,
             "perfect_reconstruction_max_abs_err": float((rec - x).abs().max().item()),
             "hbm_gbs_algorithmic": 21.25 * 3 * nb * H * W / (ms * 1e-3) / 1e9,
             "step_useful_tflops": flops / (ms * 1e-3) / 1e12,
-            "lift_step_tc_kernel": {"view": [nb, H // 2, W], "ms": k_ms, "useful_tflops": k_flop / (k_ms * 1e-3) / 1e12,
-                                    "useful_frac_of_tf32_peak": k_flop / (k_ms * 1e-3) / 1e12 / tf32_peak,
-                                    "issued_frac_of_tf32_peak": k_flop * 0.94 * 3 * 128 / 80 / (k_ms * 1e-3) / 1e12 / tf32_peak,
-                                    "tf32_peak_measured": tf32_peak},
+            "lift_step_tc_kernel": {"view": [nb, H // 2, W], "ms": k_ms, "arithmetic": "3xFP16 split on tcgen05 kind::f16 (conv2, conv3, conv4)",
+                                    "useful_tflops": k_flop / (k_ms * 1e-3) / 1e12,
+                                    "useful_frac_of_16bit_tensor_peak": k_flop / (k_ms * 1e-3) / 1e12 / peak16,
+                                    "issued_frac_of_16bit_tensor_peak": k_issued / (k_ms * 1e-3) / 1e12 / peak16,
+                                    "tensor_peak_16bit": peak16},
             "fp32_fma_path": {"ms_per_step": ms32, "useful_frac_of_ffma2_peak": flops / (ms32 * 1e-3) / 1e12 / fma_peak,
                               "ffma2_peak_measured": fma_peak}}
 

@@ -938,26 +938,28 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       if (HEAD) {
         // E1 (head): y = Conv2d(iC, N, 3, padding=1)(x) + bias in exact FP32 FMA, one pixel per thread, -> tensor memory
         for (int c = grp; c < nch; c += 4) {
-          float acc[16];
+          float2 acc[8];          // packed FFMA2: two output channels per instruction, the window sample broadcast
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = s_bias[c * 16 + j];
+          for (int j = 0; j < 8; ++j) acc[j] = *reinterpret_cast<const float2*>(s_bias + c * 16 + 2 * j);
 #pragma unroll
           for (int k = 0; k < 27; ++k) {
             if (k < 9 * p.iC) {
               const float4* wr = reinterpret_cast<const float4*>(s_w0 + k * p.N + c * 16);
+              const float2 xx = make_float2(win[k], win[k]);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 w4 = wr[j4];
-                acc[4 * j4 + 0] = fmaf(win[k], w4.x, acc[4 * j4 + 0]);
-                acc[4 * j4 + 1] = fmaf(win[k], w4.y, acc[4 * j4 + 1]);
-                acc[4 * j4 + 2] = fmaf(win[k], w4.z, acc[4 * j4 + 2]);
-                acc[4 * j4 + 3] = fmaf(win[k], w4.w, acc[4 * j4 + 3]);
+                acc[2 * j4 + 0] = __ffma2_rn(xx, make_float2(w4.x, w4.y), acc[2 * j4 + 0]);
+                acc[2 * j4 + 1] = __ffma2_rn(xx, make_float2(w4.z, w4.w), acc[2 * j4 + 1]);
               }
             }
           }
           uint32_t v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(acc[j]);
+          for (int j = 0; j < 8; ++j) {
+            v[2 * j] = __float_as_uint(acc[j].x);
+            v[2 * j + 1] = __float_as_uint(acc[j].y);
+          }
           tmem_st16(tlane + c * 16, v);
         }
         load_window(pt + pair_step);
