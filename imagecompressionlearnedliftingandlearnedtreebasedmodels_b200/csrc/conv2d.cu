@@ -144,61 +144,112 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constan
 // the quantiser / the inverse transform) straight from the tensor-core chain's activations: z is channels-last
 // fp32 [hi | lo] (B,H,W,2C); the kernel forms hi + lo on load and writes fp32 NCHW.  Replaces the
 // NHWC -> NCHW conversion + generic NCHW conv pair (2.45 ms -> one HBM-bound pass over z).
-// CTA = 8x32 pixels, thread = 1 pixel x CO outputs, 16 input channels per stage ([py][px][20] floats: the 80-byte
-// pixel pitch makes the 16-byte channel-quad reads of 8 neighbouring pixels hit 8 distinct bank groups).
-constexpr int TL_TH = 8, TL_TW = 32, TL_CC = 16, TL_PITCH = 20;
+// CTA = 4 warps = 16 rows x 32 columns, thread = 4 vertically adjacent pixels x CO outputs, 16 input channels per stage
+// ([py][px][20] floats: the 80-byte pixel pitch makes the 16-byte channel-quad reads of 8 neighbouring pixels hit 8
+// distinct bank groups; 64 contiguous bytes per pixel per stage = the L2's fetch granule).  The one-pixel-per-thread
+// version was bound by shared memory (ncu: LSU data pipe 75 %, FMA 25 %: one activation and CO weight LDS.128 per 4 CO
+// FMAs); here the six rows a thread's four pixels need are read once per (channel quad, dx) and every broadcast weight
+// quad feeds four pixels: 15 LDS.128 per 144 FMAs at CO = 3.
+constexpr int TL_TH = 8, TL_TW = 32, TL_CC = 32, TL_PITCH = 36, TL_PY = 2, TL_THREADS = 128, TL_MLP = 6;
 
 template <int CO>
-__global__ void __launch_bounds__(256) nhwc_split_conv3_kernel(const float* __restrict__ z, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                               int B, int C, int H, int W, int tiles_x) {
-  __shared__ __align__(16) float tile[(TL_TH + 2) * (TL_TW + 2) * TL_PITCH];
-  __shared__ __align__(16) float wsm[9 * CO * TL_CC];   // [tap][co][16 ch]
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+constexpr int tl_smem_bytes() { return ((TL_TH + 2) * (TL_TW + 2) * TL_PITCH + 9 * CO * TL_CC) * (int)sizeof(float); }
+
+template <int CO>
+__global__ void __launch_bounds__(TL_THREADS) nhwc_split_conv3_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                                      int B, int C, int H, int W, int tiles_x) {
+  extern __shared__ __align__(16) float tl_smem[];
+  float* tile = tl_smem;                                        // [TL_TH + 2][TL_TW + 2][TL_PITCH]
+  float* wsm = tl_smem + (TL_TH + 2) * (TL_TW + 2) * TL_PITCH;  // [tap][co][16 ch]
+  const int tid = threadIdx.x, tx = tid & 31, wy = tid >> 5;
   const int x0 = (blockIdx.x % tiles_x) * TL_TW, y0 = (blockIdx.x / tiles_x) * TL_TH, b = blockIdx.y;
   const float* zb = z + (long long)b * H * W * 2 * C;
-  float acc[CO];
+  float acc[TL_PY][CO];
 #pragma unroll
-  for (int o = 0; o < CO; ++o) acc[o] = bias ? bias[o] : 0.f;
+  for (int i = 0; i < TL_PY; ++i)
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[i][o] = bias ? bias[o] : 0.f;
   for (int c0 = 0; c0 < C; c0 += TL_CC) {
     __syncthreads();
-    for (int e = tid; e < (TL_TH + 2) * (TL_TW + 2) * (TL_CC / 4); e += 256) {
-      const int q = e & 3, px = (e >> 2) % (TL_TW + 2), py = (e >> 2) / (TL_TW + 2);
-      const int gy = y0 + py - 1, gx = x0 + px - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const float* s = zb + ((long long)gy * W + gx) * (2 * C) + c0 + 4 * q;
-        const float4 hi = *reinterpret_cast<const float4*>(s), lo = *reinterpret_cast<const float4*>(s + C);
-        v = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
-      }
-      *reinterpret_cast<float4*>(&tile[(py * (TL_TW + 2) + px) * TL_PITCH + 4 * q]) = v;
-    }
-    for (int e = tid; e < 9 * CO * TL_CC; e += 256) {
+    // this stage's weights first: their (strided, L2-latency) loads are in flight while the tile is fetched; as a
+    // load -> store loop after the tile they cost seven serial L2 round trips per stage (ncu: 7 % of the samples)
+    constexpr int NW = 9 * CO * TL_CC, WPT = (NW + TL_THREADS - 1) / TL_THREADS;
+    float wreg[WPT];
+#pragma unroll
+    for (int u = 0; u < WPT; ++u) {
+      const int e = tid + u * TL_THREADS;
       const int c = e % TL_CC, o = (e / TL_CC) % CO, t = e / (TL_CC * CO);
-      wsm[e] = w[((long long)o * C + c0 + c) * 9 + t];
+      wreg[u] = e < NW ? __ldg(w + ((long long)o * C + c0 + c) * 9 + t) : 0.f;
+    }
+    // TL_MLP tile elements per thread in flight: all 2 TL_MLP 16-byte loads are issued before the first one is consumed
+    // (with one element per iteration the fill ran load -> add -> store serially at 16 warps per SM)
+    constexpr int NE = (TL_TH + 2) * (TL_TW + 2) * (TL_CC / 4);
+    for (int e0 = tid; e0 < NE; e0 += TL_MLP * TL_THREADS) {
+      float4 hi[TL_MLP], lo[TL_MLP];
+#pragma unroll
+      for (int u = 0; u < TL_MLP; ++u) {
+        const int e = e0 + u * TL_THREADS;
+        const int q = e % (TL_CC / 4), px = (e / (TL_CC / 4)) % (TL_TW + 2), py = (e / (TL_CC / 4)) / (TL_TW + 2);
+        const int gy = y0 + py - 1, gx = x0 + px - 1;
+        hi[u] = lo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < NE && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const float* s = zb + ((long long)gy * W + gx) * (2 * C) + c0 + 4 * q;
+          hi[u] = __ldg(reinterpret_cast<const float4*>(s));
+          lo[u] = __ldg(reinterpret_cast<const float4*>(s + C));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < TL_MLP; ++u) {
+        const int e = e0 + u * TL_THREADS;
+        if (e < NE) {
+          const int q = e % (TL_CC / 4), pxy = e / (TL_CC / 4);
+          *reinterpret_cast<float4*>(&tile[pxy * TL_PITCH + 4 * q]) =
+              make_float4(hi[u].x + lo[u].x, hi[u].y + lo[u].y, hi[u].z + lo[u].z, hi[u].w + lo[u].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < WPT; ++u) {
+      const int e = tid + u * TL_THREADS;
+      if (e < NW) wsm[e] = wreg[u];
     }
     __syncthreads();
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float* a = &tile[((ty + t / 3) * (TL_TW + 2) + tx + t % 3) * TL_PITCH];
+    for (int q = 0; q < TL_CC / 4; ++q) {
 #pragma unroll
-      for (int q = 0; q < TL_CC / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(a + 4 * q);
+      for (int dx = 0; dx < 3; ++dx) {
+        float4 a[TL_PY + 2];
 #pragma unroll
-        for (int o = 0; o < CO; ++o) {
-          const float4 k = *reinterpret_cast<const float4*>(&wsm[(t * CO + o) * TL_CC + 4 * q]);
-          acc[o] = fmaf(v.x, k.x, acc[o]);
-          acc[o] = fmaf(v.y, k.y, acc[o]);
-          acc[o] = fmaf(v.z, k.z, acc[o]);
-          acc[o] = fmaf(v.w, k.w, acc[o]);
+        for (int r = 0; r < TL_PY + 2; ++r)
+          a[r] = *reinterpret_cast<const float4*>(&tile[((wy * TL_PY + r) * (TL_TW + 2) + tx + dx) * TL_PITCH + 4 * q]);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int o = 0; o < CO; ++o) {
+            const float4 k = *reinterpret_cast<const float4*>(&wsm[((dy * 3 + dx) * CO + o) * TL_CC + 4 * q]);
+#pragma unroll
+            for (int i = 0; i < TL_PY; ++i) {
+              acc[i][o] = fmaf(a[i + dy].x, k.x, acc[i][o]);
+              acc[i][o] = fmaf(a[i + dy].y, k.y, acc[i][o]);
+              acc[i][o] = fmaf(a[i + dy].z, k.z, acc[i][o]);
+              acc[i][o] = fmaf(a[i + dy].w, k.w, acc[i][o]);
+            }
+          }
         }
       }
     }
   }
-  const int gy = y0 + ty, gx = x0 + tx;
-  if (gy < H && gx < W) {
+  const int gx = x0 + tx;
+  if (gx < W) {
 #pragma unroll
-    for (int o = 0; o < CO; ++o) out[(((long long)b * CO + o) * H + gy) * W + gx] = acc[o];
+    for (int i = 0; i < TL_PY; ++i) {
+      const int gy = y0 + wy * TL_PY + i;
+      if (gy < H) {
+#pragma unroll
+        for (int o = 0; o < CO; ++o) out[(((long long)b * CO + o) * H + gy) * W + gx] = acc[i][o];
+      }
+    }
   }
 }
 
@@ -297,8 +348,14 @@ int ll_nhwc_split_conv3(const float* z, const float* w, const float* bias, float
   const int tiles_x = (W + TL_TW - 1) / TL_TW, tiles_y = (H + TL_TH - 1) / TL_TH;
   if (B > 65535) return fail(LL_EINVAL, "ll_nhwc_split_conv3: batch too large");
   dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)B);
-  if (Cout == 1) nhwc_split_conv3_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
-  else nhwc_split_conv3_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
+  static bool attr_set = false;      // > 48 KB of dynamic shared memory needs the opt-in, once per process (idempotent)
+  if (!attr_set) {
+    LL_CUDA_OK(cudaFuncSetAttribute(nhwc_split_conv3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl_smem_bytes<1>()));
+    LL_CUDA_OK(cudaFuncSetAttribute(nhwc_split_conv3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl_smem_bytes<3>()));
+    attr_set = true;
+  }
+  if (Cout == 1) nhwc_split_conv3_kernel<1><<<grid, TL_THREADS, tl_smem_bytes<1>(), as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
+  else nhwc_split_conv3_kernel<3><<<grid, TL_THREADS, tl_smem_bytes<3>(), as_stream(stream)>>>(z, w, bias, out, B, C, H, W, tiles_x);
   LL_LAUNCH_OK("nhwc_split_conv3_kernel");
   return LL_OK;
 }

@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <type_traits>
 #include "ll_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -658,11 +659,15 @@ struct GdnPairParams {
   int NP, KS, passes, rpp;                 // outputs per pass, channels per staging round, passes, rounds per pass
   int ghalf_bytes;                         // (NP / 2) rows x 128 B
   int col_nm, col_ns, col_st;
-  // head mode (first layer of the scaling network: Conv2d(iC, N, 3, padding=1), iC <= 3, K = 9 iC <= 27): y is computed by
-  // the epilogue warps in exact FP32 FMA from the fp32 NCHW input instead of by the tensor cores; everything after E1 is shared
+  // head mode (first layer of the scaling network: Conv2d(iC, N, 3, padding=1), iC <= 3, K = 9 iC <= 27 padded to 32): the
+  // epilogue warps build the A operand -- the [hi | lo] split of every pixel's 3x3 x iC window of the fp32 NCHW input --
+  // straight in tensor memory, the weights sit in shared memory for the whole launch, and the conv is twelve 3xTF32 MMAs
+  // per tile; everything from E1 on is shared.  (The first version computed y on the FP32 pipe, one pixel per thread: 864
+  // broadcast LDS.128 + 1 728 FFMA2 per warp and tile, 10 k of the tile's 28 k cycles.)
   int head, iC;
   const float* x;                          // (B, iC, H, W)
   const float* w0;                         // (N, iC, 3, 3) torch layout
+  int wstage;                              // head mode: one extra ring-sized slot behind the ring holds this CTA's half of w0
 #ifdef LL_TIMELINE
   long long* tl;                           // probe build only (csrc/probe/igemm_timeline.cu): clock64 stamps of CTA 0
 #endif
@@ -683,7 +688,8 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
-  const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
+  const uint32_t ring_bytes = (uint32_t)(p.stages + p.wstage) * p.stage_bytes;
+  const uint32_t wbuf = base + (uint32_t)p.stages * p.stage_bytes;     // head mode: [hi | lo] of w0, (N / 2) x 128 B each
   const uint32_t bars = base + ring_bytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PR_MAXST + s); };
@@ -701,7 +707,6 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 8 * (2 * PR_MAXST + 16));
   float* s_bias = reinterpret_cast<float*>(gen + ring_bytes + 256);
   float* s_beta = s_bias + IG_MAXN;
-  float* s_w0 = s_beta + IG_MAXN;                        // head mode: [k = ci*9 + tap][N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -712,8 +717,20 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     s_beta[i] = i < p.N ? p.beta[i] : 1.f;
   }
   if (HEAD) {
-    const int K0 = 9 * p.iC;
-    for (int i = threadIdx.x; i < K0 * p.N; i += GD_THREADS) s_w0[i] = p.w0[(i % p.N) * K0 + i / p.N];
+    // B operand of the head conv: this CTA's N / 2 output channels x K = 32 (k = ci * 9 + tap, zero beyond 9 iC), split
+    // [hi | lo], in the K-major SWIZZLE_128B layout a TMA box {32, N / 2} would produce (row = 128 B, 16-byte chunk index
+    // XOR row mod 8) -- written once per CTA with generic stores, made visible to the tensor core by the proxy fence
+    const int K0 = 9 * p.iC, nhalf = p.N / 2;
+    uint8_t* wb = gen + (size_t)p.stages * p.stage_bytes;
+    for (int i = threadIdx.x; i < nhalf * 32; i += GD_THREADS) {
+      const int r = i >> 5, k = i & 31;
+      const float v = k < K0 ? p.w0[((int)rank * nhalf + r) * K0 + k] : 0.f;
+      const float h = tf32_rna(v);
+      const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)k & 3u) * 4u;
+      *reinterpret_cast<float*>(wb + off) = h;
+      *reinterpret_cast<float*>(wb + p.bhalf_bytes + off) = tf32_rna(v - h);
+    }
+    fence_proxy_async();
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -809,7 +826,31 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const uint32_t a_st = tmem_base + (uint32_t)p.col_st;
       int tli = 0;
       for (long long pt = pair0; pt < p.npairs; pt += pair_step, ++tli) {
-        if (!HEAD) {
+        if (HEAD) {
+          // head conv: A = the [hi | lo] split of the 3x3 x iC input windows, staged in tensor memory by the epilogue warps
+          // (K = 32), B = w0 from shared memory; same three-term split and accumulator plan as the mainloop below
+          LL_TL(tli, 0);
+          mbar_wait_spin(tempty_bar, te_phase ^ 1);      // the previous tile's E2 has read y and the norm
+          te_phase ^= 1;
+          LL_TL(tli, 3);
+          mbar_wait_spin(e2done_bar, e2_phase);          // every warp of the pair has staged its windows
+          e2_phase ^= 1;
+          tc_fence_after();
+          LL_TL(tli, 1);
+          if (elect_one()) {
+            const uint64_t b_hi = umma_desc_sw128(wbuf), b_lo = umma_desc_sw128(wbuf + p.bhalf_bytes);
+            const uint32_t ah = a_st, al = a_st + (uint32_t)p.KS;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts_2sm(d_small, al + 8 * k, b_hi + 2 * k, idesc, (uint32_t)(k != 0));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts_2sm(d_small, ah + 8 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32_ts_2sm(d_main, ah + 8 * k, b_hi + 2 * k, idesc, (uint32_t)(k != 0));
+            tc_commit_2sm(tfull_bar, 3);
+          }
+          __syncwarp();
+          LL_TL(tli, 2);
+        } else {
           LL_TL(tli, 0);
           mbar_wait_spin(tempty_bar, te_phase ^ 1);
           te_phase ^= 1;
@@ -903,22 +944,34 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     // head mode: the 3x3 x iC input window of this thread's pixel; the NEXT tile's window is requested as soon as the
     // current one has been consumed, so its global-load latency hides behind the GDN phases (ncu: 22 % of the kernel's
     // stall samples sat on the first use of these loads when they were issued at the top of the tile)
-    float win[27];
+    // Only the 16 window samples this warp stages (k = 16 (grp & 1) + j, k = ci * 9 + tap) are loaded, with compile-time
+    // (ci, dy, dx) per branch.  (With all 27 samples per thread the kernel spilled them under its 96-register cap and the
+    // loads ran one after the other: the timeline probe showed 8 k of a tile's 26 k cycles between the conv's issue and
+    // the epilogue seeing its result, spent inside this prefetch.)
+    float win[16];
     auto load_window = [&](long long pt_) {
       const long long t_ = 2 * pt_ + rank;
       const int b_ = (int)(t_ / per_img);
       const int r_ = (int)(t_ % per_img);
       const int y_ = (r_ / p.tiles_x) * IG_TH + ty, x_ = (r_ % p.tiles_x) * IG_TW + tx;
       const bool ok_ = pt_ < p.npairs && t_ < p.ntiles && y_ < p.H && x_ < p.W;
+      const float* xb_ = p.x + (long long)b_ * p.iC * p.H * p.W + (long long)y_ * p.W + x_;
+      const long long hw_ = (long long)p.H * p.W;
+      auto fetch = [&](auto kb0) {
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        const int ci = k / 9, dy = (k % 9) / 3 - 1, dx = k % 3 - 1;
-        const int gy = y_ + dy, gx = x_ + dx;
-        float v = 0.f;
-        if (ok_ && ci < p.iC && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-          v = __ldg(p.x + (((long long)b_ * p.iC + ci) * p.H + gy) * p.W + gx);
-        win[k] = v;
-      }
+        for (int j = 0; j < 16; ++j) {
+          constexpr int K0 = decltype(kb0)::value;
+          const int k = K0 + j;
+          const int ci = k / 9, dy = (k % 9) / 3 - 1, dx = k % 3 - 1;
+          const int gy = y_ + dy, gx = x_ + dx;
+          float v = 0.f;
+          if (k < 27 && ok_ && ci < p.iC && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+            v = __ldg(xb_ + ci * hw_ + dy * p.W + dx);
+          win[j] = v;
+        }
+      };
+      if ((grp & 1) == 0) fetch(std::integral_constant<int, 0>{});
+      else fetch(std::integral_constant<int, 16>{});
     };
     if (HEAD) load_window(pair0);
     int tli = 0;
@@ -936,34 +989,27 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const bool valid = t < p.ntiles && y < p.H && x < p.W;
       const long long px = ((long long)b * p.H + y) * p.W + x;
       if (HEAD) {
-        // E1 (head): y = Conv2d(iC, N, 3, padding=1)(x) + bias in exact FP32 FMA, one pixel per thread, -> tensor memory
-        for (int c = grp; c < nch; c += 4) {
-          float2 acc[8];          // packed FFMA2: two output channels per instruction, the window sample broadcast
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = *reinterpret_cast<const float2*>(s_bias + c * 16 + 2 * j);
-#pragma unroll
-          for (int k = 0; k < 27; ++k) {
-            if (k < 9 * p.iC) {
-              const float4* wr = reinterpret_cast<const float4*>(s_w0 + k * p.N + c * 16);
-              const float2 xx = make_float2(win[k], win[k]);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 w4 = wr[j4];
-                acc[2 * j4 + 0] = __ffma2_rn(xx, make_float2(w4.x, w4.y), acc[2 * j4 + 0]);
-                acc[2 * j4 + 1] = __ffma2_rn(xx, make_float2(w4.z, w4.w), acc[2 * j4 + 1]);
-              }
-            }
-          }
+        // head: this thread's 3x3 x iC window -> [hi | lo] split -> the A operand of the head conv in tensor memory (the
+        // staging columns are free: the previous tile's norm MMAs completed before its E2).  The four groups of a lane
+        // quarter share the work: groups 0 / 1 write k = 0..15 / 16..31 of the hi half, groups 2 / 3 of the lo half.
+        LL_TLE(30);
+        {
           uint32_t v[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[2 * j] = __float_as_uint(acc[j].x);
-            v[2 * j + 1] = __float_as_uint(acc[j].y);
+          for (int j = 0; j < 16; ++j) {
+            const float h = tf32_rna(win[j]);
+            v[j] = __float_as_uint(grp < 2 ? h : tf32_rna(win[j] - h));
           }
-          tmem_st16(tlane + c * 16, v);
+          tmem_st16(tlane + p.col_st + (grp < 2 ? 0 : p.KS) + (grp & 1) * 16, v);
         }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(e2done_bar);
+        LL_TLE(31);
         load_window(pt + pair_step);
-      } else {
+      }
+      {
         LL_TLE(32);
         mbar_wait_spin(tfull_bar, tf_phase);
         tf_phase ^= 1;
@@ -1853,11 +1899,12 @@ static int launch_gdn_pair(const float* a_nhwc, const float* wp, const float* bi
   p.bhalf_bytes = (N / 2) * 128;
   p.ghalf_bytes = (p.NP / 2) * 128;
   p.stage_bytes = head ? 2 * p.ghalf_bytes : 2 * PR_A_BYTES + 2 * p.bhalf_bytes;
-  const int tail = PR_TAIL_BYTES + IG_MAXN * 4 + (head ? 27 * IG_MAXN * 4 : 0);
-  p.stages = (PR_SMEM_LIMIT - 1024 - tail) / p.stage_bytes;
+  p.wstage = head ? 1 : 0;                   // head: [hi | lo] of this CTA's half of w0 = 2 bhalf_bytes = one gamma stage
+  const int tail = PR_TAIL_BYTES + IG_MAXN * 4;
+  p.stages = (PR_SMEM_LIMIT - 1024 - tail) / p.stage_bytes - p.wstage;
   if (p.stages > PR_MAXST) p.stages = PR_MAXST;
   if (p.stages < 2) return fail(LL_EINVAL, "ll_igemm_tf32_gdn: stage of %d bytes leaves fewer than 2 pipeline stages", p.stage_bytes);
-  const int smem = 1024 + p.stages * p.stage_bytes + tail;
+  const int smem = 1024 + (p.stages + p.wstage) * p.stage_bytes + tail;
   static thread_local bool attr[64] = {false};
   int dev = 0;
   LL_CUDA_OK(cudaGetDevice(&dev));
@@ -1881,7 +1928,8 @@ int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, c
 }
 
 // First layer of SubbandAutoEncoderBerk fused with its GDN: x (B,iC,H,W) fp32 NCHW, w0 (N,iC,3,3) (for the decoder: the
-// equivalent conv of the ConvTranspose2d), exact FP32 FMA conv -> GDN / inverse GDN on the tensor cores -> sz (B,H,W,2N).
+// equivalent conv of the ConvTranspose2d), 3xTF32 conv (K = 9 iC padded to 32, operands split in the kernel) -> GDN /
+// inverse GDN on the tensor cores -> sz (B,H,W,2N).
 int ll_conv3_gdn_head(const float* x, const float* w0, const float* bias, const float* gp, const float* beta, int B, int iC, int H,
                       int W, int N, int inverse, float* sz, ll_stream_t stream) {
   if (!x) return fail(LL_EINVAL, "ll_conv3_gdn_head: null input");
