@@ -973,7 +973,6 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       if ((grp & 1) == 0) fetch(std::integral_constant<int, 0>{});
       else fetch(std::integral_constant<int, 16>{});
     };
-    if (HEAD) load_window(pair0);
     int tli = 0;
 #ifdef LL_TIMELINE
     const bool tlw = warp == 2 && lane == 0;
@@ -981,6 +980,32 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 #else
 #define LL_TLE(slot) do { } while (0)
 #endif
+    // head: this thread's 3x3 x iC window -> [hi | lo] split -> the A operand of the head conv in tensor memory (the
+    // staging columns are free: the previous tile's norm MMAs completed before its E2).  The four groups of a lane
+    // quarter share the work: groups 0 / 1 write k = 0..15 / 16..31 of the hi half, groups 2 / 3 of the lo half.
+    // Called for tile t + 1 between the register half of tile t's E2 and its global stores: the stores keep the LSU busy
+    // for ~6 k cycles per tile (32 scattered sectors per instruction), and the hand-off -> conv MMAs -> accumulator
+    // round trip of the next tile (~3.5 k cycles) now runs underneath them instead of after them.
+    auto stage_window = [&]() {
+      LL_TLE(30);
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float h = tf32_rna(win[j]);
+        v[j] = __float_as_uint(grp < 2 ? h : tf32_rna(win[j] - h));
+      }
+      tmem_st16(tlane + p.col_st + (grp < 2 ? 0 : p.KS) + (grp & 1) * 16, v);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(e2done_bar);
+      LL_TLE(31);
+    };
+    if (HEAD && pair0 < p.npairs) {
+      load_window(pair0);
+      stage_window();
+      load_window(pair0 + pair_step);
+    }
     for (long long pt = pair0; pt < p.npairs; pt += pair_step, ++tli) {
       const long long t = 2 * pt + rank;
       const int b = (int)(t / per_img);
@@ -988,27 +1013,6 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       const int y = (r / p.tiles_x) * IG_TH + ty, x = (r % p.tiles_x) * IG_TW + tx;
       const bool valid = t < p.ntiles && y < p.H && x < p.W;
       const long long px = ((long long)b * p.H + y) * p.W + x;
-      if (HEAD) {
-        // head: this thread's 3x3 x iC window -> [hi | lo] split -> the A operand of the head conv in tensor memory (the
-        // staging columns are free: the previous tile's norm MMAs completed before its E2).  The four groups of a lane
-        // quarter share the work: groups 0 / 1 write k = 0..15 / 16..31 of the hi half, groups 2 / 3 of the lo half.
-        LL_TLE(30);
-        {
-          uint32_t v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float h = tf32_rna(win[j]);
-            v[j] = __float_as_uint(grp < 2 ? h : tf32_rna(win[j] - h));
-          }
-          tmem_st16(tlane + p.col_st + (grp < 2 ? 0 : p.KS) + (grp & 1) * 16, v);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(e2done_bar);
-        LL_TLE(31);
-        load_window(pt + pair_step);
-      }
       {
         LL_TLE(32);
         mbar_wait_spin(tfull_bar, tf_phase);
@@ -1090,6 +1094,10 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(ps + 1 < p.passes ? e2done_bar : tempty_bar);
+        if (HEAD && ps + 1 == p.passes && pt + pair_step < p.npairs) {
+          stage_window();
+          load_window(pt + 2 * pair_step);
+        }
         // E2, second half: [hi | lo] split and the kernel's only global stores, overlapping the tensor work that follows
         if (valid) {
 #pragma unroll
