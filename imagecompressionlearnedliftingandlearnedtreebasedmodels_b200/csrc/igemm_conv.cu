@@ -48,6 +48,21 @@ constexpr int IG_MAXSLOTS = 24;  // k-blocks per (group, tap); the 3xTF32 chain 
 constexpr int IG_SMEM_BYTES = 1024 /*align slack*/ + IG_STAGES * IG_STAGE_BYTES + 1024 /*barriers*/ + 2 * IG_MAXG * IG_MAXN * 4 +
                               IG_MAXG * (64 * 20 + 20 + 40 + 4) * 4 /*cgp tail weights (epi 4)*/;
 
+// GDN epilogues: a = beta + gamma . y^2 is a normal positive float (beta >= the reparametrisation's pedestal), so the one-MUFU
+// forms apply: rsqrt.approx.ftz returns what rsqrtf() returns for normal inputs (rsqrtf only adds the denormal rescaling:
+// FSETP + two predicated FMULs per value), sqrt.approx.ftz is within 1 ulp of sqrtf() (inverse GDN = decoder side only:
+// it moves the reconstruction by <= 1 ulp per layer, not the symbols) and has no slow-path call.
+__device__ __forceinline__ float rsqrt_approx(float a) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float a) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+
 struct IgemmParams {
   const float* bias;
   float* out_f32;          // NCHW fp32 (may be null)
@@ -334,7 +349,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; ++j) {
               const float a = __uint_as_float(v[j]) + gb[c * 32 + j];
               float r;
-              if (p.epi == 2) r = o[j] * (p.inverse ? sqrtf(a) : rsqrtf(a));   // GDN / inverse GDN
+              if (p.epi == 2) r = o[j] * (p.inverse ? sqrt_approx(a) : rsqrt_approx(a));   // GDN / inverse GDN
               else { o[j] = a; r = a * a; }                                       // conv: raw output, square for the GDN norm
               hi[j] = tf32_rna(r);
               lo[j] = tf32_rna(r - hi[j]);
@@ -590,7 +605,7 @@ igemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 32; ++j) {
             const float a = (__uint_as_float(v[j]) + __uint_as_float(w[j])) + s_bias[c * 32 + j];
             float rr;
-            if (p.epi == 2) rr = o[j] * (p.inverse ? sqrtf(a) : rsqrtf(a));
+            if (p.epi == 2) rr = o[j] * (p.inverse ? sqrt_approx(a) : rsqrt_approx(a));
             else { o[j] = a; rr = a * a; }
             hi[j] = tf32_rna(rr);
             lo[j] = tf32_rna(rr - hi[j]);
@@ -1086,7 +1101,7 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float a = (__uint_as_float(nm[j]) + __uint_as_float(ns[j])) + s_beta[gc * 16 + j];
-              rr[i][j] = __uint_as_float(yv[j]) * (p.inverse ? sqrtf(a) : rsqrtf(a));
+              rr[i][j] = __uint_as_float(yv[j]) * (p.inverse ? sqrt_approx(a) : rsqrt_approx(a));
             }
           }
         }
