@@ -27,6 +27,7 @@ SCALES_LEVELS = 64
 # images per launch group inside the context models: bounds the 243/486-channel intermediates
 # (level 0 of a 512x768 plane needs ~0.6 GB per image in fp32)
 CTX_BATCH_CHUNK = 16
+CTX_TC_CHAIN = True     # coarsest-level causal chains: the two dense masked 3x3 layers on the BF16 tensor path
 # A/B switches of the tensor-core context path (measurement scripts only; both on in the product):
 CTX_GEMM_HEAD = True     # plc head / masked csc as 1-tap igemm layers over ops.ctx_im2col (else the fp32 SIMT ctx_conv_nhwc)
 CTX_FUSED_TAIL = True    # cgp layers 2-4 + rate in one launch (else igemm_conv + cgp_tail_rate)
@@ -344,6 +345,7 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         # "fp32": everything on the exact-fp32 SIMT kernels.  Only (sigma, mu) -- i.e. bpp -- differ.
         self.ctx_precision = _ctx_precision(config)
         self._tc_cache = [PackCache() for _ in range(self.num_lifting_layers)]
+        self._chain_cache = {"xe": PackCache(), "xo": PackCache()}
 
     @staticmethod
     def _causal_chain(inn):
@@ -353,6 +355,50 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         return nn.Sequential(mk('A', inn, o), nn.LeakyReLU(inplace=True), mk('B', o, o), nn.LeakyReLU(inplace=True),
                              mk('B', o, o // 3), nn.LeakyReLU(inplace=True), mk('B', o // 3, o // 9),
                              nn.LeakyReLU(inplace=True), mk('B', o // 9, inn * 2))
+
+    def _chain_bits_input(self, key, seq, q):
+        """(sigma, mu) map of a coarsest-level causal chain (:298-317: masked 3x3 convs inn -> 81 inn -> 81 inn -> 27 inn ->
+        9 inn -> 2 inn, groups = inn).  Inference with ``ctx_precision: "bf16"``: the two dense layers (81 -> 81 and 81 -> 27
+        per group, 96 % of the chain's MACs) run as grouped 9-tap tcgen05 implicit GEMMs on channels-last bf16 -- the mask
+        is zeros in the packed weights -- and the thin layers around them stay on the exact-fp32 direct-conv kernel.  Like
+        every other context CNN on this path the result only moves (sigma, mu), i.e. bpp."""
+        convs = [m for m in seq if isinstance(m, MaskedConv2d)]
+        G = convs[0].groups if convs else 0
+        fits = CTX_TC_CHAIN and self.ctx_precision == "bf16" and len(convs) == 5 and 1 <= G <= 3 and \
+            all(c.groups == G and tuple(c.kernel_size) == (3, 3) for c in convs) and \
+            convs[0].out_channels // G <= 128 and convs[2].out_channels // G <= 32 and \
+            not _autograd.needs_grad([q] + [p for c in convs for p in c.parameters()])
+        if not fits:
+            return _chain(seq, q)
+        n1, n3 = convs[0].out_channels // G, convs[2].out_channels // G
+        for c in convs:
+            c.apply_mask()
+
+        def build():
+            w2, w3 = convs[1].weight.detach(), convs[2].weight.detach()
+            l2 = [ops.pack_igemm_weight(w2[n1 * g:n1 * (g + 1)].contiguous(), npad=128, kpad=128) for g in range(G)]
+            l3 = [ops.pack_igemm_weight(w3[n3 * g:n3 * (g + 1)].contiguous(), npad=32, kpad=128) for g in range(G)]
+            return dict(l2=torch.stack(l2).contiguous(), l3=torch.stack(l3).contiguous())
+
+        pk = self._chain_cache[key].get([convs[1].weight, convs[2].weight], build)
+        koff = [[128 * g, 128 * g + 64] for g in range(G)]
+        B, _, h, w = q.shape
+        outs = []
+        for b0 in range(0, B, 4 * CTX_BATCH_CHUNK):
+            qb = q[b0:b0 + 4 * CTX_BATCH_CHUNK]
+            n = qb.shape[0]
+            t1 = torch.zeros(n, 128 * G, h, w, dtype=torch.float32, device=q.device)      # 81 live channels per 128-slot
+            ops.conv2d(qb, convs[0].weight, convs[0].bias, groups=G, lrelu=True, out=t1, co_group=n1, co_stride=128, co_off=0)
+            a = torch.empty(n, h, w, 128 * G, dtype=torch.bfloat16, device=q.device)
+            ops.nchw_to_nhwc_bf16(t1, a, 0)
+            del t1
+            t2 = torch.empty(n, h, w, 128 * G, dtype=torch.bfloat16, device=q.device)
+            ops.igemm_conv(a, pk["l2"], convs[1].bias, n1, lrelu=True, out_nhwc=t2, nhwc_coff=0, nhwc_gstride=128, koff=koff)
+            del a
+            t3 = ops.igemm_conv(t2, pk["l3"], convs[2].bias, n3, lrelu=True, koff=koff)        # fp32 NCHW (n, 27 G, h, w)
+            del t2
+            outs.append(_conv(convs[4], _conv(convs[3], t3, lrelu=True)))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     # ---- tensor-core path (default): BF16 tcgen05 implicit GEMMs, FP32 accumulation -------------
     def _tc_pack(self, i):
@@ -496,11 +542,12 @@ class DWTConditioned2EntropyLayerZTsepSubbands(nn.Module):
         mode = "noise" if self.training else "dequantize"
         acc = self.bit_acc
         xe_q = self.ent_out_xe.quantize(out_xe, mode)
-        si_xe = self.ent_out_xe.bits(out_xe, _chain(self.csc_xe, xe_q), self.training, acc=acc)
+        si_xe = self.ent_out_xe.bits(out_xe, self._chain_bits_input("xe", self.csc_xe, xe_q), self.training, acc=acc)
         qs, sis = [], []
         i = L - 1
         q = self.ent_out_xo_list[i].quantize(out_xo_list[i], mode)
-        sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], _chain(self.csc_list[i], q), self.training, acc=acc))
+        sis.append(self.ent_out_xo_list[i].bits(out_xo_list[i], self._chain_bits_input("xo", self.csc_list[i], q), self.training,
+                                                acc=acc))
         qs.append(q)
         con = q
         for i in range(L - 2, -1, -1):

@@ -406,3 +406,44 @@ def test_fused_head_conv_gdn_matches_float64(iC, N, inverse, shape):
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     print(f"head iC={iC} N={N} inverse={inverse}: {err:.2e} of the output scale vs float64")
     assert err <= 3e-6, err
+
+
+@pytest.mark.parametrize("key,inn,shape", [("xo", 3, (5, 32, 48)), ("xe", 1, (3, 32, 48)), ("xo", 3, (2, 5, 7)), ("xe", 1, (70, 8, 16))])
+def test_coarse_causal_chain_on_the_tensor_path_matches_the_fp32_chain(key, inn, shape):
+    """Coarsest-level causal chains of conditioned2ZT (masked 3x3 convs inn -> 81 inn -> 81 inn -> 27 inn -> 9 inn -> 2 inn,
+    LiftingBasedDWT_net.py:298-317 of the reference) with the two dense layers as grouped 9-tap tcgen05 GEMMs on bf16
+    (``_chain_bits_input``) against the exact-fp32 direct-conv chain on the same weights: the (sigma, mu) map may differ
+    by bf16 operand rounding only (two layers, 2^-9 per operand), and the masks must hold (a causal chain's output at a
+    pixel does not change when later pixels change)."""
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.graphs.models import LiftingBasedDWT_net as M
+    from imagecompressionlearnedliftingandlearnedtreebasedmodels_b200.utils import config as C
+    torch.manual_seed(7 + inn)
+    layer = M.DWTConditioned2EntropyLayerZTsepSubbands(C.default_config(entropy_layer="conditioned2ZTsepSubbands", dwtlevels=2)).to(DEV).eval()
+    seq = layer.csc_list[-1] if key == "xo" else layer.csc_xe
+    with torch.no_grad():
+        for m in seq:
+            if hasattr(m, "weight"):
+                m.weight.mul_(3.0)          # default init is small: make every layer matter
+        B, H, W = shape
+        q = torch.randint(-6, 7, (B, inn, H, W), device=DEV).float()
+        ref = M._chain(seq, q)
+        got = layer._chain_bits_input(key, seq, q)
+        assert got.shape == ref.shape == (B, 2 * inn, H, W)
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item() / scale
+        print(f"chain {key} {shape}: {err:.2e} of the output scale")
+        assert err <= 2e-2, err
+        assert (got - ref).abs().mean().item() <= 3e-3 * scale
+        # causality: changing q at and after (y0, x0) in raster order leaves the outputs before it untouched
+        y0, x0 = H // 2, W // 2
+        q2 = q.clone()
+        q2[:, :, y0, x0:] += 5.0
+        q2[:, :, y0 + 1:, :] -= 3.0
+        got2 = layer._chain_bits_input(key, seq, q2)
+        assert torch.equal(got2[:, :, :y0, :], got[:, :, :y0, :])
+        assert torch.equal(got2[:, :, y0, :x0 + 1], got[:, :, y0, :x0 + 1])   # type-A first layer: pixel (y0, x0) itself is not an input
+        M.CTX_TC_CHAIN = False
+        try:
+            assert torch.equal(layer._chain_bits_input(key, seq, q), ref)
+        finally:
+            M.CTX_TC_CHAIN = True
