@@ -144,12 +144,13 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(const __grid_constan
 // the quantiser / the inverse transform) straight from the tensor-core chain's activations: z is channels-last
 // fp32 [hi | lo] (B,H,W,2C); the kernel forms hi + lo on load and writes fp32 NCHW.  Replaces the
 // NHWC -> NCHW conversion + generic NCHW conv pair (2.45 ms -> one HBM-bound pass over z).
-// CTA = 4 warps = 16 rows x 32 columns, thread = 4 vertically adjacent pixels x CO outputs, 16 input channels per stage
-// ([py][px][20] floats: the 80-byte pixel pitch makes the 16-byte channel-quad reads of 8 neighbouring pixels hit 8
-// distinct bank groups; 64 contiguous bytes per pixel per stage = the L2's fetch granule).  The one-pixel-per-thread
-// version was bound by shared memory (ncu: LSU data pipe 75 %, FMA 25 %: one activation and CO weight LDS.128 per 4 CO
-// FMAs); here the six rows a thread's four pixels need are read once per (channel quad, dx) and every broadcast weight
-// quad feeds four pixels: 15 LDS.128 per 144 FMAs at CO = 3.
+// CTA = 4 warps = 8 rows x 32 columns, thread = 2 vertically adjacent pixels x CO outputs, 32 input channels per stage
+// ([py][px][36] floats: the 144-byte pixel pitch makes the 16-byte channel-quad reads of 8 neighbouring pixels hit 8
+// distinct bank groups; 128 contiguous bytes per pixel, half and stage).  The one-pixel-per-thread version was bound by
+// shared memory (ncu: LSU data pipe 75 %, FMA 25 %: one activation and CO weight LDS.128 per 4 CO FMAs); here the four
+// rows a thread's two pixels need are read once per (channel quad, dx) and every broadcast weight quad feeds both pixels:
+// 13 LDS.128 per 72 FMAs at CO = 3.  With that fixed the kernel is bound by the memory system: 64-byte pieces per pixel
+// and stage streamed at 2.1 TB/s, 128-byte pieces at 2.6 TB/s (an L2 prefetch of the rest of the pixel's row did not help).
 constexpr int TL_TH = 8, TL_TW = 32, TL_CC = 32, TL_PITCH = 36, TL_PY = 2, TL_THREADS = 128, TL_MLP = 6;
 
 template <int CO>

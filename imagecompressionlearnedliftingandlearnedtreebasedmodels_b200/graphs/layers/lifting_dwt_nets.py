@@ -70,8 +70,8 @@ class SubbandAutoEncoder(nn.Module):
 
 class SubbandAutoEncoderBerk(nn.Module):
     """3x3 conv + GDN / inverse-GDN scaling network (lifting_dwt_nets.py:126-165).  It feeds the quantiser, so it runs
-    at fp32-level accuracy: convs 2-3 and the three GDN norms as 3xTF32 tcgen05 implicit GEMMs (csrc/igemm_conv.cu),
-    the first / last conv on the exact FP32 kernels.  With autograd on (training), forward and backward run through torch
+    at fp32-level accuracy: convs 1-3 and the three GDN norms as 3xTF32 tcgen05 implicit GEMMs (csrc/igemm_conv.cu: every
+    conv fused with its GDN, the first one in the kernel's head mode), the last conv on the exact FP32 kernel.  With autograd on (training), forward and backward run through torch
     fp32 ops (TF32 off) -- the recompute path of ``_autograd`` -- there is no inference-time backend switch."""
 
     def __init__(self, in_ch):

@@ -256,8 +256,9 @@ int ll_igemm_tf32(const float* a_nhwc, const float* wp, const float* bias, int B
 int ll_igemm_tf32_gdn(const float* a_nhwc, const float* wp, const float* bias, const float* gp, const float* beta, int B, int H,
                       int W, int C, int N, int taps, int inverse, float* sz, ll_stream_t stream);
 /* First layer of SubbandAutoEncoderBerk (Conv2d(iC, N, 3, padding=1), iC <= 3; for ae_up the equivalent conv of the
- * ConvTranspose2d) fused with its GDN / inverse GDN: x (B,iC,H,W) fp32 NCHW, w0 (N,iC,3,3); the conv runs in exact FP32 FMA
- * inside the same CTA-pair kernel, the norm on the tensor cores; sz as ll_igemm_tf32_gdn. */
+ * ConvTranspose2d) fused with its GDN / inverse GDN: x (B,iC,H,W) fp32 NCHW, w0 (N,iC,3,3); the conv (K = 9 iC padded to
+ * 32) runs as a 3xTF32 split on the tensor cores inside the same CTA-pair kernel -- the input windows are split and staged
+ * in tensor memory by the kernel, w0 is split and packed by the kernel -- like the norm; sz as ll_igemm_tf32_gdn. */
 int ll_conv3_gdn_head(const float* x, const float* w0, const float* bias, const float* gp, const float* beta, int B, int iC, int H,
                       int W, int N, int inverse, float* sz, ll_stream_t stream);
 /* fp32 NCHW (B,C,H,W) -> y NHWC raw (optional) and sz NHWC (B,H,W,2C) = split of x^2 (mode 0) or of x (mode 1). */
@@ -267,7 +268,7 @@ int ll_nhwc_split_to_nchw(const float* z, float* out, int B, int C, int H, int W
 /* Last 3x3 conv of SubbandAutoEncoderBerk.ae_down / ae_up (nn.Conv2d / ConvTranspose2d(iC*32, iC, 3, padding=1),
  * lifting_dwt_nets.py:133,143) on the chain's own activations: z NHWC (B,H,W,2C) [hi | lo], w (Cout,C,3,3) in
  * cross-correlation layout (ConvTranspose weights flipped / transposed by the caller), bias (Cout) or NULL ->
- * out fp32 NCHW (B,Cout,H,W).  Exact fp32 FMA (feeds the quantiser).  C % 16 == 0, Cout in {1, 3}. */
+ * out fp32 NCHW (B,Cout,H,W).  Exact fp32 FMA (feeds the quantiser).  C % 32 == 0, Cout in {1, 3}. */
 int ll_nhwc_split_conv3(const float* z, const float* w, const float* bias, float* out, int B, int C, int Cout, int H, int W,
                         ll_stream_t stream);
 /* 1x1 head of onlyEZWT's parent context net (LeakyReLU + nn.Conv2d(243, 6, 1), LiftingBasedDWT_net.py:792-794) on

@@ -387,8 +387,8 @@ def test_fused_conv_gdn_matches_two_kernel_chain_and_float64(C, N, taps, inverse
 
 @pytest.mark.parametrize("iC,N,inverse,shape", [(3, 96, False, (2, 37, 50)), (1, 32, False, (3, 16, 16)), (3, 96, True, (1, 9, 33)), (1, 32, True, (1, 8, 16))])
 def test_fused_head_conv_gdn_matches_float64(iC, N, inverse, shape):
-    """``ll_conv3_gdn_head``: first layer of SubbandAutoEncoderBerk (3x3 conv of the 1- or 3-channel subband tensor, exact FP32
-    FMA in the epilogue warps) + its GDN on the tensor cores, against float64."""
+    """``ll_conv3_gdn_head``: first layer of SubbandAutoEncoderBerk (3x3 conv of the 1- or 3-channel subband tensor as a 3xTF32
+    split on the tensor cores, windows staged in tensor memory by the epilogue warps) + its GDN, against float64."""
     ops = _ops()
     torch.manual_seed(iC + N)
     B, H, W = shape

@@ -60,7 +60,8 @@ def test_model_forward_matches_reference_golden(name, prec):
                 n, bad = flip_audit(xo_q[i].cpu(), g[f"xo_q_{c}_{i}"], g[f"out_xo_{c}_{i}"], label=f"{name}/{prec}/xo{c}_{i}")
                 assert bad == 0 and n == 0, (c, i, n, bad)
     assert rel_err(xhat.cpu(), g["xhat"]) < 1e-4
-    assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=1e-3)[2]
+    # (bf16: the coarsest-level causal chains -- si_xe and the last si_xo -- run their two dense layers on the tensor path too)
+    assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=tol_sub, frac_outliers=fo)[2], bits_check(si_xe.cpu(), g["si_xe"])
     for i, s in enumerate(si_xo):
         assert bits_check(s.cpu(), g[f"si_xo_{i}"], tol_sum=tol_sub, frac_outliers=fo)[2], \
             (i, bits_check(s.cpu(), g[f"si_xo_{i}"]))
@@ -93,7 +94,8 @@ def test_training_mode_noise_parity(prec):
     finally:
         compat.draw_noise = orig
     assert rel_err(xhat.cpu(), g["xhat"]) < 1e-4
-    assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=1e-3)[2]
+    assert bits_check(si_xe.cpu(), g["si_xe"], tol_sum=1e-3 if prec == "fp32" else 5e-3,
+                      frac_outliers=1e-3 if prec == "fp32" else 1.0)[2], bits_check(si_xe.cpu(), g["si_xe"])
     tot, ref = float(si_xe.double().sum()), float(g["si_xe"].double().sum())
     for i, s in enumerate(si_xo):
         assert bits_check(s.cpu(), g[f"si_xo_{i}"], tol_sum=1e-3 if prec == "fp32" else 5e-3,
