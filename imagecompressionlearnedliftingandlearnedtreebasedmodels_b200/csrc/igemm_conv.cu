@@ -1051,7 +1051,11 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(e2done_bar);
-      for (int ps = 0; ps < p.passes; ++ps) {
+      // staging rounds of one GDN pass.  Pass ps + 1 is staged between the register half of pass ps's E2 and its global
+      // stores: the stores keep the LSU busy for thousands of cycles (one 32-byte sector per lane and instruction), and the
+      // next pass's norm MMAs now run underneath them instead of after them (conv 96->192: E2[0] took 7 k of the tile's
+      // 59 k cycles with the tensor pipe idle)
+      auto stage_pass = [&](int ps) {
         for (int rd = 0; rd < p.rpp; ++rd, ++ground) {
           LL_TLE(36 + 2 * (ps * p.rpp + rd));
           for (int cc = grp; cc < slots; cc += 4) {              // the slots this warp owns (slot index = chunk index mod 4)
@@ -1079,6 +1083,9 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
           }
           LL_TLE(37 + 2 * (ps * p.rpp + rd));
         }
+      };
+      stage_pass(0);
+      for (int ps = 0; ps < p.passes; ++ps) {
         // norm of channels [ps NP, ps NP + NP) complete
         mbar_wait_spin(pdone_bar, pd_phase);
         pd_phase ^= 1;
@@ -1109,6 +1116,7 @@ igemm_tf32_gdn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(ps + 1 < p.passes ? e2done_bar : tempty_bar);
+        if (ps + 1 < p.passes) stage_pass(ps + 1);
         if (HEAD && ps + 1 == p.passes && pt + pair_step < p.npairs) {
           stage_window();
           load_window(pt + 2 * pair_step);
